@@ -1,0 +1,9 @@
+"""cosmic_profiles_b200 -- B200 (sm_100a) drop-in for the per-halo shape / density hot path of
+tibordome/cosmic_profiles.  See DESIGN.md and INTEGRATION.md.
+
+    import cosmic_profiles_b200 as cpb
+    cpb.install()          # rebinds the 8 driver names inside cosmic_profiles.common.cosmic_base_class
+"""
+from .install import install, uninstall, DRIVER_NAMES  # noqa: F401
+
+__all__ = ["install", "uninstall", "DRIVER_NAMES"]

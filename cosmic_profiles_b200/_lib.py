@@ -1,0 +1,186 @@
+"""ctypes binding of libcosmicgpu.so (include/cosmic_gpu.h).  No CPU fallback: a missing library or a
+missing CUDA device raises, loudly."""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcosmicgpu.so")
+
+_D = ctypes.POINTER(ctypes.c_double)
+_I = ctypes.POINTER(ctypes.c_int32)
+_lib = None
+
+
+class CosmicGpuError(RuntimeError):
+    pass
+
+
+class Timing(ctypes.Structure):
+    _fields_ = [("h2d_ms", ctypes.c_double), ("gather_ms", ctypes.c_double), ("kernel_ms", ctypes.c_double),
+                ("d2h_ms", ctypes.c_double), ("kernel_launches", ctypes.c_int32),
+                ("hot_kernel_launches", ctypes.c_int32), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = ["cpg_device_count", "cpg_last_error", "cpg_version", "cpg_create", "cpg_destroy", "cpg_set_particles",
+           "cpg_set_catalogue", "cpg_shape", "cpg_dens_sph", "cpg_dens_ell", "cpg_dens_kernel", "cpg_obj_masses",
+           "cpg_get_timing", "cpg_set_option"]
+
+
+def load():
+    """dlopen the library and declare every prototype of include/cosmic_gpu.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CosmicGpuError("%s not built: run `python -c 'import __graft_entry__ as g; g.build()'` or "
+                             "`make -C cosmic_profiles_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp = ctypes.c_void_p
+    L.cpg_device_count.restype = ctypes.c_int
+    L.cpg_last_error.restype = ctypes.c_char_p
+    L.cpg_version.restype = ctypes.c_char_p
+    L.cpg_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+    L.cpg_destroy.argtypes = [vp]
+    L.cpg_destroy.restype = None
+    L.cpg_set_particles.argtypes = [vp, _D, _D, _D, ctypes.c_int64]
+    L.cpg_set_catalogue.argtypes = [vp, _I, ctypes.c_int64, _I, ctypes.c_int32]
+    L.cpg_shape.argtypes = [vp, _D, _D, _D, ctypes.c_int32, ctypes.c_int32, ctypes.c_double, ctypes.c_float,
+                            ctypes.c_double, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                            ctypes.c_int32, _D, _I, _I, _D, _D]
+    L.cpg_dens_sph.argtypes = [vp, _D, _D, _D, ctypes.c_int32, ctypes.c_float, _D, _I]
+    L.cpg_dens_ell.argtypes = [vp, _D, _D, _D, _D, _D, _D, _D, ctypes.c_int32, ctypes.c_float, _D, _I]
+    L.cpg_dens_kernel.argtypes = [vp, _D, _D, _D, ctypes.c_int32, ctypes.c_float, _D]
+    L.cpg_obj_masses.argtypes = [vp, _D]
+    L.cpg_get_timing.argtypes = [vp, ctypes.POINTER(Timing)]
+    L.cpg_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int64]
+    for f in EXPORTS:
+        if f not in ("cpg_last_error", "cpg_version", "cpg_destroy"):
+            getattr(L, f).restype = ctypes.c_int
+    _lib = L
+    return L
+
+
+def device_count():
+    return int(load().cpg_device_count())
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(_D)
+
+
+def _ip(a):
+    return None if a is None else a.ctypes.data_as(_I)
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise CosmicGpuError("%s failed (%d): %s" % (what, rc, load().cpg_last_error().decode()))
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Context:
+    """One CUDA device with a resident snapshot + catalogue (cpg_ctx)."""
+
+    def __init__(self, device=0):
+        self._h = ctypes.c_void_p()
+        self._L = load()
+        _check(self._L.cpg_create(int(device), ctypes.byref(self._h)), "cpg_create")
+        self.device = int(device)
+        self.n_obj = 0
+        self.have_vel = False
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.cpg_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name, value):
+        _check(self._L.cpg_set_option(self._h, name.encode(), int(value)), "cpg_set_option")
+
+    def set_particles(self, xyz, vxyz, masses):
+        xyz = f64(xyz)
+        masses = f64(masses)
+        vxyz = None if vxyz is None else f64(vxyz)
+        if xyz.ndim != 2 or xyz.shape[1] != 3 or masses.shape[0] != xyz.shape[0]:
+            raise ValueError("xyz must be (N,3) and masses (N,)")
+        if vxyz is not None and vxyz.shape != xyz.shape:
+            raise ValueError("vxyz must match xyz")
+        _check(self._L.cpg_set_particles(self._h, _dp(xyz), _dp(vxyz), _dp(masses), xyz.shape[0]), "cpg_set_particles")
+        self.have_vel = vxyz is not None
+
+    def set_catalogue(self, idx_cat, obj_size):
+        idx_cat = i32(idx_cat)
+        obj_size = i32(obj_size)
+        _check(self._L.cpg_set_catalogue(self._h, _ip(idx_cat), idx_cat.shape[0], _ip(obj_size), obj_size.shape[0]),
+               "cpg_set_catalogue")
+        self.n_obj = int(obj_size.shape[0])
+
+    def shape(self, centers, r200, r_over_r200, local, SAFE, L_BOX, IT_TOL, IT_WALL, IT_MIN, reduced, shell_based,
+              use_vel):
+        n = self.n_obj
+        centers = f64(centers)
+        r200 = f64(r200)
+        rr = f64(r_over_r200) if local else None
+        R = int(rr.shape[0]) if local else 1
+        out = np.zeros((n, R, 12))
+        nit = np.full((n, R), -1, dtype=np.int32)
+        npt = np.full((n, R), -1, dtype=np.int32)
+        m = np.zeros(n)
+        vc = np.zeros((n, 3))
+        _check(self._L.cpg_shape(self._h, _dp(centers), _dp(r200), _dp(rr), R, int(bool(local)), float(SAFE),
+                                 float(L_BOX), float(IT_TOL), int(IT_WALL), int(IT_MIN), int(bool(reduced)),
+                                 int(bool(shell_based)), int(bool(use_vel)), _dp(out), _ip(nit), _ip(npt), _dp(m),
+                                 _dp(vc)), "cpg_shape")
+        return out, nit, npt, m, vc
+
+    def dens_sph(self, centers, r200, bin_edges, L_BOX):
+        n, R = self.n_obj, len(bin_edges) - 1
+        dens = np.zeros((n, R))
+        cnt = np.zeros((n, R), dtype=np.int32)
+        _check(self._L.cpg_dens_sph(self._h, _dp(f64(centers)), _dp(f64(r200)), _dp(f64(bin_edges)), R, float(L_BOX),
+                                    _dp(dens), _ip(cnt)), "cpg_dens_sph")
+        return dens, cnt
+
+    def dens_ell(self, centers, a, b, c, major, inter, minor, L_BOX):
+        n, R = self.n_obj, major.shape[1]
+        dens = np.zeros((n, R))
+        cnt = np.zeros((n, R), dtype=np.int32)
+        _check(self._L.cpg_dens_ell(self._h, _dp(f64(centers)), _dp(f64(a)), _dp(f64(b)), _dp(f64(c)), _dp(f64(major)),
+                                    _dp(f64(inter)), _dp(f64(minor)), R, float(L_BOX), _dp(dens), _ip(cnt)),
+               "cpg_dens_ell")
+        return dens, cnt
+
+    def dens_kernel(self, centers, r200, r_over_r200, L_BOX):
+        n, R = self.n_obj, len(r_over_r200)
+        dens = np.zeros((n, R))
+        _check(self._L.cpg_dens_kernel(self._h, _dp(f64(centers)), _dp(f64(r200)), _dp(f64(r_over_r200)), R,
+                                       float(L_BOX), _dp(dens)), "cpg_dens_kernel")
+        return dens
+
+    def obj_masses(self):
+        m = np.zeros(self.n_obj)
+        _check(self._L.cpg_obj_masses(self._h, _dp(m)), "cpg_obj_masses")
+        return m
+
+    def timing(self):
+        t = Timing()
+        _check(self._L.cpg_get_timing(self._h, ctypes.byref(t)), "cpg_get_timing")
+        return t.as_dict()

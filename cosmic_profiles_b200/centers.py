@@ -1,0 +1,76 @@
+"""Host-side centre finding, as the reference does it before entering the hot path.
+
+The reference computes object centres in a serial Python loop ahead of every driver
+(cosmic_profiles/shape_profs/shape_profs_algos.pyx:586-591, dens_profs/dens_profs_algos.pyx:39-44,96-101)
+with the helpers of cosmic_profiles/common/python_routines.py (calcMode :287-306, respectPBCNoRef :499-528,
+calcCoM :530-547, recentreObject :549-565).  Centres are an INPUT of the GPU path (BASELINE.json
+north_star); they are produced here with the same numpy operations so that they are bit-identical to the
+reference's.  A device-side centre finder is SURVEY.md section 8(f) "next" row 1.
+"""
+import numpy as np
+from numpy.random import default_rng
+
+
+def _reference_points(n):
+    rng = default_rng(seed=0)
+    return rng.choice(np.arange(n), (min(50, n),), replace=False)
+
+
+def respect_pbc_noref(xyz, L_BOX):
+    if L_BOX == 0.0:
+        return xyz
+    out = xyz.copy()
+    ref = np.average(out[_reference_points(len(xyz))], axis=0)
+    for ax in range(3):
+        dist = out[:, ax] - ref[ax]
+        far = dist > L_BOX / 2
+        near = dist < -L_BOX / 2
+        out[:, ax][far] = out[:, ax][far] - L_BOX
+        out[:, ax][near] = out[:, ax][near] + L_BOX
+    return out
+
+
+def calc_com(xyz, masses):
+    ref = np.average(xyz[_reference_points(len(xyz))], axis=0)
+    delta = xyz.copy() - ref
+    mass_total = np.sum(masses)
+    com = np.sum(np.reshape(masses, (len(masses), 1)) * delta / mass_total, axis=0)
+    return com + ref
+
+
+def calc_mode(xyz, masses, rad):
+    while True:
+        com = np.sum(xyz * np.reshape(masses, (masses.shape[0], 1)), axis=0) / masses.sum()
+        keep = np.linalg.norm(xyz - com, axis=1) < rad
+        if np.count_nonzero(keep) < 5:
+            return com
+        xyz, masses, rad = xyz[keep], masses[keep], rad * 0.83
+
+
+def recentre(centers, L_BOX):
+    out = centers.copy()
+    for ax in range(3):
+        hi = out[:, ax] >= L_BOX
+        out[:, ax][hi] = out[:, ax][hi] - L_BOX
+        lo = out[:, ax] < 0.0
+        out[:, ax][lo] = out[:, ax][lo] + L_BOX
+    return out
+
+
+def compute_centers(xyz, masses, idx_cat, obj_size, L_BOX, CENTER, shape_path):
+    """shape_path=True: 'mode' starts from the object's bounding-box extent (shape_profs_algos.pyx:589);
+    False: from rad=1000 (dens_profs_algos.pyx:42)."""
+    off = np.concatenate(([0], np.cumsum(np.asarray(obj_size, dtype=np.int64))))
+    cen = np.zeros((len(obj_size), 3), dtype=np.float64)
+    for p in range(len(obj_size)):
+        sel = idx_cat[off[p]:off[p + 1]]
+        x = respect_pbc_noref(xyz[sel], L_BOX)
+        if CENTER == 'mode':
+            if shape_path:
+                rad = max(x[:, 0].max() - x[:, 0].min(), x[:, 1].max() - x[:, 1].min(), x[:, 2].max() - x[:, 2].min())
+            else:
+                rad = 1000
+            cen[p] = calc_mode(x, masses[sel], rad)
+        else:
+            cen[p] = calc_com(x, masses[sel])
+    return cen

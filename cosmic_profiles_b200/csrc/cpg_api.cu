@@ -1,0 +1,780 @@
+// cpg_api.cu -- C ABI (include/cosmic_gpu.h) and host-side orchestration of libcosmicgpu.
+//
+// Host logic mirrors the reference drivers (cosmic_profiles/shape_profs/shape_profs_algos.pyx:517-972,
+// cosmic_profiles/dens_profs/dens_profs_algos.pyx:15-280) minus everything that is arithmetic: that all
+// happens in the kernels of cpg_gather.cuh / cpg_morph.cuh / cpg_dens.cuh.  There is no CPU fallback.
+#include <math.h>
+#include <stdarg.h>
+
+#include <algorithm>
+#include <new>
+#include <numeric>
+#include <vector>
+
+#include "cpg_dens.cuh"
+#include "cpg_gather.cuh"
+#include "cpg_morph.cuh"
+
+namespace cpg {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n)
+    {
+        if (n <= cap && p) return CPG_OK;
+        release();
+        const size_t want = n ? n : 1;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMalloc of %zu bytes failed: %s", want * sizeof(T), cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            return CPG_ERR_NOMEM;
+        }
+        cap = want;
+        return CPG_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+#define CPG_TRY(expr)                  \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != CPG_OK) return rc__; \
+    } while (0)
+
+}  // namespace cpg
+
+using namespace cpg;
+
+struct cpg_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    // snapshot
+    DevBuf<double> xyz, vxyz, masses;
+    int64_t n_part = 0;
+    bool have_vel = false;
+    // catalogue
+    DevBuf<int32_t> idx, size;
+    DevBuf<int64_t> off, poff;
+    int64_t n_idx = 0, n_pad = 0;
+    int32_t n_obj = 0;
+    std::vector<int32_t> h_size;
+    std::vector<int32_t> order;   // objects sorted by size, largest first
+    // chunk lists
+    std::vector<Chunk> h_chunks, h_kchunks;
+    std::vector<int32_t> h_chunk_first, h_kchunk_first;
+    DevBuf<Chunk> chunks, kchunks;
+    DevBuf<int32_t> chunk_first, kchunk_first;
+    // gathered SoA
+    DevBuf<double> g_dx, g_dy, g_dz, g_m, g_vx, g_vy, g_vz;
+    bool mass_stream_valid = false;
+    // per-object scratch
+    DevBuf<double> centers, vcenters, r200, rr, obj_mass, part_mass, vpart;
+    DevBuf<int32_t> part_flag;
+    DevBuf<float> mass32;
+    DevBuf<uint8_t> skip;
+    // morphology
+    DevBuf<Task> tasks;
+    DevBuf<int32_t> task_counter;
+    DevBuf<double> out12;
+    DevBuf<int32_t> n_iter, n_pts;
+    // densities
+    DevBuf<double> d_a, d_b, d_c, d_major, d_inter, d_minor, d_edges, dens, bin_mass;
+    DevBuf<int32_t> bin_cnt, counts;
+    // options
+    int opt_shells_per_pass = 0;
+    int64_t opt_large_halo_min = 0;
+    int opt_cluster_size = 0;
+    cpg_timing timing = {};
+};
+
+namespace {
+
+int use_device(cpg_ctx *c)
+{
+    if (!c) {
+        set_error("null context");
+        return CPG_ERR_ARGUMENT;
+    }
+    CPG_CUDA(cudaSetDevice(c->device));
+    return CPG_OK;
+}
+
+int grid_for(int64_t n, int block, int cap)
+{
+    int64_t g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+SoA soa_view(cpg_ctx *c)
+{
+    SoA s;
+    s.dx = c->g_dx.p; s.dy = c->g_dy.p; s.dz = c->g_dz.p; s.m = c->g_m.p;
+    s.vx = c->g_vx.p; s.vy = c->g_vy.p; s.vz = c->g_vz.p;
+    s.poff = c->poff.p;
+    s.size = c->size.p;
+    return s;
+}
+
+GatherParams gather_view(cpg_ctx *c, float L_BOX)
+{
+    GatherParams G;
+    G.xyz = c->xyz.p; G.vxyz = c->vxyz.p; G.masses = c->masses.p;
+    G.idx = c->idx.p; G.off = c->off.p; G.poff = c->poff.p;
+    G.centers = c->centers.p; G.vcenters = c->vcenters.p;
+    G.n_obj = c->n_obj; G.n_idx = c->n_idx; G.L_BOX = L_BOX;
+    G.dx = c->g_dx.p; G.dy = c->g_dy.p; G.dz = c->g_dz.p; G.m = c->g_m.p;
+    G.vx = c->g_vx.p; G.vy = c->g_vy.p; G.vz = c->g_vz.p;
+    return G;
+}
+
+__global__ void idx_range_kernel(const int32_t *idx, int64_t n, int32_t *minmax)
+{
+    int lo = 0x7fffffff, hi = -0x7fffffff - 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const int v = idx[j];
+        lo = min(lo, v);
+        hi = max(hi, v);
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&minmax[0], lo);
+        atomicMax(&minmax[1], hi);
+    }
+}
+
+struct Timer {
+    cpg_ctx *c;
+    explicit Timer(cpg_ctx *ctx) : c(ctx) { memset(&c->timing, 0, sizeof c->timing); }
+    void mark(int i) { cudaEventRecord(c->ev[i], c->stream); }
+    static double ms(cudaEvent_t a, cudaEvent_t b)
+    {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, a, b);
+        return (double)t;
+    }
+};
+
+// Gather positions (+ statistics); requires centres on the device.  Launch count is added to timing.
+int run_gather(cpg_ctx *c, float L_BOX)
+{
+    const int64_t n = c->n_idx;
+    CPG_TRY(c->g_dx.ensure(c->n_pad)); CPG_TRY(c->g_dy.ensure(c->n_pad));
+    CPG_TRY(c->g_dz.ensure(c->n_pad)); CPG_TRY(c->g_m.ensure(c->n_pad));
+    if (n > 0) {
+        gather_pos_kernel<<<grid_for(n, 256, c->sm_count * 32), 256, 0, c->stream>>>(gather_view(c, L_BOX));
+        c->timing.kernel_launches++;
+    }
+    CPG_CUDA(cudaGetLastError());
+    c->mass_stream_valid = true;
+    return CPG_OK;
+}
+
+int run_stats(cpg_ctx *c)
+{
+    const int nc = (int)c->h_chunks.size();
+    CPG_TRY(c->part_mass.ensure(nc)); CPG_TRY(c->part_flag.ensure(nc));
+    CPG_TRY(c->obj_mass.ensure(c->n_obj)); CPG_TRY(c->skip.ensure(c->n_obj));
+    if (nc > 0) {
+        stats_chunk_kernel<<<nc, 256, 0, c->stream>>>(soa_view(c), c->chunks.p, nc, c->part_mass.p, c->part_flag.p);
+        c->timing.kernel_launches++;
+    }
+    if (c->n_obj > 0) {
+        stats_final_kernel<<<grid_for(c->n_obj, 128, 1 << 30), 128, 0, c->stream>>>(
+            c->chunk_first.p, c->size.p, c->n_obj, c->part_mass.p, c->part_flag.p, c->obj_mass.p, c->skip.p);
+        c->timing.kernel_launches++;
+    }
+    CPG_CUDA(cudaGetLastError());
+    return CPG_OK;
+}
+
+int run_vcenters(cpg_ctx *c, float L_BOX)
+{
+    const int nc = (int)c->h_chunks.size();
+    CPG_TRY(c->mass32.ensure(c->n_obj)); CPG_TRY(c->vpart.ensure((size_t)nc * 3));
+    CPG_TRY(c->vcenters.ensure((size_t)c->n_obj * 3));
+    CPG_TRY(c->g_vx.ensure(c->n_pad)); CPG_TRY(c->g_vy.ensure(c->n_pad)); CPG_TRY(c->g_vz.ensure(c->n_pad));
+    if (c->n_obj > 0) {
+        mass32_kernel<<<grid_for((int64_t)c->n_obj * 32, 128, c->sm_count * 16), 128, 0, c->stream>>>(
+            soa_view(c), c->n_obj, c->mass32.p);
+        if (nc > 0)
+            vsum_chunk_kernel<<<nc, 256, 0, c->stream>>>(gather_view(c, L_BOX), soa_view(c), c->chunks.p, nc, c->vpart.p);
+        vcenter_final_kernel<<<grid_for(c->n_obj, 128, 1 << 30), 128, 0, c->stream>>>(c->chunk_first.p, c->n_obj,
+                                                                                       c->vpart.p, c->mass32.p,
+                                                                                       c->vcenters.p);
+        if (c->n_idx > 0)
+            gather_vel_kernel<<<grid_for(c->n_idx, 256, c->sm_count * 32), 256, 0, c->stream>>>(gather_view(c, L_BOX));
+        c->timing.kernel_launches += 4;
+    }
+    CPG_CUDA(cudaGetLastError());
+    return CPG_OK;
+}
+
+template <int S, bool SHELL, bool REDUCED, bool VDISP>
+int launch_morph(cpg_ctx *c, MorphParams P, int n_warp_tasks, int n_cluster_tasks, int cluster_size)
+{
+    if (n_warp_tasks > 0) {
+        auto kern = morph_warp_kernel<S, SHELL, REDUCED, VDISP>;
+        int per_sm = 0;
+        CPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARP_KERNEL_WARPS * 32, 0));
+        if (per_sm < 1) per_sm = 1;
+        const int grid = std::min((n_warp_tasks + WARP_KERNEL_WARPS - 1) / WARP_KERNEL_WARPS, c->sm_count * per_sm);
+        MorphParams Pw = P;
+        Pw.n_tasks = n_warp_tasks;
+        kern<<<grid, WARP_KERNEL_WARPS * 32, 0, c->stream>>>(Pw);
+        c->timing.kernel_launches++;
+        c->timing.hot_kernel_launches++;
+        CPG_CUDA(cudaGetLastError());
+    }
+    if (n_cluster_tasks > 0) {
+        auto kern = morph_cluster_kernel<S, SHELL, REDUCED, VDISP>;
+        if (cluster_size > 8)
+            CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        MorphParams Pc = P;
+        Pc.tasks = P.tasks + n_warp_tasks;   // cluster tasks are stored behind the warp tasks
+        Pc.n_tasks = n_cluster_tasks;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)n_cluster_tasks * cluster_size);
+        cfg.blockDim = dim3(CLUSTER_KERNEL_WARPS * 32);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cluster_size;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CPG_CUDA(cudaLaunchKernelEx(&cfg, kern, Pc));
+        c->timing.kernel_launches++;
+        c->timing.hot_kernel_launches++;
+    }
+    return CPG_OK;
+}
+
+template <int S>
+int dispatch_morph(cpg_ctx *c, const MorphParams &P, bool shell, bool reduced, bool vdisp, int nw, int ncl, int cs)
+{
+#define CPG_CASE(SH, RE, VD) \
+    if (shell == SH && reduced == RE && vdisp == VD) return launch_morph<S, SH, RE, VD>(c, P, nw, ncl, cs);
+    CPG_CASE(false, false, false) CPG_CASE(false, true, false) CPG_CASE(true, false, false) CPG_CASE(true, true, false)
+    CPG_CASE(false, false, true) CPG_CASE(false, true, true) CPG_CASE(true, false, true) CPG_CASE(true, true, true)
+#undef CPG_CASE
+    return CPG_ERR_ARGUMENT;
+}
+
+int pow2_floor(int64_t v)
+{
+    int p = 1;
+    while ((int64_t)p * 2 <= v) p *= 2;
+    return p;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------ C ABI
+
+extern "C" {
+
+CPG_API int cpg_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+CPG_API const char *cpg_last_error(void) { return g_err; }
+
+CPG_API const char *cpg_version(void) { return "cosmicgpu 0.1 (sm_100a)"; }
+
+CPG_API int cpg_create(int device, cpg_ctx **out)
+{
+    if (!out) {
+        set_error("cpg_create: out is NULL");
+        return CPG_ERR_ARGUMENT;
+    }
+    *out = nullptr;
+    const int n = cpg_device_count();
+    if (n <= 0 || device < 0 || device >= n) {
+        set_error("cpg_create: CUDA device %d not available (%d visible); this library has no CPU fallback", device, n);
+        return CPG_ERR_NO_DEVICE;
+    }
+    cpg_ctx *c = new (std::nothrow) cpg_ctx();
+    if (!c) return CPG_ERR_NOMEM;
+    c->device = device;
+    CPG_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CPG_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 9) {
+        set_error("cpg_create: device %d is sm_%d%d; this build targets sm_100a (thread-block clusters required)",
+                  device, prop.major, prop.minor);
+        delete c;
+        return CPG_ERR_NO_DEVICE;
+    }
+    c->sm_count = prop.multiProcessorCount;
+    CPG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto &e : c->ev) CPG_CUDA(cudaEventCreate(&e));
+    *out = c;
+    return CPG_OK;
+}
+
+CPG_API void cpg_destroy(cpg_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf<double> *dbl[] = {&c->xyz, &c->vxyz, &c->masses, &c->g_dx, &c->g_dy, &c->g_dz, &c->g_m, &c->g_vx, &c->g_vy,
+                             &c->g_vz, &c->centers, &c->vcenters, &c->r200, &c->rr, &c->obj_mass, &c->part_mass,
+                             &c->vpart, &c->out12, &c->d_a, &c->d_b, &c->d_c, &c->d_major, &c->d_inter, &c->d_minor,
+                             &c->d_edges, &c->dens, &c->bin_mass};
+    for (auto *b : dbl) b->release();
+    DevBuf<int32_t> *i32[] = {&c->idx, &c->size, &c->chunk_first, &c->kchunk_first, &c->part_flag, &c->task_counter,
+                              &c->n_iter, &c->n_pts, &c->bin_cnt, &c->counts};
+    for (auto *b : i32) b->release();
+    c->off.release(); c->poff.release(); c->chunks.release(); c->kchunks.release();
+    c->mass32.release(); c->skip.release(); c->tasks.release();
+    for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+CPG_API int cpg_set_option(cpg_ctx *c, const char *name, int64_t value)
+{
+    if (!c || !name) return CPG_ERR_ARGUMENT;
+    if (!strcmp(name, "shells_per_pass")) {
+        if (value != 0 && value != 1 && value != 2 && value != 4) {
+            set_error("shells_per_pass must be 0, 1, 2 or 4");
+            return CPG_ERR_ARGUMENT;
+        }
+        c->opt_shells_per_pass = (int)value;
+    } else if (!strcmp(name, "large_halo_min")) {
+        c->opt_large_halo_min = value;
+    } else if (!strcmp(name, "cluster_size")) {
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16) {
+            set_error("cluster_size must be 0, 1, 2, 4, 8 or 16");
+            return CPG_ERR_ARGUMENT;
+        }
+        c->opt_cluster_size = (int)value;
+    } else {
+        set_error("unknown option %s", name);
+        return CPG_ERR_ARGUMENT;
+    }
+    return CPG_OK;
+}
+
+CPG_API int cpg_set_particles(cpg_ctx *c, const double *xyz, const double *vxyz, const double *masses, int64_t n_part)
+{
+    CPG_TRY(use_device(c));
+    if (n_part < 0 || (n_part > 0 && (!xyz || !masses))) {
+        set_error("cpg_set_particles: bad arguments");
+        return CPG_ERR_ARGUMENT;
+    }
+    CPG_TRY(c->xyz.ensure((size_t)n_part * 3));
+    CPG_TRY(c->masses.ensure((size_t)n_part));
+    CPG_CUDA(cudaMemcpyAsync(c->xyz.p, xyz, sizeof(double) * 3 * n_part, cudaMemcpyHostToDevice, c->stream));
+    CPG_CUDA(cudaMemcpyAsync(c->masses.p, masses, sizeof(double) * n_part, cudaMemcpyHostToDevice, c->stream));
+    c->have_vel = vxyz != nullptr;
+    if (vxyz) {
+        CPG_TRY(c->vxyz.ensure((size_t)n_part * 3));
+        CPG_CUDA(cudaMemcpyAsync(c->vxyz.p, vxyz, sizeof(double) * 3 * n_part, cudaMemcpyHostToDevice, c->stream));
+    }
+    CPG_CUDA(cudaStreamSynchronize(c->stream));
+    c->n_part = n_part;
+    c->mass_stream_valid = false;
+    return CPG_OK;
+}
+
+CPG_API int cpg_set_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, const int32_t *obj_size, int32_t n_obj)
+{
+    CPG_TRY(use_device(c));
+    if (n_idx < 0 || n_obj < 0 || (n_idx > 0 && !idx_cat) || (n_obj > 0 && !obj_size)) {
+        set_error("cpg_set_catalogue: bad arguments");
+        return CPG_ERR_ARGUMENT;
+    }
+    std::vector<int64_t> off(n_obj + 1, 0), poff(n_obj + 1, 0);
+    c->h_size.assign(obj_size, obj_size + n_obj);
+    c->h_chunks.clear(); c->h_kchunks.clear();
+    c->h_chunk_first.assign(n_obj + 1, 0); c->h_kchunk_first.assign(n_obj + 1, 0);
+    for (int h = 0; h < n_obj; h++) {
+        if (obj_size[h] < 0) {
+            set_error("cpg_set_catalogue: obj_size[%d] < 0", h);
+            return CPG_ERR_ARGUMENT;
+        }
+        off[h + 1] = off[h] + obj_size[h];
+        poff[h + 1] = poff[h] + ((obj_size[h] + 1) & ~1);
+        for (int s = 0; s < obj_size[h]; s += CHUNK) c->h_chunks.push_back(Chunk{h, s});
+        for (int s = 0; s < obj_size[h]; s += KDE_CHUNK) c->h_kchunks.push_back(Chunk{h, s});
+        c->h_chunk_first[h + 1] = (int32_t)c->h_chunks.size();
+        c->h_kchunk_first[h + 1] = (int32_t)c->h_kchunks.size();
+    }
+    if (off[n_obj] != n_idx) {
+        set_error("cpg_set_catalogue: sum(obj_size) = %lld but idx_cat has %lld entries", (long long)off[n_obj],
+                  (long long)n_idx);
+        return CPG_ERR_ARGUMENT;
+    }
+    c->order.resize(n_obj);
+    std::iota(c->order.begin(), c->order.end(), 0);
+    std::stable_sort(c->order.begin(), c->order.end(), [&](int a, int b) { return obj_size[a] > obj_size[b]; });
+
+    CPG_TRY(c->idx.ensure(n_idx)); CPG_TRY(c->size.ensure(n_obj));
+    CPG_TRY(c->off.ensure(n_obj + 1)); CPG_TRY(c->poff.ensure(n_obj + 1));
+    CPG_TRY(c->chunks.ensure(c->h_chunks.size())); CPG_TRY(c->kchunks.ensure(c->h_kchunks.size()));
+    CPG_TRY(c->chunk_first.ensure(n_obj + 1)); CPG_TRY(c->kchunk_first.ensure(n_obj + 1));
+    CPG_TRY(c->task_counter.ensure(4));
+    if (n_idx) CPG_CUDA(cudaMemcpyAsync(c->idx.p, idx_cat, sizeof(int32_t) * n_idx, cudaMemcpyHostToDevice, c->stream));
+    if (n_obj) CPG_CUDA(cudaMemcpyAsync(c->size.p, obj_size, sizeof(int32_t) * n_obj, cudaMemcpyHostToDevice, c->stream));
+    CPG_CUDA(cudaMemcpyAsync(c->off.p, off.data(), sizeof(int64_t) * (n_obj + 1), cudaMemcpyHostToDevice, c->stream));
+    CPG_CUDA(cudaMemcpyAsync(c->poff.p, poff.data(), sizeof(int64_t) * (n_obj + 1), cudaMemcpyHostToDevice, c->stream));
+    if (!c->h_chunks.empty())
+        CPG_CUDA(cudaMemcpyAsync(c->chunks.p, c->h_chunks.data(), sizeof(Chunk) * c->h_chunks.size(),
+                                 cudaMemcpyHostToDevice, c->stream));
+    if (!c->h_kchunks.empty())
+        CPG_CUDA(cudaMemcpyAsync(c->kchunks.p, c->h_kchunks.data(), sizeof(Chunk) * c->h_kchunks.size(),
+                                 cudaMemcpyHostToDevice, c->stream));
+    CPG_CUDA(cudaMemcpyAsync(c->chunk_first.p, c->h_chunk_first.data(), sizeof(int32_t) * (n_obj + 1),
+                             cudaMemcpyHostToDevice, c->stream));
+    CPG_CUDA(cudaMemcpyAsync(c->kchunk_first.p, c->h_kchunk_first.data(), sizeof(int32_t) * (n_obj + 1),
+                             cudaMemcpyHostToDevice, c->stream));
+    // index range check on the device: an out-of-range index would be an illegal address in the gather
+    if (n_idx > 0) {
+        const int32_t init[2] = {0x7fffffff, -0x7fffffff - 1};
+        int32_t got[2];
+        CPG_CUDA(cudaMemcpyAsync(c->task_counter.p, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+        idx_range_kernel<<<grid_for(n_idx, 256, c->sm_count * 16), 256, 0, c->stream>>>(c->idx.p, n_idx, c->task_counter.p);
+        CPG_CUDA(cudaGetLastError());
+        CPG_CUDA(cudaMemcpyAsync(got, c->task_counter.p, sizeof got, cudaMemcpyDeviceToHost, c->stream));
+        CPG_CUDA(cudaStreamSynchronize(c->stream));
+        if (got[0] < 0 || (int64_t)got[1] >= c->n_part) {
+            set_error("cpg_set_catalogue: idx_cat range [%d, %d] outside the %lld uploaded particles", got[0], got[1],
+                      (long long)c->n_part);
+            c->n_idx = 0; c->n_obj = 0;
+            return CPG_ERR_ARGUMENT;
+        }
+    }
+    CPG_CUDA(cudaStreamSynchronize(c->stream));
+    c->n_idx = n_idx;
+    c->n_pad = poff[n_obj];
+    c->n_obj = n_obj;
+    c->mass_stream_valid = false;
+    return CPG_OK;
+}
+
+CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, const double *r_over_r200, int32_t R,
+                      int32_t local, double SAFE, float L_BOX, double IT_TOL, int32_t IT_WALL, int32_t IT_MIN,
+                      int32_t reduced, int32_t shell_based, int32_t use_vel, double *out12, int32_t *n_iter,
+                      int32_t *n_pts, double *obj_mass, double *vcenters)
+{
+    CPG_TRY(use_device(c));
+    const int n = c->n_obj;
+    if (!local) R = 1;
+    if (R < 1 || R > 32767 || (n > 0 && (!centers || !r200 || !out12 || !n_iter || !n_pts)) || (local && !r_over_r200)) {
+        set_error("cpg_shape: bad arguments");
+        return CPG_ERR_ARGUMENT;
+    }
+    if (use_vel && !c->have_vel) {
+        set_error("cpg_shape: use_vel set but no velocities were uploaded");
+        return CPG_ERR_STATE;
+    }
+    if (!local) shell_based = 0;   // calcObjMorphGlobal always runs the ellipsoid variant (:1099)
+    Timer T(c);
+    if (n == 0) return CPG_OK;
+    const size_t nR = (size_t)n * R;
+    T.mark(0);
+    CPG_TRY(c->centers.ensure((size_t)n * 3)); CPG_TRY(c->r200.ensure(n)); CPG_TRY(c->rr.ensure(R));
+    CPG_CUDA(cudaMemcpyAsync(c->centers.p, centers, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    CPG_CUDA(cudaMemcpyAsync(c->r200.p, r200, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    if (local) CPG_CUDA(cudaMemcpyAsync(c->rr.p, r_over_r200, sizeof(double) * R, cudaMemcpyHostToDevice, c->stream));
+    c->timing.h2d_bytes = (int64_t)sizeof(double) * (4 * (int64_t)n + (local ? R : 0));
+
+    // ---- task list: objects largest first; S shells of one object per task
+    const int warp_slots = c->sm_count * 16;
+    int64_t n_units = (int64_t)n * R;
+    int S = c->opt_shells_per_pass;
+    if (S == 0) {
+        S = 1;
+        if (R >= 2 && n_units / 2 >= 4 * (int64_t)warp_slots) S = 2;
+        if (R >= 4 && n_units / 4 >= 4 * (int64_t)warp_slots) S = 4;
+    }
+    if (S > R) S = pow2_floor(R);
+    int64_t large_min = c->opt_large_halo_min > 0 ? c->opt_large_halo_min : (int64_t)131072;
+    if (c->opt_large_halo_min == 0 && n_units < warp_slots / 2) large_min = 8192;   // few units: spread each over CTAs
+    std::vector<Task> warp_tasks, cl_tasks;
+    int64_t largest = 0;
+    for (int oi = 0; oi < n; oi++) {
+        const int h = c->order[oi];
+        const int64_t N = c->h_size[h];
+        largest = std::max(largest, N);
+        std::vector<Task> &dst = (N >= large_min) ? cl_tasks : warp_tasks;
+        for (int k0 = 0; k0 < R; k0 += S)
+            dst.push_back(Task{h, (int16_t)k0, (int16_t)std::min(S, R - k0)});
+    }
+    int cluster_size = c->opt_cluster_size;
+    if (cluster_size == 0) {
+        cluster_size = 1;
+        if (!cl_tasks.empty()) {
+            // enough CTAs to cover the GPU about twice, bounded by the largest object (>= 32k particles per CTA)
+            const int64_t want = (2 * (int64_t)c->sm_count + (int64_t)cl_tasks.size() - 1) / (int64_t)cl_tasks.size();
+            const int64_t by_size = std::max<int64_t>(1, largest / 32768);
+            cluster_size = pow2_floor(std::max<int64_t>(1, std::min<int64_t>(std::min(want, by_size), 16)));
+        }
+    }
+    const int nw = (int)warp_tasks.size(), ncl = (int)cl_tasks.size();
+    warp_tasks.insert(warp_tasks.end(), cl_tasks.begin(), cl_tasks.end());
+    CPG_TRY(c->tasks.ensure(warp_tasks.size()));
+    CPG_CUDA(cudaMemcpyAsync(c->tasks.p, warp_tasks.data(), sizeof(Task) * warp_tasks.size(), cudaMemcpyHostToDevice,
+                             c->stream));
+    c->timing.h2d_bytes += (int64_t)(sizeof(Task) * warp_tasks.size());
+    CPG_TRY(c->out12.ensure(nR * 12)); CPG_TRY(c->n_iter.ensure(nR)); CPG_TRY(c->n_pts.ensure(nR));
+    CPG_CUDA(cudaMemsetAsync(c->out12.p, 0, sizeof(double) * 12 * nR, c->stream));
+    CPG_CUDA(cudaMemsetAsync(c->n_iter.p, 0xff, sizeof(int32_t) * nR, c->stream));
+    CPG_CUDA(cudaMemsetAsync(c->n_pts.p, 0xff, sizeof(int32_t) * nR, c->stream));
+    CPG_CUDA(cudaMemsetAsync(c->task_counter.p, 0, sizeof(int32_t) * 4, c->stream));
+    T.mark(1);
+
+    // ---- gather (positions, masses, statistics, velocity centres)
+    CPG_TRY(run_gather(c, L_BOX));
+    CPG_TRY(run_stats(c));
+    if (use_vel) CPG_TRY(run_vcenters(c, L_BOX));
+    T.mark(2);
+
+    // ---- the morphology loop
+    MorphParams P;
+    P.soa = soa_view(c);
+    P.r200 = c->r200.p; P.rr = c->rr.p; P.skip = c->skip.p;
+    P.tasks = c->tasks.p; P.n_tasks = 0; P.task_counter = c->task_counter.p;
+    P.R = R; P.local = local ? 1 : 0; P.SAFE = SAFE;
+    P.tol = IT_TOL; P.wall = IT_WALL; P.itmin = IT_MIN;
+    P.out12 = c->out12.p; P.n_iter = c->n_iter.p; P.n_pts = c->n_pts.p;
+    int rc;
+    if (S == 4) rc = dispatch_morph<4>(c, P, shell_based != 0, reduced != 0, use_vel != 0, nw, ncl, cluster_size);
+    else if (S == 2) rc = dispatch_morph<2>(c, P, shell_based != 0, reduced != 0, use_vel != 0, nw, ncl, cluster_size);
+    else rc = dispatch_morph<1>(c, P, shell_based != 0, reduced != 0, use_vel != 0, nw, ncl, cluster_size);
+    CPG_TRY(rc);
+    T.mark(3);
+
+    // ---- results
+    CPG_CUDA(cudaMemcpyAsync(out12, c->out12.p, sizeof(double) * 12 * nR, cudaMemcpyDeviceToHost, c->stream));
+    CPG_CUDA(cudaMemcpyAsync(n_iter, c->n_iter.p, sizeof(int32_t) * nR, cudaMemcpyDeviceToHost, c->stream));
+    CPG_CUDA(cudaMemcpyAsync(n_pts, c->n_pts.p, sizeof(int32_t) * nR, cudaMemcpyDeviceToHost, c->stream));
+    c->timing.d2h_bytes = (int64_t)(nR * (12 * sizeof(double) + 2 * sizeof(int32_t)));
+    if (obj_mass) {
+        CPG_CUDA(cudaMemcpyAsync(obj_mass, c->obj_mass.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+        c->timing.d2h_bytes += (int64_t)sizeof(double) * n;
+    }
+    if (use_vel && vcenters) {
+        CPG_CUDA(cudaMemcpyAsync(vcenters, c->vcenters.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+        c->timing.d2h_bytes += (int64_t)sizeof(double) * 3 * n;
+    }
+    T.mark(4);
+    CPG_CUDA(cudaStreamSynchronize(c->stream));
+    c->timing.h2d_ms = Timer::ms(c->ev[0], c->ev[1]);
+    c->timing.gather_ms = Timer::ms(c->ev[1], c->ev[2]);
+    c->timing.kernel_ms = Timer::ms(c->ev[2], c->ev[3]);
+    c->timing.d2h_ms = Timer::ms(c->ev[3], c->ev[4]);
+    return CPG_OK;
+}
+
+static int dens_common_begin(cpg_ctx *c, Timer &T, const double *centers, const double *r200, float L_BOX)
+{
+    const int n = c->n_obj;
+    T.mark(0);
+    CPG_TRY(c->centers.ensure((size_t)n * 3)); CPG_TRY(c->r200.ensure(n));
+    CPG_CUDA(cudaMemcpyAsync(c->centers.p, centers, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+    if (r200) CPG_CUDA(cudaMemcpyAsync(c->r200.p, r200, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    c->timing.h2d_bytes = (int64_t)sizeof(double) * (r200 ? 4 : 3) * n;
+    return CPG_OK;
+}
+
+static int dens_common_end(cpg_ctx *c, Timer &T, double *dens, int32_t *counts, size_t nR)
+{
+    T.mark(3);
+    CPG_CUDA(cudaMemcpyAsync(dens, c->dens.p, sizeof(double) * nR, cudaMemcpyDeviceToHost, c->stream));
+    c->timing.d2h_bytes = (int64_t)(sizeof(double) * nR);
+    if (counts) {
+        CPG_CUDA(cudaMemcpyAsync(counts, c->counts.p, sizeof(int32_t) * nR, cudaMemcpyDeviceToHost, c->stream));
+        c->timing.d2h_bytes += (int64_t)(sizeof(int32_t) * nR);
+    }
+    T.mark(4);
+    CPG_CUDA(cudaStreamSynchronize(c->stream));
+    c->timing.h2d_ms = Timer::ms(c->ev[0], c->ev[1]);
+    c->timing.gather_ms = Timer::ms(c->ev[1], c->ev[2]);
+    c->timing.kernel_ms = Timer::ms(c->ev[2], c->ev[3]);
+    c->timing.d2h_ms = Timer::ms(c->ev[3], c->ev[4]);
+    return CPG_OK;
+}
+
+CPG_API int cpg_dens_sph(cpg_ctx *c, const double *centers, const double *r200, const double *bin_edges, int32_t R,
+                         float L_BOX, double *dens, int32_t *counts)
+{
+    CPG_TRY(use_device(c));
+    const int n = c->n_obj;
+    if (R < 1 || R > DENS_MAX_R || (n > 0 && (!centers || !r200 || !bin_edges || !dens))) {
+        set_error("cpg_dens_sph: bad arguments (1 <= R <= %d)", DENS_MAX_R);
+        return CPG_ERR_ARGUMENT;
+    }
+    Timer T(c);
+    if (n == 0) return CPG_OK;
+    const size_t nR = (size_t)n * R;
+    const int nc = (int)c->h_chunks.size();
+    CPG_TRY(dens_common_begin(c, T, centers, r200, L_BOX));
+    CPG_TRY(c->d_edges.ensure(R + 1));
+    CPG_CUDA(cudaMemcpyAsync(c->d_edges.p, bin_edges, sizeof(double) * (R + 1), cudaMemcpyHostToDevice, c->stream));
+    CPG_TRY(c->bin_mass.ensure((size_t)nc * R)); CPG_TRY(c->bin_cnt.ensure((size_t)nc * R));
+    CPG_TRY(c->dens.ensure(nR)); CPG_TRY(c->counts.ensure(nR));
+    T.mark(1);
+    CPG_TRY(run_gather(c, L_BOX));
+    T.mark(2);
+    DensParams D = {};
+    D.soa = soa_view(c); D.chunks = c->chunks.p; D.n_chunks = nc; D.R = R; D.r200 = c->r200.p; D.edges = c->d_edges.p;
+    D.part_mass = c->bin_mass.p; D.part_cnt = c->bin_cnt.p;
+    D.monotone = 1;
+    for (int k = 0; k < R; k++)
+        if (!(bin_edges[k + 1] > bin_edges[k]) || !(bin_edges[k] >= 0.0)) D.monotone = 0;
+    if (nc > 0) {
+        dens_sph_kernel<<<nc, 256, 0, c->stream>>>(D);
+        c->timing.kernel_launches++; c->timing.hot_kernel_launches++;
+    }
+    dens_bins_final_kernel<<<grid_for((int64_t)nR, 128, 1 << 30), 128, 0, c->stream>>>(D, c->chunk_first.p, n, 0,
+                                                                                        c->dens.p, c->counts.p);
+    c->timing.kernel_launches++;
+    CPG_CUDA(cudaGetLastError());
+    return dens_common_end(c, T, dens, counts, nR);
+}
+
+CPG_API int cpg_dens_ell(cpg_ctx *c, const double *centers, const double *a, const double *b, const double *cc,
+                         const double *major, const double *inter, const double *minor, int32_t R, float L_BOX,
+                         double *dens, int32_t *counts)
+{
+    CPG_TRY(use_device(c));
+    const int n = c->n_obj;
+    if (R < 1 || R > DENS_MAX_R || (n > 0 && (!centers || !a || !b || !cc || !major || !inter || !minor || !dens))) {
+        set_error("cpg_dens_ell: bad arguments (1 <= R <= %d)", DENS_MAX_R);
+        return CPG_ERR_ARGUMENT;
+    }
+    Timer T(c);
+    if (n == 0) return CPG_OK;
+    const size_t nR = (size_t)n * R, nR1 = (size_t)n * (R + 1);
+    const int nc = (int)c->h_chunks.size();
+    CPG_TRY(dens_common_begin(c, T, centers, nullptr, L_BOX));
+    CPG_TRY(c->d_a.ensure(nR1)); CPG_TRY(c->d_b.ensure(nR1)); CPG_TRY(c->d_c.ensure(nR1));
+    CPG_TRY(c->d_major.ensure(nR * 3)); CPG_TRY(c->d_inter.ensure(nR * 3)); CPG_TRY(c->d_minor.ensure(nR * 3));
+    CPG_CUDA(cudaMemcpyAsync(c->d_a.p, a, sizeof(double) * nR1, cudaMemcpyHostToDevice, c->stream));
+    CPG_CUDA(cudaMemcpyAsync(c->d_b.p, b, sizeof(double) * nR1, cudaMemcpyHostToDevice, c->stream));
+    CPG_CUDA(cudaMemcpyAsync(c->d_c.p, cc, sizeof(double) * nR1, cudaMemcpyHostToDevice, c->stream));
+    CPG_CUDA(cudaMemcpyAsync(c->d_major.p, major, sizeof(double) * nR * 3, cudaMemcpyHostToDevice, c->stream));
+    CPG_CUDA(cudaMemcpyAsync(c->d_inter.p, inter, sizeof(double) * nR * 3, cudaMemcpyHostToDevice, c->stream));
+    CPG_CUDA(cudaMemcpyAsync(c->d_minor.p, minor, sizeof(double) * nR * 3, cudaMemcpyHostToDevice, c->stream));
+    c->timing.h2d_bytes += (int64_t)(sizeof(double) * (3 * nR1 + 9 * nR));
+    CPG_TRY(c->bin_mass.ensure((size_t)nc * R)); CPG_TRY(c->bin_cnt.ensure((size_t)nc * R));
+    CPG_TRY(c->dens.ensure(nR)); CPG_TRY(c->counts.ensure(nR));
+    T.mark(1);
+    CPG_TRY(run_gather(c, L_BOX));
+    T.mark(2);
+    DensParams D = {};
+    D.soa = soa_view(c); D.chunks = c->chunks.p; D.n_chunks = nc; D.R = R;
+    D.a = c->d_a.p; D.b = c->d_b.p; D.c = c->d_c.p;
+    D.major = c->d_major.p; D.inter = c->d_inter.p; D.minor = c->d_minor.p;
+    D.part_mass = c->bin_mass.p; D.part_cnt = c->bin_cnt.p;
+    const size_t smem = (size_t)R * (EB_SLOTS * sizeof(double) + sizeof(double) + sizeof(int));
+    if (smem > 48 * 1024)
+        CPG_CUDA(cudaFuncSetAttribute(dens_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (nc > 0) {
+        dens_ell_kernel<<<nc, 256, smem, c->stream>>>(D);
+        c->timing.kernel_launches++; c->timing.hot_kernel_launches++;
+    }
+    dens_bins_final_kernel<<<grid_for((int64_t)nR, 128, 1 << 30), 128, 0, c->stream>>>(D, c->chunk_first.p, n, 1,
+                                                                                        c->dens.p, c->counts.p);
+    c->timing.kernel_launches++;
+    CPG_CUDA(cudaGetLastError());
+    return dens_common_end(c, T, dens, counts, nR);
+}
+
+CPG_API int cpg_dens_kernel(cpg_ctx *c, const double *centers, const double *r200, const double *r_over_r200, int32_t R,
+                            float L_BOX, double *dens)
+{
+    CPG_TRY(use_device(c));
+    const int n = c->n_obj;
+    if (R < 1 || R > DENS_MAX_R || (n > 0 && (!centers || !r200 || !r_over_r200 || !dens))) {
+        set_error("cpg_dens_kernel: bad arguments (1 <= R <= %d)", DENS_MAX_R);
+        return CPG_ERR_ARGUMENT;
+    }
+    Timer T(c);
+    if (n == 0) return CPG_OK;
+    const size_t nR = (size_t)n * R;
+    const int nc = (int)c->h_kchunks.size();
+    CPG_TRY(dens_common_begin(c, T, centers, r200, L_BOX));
+    CPG_TRY(c->d_edges.ensure(R + 1));
+    CPG_CUDA(cudaMemcpyAsync(c->d_edges.p, r_over_r200, sizeof(double) * R, cudaMemcpyHostToDevice, c->stream));
+    CPG_TRY(c->bin_mass.ensure((size_t)nc * R));
+    CPG_TRY(c->dens.ensure(nR));
+    T.mark(1);
+    CPG_TRY(run_gather(c, L_BOX));
+    T.mark(2);
+    DensParams D = {};
+    D.soa = soa_view(c); D.chunks = c->kchunks.p; D.n_chunks = nc; D.R = R; D.r200 = c->r200.p; D.edges = c->d_edges.p;
+    D.part_mass = c->bin_mass.p;
+    D.ktilde_c0 = 1.0 / (2.0 * pow(2.0 * M_PI, 1.5));   // host libm, like the reference's generated C
+    if (nc > 0) {
+        dens_kernel_kernel<<<nc, 256, 0, c->stream>>>(D);
+        c->timing.kernel_launches++; c->timing.hot_kernel_launches++;
+    }
+    dens_kernel_final_kernel<<<grid_for((int64_t)nR, 128, 1 << 30), 128, 0, c->stream>>>(D, c->kchunk_first.p, n,
+                                                                                          c->dens.p);
+    c->timing.kernel_launches++;
+    CPG_CUDA(cudaGetLastError());
+    return dens_common_end(c, T, dens, nullptr, nR);
+}
+
+CPG_API int cpg_obj_masses(cpg_ctx *c, double *obj_mass)
+{
+    CPG_TRY(use_device(c));
+    const int n = c->n_obj;
+    if (n > 0 && !obj_mass) return CPG_ERR_ARGUMENT;
+    Timer T(c);
+    if (n == 0) return CPG_OK;
+    if (!c->mass_stream_valid) {
+        CPG_TRY(c->centers.ensure((size_t)n * 3));
+        CPG_CUDA(cudaMemsetAsync(c->centers.p, 0, sizeof(double) * 3 * n, c->stream));
+        CPG_TRY(run_gather(c, 0.0f));
+    }
+    CPG_TRY(run_stats(c));
+    CPG_CUDA(cudaMemcpyAsync(obj_mass, c->obj_mass.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CPG_CUDA(cudaStreamSynchronize(c->stream));
+    return CPG_OK;
+}
+
+CPG_API int cpg_get_timing(cpg_ctx *c, cpg_timing *out)
+{
+    if (!c || !out) return CPG_ERR_ARGUMENT;
+    *out = c->timing;
+    return CPG_OK;
+}
+
+}  // extern "C"

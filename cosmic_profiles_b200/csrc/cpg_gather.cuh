@@ -1,0 +1,223 @@
+// cpg_gather.cuh -- catalogue gather: AoS snapshot + int32 index catalogue -> per-object, centre-relative,
+// 16-byte aligned SoA streams, plus the per-object statistics the drivers need.
+//
+// Replaces the gather / PBC / mass loops of the reference drivers
+// (cosmic_profiles/shape_profs/shape_profs_algos.pyx:593-599, :703-707, :820-827, :937-943;
+//  cosmic_profiles/dens_profs/dens_profs_algos.pyx:45-47, :103-106, :211-214, :270-273) and
+// CythonHelpers.respectPBCNoRef / calcCoM / calcLocalSpread (cython_helpers/helper_class.pyx:169-199,
+// :85-105, :62-80).
+#pragma once
+#include "cpg_common.cuh"
+
+namespace cpg {
+
+constexpr int CHUNK = 16384;   // particles per statistics / binning chunk (one CTA each)
+
+struct Chunk {
+    int32_t halo;
+    int32_t start;   // first particle of the chunk inside the object
+};
+
+struct GatherParams {
+    const double *xyz;       // (n_part,3)
+    const double *vxyz;      // (n_part,3) or nullptr
+    const double *masses;    // (n_part)
+    const int32_t *idx;      // (n_idx)
+    const int64_t *off;      // (n_obj+1) catalogue offsets
+    const int64_t *poff;     // (n_obj+1) padded SoA offsets (even)
+    const double *centers;   // (n_obj,3)
+    const double *vcenters;  // (n_obj,3) (velocity gather only)
+    int32_t n_obj;
+    int64_t n_idx;
+    float L_BOX;
+    double *dx, *dy, *dz, *m, *vx, *vy, *vz;
+};
+
+__device__ __forceinline__ int find_object(const int64_t *off, int n_obj, int64_t j)
+{
+    int lo = 0, hi = n_obj;   // invariant: off[lo] <= j < off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (off[mid] <= j) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// helper_class.pyx:169-199 for one particle: reflection about L/2 relative to the object's particle 0,
+// distances truncated to fp32, the z test re-uses the (already updated) y distance (line 196).
+__device__ __forceinline__ void pbc_reflect(double &x, double &y, double &z, double x0, double y0, float L_BOX)
+{
+    const float half = L_BOX / 2;
+    const double L = (double)L_BOX;
+    if (fabsf((float)__dsub_rn(x0, x)) > half) x = __dsub_rn(L, x);
+    if (fabsf((float)__dsub_rn(y0, y)) > half) y = __dsub_rn(L, y);
+    if (fabsf((float)__dsub_rn(y0, y)) > half) z = __dsub_rn(L, z);
+}
+
+// Positions and masses.  One thread per catalogue entry; consecutive threads write consecutive SoA slots.
+__global__ void __launch_bounds__(256) gather_pos_kernel(const GatherParams G)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < G.n_idx; j += stride) {
+        const int h = find_object(G.off, G.n_obj, j);
+        const int64_t first = G.off[h], last = G.off[h + 1];
+        const int64_t g = G.idx[j];
+        double x = G.xyz[3 * g], y = G.xyz[3 * g + 1], z = G.xyz[3 * g + 2];
+        if (G.L_BOX != 0.0f) {
+            const int64_t g0 = G.idx[first];
+            pbc_reflect(x, y, z, G.xyz[3 * g0], G.xyz[3 * g0 + 1], G.L_BOX);
+        }
+        const int64_t o = G.poff[h] + (j - first);
+        G.dx[o] = __dsub_rn(x, G.centers[3 * h]);
+        G.dy[o] = __dsub_rn(y, G.centers[3 * h + 1]);
+        G.dz[o] = __dsub_rn(z, G.centers[3 * h + 2]);
+        G.m[o] = G.masses[g];
+        if (j == last - 1 && ((last - first) & 1)) {   // pad element of an odd-sized object
+            G.dx[o + 1] = 1e150; G.dy[o + 1] = 1e150; G.dz[o + 1] = 1e150; G.m[o + 1] = 0.0;
+        }
+    }
+}
+
+// Velocities relative to the object's velocity centre (shape_profs_algos.pyx:342: vxyz[run,i]-vcenter[i]).
+__global__ void __launch_bounds__(256) gather_vel_kernel(const GatherParams G)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < G.n_idx; j += stride) {
+        const int h = find_object(G.off, G.n_obj, j);
+        const int64_t first = G.off[h], last = G.off[h + 1];
+        const int64_t g = G.idx[j];
+        const int64_t o = G.poff[h] + (j - first);
+        G.vx[o] = __dsub_rn(G.vxyz[3 * g], G.vcenters[3 * h]);
+        G.vy[o] = __dsub_rn(G.vxyz[3 * g + 1], G.vcenters[3 * h + 1]);
+        G.vz[o] = __dsub_rn(G.vxyz[3 * g + 2], G.vcenters[3 * h + 2]);
+        if (j == last - 1 && ((last - first) & 1)) { G.vx[o + 1] = 0.0; G.vy[o + 1] = 0.0; G.vz[o + 1] = 0.0; }
+    }
+}
+
+// Deterministic block sum of up to 4 values (fixed tree), result valid in thread 0.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double *scratch /* [8][NV] */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; k++) v[k] = warp_sum(v[k]);
+    __syncthreads();
+    if (lane == 0)
+        for (int k = 0; k < NV; k++) scratch[warp * NV + k] = v[k];
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int k = 0; k < NV; k++) {
+            double s = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += scratch[w * NV + k];
+            v[k] = s;
+        }
+}
+
+// Per-chunk partial statistics: mass, "some particle differs from particle 0" flag (the only thing the
+// reference consumes of calcLocalSpread is ==0, i.e. an empty or fully coincident cloud).
+__global__ void __launch_bounds__(256) stats_chunk_kernel(const SoA soa, const Chunk *chunks, int n_chunks,
+                                                          double *part_mass, int32_t *part_spread)
+{
+    __shared__ double scratch[8 * 1];
+    __shared__ int s_flag;
+    const int c = blockIdx.x;
+    if (c >= n_chunks) return;
+    const Chunk ck = chunks[c];
+    const int N = soa.size[ck.halo];
+    const int64_t base = soa.poff[ck.halo];
+    const int end = min(N, ck.start + CHUNK);
+    if (threadIdx.x == 0) s_flag = 0;
+    __syncthreads();
+    const double x0 = soa.dx[base], y0 = soa.dy[base], z0 = soa.dz[base];
+    double v[1] = {0.0};
+    int differs = 0;
+    for (int i = ck.start + threadIdx.x; i < end; i += blockDim.x) {
+        v[0] += soa.m[base + i];
+        differs |= (soa.dx[base + i] != x0) | (soa.dy[base + i] != y0) | (soa.dz[base + i] != z0);
+    }
+    if (differs) s_flag = 1;
+    block_sum<1>(v, scratch);
+    if (threadIdx.x == 0) {
+        part_mass[c] = v[0];
+        part_spread[c] = s_flag;
+    }
+}
+
+// Combine the chunk partials of every object in chunk order.
+__global__ void stats_final_kernel(const int32_t *chunk_first /* n_obj+1 */, const int32_t *size, int n_obj,
+                                   const double *part_mass, const int32_t *part_spread, double *obj_mass,
+                                   uint8_t *skip)
+{
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n_obj) return;
+    double m = 0.0;
+    int spread = 0;
+    for (int c = chunk_first[h]; c < chunk_first[h + 1]; c++) {
+        m += part_mass[c];
+        spread |= part_spread[c];
+    }
+    obj_mass[h] = m;
+    skip[h] = (size[h] == 0 || !spread) ? 1 : 0;
+}
+
+// helper_class.pyx:98-100: `cdef float mass_total` accumulated sequentially in catalogue order
+// (mass_total = (float)((double)mass_total + m)).  The order is part of the result, so one lane walks the
+// object while the warp streams the masses in coalesced 32-element batches.
+__global__ void __launch_bounds__(128) mass32_kernel(const SoA soa, int n_obj, float *mass32)
+{
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; h < n_obj; h += warps) {
+        const int N = soa.size[h];
+        const double *m = soa.m + soa.poff[h];
+        float acc = 0.0f;
+        for (int i0 = 0; i0 < N; i0 += 32) {
+            const double mine = (i0 + lane < N) ? m[i0 + lane] : 0.0;
+            const int cntb = min(32, N - i0);
+            for (int j = 0; j < cntb; j++) {
+                const double mj = __shfl_sync(0xffffffffu, mine, j);
+                acc = (float)__dadd_rn((double)acc, mj);
+            }
+        }
+        if (lane == 0) mass32[h] = acc;
+    }
+}
+
+// Per-chunk partial sums of m*v (raw velocities through the catalogue), for vcenter.
+__global__ void __launch_bounds__(256) vsum_chunk_kernel(const GatherParams G, const SoA soa, const Chunk *chunks,
+                                                         int n_chunks, double *part /* [n_chunks][3] */)
+{
+    __shared__ double scratch[8 * 3];
+    const int c = blockIdx.x;
+    if (c >= n_chunks) return;
+    const Chunk ck = chunks[c];
+    const int N = soa.size[ck.halo];
+    const int64_t first = G.off[ck.halo];
+    const int64_t base = soa.poff[ck.halo];
+    const int end = min(N, ck.start + CHUNK);
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int i = ck.start + threadIdx.x; i < end; i += blockDim.x) {
+        const int64_t g = G.idx[first + i];
+        const double m = soa.m[base + i];
+        v[0] = fma(m, G.vxyz[3 * g], v[0]);
+        v[1] = fma(m, G.vxyz[3 * g + 1], v[1]);
+        v[2] = fma(m, G.vxyz[3 * g + 2], v[2]);
+    }
+    block_sum<3>(v, scratch);
+    if (threadIdx.x == 0) { part[3 * c] = v[0]; part[3 * c + 1] = v[1]; part[3 * c + 2] = v[2]; }
+}
+
+__global__ void vcenter_final_kernel(const int32_t *chunk_first, int n_obj, const double *part, const float *mass32,
+                                     double *vcenters)
+{
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n_obj) return;
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int c = chunk_first[h]; c < chunk_first[h + 1]; c++) {
+        s[0] += part[3 * c]; s[1] += part[3 * c + 1]; s[2] += part[3 * c + 2];
+    }
+    const double M = (double)mass32[h];
+    vcenters[3 * h] = s[0] / M; vcenters[3 * h + 1] = s[1] / M; vcenters[3 * h + 2] = s[2] / M;
+}
+
+}  // namespace cpg

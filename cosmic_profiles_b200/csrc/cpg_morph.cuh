@@ -1,0 +1,427 @@
+// cpg_morph.cuh -- the Katz-Dubinski morphology loop on sm_100a.
+//
+// Replaces runEllAlgo / runShellAlgo / runEllVDispAlgo / runShellVDispAlgo
+// (cosmic_profiles/shape_profs/shape_profs_algos.pyx:148-262, :16-145, :265-383, :386-514),
+// CythonHelpers.calcShapeTensor (cython_helpers/helper_class.pyx:19-57) and the LAPACK call at :155.
+//
+// Formulation: iteration k's tensor uses the membership and r_ell produced with
+// frame k-1, so "rotate with frame k-1 -> test -> accumulate" is ONE pass over (dx,dy,dz,m[,dv]) per
+// iteration; nothing per-particle is ever written back.  S shells of the same object share that pass
+// (each shell has its own frame in shared memory and its own 7 fp64 + 1 int accumulators in registers),
+// so the particle streams are read once per S halo-shell iterations.
+//
+// Arithmetic: pass 0 (identity frame, sphere / spherical shell) is evaluated with the reference's exact
+// operand order (__dmul_rn/__dadd_rn, no contraction) -- its particle counts are bit-exact by
+// construction.  Later passes rotate with eigenvectors that cannot be bit-identical to LAPACK's, so
+// they use FMAs; q, s and the axes agree to ~1e-14 and the integer counts are verified equal in tests.
+#pragma once
+#include <cooperative_groups.h>
+
+#include "cpg_common.cuh"
+
+namespace cpg {
+namespace cg = cooperative_groups;
+
+// frame slots (doubles) per shell in shared memory
+enum {
+    F_E2X = 0, F_E2Y, F_E2Z,   // major axis   (eigenvector of the largest eigenvalue)
+    F_E1X, F_E1Y, F_E1Z,       // intermediate
+    F_E0X, F_E0Y, F_E0Z,       // minor
+    F_IQ2, F_IS2,              // 1/q^2, 1/s^2
+    F_D2,                      // d^2
+    F_IA2, F_IB2, F_IC2,       // 1/(d-delta)^2, 1/(q d-delta)^2, 1/(s d-delta)^2   (shell variant)
+    F_THR,                     // inner-ellipsoid threshold: 1 (shell), -1 (first shell: test disabled)
+    F_SLOTS = 16
+};
+// pass-0 constants are parked in the slots that pass 0 does not need
+enum { F0_IN2 = F_IA2 };       // (d-delta)^2
+
+struct Particle4 {             // one particle as seen by the accumulators
+    double x, y, z, m;         // centre-relative position, mass
+    double tx, ty, tz;         // coordinates the tensor is built from (== x,y,z unless VDISP)
+};
+
+template <bool REDUCED>
+__device__ __forceinline__ void accumulate(double (&acc)[7], int &cnt, bool sel, double v, const Particle4 &p)
+{
+    // weight: m (non-reduced) or m / r_ell^2 (reduced, helper_class.pyx:54); the common 1/mass_tot factor
+    // is applied once per iteration after the reduction (it only rescales the tensor).
+    double w = REDUCED ? p.m / v : p.m;
+    w = sel ? w : 0.0;
+    const double wx = w * p.tx, wy = w * p.ty, wz = w * p.tz;
+    acc[0] = fma(wx, p.tx, acc[0]);
+    acc[1] = fma(wx, p.ty, acc[1]);
+    acc[2] = fma(wx, p.tz, acc[2]);
+    acc[3] = fma(wy, p.ty, acc[3]);
+    acc[4] = fma(wy, p.tz, acc[4]);
+    acc[5] = fma(wz, p.tz, acc[5]);
+    acc[6] += sel ? p.m : 0.0;
+    cnt += sel ? 1 : 0;
+}
+
+// Pass 0: spherical start (shape_profs_algos.pyx:206-212 / :81-87), exact reference arithmetic.
+template <int S, bool SHELL, bool REDUCED>
+__device__ __forceinline__ void pass0_particle(const Particle4 &p, const double *frames, unsigned amask,
+                                               double (&acc)[S][7], int (&cnt)[S])
+{
+    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(p.x, p.x), __dmul_rn(p.y, p.y)), __dmul_rn(p.z, p.z));
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        if (amask & (1u << s)) {
+            const double *F = frames + s * F_SLOTS;
+            bool sel = r2 < F[F_D2];
+            if (SHELL)
+                sel = sel && (r2 >= F[F0_IN2]);
+            accumulate<REDUCED>(acc[s], cnt[s], sel, r2, p);
+        }
+    }
+}
+
+// Pass k>=1: rotate into the frame of the previous eigen-decomposition and re-select
+// (shape_profs_algos.pyx:247-260 / :122-143) fused with the next tensor accumulation.
+template <int S, bool SHELL, bool REDUCED, int NP>
+__device__ __forceinline__ void passk_particles(const Particle4 (&p)[NP], const double *frames, unsigned amask,
+                                                double (&acc)[S][7], int (&cnt)[S])
+{
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        if (amask & (1u << s)) {
+            const double2 *F2 = reinterpret_cast<const double2 *>(frames + s * F_SLOTS);
+            const double2 f0 = F2[0], f1 = F2[1], f2 = F2[2], f3 = F2[3], f4 = F2[4], f5 = F2[5];
+            // f0=(e2x,e2y) f1=(e2z,e1x) f2=(e1y,e1z) f3=(e0x,e0y) f4=(e0z,iq2) f5=(is2,d2)
+            double2 f6, f7;
+            if (SHELL) { f6 = F2[6]; f7 = F2[7]; }   // f6=(ia2,ib2) f7=(ic2,thr)
+#pragma unroll
+            for (int j = 0; j < NP; j++) {
+                const double p0 = fma(f1.x, p[j].z, fma(f0.y, p[j].y, f0.x * p[j].x));
+                const double p1 = fma(f2.y, p[j].z, fma(f2.x, p[j].y, f1.y * p[j].x));
+                const double p2 = fma(f4.x, p[j].z, fma(f3.y, p[j].y, f3.x * p[j].x));
+                const double s0 = p0 * p0, s1 = p1 * p1, s2 = p2 * p2;
+                const double v = fma(s2, f5.x, fma(s1, f4.y, s0));
+                bool sel = v < f5.y;
+                if (SHELL) {
+                    const double u = fma(s2, f7.x, fma(s1, f6.y, s0 * f6.x));
+                    sel = sel && (u >= f7.y);
+                }
+                accumulate<REDUCED>(acc[s], cnt[s], sel, v, p[j]);
+            }
+        }
+    }
+}
+
+// Per halo-shell iteration state, replicated in every lane that serves the shell.
+struct KatzState {
+    double q, s;        // current axis ratios
+    double d, delta;    // ellipsoidal radius, shell width (delta == d: first shell / ellipsoid mode)
+    int iteration;      // the reference's `iteration` (starts at 1)
+    bool active;
+};
+
+// One trip through the body of the reference's while-loop for one shell, given the reduced sums of the
+// pass that just finished.  tot = {Sxx,Sxy,Sxz,Syy,Syz,Szz,M}.  Writes the next frame into `frame`
+// (shared, 16 doubles) when the iteration goes on and the 12 outputs when it ends.  `writer` lanes do
+// the global/shared stores; all lanes of a shell compute identical values.
+template <bool SHELL>
+__device__ __forceinline__ void katz_step(KatzState &st, const double (&tot)[7], int pts, const MorphParams &P,
+                                          double *frame, bool frame_writer, size_t out_idx, bool out_writer)
+{
+    if (!st.active)
+        return;
+    if (st.iteration > P.wall || pts < P.itmin) {   // shape_profs_algos.pyx:214-219: zeros (already there)
+        if (out_writer) {
+            P.n_iter[out_idx] = st.iteration - 1;
+            P.n_pts[out_idx] = pts;
+        }
+        st.active = false;
+        return;
+    }
+    const double im = 1.0 / tot[6];
+    double w[3], v[9];
+    eigh3(tot[0] * im, tot[1] * im, tot[2] * im, tot[3] * im, tot[4] * im, tot[5] * im, w, v);
+    const double q_old = st.q, s_old = st.s;
+    st.q = sqrt(w[1] / w[2]);
+    st.s = sqrt(w[0] / w[2]);
+    // helper_class.pyx:110-120: the difference is truncated to fp32 before abs()
+    const double eq = (double)fabsf((float)(st.q - q_old)) / q_old;
+    const double es = (double)fabsf((float)(st.s - s_old)) / s_old;
+    const double err = es > eq ? es : eq;   // Python max(eq, es)
+    if (!(err > P.tol)) {                   // converged (or NaN): these are the returned values
+        if (out_writer) {
+            double *o = P.out12 + 12 * out_idx;
+            o[0] = st.d; o[1] = st.q; o[2] = st.s;
+#pragma unroll
+            for (int r = 0; r < 3; r++) { o[3 + r] = v[6 + r]; o[6 + r] = v[3 + r]; o[9 + r] = v[r]; }
+            P.n_iter[out_idx] = st.iteration;
+            P.n_pts[out_idx] = pts;
+        }
+        st.active = false;
+        return;
+    }
+    if (frame_writer) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) { frame[F_E2X + r] = v[6 + r]; frame[F_E1X + r] = v[3 + r]; frame[F_E0X + r] = v[r]; }
+        frame[F_IQ2] = 1.0 / (st.q * st.q);
+        frame[F_IS2] = 1.0 / (st.s * st.s);
+        if (SHELL) {
+            const bool first = (st.d == st.delta);   // shape_profs_algos.pyx:130
+            const double a = st.d - st.delta, b = st.q * st.d - st.delta, c = st.s * st.d - st.delta;
+            frame[F_IA2] = first ? 0.0 : 1.0 / (a * a);
+            frame[F_IB2] = first ? 0.0 : 1.0 / (b * b);
+            frame[F_IC2] = first ? 0.0 : 1.0 / (c * c);
+            frame[F_THR] = first ? -1.0 : 1.0;
+        }
+    }
+    st.iteration += 1;
+}
+
+// Shell geometry (shape_profs_algos.pyx:1035-1044 local, :1096 global), exact reference arithmetic.
+__device__ __forceinline__ void shell_geometry(const MorphParams &P, int halo, int k, double &d, double &delta)
+{
+    const double r200 = P.r200[halo];
+    if (P.local) {
+        d = __dmul_rn(r200, P.rr[k]);
+        delta = (k == 0) ? d : __dsub_rn(d, __dmul_rn(r200, P.rr[k - 1]));
+    } else {
+        d = __dadd_rn(r200, P.SAFE);
+        delta = d;
+    }
+}
+
+template <bool VDISP>
+__device__ __forceinline__ void load_pair(const SoA &soa, int64_t base, int i2, Particle4 &a, Particle4 &b)
+{
+    const double2 x = reinterpret_cast<const double2 *>(soa.dx + base)[i2];
+    const double2 y = reinterpret_cast<const double2 *>(soa.dy + base)[i2];
+    const double2 z = reinterpret_cast<const double2 *>(soa.dz + base)[i2];
+    const double2 m = reinterpret_cast<const double2 *>(soa.m + base)[i2];
+    a.x = x.x; a.y = y.x; a.z = z.x; a.m = m.x;
+    b.x = x.y; b.y = y.y; b.z = z.y; b.m = m.y;
+    if (VDISP) {
+        const double2 u = reinterpret_cast<const double2 *>(soa.vx + base)[i2];
+        const double2 v = reinterpret_cast<const double2 *>(soa.vy + base)[i2];
+        const double2 w = reinterpret_cast<const double2 *>(soa.vz + base)[i2];
+        a.tx = u.x; a.ty = v.x; a.tz = w.x;
+        b.tx = u.y; b.ty = v.y; b.tz = w.y;
+    } else {
+        a.tx = a.x; a.ty = a.y; a.tz = a.z;
+        b.tx = b.x; b.ty = b.y; b.tz = b.z;
+    }
+}
+
+// One full pass of `nthreads` cooperating threads (thread `tid`) over the object's particle pairs.
+template <int S, bool SHELL, bool REDUCED, bool VDISP, bool FIRST>
+__device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npairs, int tid, int nthreads,
+                                         const double *frames, unsigned amask, double (&acc)[S][7], int (&cnt)[S])
+{
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        cnt[s] = 0;
+#pragma unroll
+        for (int k = 0; k < 7; k++) acc[s][k] = 0.0;
+    }
+    int i2 = tid;
+    if (!FIRST && !VDISP) {
+        // two pairs in flight per thread: more loads outstanding, frame registers reused over 4 particles
+        for (; i2 + nthreads < npairs; i2 += 2 * nthreads) {
+            Particle4 p[4];
+            load_pair<VDISP>(soa, base, i2, p[0], p[1]);
+            load_pair<VDISP>(soa, base, i2 + nthreads, p[2], p[3]);
+            passk_particles<S, SHELL, REDUCED, 4>(p, frames, amask, acc, cnt);
+        }
+    }
+    for (; i2 < npairs; i2 += nthreads) {
+        Particle4 p[2];
+        load_pair<VDISP>(soa, base, i2, p[0], p[1]);
+        if (FIRST) {
+            pass0_particle<S, SHELL, REDUCED>(p[0], frames, amask, acc, cnt);
+            pass0_particle<S, SHELL, REDUCED>(p[1], frames, amask, acc, cnt);
+        } else {
+            passk_particles<S, SHELL, REDUCED, 2>(p, frames, amask, acc, cnt);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 1: a WARP per task (object, group of <= S shells).  No block-level synchronisation at all:
+// warp-shuffle reductions, eigen-solves spread over lanes (lane l serves shell l % S), persistent
+// warps pulling tasks (sorted largest first) from an atomic queue.
+// ------------------------------------------------------------------------------------------------
+constexpr int WARP_KERNEL_WARPS = 4;
+
+template <int S, bool SHELL, bool REDUCED, bool VDISP>
+__global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) morph_warp_kernel(const MorphParams P)
+{
+    __shared__ __align__(16) double s_frames[WARP_KERNEL_WARPS][S * F_SLOTS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *frames = s_frames[warp];
+    const int ls = lane & (S - 1);
+
+    for (;;) {
+        int t = 0;
+        if (lane == 0)
+            t = atomicAdd(P.task_counter, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= P.n_tasks)
+            break;
+        const Task tk = P.tasks[t];
+        const int halo = tk.halo;
+        if (P.skip[halo] || (P.local && P.r200[halo] == 0.0))
+            continue;   // shape_profs_algos.pyx:1024-1029: outputs stay zero, counters stay -1
+        const int N = P.soa.size[halo];
+        const int64_t base = P.soa.poff[halo];
+        const int npairs = (N + 1) >> 1;
+
+        KatzState st;
+        st.q = 1.0; st.s = 1.0; st.iteration = 1;
+        st.active = ls < tk.nshell;
+        const int k = tk.shell0 + (st.active ? ls : 0);
+        shell_geometry(P, halo, k, st.d, st.delta);
+        const size_t out_idx = (size_t)halo * P.R + k;
+        __syncwarp();
+        if (lane < S) {
+            frames[ls * F_SLOTS + F_D2] = __dmul_rn(st.d, st.d);
+            const double in = __dsub_rn(st.d, st.delta);
+            frames[ls * F_SLOTS + F0_IN2] = __dmul_rn(in, in);
+        }
+        __syncwarp();
+        unsigned amask = __ballot_sync(0xffffffffu, st.active && lane < S);
+
+        double acc[S][7];
+        int cnt[S];
+        run_pass<S, SHELL, REDUCED, VDISP, true>(P.soa, base, npairs, lane, 32, frames, amask, acc, cnt);
+        while (true) {
+            // warp reduction, then every lane keeps the sums of the shell it serves
+            double tot[7] = {0, 0, 0, 0, 0, 0, 0};
+            int pts = 0;
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                if (amask & (1u << s)) {
+#pragma unroll
+                    for (int c = 0; c < 7; c++) {
+                        const double r = warp_sum(acc[s][c]);
+                        tot[c] = (ls == s) ? r : tot[c];
+                    }
+                    const int n = warp_sum_int(cnt[s]);
+                    pts = (ls == s) ? n : pts;
+                }
+            }
+            __syncwarp();
+            katz_step<SHELL>(st, tot, pts, P, frames + ls * F_SLOTS, lane < S, out_idx, lane < S);
+            __syncwarp();
+            amask = __ballot_sync(0xffffffffu, st.active && lane < S);
+            if (amask == 0)
+                break;
+            run_pass<S, SHELL, REDUCED, VDISP, false>(P.soa, base, npairs, lane, 32, frames, amask, acc, cnt);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 2: a thread-block CLUSTER per task, for objects too large for one warp.  The C CTAs of a
+// cluster interleave over the object's particle pairs; per iteration every CTA publishes its S x 8
+// partial sums in its own shared memory, one cluster barrier later every CTA reads all C partials
+// through distributed shared memory in rank order, so all CTAs hold bit-identical totals and take the
+// same convergence decisions without any global-memory traffic.  C == 1 degenerates to a plain CTA
+// per task (no cluster barrier).  Partials are double-buffered: one barrier per iteration.
+// ------------------------------------------------------------------------------------------------
+constexpr int CLUSTER_KERNEL_WARPS = 8;
+
+template <int S, bool SHELL, bool REDUCED, bool VDISP>
+__global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kernel(const MorphParams P)
+{
+    constexpr int NW = CLUSTER_KERNEL_WARPS;
+    __shared__ __align__(16) double s_frames[NW][S * F_SLOTS];   // warp-private frames (no CTA barrier to publish)
+    __shared__ double s_part[2][NW][S][8];                      // per-warp partial sums
+    __shared__ double s_cta[2][S][8];                           // per-CTA partial sums, read by the cluster
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int rank = (int)cluster.block_rank();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *frames = s_frames[warp];
+    const int ls = lane & (S - 1);
+
+    const int t = blockIdx.x / C;
+    const Task tk = P.tasks[t];
+    const int halo = tk.halo;
+    if (P.skip[halo] || (P.local && P.r200[halo] == 0.0))
+        return;   // uniform over the cluster
+    const int N = P.soa.size[halo];
+    const int64_t base = P.soa.poff[halo];
+    const int npairs = (N + 1) >> 1;
+    const int tid = rank * (NW * 32) + threadIdx.x, nthreads = C * NW * 32;
+
+    KatzState st;
+    st.q = 1.0; st.s = 1.0; st.iteration = 1;
+    st.active = ls < tk.nshell;
+    const int k = tk.shell0 + (st.active ? ls : 0);
+    shell_geometry(P, halo, k, st.d, st.delta);
+    const size_t out_idx = (size_t)halo * P.R + k;
+    if (lane < S) {
+        frames[ls * F_SLOTS + F_D2] = __dmul_rn(st.d, st.d);
+        const double in = __dsub_rn(st.d, st.delta);
+        frames[ls * F_SLOTS + F0_IN2] = __dmul_rn(in, in);
+    }
+    __syncwarp();
+    unsigned amask = __ballot_sync(0xffffffffu, st.active && lane < S);
+    const bool out_writer = (rank == 0 && warp == 0 && lane < S);
+
+    double acc[S][7];
+    int cnt[S];
+    int buf = 0;
+    run_pass<S, SHELL, REDUCED, VDISP, true>(P.soa, base, npairs, tid, nthreads, frames, amask, acc, cnt);
+    while (true) {
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            if (amask & (1u << s)) {
+#pragma unroll
+                for (int c = 0; c < 7; c++) {
+                    const double r = warp_sum(acc[s][c]);
+                    if (lane == 0) s_part[buf][warp][s][c] = r;
+                }
+                const int n = warp_sum_int(cnt[s]);
+                if (lane == 0) s_part[buf][warp][s][7] = (double)n;   // exact below 2^53
+            }
+        }
+        __syncthreads();
+        double tot[7] = {0, 0, 0, 0, 0, 0, 0};
+        double ptsd = 0.0;
+        if (C == 1) {
+            if (st.active) {
+#pragma unroll
+                for (int w = 0; w < NW; w++) {
+#pragma unroll
+                    for (int c = 0; c < 7; c++) tot[c] += s_part[buf][w][ls][c];
+                    ptsd += s_part[buf][w][ls][7];
+                }
+            }
+        } else {
+            if (threadIdx.x < S * 8) {
+                const int s = threadIdx.x >> 3, c = threadIdx.x & 7;
+                double v = 0.0;
+                if (amask & (1u << s))
+                    for (int w = 0; w < NW; w++) v += s_part[buf][w][s][c];
+                s_cta[buf][s][c] = v;
+            }
+            cluster.sync();
+            if (st.active) {
+                for (int r = 0; r < C; r++) {
+                    const double *remote = cluster.map_shared_rank(&s_cta[buf][ls][0], r);
+#pragma unroll
+                    for (int c = 0; c < 7; c++) tot[c] += remote[c];
+                    ptsd += remote[7];
+                }
+            }
+        }
+        katz_step<SHELL>(st, tot, (int)ptsd, P, frames + ls * F_SLOTS, lane < S, out_idx, out_writer);
+        __syncwarp();
+        amask = __ballot_sync(0xffffffffu, st.active && lane < S);
+        buf ^= 1;
+        if (amask == 0)
+            break;
+        run_pass<S, SHELL, REDUCED, VDISP, false>(P.soa, base, npairs, tid, nthreads, frames, amask, acc, cnt);
+    }
+    if (C > 1)
+        cluster.sync();   // nobody leaves while a peer may still read its shared memory
+}
+
+}  // namespace cpg

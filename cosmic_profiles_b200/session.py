@@ -1,0 +1,29 @@
+"""Device sessions shared by the drop-in driver functions."""
+import threading
+
+from . import _lib
+
+_lock = threading.Lock()
+_contexts = {}
+
+# Public knobs ------------------------------------------------------------------------------------
+devices = None          # list of CUDA device ordinals to shard objects over; None = [current default 0]
+options = {}            # forwarded to cpg_set_option on every context (e.g. {"shells_per_pass": 4})
+
+
+def get_context(device=0):
+    with _lock:
+        ctx = _contexts.get(device)
+        if ctx is None:
+            ctx = _lib.Context(device)
+            _contexts[device] = ctx
+        for k, v in options.items():
+            ctx.set_option(k, v)
+        return ctx
+
+
+def close_all():
+    with _lock:
+        for ctx in _contexts.values():
+            ctx.close()
+        _contexts.clear()

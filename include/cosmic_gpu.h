@@ -1,0 +1,138 @@
+/*
+ * cosmic_gpu.h -- C ABI of libcosmicgpu.so, the B200 (sm_100a) replacement for the
+ * per-halo shape / density hot path of tibordome/cosmic_profiles.
+ *
+ * The reference has no FFI for this path: its orchestration layer calls eight Cython `def`
+ * functions by module-global name (cosmic_profiles/common/cosmic_base_class.pyx:11-12, call
+ * sites :80,:155,:232,:324,:404,:825,:863,:887).  A ctypes shim
+ * (cosmic_profiles_b200/{shape_profs_algos,dens_profs_algos}.py) keeps those eight Python
+ * signatures and binds the entry points below; INTEGRATION.md shows the rebind.
+ *
+ * Conventions: plain pointers and sizes, no exceptions, every function returns 0 on success
+ * or a negative cpg_status and leaves a message for cpg_last_error().  All array arguments
+ * are HOST pointers owned by the caller (borrowed for the duration of the call, never
+ * mutated); results are written into caller-allocated host buffers.  Units are the
+ * reference's internal ones (Mpc/h, 1e10 Msun/h, km/s).  One caller thread per context.
+ * There is no CPU fallback: without a CUDA device cpg_create fails with CPG_ERR_NO_DEVICE.
+ */
+#ifndef COSMIC_GPU_H
+#define COSMIC_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CPG_API __attribute__((visibility("default")))
+#else
+#define CPG_API
+#endif
+
+typedef enum cpg_status {
+    CPG_OK = 0,
+    CPG_ERR_NO_DEVICE = -1,   /* no usable CUDA device / driver */
+    CPG_ERR_CUDA = -2,        /* a CUDA runtime call or kernel failed; see cpg_last_error() */
+    CPG_ERR_ARGUMENT = -3,    /* bad argument (NULL, negative size, catalogue out of range ...) */
+    CPG_ERR_STATE = -4,       /* call order: particles / catalogue not set */
+    CPG_ERR_NOMEM = -5
+} cpg_status;
+
+typedef struct cpg_ctx cpg_ctx; /* opaque: one device, one stream, device-resident snapshot + catalogue */
+
+/* Timing of the most recent compute call on a context, measured with CUDA events on the
+ * context's own stream (bench.py's roofline numbers come from here). */
+typedef struct cpg_timing {
+    double h2d_ms;          /* host->device copies issued by the call (centres, radii ...) */
+    double gather_ms;       /* catalogue gather + PBC + centre-relative SoA + per-halo statistics kernels */
+    double kernel_ms;       /* the hot kernels (morphology loop / binning / kernel estimator) */
+    double d2h_ms;          /* device->host copy of the results */
+    int32_t kernel_launches;        /* number of library kernels launched by the call */
+    int32_t hot_kernel_launches;    /* of which hot kernels (the ones kernel_ms covers) */
+    int64_t h2d_bytes;
+    int64_t d2h_bytes;
+} cpg_timing;
+
+CPG_API int cpg_device_count(void);
+CPG_API const char *cpg_last_error(void);
+CPG_API const char *cpg_version(void);
+
+/* Create / destroy a context bound to CUDA device `device`. */
+CPG_API int cpg_create(int device, cpg_ctx **out);
+CPG_API void cpg_destroy(cpg_ctx *ctx);
+
+/* Upload the snapshot: xyz (n_part,3) C-contiguous fp64, optional vxyz (n_part,3) or NULL,
+ * masses (n_part).  Replaces: the `xyz`, `vxyz`, `masses` arguments of every calcMorph* /
+ * calcDensProfs* call (shape_profs_algos.pyx:517,631,739,859; dens_profs_algos.pyx:15,54,112,221). */
+CPG_API int cpg_set_particles(cpg_ctx *ctx, const double *xyz, const double *vxyz, const double *masses,
+                              int64_t n_part);
+
+/* Upload the index catalogue: idx_cat (n_idx) int32 particle indices, obj_size (n_obj) int32.
+ * Replaces the `idx_cat`, `obj_size` arguments and the int32 `offsets` the reference derives from
+ * them (shape_profs_algos.pyx:557); offsets are 64-bit here. */
+CPG_API int cpg_set_catalogue(cpg_ctx *ctx, const int32_t *idx_cat, int64_t n_idx, const int32_t *obj_size,
+                              int32_t n_obj);
+
+/*
+ * Katz-Dubinski iterative morphology for every object of the catalogue.
+ * Replaces calcMorphLocal (shape_profs_algos.pyx:517-628), calcMorphGlobal (:631-736),
+ * calcMorphLocalVelDisp (:739-856), calcMorphGlobalVelDisp (:859-972) and everything below them
+ * (runEllAlgo :148, runShellAlgo :16, run*VDispAlgo :265,:386, calcObjMorph* :975-1240,
+ * CythonHelpers.calcShapeTensor / ZHEEVR / respectPBCNoRef / calcCoM / calcLocalSpread).
+ *
+ *   centers      (n_obj,3)  object centres (the reference computes them in Python, :586-591)
+ *   r200         (n_obj)
+ *   r_over_r200  (R)        local != 0: shells at d = r200*r_over_r200[k] (:1035-1044);
+ *                           local == 0: R must be 1 and d = r200 + SAFE (:1096), pointer may be NULL
+ *   use_vel      != 0: tensor from velocities about vcenter = calcCoM(v, m) (helper_class.pyx:85-105,
+ *                fp32 sequential mass normaliser reproduced); selection stays positional
+ *   out12        (n_obj,R,12): d, q, s, major xyz, inter xyz, minor xyz; all zeros where the
+ *                reference returns zeros (IT_WALL / IT_MIN / r200==0 / degenerate object)
+ *   n_iter,n_pts (n_obj,R) int32: shape-tensor evaluations performed; particle count of the last
+ *                evaluation (or the count that failed the test); -1 where the per-object exit hit
+ *   obj_mass     (n_obj) sum of member masses (:598); may be NULL
+ *   vcenters     (n_obj,3) output, only written when use_vel; may be NULL
+ */
+CPG_API int cpg_shape(cpg_ctx *ctx, const double *centers, const double *r200, const double *r_over_r200, int32_t R,
+                      int32_t local, double SAFE, float L_BOX, double IT_TOL, int32_t IT_WALL, int32_t IT_MIN,
+                      int32_t reduced, int32_t shell_based, int32_t use_vel, double *out12, int32_t *n_iter,
+                      int32_t *n_pts, double *obj_mass, double *vcenters);
+
+/* Spherical direct binning.  Replaces calcDensProfsSphDirectBinning (dens_profs_algos.pyx:54-109) and
+ * CythonHelpers.calcDensProfBruteForceSph (helper_class.pyx:204-241).  bin_edges (R+1) in units of r200
+ * (built by the shim exactly as :83).  dens (n_obj,R); counts (n_obj,R) int32 may be NULL. */
+CPG_API int cpg_dens_sph(cpg_ctx *ctx, const double *centers, const double *r200, const double *bin_edges, int32_t R,
+                         float L_BOX, double *dens, int32_t *counts);
+
+/* Ellipsoidal-shell direct binning.  Replaces the prange part of calcDensProfsEllDirectBinning
+ * (dens_profs_algos.pyx:196-218) and CythonHelpers.calcDensProfBruteForceEll (helper_class.pyx:246-306).
+ * a,b,c (n_obj,R+1) and major,inter,minor (n_obj,R,3) are the scipy-interpolated profiles of :163-195
+ * (computed by the shim with the same scipy).  Empty bin -> NaN. */
+CPG_API int cpg_dens_ell(cpg_ctx *ctx, const double *centers, const double *a, const double *b, const double *c,
+                         const double *major, const double *inter, const double *minor, int32_t R, float L_BOX,
+                         double *dens, int32_t *counts);
+
+/* Kernel-based estimator.  Replaces calcDensProfsKernelBased (dens_profs_algos.pyx:221-280) and
+ * CythonHelpers.calcKTilde (helper_class.pyx:417-428), mixed fp32/fp64 expression tree reproduced. */
+CPG_API int cpg_dens_kernel(cpg_ctx *ctx, const double *centers, const double *r200, const double *r_over_r200,
+                            int32_t R, float L_BOX, double *dens);
+
+/* Per-object total mass in catalogue order.  Replaces the prange of calcMassesCenters
+ * (dens_profs_algos.pyx:45-47). */
+CPG_API int cpg_obj_masses(cpg_ctx *ctx, double *obj_mass);
+
+/* Timing breakdown of the most recent compute call on this context. */
+CPG_API int cpg_get_timing(cpg_ctx *ctx, cpg_timing *out);
+
+/* Tunables (scheduling only; results do not depend on them beyond fp64 summation order):
+ *   "shells_per_pass"  1,2,4 or 0=auto   how many shells of one object share one read of its particles
+ *   "large_halo_min"   particles from which a thread-block cluster works on one object
+ *   "cluster_size"     CTAs per cluster for large objects (1,2,4,8,16; 0=auto)
+ */
+CPG_API int cpg_set_option(cpg_ctx *ctx, const char *name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COSMIC_GPU_H */

@@ -1,0 +1,225 @@
+"""CUDA path (through the ctypes shim -> C ABI of libcosmicgpu.so) against
+ (a) golden vectors produced by the compiled reference (tests/golden/*.npz), and
+ (b) the CPU oracle on larger seeded catalogues, for every scheduling variant
+     (shells per pass 1/2/4, warp kernel, CTA kernel, thread-block clusters of 2..16).
+Gates (tests/parity.py): iteration and particle counts bit-exact, q/s/d/densities <= 1e-9 relative,
+axes <= 1e-8 absolute after sign alignment, identical NaN pattern."""
+import numpy as np
+import pytest
+
+from tests import parity as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    from cosmic_profiles_b200 import dens_profs_algos, session, shape_profs_algos
+    session.options.clear()
+    yield shape_profs_algos, dens_profs_algos, session
+    session.options.clear()
+    session.close_all()
+
+
+def _args(cat):
+    return cat["xyz"], cat["masses"], cat["r200"], cat["idx_cat"], cat["obj_size"]
+
+
+@pytest.mark.parametrize("kind", ["main", "pbc"])
+def test_golden_shapes(gpu, kind):
+    S, D, sess = gpu
+    z, meta, cat = P.load_golden(kind)
+    X, M, R2, I, Z = _args(cat)
+    k = meta["katz"]
+    L = meta["L_BOX"]
+    for center in (("com", "mode") if kind == "main" else ("com",)):
+        for reduced in (0, 1):
+            for shell in (0, 1):
+                tag = "local_%s_r%d_s%d" % (center, reduced, shell)
+                got = S.calcMorphLocal(X, M, R2, I, Z, L, cat["rr_shape"], k["IT_TOL"], k["IT_WALL"], k["IT_MIN"],
+                                       center, bool(reduced), bool(shell))
+                P.assert_ints(S.last_info["n_iter"], z[tag + "/n_iter"], tag + "/n_iter")
+                P.assert_ints(S.last_info["n_pts"], z[tag + "/n_pts"], tag + "/n_pts")
+                P.assert_shape_tuple(got, P.golden_tuple(z, tag), tag)
+            tag = "global_%s_r%d" % (center, reduced)
+            got = S.calcMorphGlobal(X, M, R2, I, Z, L, k["IT_TOL"], k["IT_WALL"], k["IT_MIN"], center, meta["SAFE"],
+                                    bool(reduced))
+            P.assert_ints(S.last_info["n_iter"], z[tag + "/n_iter"][:, 0], tag + "/n_iter")
+            P.assert_ints(S.last_info["n_pts"], z[tag + "/n_pts"][:, 0], tag + "/n_pts")
+            P.assert_shape_tuple(got, P.golden_tuple(z, tag), tag)
+
+
+def test_golden_velocity_dispersion(gpu):
+    S, D, sess = gpu
+    z, meta, cat = P.load_golden("main")
+    X, M, R2, I, Z = _args(cat)
+    V = cat["vxyz"]
+    k = meta["katz"]
+    for reduced in (0, 1):
+        tag = "vglobal_com_r%d" % reduced
+        got = S.calcMorphGlobalVelDisp(X, V, M, R2, I, Z, 0.0, k["IT_TOL"], k["IT_WALL"], k["IT_MIN"], "com",
+                                       meta["SAFE"], bool(reduced))
+        P.assert_ints(S.last_info["n_iter"], z[tag + "/n_iter"][:, 0], tag + "/n_iter")
+        P.assert_shape_tuple(got, P.golden_tuple(z, tag), tag)
+        for shell in (0, 1):
+            tag = "vlocal_com_r%d_s%d" % (reduced, shell)   # reference patched for defect (ii)
+            got = S.calcMorphLocalVelDisp(X, V, M, R2, I, Z, 0.0, cat["rr_shape"], k["IT_TOL"], k["IT_WALL"],
+                                          k["IT_MIN"], "com", bool(reduced), bool(shell))
+            P.assert_ints(S.last_info["n_iter"], z[tag + "/n_iter"], tag + "/n_iter")
+            P.assert_ints(S.last_info["n_pts"], z[tag + "/n_pts"], tag + "/n_pts")
+            P.assert_shape_tuple(got, P.golden_tuple(z, tag), tag)
+
+
+@pytest.mark.parametrize("kind", ["main", "pbc"])
+def test_golden_densities(gpu, kind):
+    S, D, sess = gpu
+    z, meta, cat = P.load_golden(kind)
+    X, M, R2, I, Z = _args(cat)
+    L = meta["L_BOX"]
+    rb = cat["rr_dens"]
+    for center in ("com", "mode"):
+        P.assert_close(D.calcDensProfsSphDirectBinning(X, M, R2, rb, I, Z, L, center), z["dens_sph_" + center],
+                       "sph_" + center)
+        P.assert_close(D.calcDensProfsKernelBased(X, M, R2, rb, I, Z, L, center), z["dens_kernel_" + center],
+                       "kernel_" + center)
+        cen, m = D.calcMassesCenters(X, M, I, Z, L, center)
+        P.assert_close(cen, z["masses_centers_%s/centers" % center], "centers")
+        P.assert_close(m, z["masses_centers_%s/m" % center], "m")
+    tag = "local_com_r0_s0"
+    d, q, s = z[tag + "/d"], z[tag + "/q"], z[tag + "/s"]
+    got = D.calcDensProfsEllDirectBinning(X, M, R2, rb, d, d * q, d * s, z[tag + "/major"], z[tag + "/inter"],
+                                          z[tag + "/minor"], I.copy(), Z, L, "com")
+    P.assert_close(got, z["dens_ell_com"], "ell_com (reference patched for defect i)")
+
+
+@pytest.fixture(scope="module")
+def big():
+    from cosmic_profiles_b200.mock import make_catalogue
+    from oracle import cp_oracle as O
+    sizes = [30000, 12000, 9001, 7000, 5000, 4000, 3000, 2500, 2000, 1500, 1200, 1000, 700, 300, 120, 40, 9, 1]
+    cat = make_catalogue(sizes, seed=5, with_velocities=True, shuffle_particles=True)
+    rr = np.logspace(-1.5, 0, 13)
+    cen = O.centres(cat["xyz"], cat["masses"], cat["idx_cat"], cat["obj_size"], 0.0, "com", True)
+    return cat, rr, cen, {}
+
+
+def _oracle(big, vel, reduced, shell, local):
+    from oracle import cp_oracle as O
+    cat, rr, cen, cache = big
+    key = (vel, reduced, shell, local)
+    if key not in cache:
+        cache[key] = O.morph(cat["xyz"], cat["vxyz"] if vel else None, cat["masses"], cat["r200"], cat["idx_cat"],
+                             cat["obj_size"], 0.0, rr if local else None, 1e-2, 100, 10, "com", reduced, shell, local,
+                             SAFE=6.0, centers=cen)
+    return cache[key]
+
+
+SCHED = [dict(shells_per_pass=1, large_halo_min=1 << 40, cluster_size=0),     # warp kernel only
+         dict(shells_per_pass=2, large_halo_min=1 << 40, cluster_size=0),
+         dict(shells_per_pass=4, large_halo_min=1 << 40, cluster_size=0),
+         dict(shells_per_pass=4, large_halo_min=1, cluster_size=1),           # CTA per task
+         dict(shells_per_pass=1, large_halo_min=1, cluster_size=2),           # clusters + DSMEM
+         dict(shells_per_pass=2, large_halo_min=2000, cluster_size=4),
+         dict(shells_per_pass=4, large_halo_min=1, cluster_size=8),
+         dict(shells_per_pass=4, large_halo_min=5000, cluster_size=16),
+         dict(shells_per_pass=0, large_halo_min=0, cluster_size=0)]           # auto
+
+
+@pytest.mark.parametrize("sched", SCHED, ids=lambda s: "S%d_L%d_C%d" % (s["shells_per_pass"], min(s["large_halo_min"], 99999), s["cluster_size"]))
+def test_oracle_shapes_all_schedules(gpu, big, sched):
+    S, D, sess = gpu
+    cat, rr, cen, _ = big
+    X, M, R2, I, Z = _args(cat)
+    sess.options.clear()
+    sess.options.update(sched)
+    try:
+        for reduced in (False, True):
+            for shell in (False, True):
+                ref, (nit, npt, _, _) = _oracle(big, False, reduced, shell, True)
+                got = S.calcMorphLocal(X, M, R2, I, Z, 0.0, rr, 1e-2, 100, 10, "com", reduced, shell, centers=cen)
+                tag = "local r%d s%d %s" % (reduced, shell, sched)
+                P.assert_ints(S.last_info["n_iter"], nit, tag + " n_iter")
+                P.assert_ints(S.last_info["n_pts"], npt, tag + " n_pts")
+                P.assert_shape_tuple(got, ref, tag)
+            ref, (nit, npt, _, _) = _oracle(big, False, reduced, False, False)
+            got = S.calcMorphGlobal(X, M, R2, I, Z, 0.0, 1e-2, 100, 10, "com", 6.0, reduced, centers=cen)
+            P.assert_ints(S.last_info["n_iter"], nit, "global n_iter")
+            P.assert_shape_tuple(got, ref, "global r%d %s" % (reduced, sched))
+    finally:
+        sess.options.clear()
+
+
+@pytest.mark.parametrize("sched", [SCHED[2], SCHED[5], SCHED[8]], ids=["warpS4", "clusterS2C4", "auto"])
+def test_oracle_velocity_dispersion(gpu, big, sched):
+    S, D, sess = gpu
+    cat, rr, cen, _ = big
+    X, M, R2, I, Z = _args(cat)
+    V = cat["vxyz"]
+    sess.options.clear()
+    sess.options.update(sched)
+    try:
+        for reduced in (False, True):
+            for shell in (False, True):
+                ref, (nit, npt, vc, _) = _oracle(big, True, reduced, shell, True)
+                got = S.calcMorphLocalVelDisp(X, V, M, R2, I, Z, 0.0, rr, 1e-2, 100, 10, "com", reduced, shell,
+                                              centers=cen)
+                P.assert_ints(S.last_info["n_iter"], nit, "vlocal n_iter")
+                P.assert_ints(S.last_info["n_pts"], npt, "vlocal n_pts")
+                P.assert_shape_tuple(got, ref, "vlocal r%d s%d" % (reduced, shell))
+                ok = Z > 0
+                P.assert_close(S.last_info["vcenters"][ok], vc[ok], "vcenters")
+            ref, (nit, npt, _, _) = _oracle(big, True, reduced, False, False)
+            got = S.calcMorphGlobalVelDisp(X, V, M, R2, I, Z, 0.0, 1e-2, 100, 10, "com", 6.0, reduced, centers=cen)
+            P.assert_ints(S.last_info["n_iter"], nit, "vglobal n_iter")
+            P.assert_shape_tuple(got, ref, "vglobal r%d" % reduced)
+    finally:
+        sess.options.clear()
+
+
+def test_oracle_densities(gpu, big):
+    from oracle import cp_oracle as O
+    S, D, sess = gpu
+    cat, rr, cen, _ = big
+    X, M, R2, I, Z = _args(cat)
+    rb = np.logspace(-2, 0, 40)
+    ref, cnt = O.calcDensProfsSphDirectBinning(X, M, R2, rb, I, Z, 0.0, "com", centers=cen, return_counts=True)
+    got = D.calcDensProfsSphDirectBinning(X, M, R2, rb, I, Z, 0.0, "com", centers=cen)
+    P.assert_ints(D.last_info["counts"], cnt, "sph counts")
+    P.assert_close(got, ref, "sph")
+    ref = O.calcDensProfsKernelBased(X, M, R2, rb, I, Z, 0.0, "com", centers=cen)
+    got = D.calcDensProfsKernelBased(X, M, R2, rb, I, Z, 0.0, "com", centers=cen)
+    P.assert_close(got, ref, "kernel")
+    sh, _ = _oracle(big, False, False, False, True)
+    d, q, s, minor, inter, major = sh[:6]
+    ref, cnt = O.calcDensProfsEllDirectBinning(X, M, R2, rb, d, d * q, d * s, major, inter, minor, I, Z, 0.0, "com",
+                                               centers=cen, return_counts=True)
+    got = D.calcDensProfsEllDirectBinning(X, M, R2, rb, d, d * q, d * s, major, inter, minor, I, Z, 0.0, "com",
+                                          centers=cen)
+    P.assert_ints(D.last_info["counts"], cnt, "ell counts")
+    P.assert_close(got, ref, "ell")
+
+
+def test_edge_cases(gpu):
+    S, D, sess = gpu
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(300, 3)) + 50.0
+    X[200:] = X[200]
+    M = np.ones(300)
+    I = np.arange(300, dtype=np.int32)
+    Z = np.array([5, 195, 100], dtype=np.int32)
+    R2 = np.array([1.0, 0.0, 1.0])
+    rr = np.logspace(-1, 0, 4)
+    got = S.calcMorphLocal(X, M, R2, I, Z, 0.0, rr, 1e-2, 100, 10, "com", False, False)
+    assert np.isnan(got[1]).all() and np.isnan(got[0]).all()
+    assert (S.last_info["n_iter"][0] == 0).all()        # 5 particles < IT_MIN
+    assert (S.last_info["n_iter"][1] == -1).all()       # r200 == 0
+    assert (S.last_info["n_iter"][2] == -1).all()       # coincident cloud (degenerate)
+    np.testing.assert_allclose(got[7], [5.0, 195.0, 100.0])
+    assert D.calcDensProfsSphDirectBinning(X, M, R2, rr, I[:0], Z[:0], 0.0, "com").shape == (0, 4)
+    # catalogue index out of range must be refused, not dereferenced
+    from cosmic_profiles_b200._lib import CosmicGpuError
+    bad = I.copy()
+    bad[7] = 300
+    with pytest.raises(CosmicGpuError):
+        S.calcMorphLocal(X, M, R2, bad, Z, 0.0, rr, 1e-2, 100, 10, "com", False, False,
+                         centers=np.zeros((3, 3)))
