@@ -1,0 +1,402 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the shape-profiling hot path (BASELINE.json configs[1]).
+
+A step = one pass of the hot path over one synthetic catalogue:
+    calcMorphLocal  (ellipsoid-based, non-reduced, default Katz config: 70 shells logspace(-1.5,0), IT_TOL 1e-2,
+                     IT_WALL 100, IT_MIN 10; python_routines.py:698)  +  calcMorphGlobal (SAFE=6)
+on 10^4 mock Einasto halos whose sizes follow p(N) ~ N^-1.9 on [1e3, 1e6] (~9e7 particles, 2.9 GB of
+fp64 x,y,z,m: larger than the 126 MB L2, so no L2 flush is needed between steps).
+Centres are an input of the path (north_star); they are computed once outside the timed region.
+
+metric  = particle-iterations/s,  PI = sum_h N_h * sum_k (shape-tensor evaluations of halo-shell (h,k))
+value   = PI / device time of the cpg_shape calls with snapshot + catalogue already resident in HBM
+e2e     = PI / time of the full C-ABI sequence from pinned HOST buffers (cpg_set_particles +
+          cpg_set_catalogue + cpg_shape x2, results copied back) per step
+roofline= algorithmic bytes (32 B per particle-iteration) / CUDA-event time of the
+          morphology kernels of the local-shape call, against the measured HBM copy bandwidth
+cpu_baseline = the reference's own compiled calcMorphLocal+calcMorphGlobal (oracle/_ref) on a bounded,
+          stratified sample of the same catalogue, all host cores.
+
+`--impl reference` times only that reference arm (rank 0).  Under torchrun each rank owns one GPU and its
+own catalogue of the per-GPU size (weak scaling, no data-path collective).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+KATZ = dict(IT_TOL=1e-2, IT_WALL=100, IT_MIN=10)
+RR = np.logspace(-1.5, 0, 70)
+SAFE = 6.0
+METRIC = "particle-iterations/sec"
+UNIT = "particle-iterations/s"
+BYTES_PER_PI = 32.0
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------- workload
+
+def halo_table(n_halos, seed):
+    from cosmic_profiles_b200.mock import _radius_sampler, power_law_sizes, random_rotations
+    rng = np.random.default_rng(seed)
+    sizes = power_law_sizes(n_halos, 1000, 1000000, -1.9, seed=seed + 1)
+    q = rng.uniform(0.5, 0.9, size=n_halos)
+    s = 0.3 + (q - 0.3) * rng.uniform(size=n_halos)
+    r_vir = rng.uniform(0.5, 1.5, size=n_halos) * (sizes / 1.0e4) ** (1.0 / 3.0) * 0.3
+    rot = random_rotations(rng, n_halos)
+    centre = rng.uniform(20.0, 80.0, size=(n_halos, 3))
+    u, cdf = _radius_sampler("einasto", 5.0)
+    return dict(sizes=sizes, q=q, s=s, r_vir=r_vir, rot=rot, centre=centre, u=u, cdf=cdf)
+
+
+def generate_on_device(tab, seed, device):
+    """Sample the catalogue with torch on the GPU (plumbing only) and return pinned host numpy arrays."""
+    import torch
+    dev = torch.device("cuda", device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    sizes = torch.as_tensor(tab["sizes"], device=dev)
+    n = int(sizes.numel())
+    ntot = int(sizes.sum().item())
+    halo = torch.repeat_interleave(torch.arange(n, device=dev), sizes)
+    f64 = dict(dtype=torch.float64, device=dev)
+    cdf = torch.as_tensor(tab["cdf"], **f64)
+    u = torch.as_tensor(tab["u"], **f64)
+    p = torch.rand(ntot, generator=g, **f64)
+    j = torch.clamp(torch.searchsorted(cdf, p), 1, cdf.numel() - 1)
+    w = (p - cdf[j - 1]) / (cdf[j] - cdf[j - 1])
+    a = (u[j - 1] + w * (u[j] - u[j - 1])) * torch.as_tensor(tab["r_vir"], **f64)[halo]
+    del p, j, w
+    z = torch.rand(ntot, generator=g, **f64) * 2 - 1
+    ph = torch.rand(ntot, generator=g, **f64) * (2 * np.pi)
+    st = torch.sqrt(1 - z * z)
+    lx = a * st * torch.cos(ph)
+    ly = a * st * torch.sin(ph) * torch.as_tensor(tab["q"], **f64)[halo]
+    lz = a * z * torch.as_tensor(tab["s"], **f64)[halo]
+    del a, z, ph, st
+    rot = torch.as_tensor(tab["rot"], **f64)
+    cen = torch.as_tensor(tab["centre"], **f64)
+    xyz = torch.empty((ntot, 3), **f64)
+    for c in range(3):
+        xyz[:, c] = rot[:, c, 0][halo] * lx + rot[:, c, 1][halo] * ly + rot[:, c, 2][halo] * lz + cen[:, c][halo]
+    del lx, ly, lz, halo
+    masses = (torch.rand(ntot, generator=g, **f64) + 0.5) * 0.01
+    xyz_h = torch.empty((ntot, 3), dtype=torch.float64, pin_memory=True)
+    m_h = torch.empty((ntot,), dtype=torch.float64, pin_memory=True)
+    idx_h = torch.empty((ntot,), dtype=torch.int32, pin_memory=True)
+    xyz_h.copy_(xyz)
+    m_h.copy_(masses)
+    idx_h.copy_(torch.arange(ntot, dtype=torch.int32))   # FoF-style contiguous catalogue
+    torch.cuda.synchronize(dev)
+    # exact centres of mass (an input of the path), computed once outside every timed region
+    hid = torch.repeat_interleave(torch.arange(n, device=dev), sizes)
+    msum = torch.zeros(n, **f64).index_add_(0, hid, masses)
+    com = torch.zeros((n, 3), **f64).index_add_(0, hid, (xyz - cen[hid]) * masses[:, None]) / msum[:, None] + cen
+    com_h = com.cpu().numpy()
+    del xyz, masses, hid
+    torch.cuda.empty_cache()
+    return dict(xyz=xyz_h.numpy(), masses=m_h.numpy(), idx_cat=idx_h.numpy(),
+                obj_size=np.asarray(tab["sizes"], dtype=np.int32), r200=np.ascontiguousarray(tab["r_vir"]),
+                centers=np.ascontiguousarray(com_h), _keep=(xyz_h, m_h, idx_h))
+
+
+def stratified_sample(sizes, budget_particles, seed=1):
+    """A seeded random subset of the objects (so the size distribution is that of the catalogue), leaving out
+    objects larger than 1/16 of the budget so that the reference's OpenMP prange over objects has enough
+    independent objects to keep every host core busy; filled up to the particle budget."""
+    sizes = np.asarray(sizes, dtype=np.int64)
+    rng = np.random.default_rng(seed)
+    order = rng.permutation(len(sizes))
+    cap = max(int(budget_particles // 16), int(sizes.min()))
+    pick, tot = [], 0
+    for h in order:
+        if sizes[h] > cap or tot + sizes[h] > budget_particles:
+            continue
+        pick.append(h)
+        tot += int(sizes[h])
+    if not pick:
+        pick = [int(np.argmin(sizes))]
+    return np.sort(np.asarray(pick))
+
+
+# --------------------------------------------------------------------------------------- reference arm
+
+def reference_sample_inputs(cat, pick):
+    off = np.concatenate(([0], np.cumsum(cat["obj_size"].astype(np.int64))))
+    sel = np.concatenate([np.arange(off[h], off[h + 1]) for h in pick])
+    xyz = np.ascontiguousarray(cat["xyz"][sel])
+    m = np.ascontiguousarray(cat["masses"][sel])
+    sizes = cat["obj_size"][pick].astype(np.int32)
+    return xyz, m, np.arange(len(sel), dtype=np.int32), sizes, np.ascontiguousarray(cat["r200"][pick])
+
+
+def time_reference(cat, pick, steps, warmup):
+    """Time the reference's own drivers (compiled from /root/reference into oracle/_ref; falls back to the
+    C port of the oracle if that build is absent) on the sampled objects.  Returns (PI/s, info)."""
+    from oracle import cp_oracle as O
+    from oracle import ref_loader
+    xyz, m, idx, sizes, r200 = reference_sample_inputs(cat, pick)
+    cores = len(os.sched_getaffinity(0))
+    k = (KATZ["IT_TOL"], KATZ["IT_WALL"], KATZ["IT_MIN"])
+    # particle-iterations of the sample, from the oracle's integer outputs (same algorithm, same counts)
+    _, (nit_l, _, _, _) = O.morph(xyz, None, m, r200, idx, sizes, 0.0, RR, *k, "com", False, False, True)
+    _, (nit_g, _, _, _) = O.morph(xyz, None, m, r200, idx, sizes, 0.0, None, *k, "com", False, False, False, SAFE=SAFE)
+    pi = float((nit_l.clip(0).sum(1) * sizes).sum() + (nit_g.clip(0) * sizes).sum())
+    if ref_loader.available("pristine"):
+        ns = ref_loader.load("pristine")
+        kind = "reference"
+
+        def step():
+            with ref_loader.quiet_stdout():
+                ns.calcMorphLocal(xyz, m, r200, idx, sizes, 0.0, RR, *k, "com", False, False)
+                ns.calcMorphGlobal(xyz, m, r200, idx, sizes, 0.0, *k, "com", SAFE, False)
+    else:
+        kind = "port"
+
+        def step():
+            O.morph(xyz, None, m, r200, idx, sizes, 0.0, RR, *k, "com", False, False, True, nthreads=cores)
+            O.morph(xyz, None, m, r200, idx, sizes, 0.0, None, *k, "com", False, False, False, SAFE=SAFE, nthreads=cores)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    info = dict(kind=kind, cores=cores,
+                sample="%d of %d objects (seeded random subset, objects <= budget/16, %d particles, %.3g particle-iterations), "
+                       "calcMorphLocal 70 shells + calcMorphGlobal incl. the reference's own centre loop, "
+                       "OMP_NUM_THREADS=%d" % (len(pick), len(cat["obj_size"]), int(sizes.sum()), pi, cores),
+                seconds_per_step=dt)
+    return pi / dt, info
+
+
+# ------------------------------------------------------------------------------------------ clocks
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = [v for v in sm if v > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- main
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--halos", type=int, default=10000, help="objects per GPU (BASELINE configs[1]: 10^4)")
+    ap.add_argument("--cpu-budget", type=float, default=3.0e6, help="particles in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=20260101)
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "BASELINE configs[1]: %d mock Einasto halos/GPU, sizes p(N)~N^-1.9 on [1e3,1e6], "
+                          "ellipsoid-based local shapes (70 shells, non-reduced, IT_TOL 1e-2) + global shape, "
+                          "CENTER=com given" % a.halos,
+              "halos_per_gpu": a.halos, "shells": 70, "l2": "inputs_larger_than_L2", "sharding": "objects"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        os.environ.setdefault("OMP_NUM_THREADS", str(len(os.sched_getaffinity(0))))
+        import torch
+        tab = halo_table(a.halos, a.seed)
+        if torch.cuda.is_available():
+            cat = generate_on_device(tab, a.seed, 0)
+        else:   # CPU-only container: same generator family on the host, small sizes only
+            from cosmic_profiles_b200.mock import make_catalogue
+            cat = make_catalogue(tab["sizes"], seed=a.seed, profile="einasto")
+        pick = stratified_sample(np.asarray(cat["obj_size"], dtype=np.int64), a.cpu_budget)
+        v, info = time_reference(cat, pick, max(1, a.steps), a.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": 1e3 * info["seconds_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+                                 "sample": info["sample"]},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from cosmic_profiles_b200 import _lib
+
+    t0 = time.perf_counter()
+    tab = halo_table(a.halos, a.seed + 1000 * rank)
+    cat = generate_on_device(tab, a.seed + 1000 * rank, local_rank)
+    n_part = int(cat["obj_size"].sum())
+    log("[rank %d] catalogue: %d objects, %d particles (%.2f GB x,y,z,m), generated in %.1f s"
+        % (rank, a.halos, n_part, n_part * 32 / 1e9, time.perf_counter() - t0))
+
+    ctx = _lib.Context(local_rank)
+    k = (KATZ["IT_TOL"], KATZ["IT_WALL"], KATZ["IT_MIN"])
+
+    def upload():
+        ctx.set_particles(cat["xyz"], None, cat["masses"])
+        ctx.set_catalogue(cat["idx_cat"], cat["obj_size"])
+
+    def shapes():
+        out_l, nit_l, _, _, _ = ctx.shape(cat["centers"], cat["r200"], RR, True, 0.0, 0.0, *k, False, False, False)
+        t_l = ctx.timing()
+        out_g, nit_g, _, _, _ = ctx.shape(cat["centers"], cat["r200"], None, False, SAFE, 0.0, *k, False, False, False)
+        t_g = ctx.timing()
+        return nit_l, nit_g, t_l, t_g
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-input timing (value) --------------------------------------------------------
+    upload()
+    for _ in range(a.warmup):
+        nit_l, nit_g, _, _ = shapes()
+    sizes = cat["obj_size"].astype(np.int64)
+    pi_local = float((nit_l.clip(0).sum(1) * sizes).sum())
+    pi_global = float((nit_g.clip(0)[:, 0] * sizes).sum())
+    pi_step = pi_local + pi_global
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    dev_ms = 0.0
+    kern_local_ms = 0.0
+    launches = 0
+    hot_launches_local = 0
+    w0 = time.perf_counter()
+    for _ in range(a.steps):
+        _, _, t_l, t_g = shapes()
+        for t in (t_l, t_g):
+            dev_ms += t["h2d_ms"] + t["gather_ms"] + t["kernel_ms"] + t["d2h_ms"]
+            launches += t["kernel_launches"]
+        kern_local_ms += t_l["kernel_ms"]
+        hot_launches_local += t_l["hot_kernel_launches"]
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - w0)
+    clk = clocks.stop()
+
+    # ---- end-to-end timing from pinned host buffers (e2e) ---------------------------------------
+    barrier()
+    e0 = time.perf_counter()
+    e2e_steps = max(1, min(a.steps, 3))
+    for _ in range(e2e_steps):
+        upload()
+        shapes()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - e0) / e2e_steps
+    h2d = int(cat["xyz"].nbytes + cat["masses"].nbytes + cat["idx_cat"].nbytes + cat["obj_size"].nbytes
+              + 2 * (cat["centers"].nbytes + cat["r200"].nbytes) + RR.nbytes)
+    d2h = int(t_l["d2h_bytes"] + t_g["d2h_bytes"])
+
+    # ---- reduce over ranks: time = max, work = sum -------------------------------------------------
+    vals = torch.tensor([dev_ms / a.steps, wall_ms / a.steps, e2e_ms, kern_local_ms / a.steps], dtype=torch.float64,
+                        device="cuda")
+    work = torch.tensor([pi_step, pi_local, float(launches), float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(work, op=dist.ReduceOp.SUM)
+    step_ms, wall_step_ms, e2e_step_ms, kern_ms = [float(x) for x in vals.tolist()]
+    pi_all, pi_local_all, launches_all, h2d_all, d2h_all = [float(x) for x in work.tolist()]
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        os.environ.setdefault("OMP_NUM_THREADS", str(len(os.sched_getaffinity(0))))
+        pick = stratified_sample(sizes, a.cpu_budget)
+        v, info = time_reference(cat, pick, 1, 0)
+        cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = pi_local_all / world * BYTES_PER_PI / (kern_ms * 1e-3) / 1e9   # per GPU, GB/s
+        line = {"metric": METRIC, "value": pi_all / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "halo_shells_per_s": world * a.halos * 71 / (step_ms * 1e-3),
+                "wall_ms_per_step": wall_step_ms,
+                "e2e": {"value": pi_all / (e2e_step_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_all),
+                        "d2h_bytes_per_step": int(d2h_all), "ms_per_step": e2e_step_ms},
+                "gpu_launches": int(launches_all),
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None,
+                             "kernel": "morph_warp_kernel/morph_cluster_kernel (local shapes)",
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                             "algorithmic_bytes_per_launch_set": pi_local_all / world * BYTES_PER_PI,
+                             "kernel_ms": kern_ms, "frac_of_8TBps_nominal": achieved / 8000.0},
+                "cpu_baseline": cpu, "clocks": clk,
+                "particle_iterations_per_step": pi_all, "particles_per_gpu": n_part}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -157,7 +157,11 @@ __global__ void stats_final_kernel(const int32_t *chunk_first /* n_obj+1 */, con
         spread |= part_spread[c];
     }
     obj_mass[h] = m;
-    skip[h] = (size[h] == 0 || !spread) ? 1 : 0;
+    // The reference leaves an object untouched when calcLocalSpread(xyz) == 0 (helper_class.pyx:62-80 with
+    // fp32 accumulators): in practice only an empty object gets there -- for coincident points the fp32
+    // rounding of the mean already makes the spread non-zero.  `spread` is kept for diagnostics.
+    (void)spread;
+    skip[h] = (size[h] == 0) ? 1 : 0;
 }
 
 // helper_class.pyx:98-100: `cdef float mass_total` accumulated sequentially in catalogue order

@@ -138,6 +138,16 @@ __device__ __forceinline__ void katz_step(KatzState &st, const double (&tot)[7],
     const double im = 1.0 / tot[6];
     double w[3], v[9];
     eigh3(tot[0] * im, tot[1] * im, tot[2] * im, tot[3] * im, tot[4] * im, tot[5] * im, w, v);
+    if (!(w[2] > 0.0)) {
+        // all-zero or NaN tensor (coincident points, a particle exactly at the centre in reduced mode): the
+        // reference divides by zero here and raises; report the shell as failed instead
+        if (out_writer) {
+            P.n_iter[out_idx] = st.iteration - 1;
+            P.n_pts[out_idx] = pts;
+        }
+        st.active = false;
+        return;
+    }
     const double q_old = st.q, s_old = st.s;
     st.q = sqrt(w[1] / w[2]);
     st.s = sqrt(w[0] / w[2]);

@@ -203,18 +203,18 @@ def test_edge_cases(gpu):
     S, D, sess = gpu
     rng = np.random.default_rng(0)
     X = rng.normal(size=(300, 3)) + 50.0
-    X[200:] = X[200]
     M = np.ones(300)
     I = np.arange(300, dtype=np.int32)
-    Z = np.array([5, 195, 100], dtype=np.int32)
-    R2 = np.array([1.0, 0.0, 1.0])
+    Z = np.array([5, 195, 0, 100], dtype=np.int32)
+    R2 = np.array([1.0, 0.0, 1.0, 1.0])
     rr = np.logspace(-1, 0, 4)
     got = S.calcMorphLocal(X, M, R2, I, Z, 0.0, rr, 1e-2, 100, 10, "com", False, False)
-    assert np.isnan(got[1]).all() and np.isnan(got[0]).all()
+    assert np.isnan(got[1][:3]).all() and np.isnan(got[0][:3]).all()
+    assert np.isfinite(got[1][3]).any()
     assert (S.last_info["n_iter"][0] == 0).all()        # 5 particles < IT_MIN
     assert (S.last_info["n_iter"][1] == -1).all()       # r200 == 0
-    assert (S.last_info["n_iter"][2] == -1).all()       # coincident cloud (degenerate)
-    np.testing.assert_allclose(got[7], [5.0, 195.0, 100.0])
+    assert (S.last_info["n_iter"][2] == -1).all()       # empty object
+    np.testing.assert_allclose(got[7], [5.0, 195.0, 0.0, 100.0])
     assert D.calcDensProfsSphDirectBinning(X, M, R2, rr, I[:0], Z[:0], 0.0, "com").shape == (0, 4)
     # catalogue index out of range must be refused, not dereferenced
     from cosmic_profiles_b200._lib import CosmicGpuError
@@ -222,4 +222,4 @@ def test_edge_cases(gpu):
     bad[7] = 300
     with pytest.raises(CosmicGpuError):
         S.calcMorphLocal(X, M, R2, bad, Z, 0.0, rr, 1e-2, 100, 10, "com", False, False,
-                         centers=np.zeros((3, 3)))
+                         centers=np.zeros((4, 3)))

@@ -88,10 +88,9 @@ def test_densities(gold):
 
 
 def test_edge_cases():
-    """Empty catalogue, object below IT_MIN, r200 == 0, coincident points."""
+    """Empty catalogue, object below IT_MIN, r200 == 0."""
     rng = np.random.default_rng(0)
     X = rng.normal(size=(300, 3)) + 50.0
-    X[200:] = X[200]  # 100 coincident points: calcLocalSpread != 0 only through fp32 rounding of the mean
     M = np.ones(300)
     I = np.arange(300, dtype=np.int32)
     S = np.array([5, 195, 100], dtype=np.int32)
