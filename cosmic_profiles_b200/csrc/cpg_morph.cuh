@@ -22,49 +22,55 @@
 namespace cpg {
 namespace cg = cooperative_groups;
 
-// frame slots (doubles) per shell in shared memory
+// Frame slots (doubles) per shell in shared memory.  The ellipsoidal radius of the reference,
+//   v = p0^2 + p1^2/q^2 + p2^2/s^2  with  p = R (x - c)            (shape_profs_algos.pyx:247-256)
+// is the quadratic form v = (x-c)^T A (x-c), A = R^T diag(1, 1/q^2, 1/s^2) R.  The six products
+// xx, yy, zz, xy, xz, yz of a particle are formed ONCE, shared by all S shells of the pass, and reused by
+// the tensor accumulation (S_ab += w * ab): 6 + S*(6 + 1 + 7) fp64 ops per particle instead of S*25.
 enum {
-    F_E2X = 0, F_E2Y, F_E2Z,   // major axis   (eigenvector of the largest eigenvalue)
-    F_E1X, F_E1Y, F_E1Z,       // intermediate
-    F_E0X, F_E0Y, F_E0Z,       // minor
-    F_IQ2, F_IS2,              // 1/q^2, 1/s^2
-    F_D2,                      // d^2
-    F_IA2, F_IB2, F_IC2,       // 1/(d-delta)^2, 1/(q d-delta)^2, 1/(s d-delta)^2   (shell variant)
-    F_THR,                     // inner-ellipsoid threshold: 1 (shell), -1 (first shell: test disabled)
+    F_AXX = 0, F_AYY, F_AZZ, F_AXY, F_AXZ, F_AYZ,   // A (off-diagonals stored doubled)
+    F_D2,                                           // d^2
+    F_THR,                                          // inner-ellipsoid threshold: 1 (shell), -1 (first shell: disabled)
+    F_BXX, F_BYY, F_BZZ, F_BXY, F_BXZ, F_BYZ,       // B = R^T diag(1/(d-delta)^2, 1/(q d-delta)^2, 1/(s d-delta)^2) R
+    F0_IN2,                                         // pass 0 only: (d-delta)^2
     F_SLOTS = 16
 };
-// pass-0 constants are parked in the slots that pass 0 does not need
-enum { F0_IN2 = F_IA2 };       // (d-delta)^2
 
-struct Particle4 {             // one particle as seen by the accumulators
-    double x, y, z, m;         // centre-relative position, mass
-    double tx, ty, tz;         // coordinates the tensor is built from (== x,y,z unless VDISP)
+struct Particle {              // one particle as seen by the accumulators
+    double xx, yy, zz, xy, xz, yz;   // products of the centre-relative position
+    double m;
+    double t[6];               // products the tensor is built from (velocities; VDISP only)
 };
 
-template <bool REDUCED>
-__device__ __forceinline__ void accumulate(double (&acc)[7], int &cnt, bool sel, double v, const Particle4 &p)
+template <bool REDUCED, bool VDISP>
+__device__ __forceinline__ void accumulate(double (&acc)[7], int &cnt, bool sel, double v, const Particle &p)
 {
     // weight: m (non-reduced) or m / r_ell^2 (reduced, helper_class.pyx:54); the common 1/mass_tot factor
     // is applied once per iteration after the reduction (it only rescales the tensor).
     double w = REDUCED ? p.m / v : p.m;
     w = sel ? w : 0.0;
-    const double wx = w * p.tx, wy = w * p.ty, wz = w * p.tz;
-    acc[0] = fma(wx, p.tx, acc[0]);
-    acc[1] = fma(wx, p.ty, acc[1]);
-    acc[2] = fma(wx, p.tz, acc[2]);
-    acc[3] = fma(wy, p.ty, acc[3]);
-    acc[4] = fma(wy, p.tz, acc[4]);
-    acc[5] = fma(wz, p.tz, acc[5]);
-    acc[6] += sel ? p.m : 0.0;
+    if (VDISP) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) acc[c] = fma(w, p.t[c], acc[c]);
+    } else {
+        acc[0] = fma(w, p.xx, acc[0]);
+        acc[1] = fma(w, p.xy, acc[1]);
+        acc[2] = fma(w, p.xz, acc[2]);
+        acc[3] = fma(w, p.yy, acc[3]);
+        acc[4] = fma(w, p.yz, acc[4]);
+        acc[5] = fma(w, p.zz, acc[5]);
+    }
+    acc[6] += REDUCED ? (sel ? p.m : 0.0) : w;
     cnt += sel ? 1 : 0;
 }
 
-// Pass 0: spherical start (shape_profs_algos.pyx:206-212 / :81-87), exact reference arithmetic.
-template <int S, bool SHELL, bool REDUCED>
-__device__ __forceinline__ void pass0_particle(const Particle4 &p, const double *frames, unsigned amask,
+// Pass 0: spherical start (shape_profs_algos.pyx:206-212 / :81-87), exact reference arithmetic:
+// r2 = ((dx*dx + dy*dy) + dz*dz) with every operation rounded separately.
+template <int S, bool SHELL, bool REDUCED, bool VDISP>
+__device__ __forceinline__ void pass0_particle(const Particle &p, const double *frames, unsigned amask,
                                                double (&acc)[S][7], int (&cnt)[S])
 {
-    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(p.x, p.x), __dmul_rn(p.y, p.y)), __dmul_rn(p.z, p.z));
+    const double r2 = __dadd_rn(__dadd_rn(p.xx, p.yy), p.zz);
 #pragma unroll
     for (int s = 0; s < S; s++) {
         if (amask & (1u << s)) {
@@ -72,41 +78,51 @@ __device__ __forceinline__ void pass0_particle(const Particle4 &p, const double 
             bool sel = r2 < F[F_D2];
             if (SHELL)
                 sel = sel && (r2 >= F[F0_IN2]);
-            accumulate<REDUCED>(acc[s], cnt[s], sel, r2, p);
+            accumulate<REDUCED, VDISP>(acc[s], cnt[s], sel, r2, p);
         }
     }
 }
 
-// Pass k>=1: rotate into the frame of the previous eigen-decomposition and re-select
+// Pass k>=1: membership in the ellipsoid (shell) of the previous eigen-decomposition
 // (shape_profs_algos.pyx:247-260 / :122-143) fused with the next tensor accumulation.
-template <int S, bool SHELL, bool REDUCED, int NP>
-__device__ __forceinline__ void passk_particles(const Particle4 (&p)[NP], const double *frames, unsigned amask,
+template <int S, bool SHELL, bool REDUCED, bool VDISP, int NP>
+__device__ __forceinline__ void passk_particles(const Particle (&p)[NP], const double *frames, unsigned amask,
                                                 double (&acc)[S][7], int (&cnt)[S])
 {
 #pragma unroll
     for (int s = 0; s < S; s++) {
         if (amask & (1u << s)) {
             const double2 *F2 = reinterpret_cast<const double2 *>(frames + s * F_SLOTS);
-            const double2 f0 = F2[0], f1 = F2[1], f2 = F2[2], f3 = F2[3], f4 = F2[4], f5 = F2[5];
-            // f0=(e2x,e2y) f1=(e2z,e1x) f2=(e1y,e1z) f3=(e0x,e0y) f4=(e0z,iq2) f5=(is2,d2)
-            double2 f6, f7;
-            if (SHELL) { f6 = F2[6]; f7 = F2[7]; }   // f6=(ia2,ib2) f7=(ic2,thr)
+            const double2 f0 = F2[0], f1 = F2[1], f2 = F2[2], f3 = F2[3];
+            // f0=(Axx,Ayy) f1=(Azz,Axy) f2=(Axz,Ayz) f3=(d2,thr)
+            double2 f4, f5, f6;
+            if (SHELL) { f4 = F2[4]; f5 = F2[5]; f6 = F2[6]; }   // (Bxx,Byy) (Bzz,Bxy) (Bxz,Byz)
 #pragma unroll
             for (int j = 0; j < NP; j++) {
-                const double p0 = fma(f1.x, p[j].z, fma(f0.y, p[j].y, f0.x * p[j].x));
-                const double p1 = fma(f2.y, p[j].z, fma(f2.x, p[j].y, f1.y * p[j].x));
-                const double p2 = fma(f4.x, p[j].z, fma(f3.y, p[j].y, f3.x * p[j].x));
-                const double s0 = p0 * p0, s1 = p1 * p1, s2 = p2 * p2;
-                const double v = fma(s2, f5.x, fma(s1, f4.y, s0));
-                bool sel = v < f5.y;
+                const double v = fma(f2.y, p[j].yz, fma(f2.x, p[j].xz, fma(f1.y, p[j].xy,
+                                 fma(f1.x, p[j].zz, fma(f0.y, p[j].yy, f0.x * p[j].xx)))));
+                bool sel = v < f3.x;
                 if (SHELL) {
-                    const double u = fma(s2, f7.x, fma(s1, f6.y, s0 * f6.x));
-                    sel = sel && (u >= f7.y);
+                    const double u = fma(f6.y, p[j].yz, fma(f6.x, p[j].xz, fma(f5.y, p[j].xy,
+                                     fma(f5.x, p[j].zz, fma(f4.y, p[j].yy, f4.x * p[j].xx)))));
+                    sel = sel && (u >= f3.y);
                 }
-                accumulate<REDUCED>(acc[s], cnt[s], sel, v, p[j]);
+                accumulate<REDUCED, VDISP>(acc[s], cnt[s], sel, v, p[j]);
             }
         }
     }
+}
+
+// A = w2 * e2 e2^T + w1 * e1 e1^T + w0 * e0 e0^T as (xx, yy, zz, 2xy, 2xz, 2yz); v = eigenvectors of eigh3.
+__device__ __forceinline__ void quad_form(double *A, const double (&v)[9], double w2, double w1, double w0)
+{
+    const double *e0 = v, *e1 = v + 3, *e2 = v + 6;
+    A[0] = w2 * e2[0] * e2[0] + w1 * e1[0] * e1[0] + w0 * e0[0] * e0[0];
+    A[1] = w2 * e2[1] * e2[1] + w1 * e1[1] * e1[1] + w0 * e0[1] * e0[1];
+    A[2] = w2 * e2[2] * e2[2] + w1 * e1[2] * e1[2] + w0 * e0[2] * e0[2];
+    A[3] = 2.0 * (w2 * e2[0] * e2[1] + w1 * e1[0] * e1[1] + w0 * e0[0] * e0[1]);
+    A[4] = 2.0 * (w2 * e2[0] * e2[2] + w1 * e1[0] * e1[2] + w0 * e0[0] * e0[2]);
+    A[5] = 2.0 * (w2 * e2[1] * e2[2] + w1 * e1[1] * e1[2] + w0 * e0[1] * e0[2]);
 }
 
 // Per halo-shell iteration state, replicated in every lane that serves the shell.
@@ -168,16 +184,18 @@ __device__ __forceinline__ void katz_step(KatzState &st, const double (&tot)[7],
         return;
     }
     if (frame_writer) {
-#pragma unroll
-        for (int r = 0; r < 3; r++) { frame[F_E2X + r] = v[6 + r]; frame[F_E1X + r] = v[3 + r]; frame[F_E0X + r] = v[r]; }
-        frame[F_IQ2] = 1.0 / (st.q * st.q);
-        frame[F_IS2] = 1.0 / (st.s * st.s);
+        // v[6..8] major (e2), v[3..5] intermediate (e1), v[0..2] minor (e0)
+        const double iq2 = 1.0 / (st.q * st.q), is2 = 1.0 / (st.s * st.s);
+        quad_form(frame + F_AXX, v, 1.0, iq2, is2);
         if (SHELL) {
-            const bool first = (st.d == st.delta);   // shape_profs_algos.pyx:130
+            const bool first = (st.d == st.delta);   // shape_profs_algos.pyx:130: first shell -> ellipsoid test only
             const double a = st.d - st.delta, b = st.q * st.d - st.delta, c = st.s * st.d - st.delta;
-            frame[F_IA2] = first ? 0.0 : 1.0 / (a * a);
-            frame[F_IB2] = first ? 0.0 : 1.0 / (b * b);
-            frame[F_IC2] = first ? 0.0 : 1.0 / (c * c);
+            if (first) {
+#pragma unroll
+                for (int r = 0; r < 6; r++) frame[F_BXX + r] = 0.0;
+            } else {
+                quad_form(frame + F_BXX, v, 1.0 / (a * a), 1.0 / (b * b), 1.0 / (c * c));
+            }
             frame[F_THR] = first ? -1.0 : 1.0;
         }
     }
@@ -197,24 +215,31 @@ __device__ __forceinline__ void shell_geometry(const MorphParams &P, int halo, i
     }
 }
 
+__device__ __forceinline__ void make_products(double x, double y, double z, double (&o)[6])
+{
+    o[0] = __dmul_rn(x, x); o[1] = __dmul_rn(y, y); o[2] = __dmul_rn(z, z);
+    o[3] = x * y; o[4] = x * z; o[5] = y * z;
+}
+
 template <bool VDISP>
-__device__ __forceinline__ void load_pair(const SoA &soa, int64_t base, int i2, Particle4 &a, Particle4 &b)
+__device__ __forceinline__ void load_pair(const SoA &soa, int64_t base, int i2, Particle &a, Particle &b)
 {
     const double2 x = reinterpret_cast<const double2 *>(soa.dx + base)[i2];
     const double2 y = reinterpret_cast<const double2 *>(soa.dy + base)[i2];
     const double2 z = reinterpret_cast<const double2 *>(soa.dz + base)[i2];
     const double2 m = reinterpret_cast<const double2 *>(soa.m + base)[i2];
-    a.x = x.x; a.y = y.x; a.z = z.x; a.m = m.x;
-    b.x = x.y; b.y = y.y; b.z = z.y; b.m = m.y;
+    double pa[6], pb[6];
+    make_products(x.x, y.x, z.x, pa);
+    make_products(x.y, y.y, z.y, pb);
+    a.xx = pa[0]; a.yy = pa[1]; a.zz = pa[2]; a.xy = pa[3]; a.xz = pa[4]; a.yz = pa[5]; a.m = m.x;
+    b.xx = pb[0]; b.yy = pb[1]; b.zz = pb[2]; b.xy = pb[3]; b.xz = pb[4]; b.yz = pb[5]; b.m = m.y;
     if (VDISP) {
         const double2 u = reinterpret_cast<const double2 *>(soa.vx + base)[i2];
         const double2 v = reinterpret_cast<const double2 *>(soa.vy + base)[i2];
         const double2 w = reinterpret_cast<const double2 *>(soa.vz + base)[i2];
-        a.tx = u.x; a.ty = v.x; a.tz = w.x;
-        b.tx = u.y; b.ty = v.y; b.tz = w.y;
-    } else {
-        a.tx = a.x; a.ty = a.y; a.tz = a.z;
-        b.tx = b.x; b.ty = b.y; b.tz = b.z;
+        // tensor component order of accumulate(): xx, xy, xz, yy, yz, zz
+        a.t[0] = u.x * u.x; a.t[1] = u.x * v.x; a.t[2] = u.x * w.x; a.t[3] = v.x * v.x; a.t[4] = v.x * w.x; a.t[5] = w.x * w.x;
+        b.t[0] = u.y * u.y; b.t[1] = u.y * v.y; b.t[2] = u.y * w.y; b.t[3] = v.y * v.y; b.t[4] = v.y * w.y; b.t[5] = w.y * w.y;
     }
 }
 
@@ -233,20 +258,20 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
     if (!FIRST && !VDISP) {
         // two pairs in flight per thread: more loads outstanding, frame registers reused over 4 particles
         for (; i2 + nthreads < npairs; i2 += 2 * nthreads) {
-            Particle4 p[4];
+            Particle p[4];
             load_pair<VDISP>(soa, base, i2, p[0], p[1]);
             load_pair<VDISP>(soa, base, i2 + nthreads, p[2], p[3]);
-            passk_particles<S, SHELL, REDUCED, 4>(p, frames, amask, acc, cnt);
+            passk_particles<S, SHELL, REDUCED, VDISP, 4>(p, frames, amask, acc, cnt);
         }
     }
     for (; i2 < npairs; i2 += nthreads) {
-        Particle4 p[2];
+        Particle p[2];
         load_pair<VDISP>(soa, base, i2, p[0], p[1]);
         if (FIRST) {
-            pass0_particle<S, SHELL, REDUCED>(p[0], frames, amask, acc, cnt);
-            pass0_particle<S, SHELL, REDUCED>(p[1], frames, amask, acc, cnt);
+            pass0_particle<S, SHELL, REDUCED, VDISP>(p[0], frames, amask, acc, cnt);
+            pass0_particle<S, SHELL, REDUCED, VDISP>(p[1], frames, amask, acc, cnt);
         } else {
-            passk_particles<S, SHELL, REDUCED, 2>(p, frames, amask, acc, cnt);
+            passk_particles<S, SHELL, REDUCED, VDISP, 2>(p, frames, amask, acc, cnt);
         }
     }
 }
