@@ -324,15 +324,18 @@ def main():
     barrier()
     clocks.start()
     dev_ms = 0.0
+    brk = {}
     kern_local_ms = 0.0
     launches = 0
     hot_launches_local = 0
     w0 = time.perf_counter()
     for _ in range(a.steps):
         _, _, t_l, t_g = shapes()
-        for t in (t_l, t_g):
+        for nm, t in (("local", t_l), ("global", t_g)):
             dev_ms += t["h2d_ms"] + t["gather_ms"] + t["kernel_ms"] + t["d2h_ms"]
             launches += t["kernel_launches"]
+            for kk in ("h2d_ms", "gather_ms", "kernel_ms", "d2h_ms"):
+                brk[nm + "_" + kk] = brk.get(nm + "_" + kk, 0.0) + t[kk] / a.steps
         kern_local_ms += t_l["kernel_ms"]
         hot_launches_local += t_l["hot_kernel_launches"]
     barrier()
@@ -391,7 +394,7 @@ def main():
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                              "algorithmic_bytes_per_launch_set": pi_local_all / world * BYTES_PER_PI,
                              "kernel_ms": kern_ms, "frac_of_8TBps_nominal": achieved / 8000.0},
-                "cpu_baseline": cpu, "clocks": clk,
+                "cpu_baseline": cpu, "clocks": clk, "breakdown_ms_per_step_rank0": {k_: round(v_, 3) for k_, v_ in brk.items()},
                 "particle_iterations_per_step": pi_all, "particles_per_gpu": n_part}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -92,7 +92,9 @@ struct cpg_ctx {
     DevBuf<double> centers, vcenters, r200, rr, obj_mass, part_mass, vpart;
     DevBuf<int32_t> part_flag;
     DevBuf<float> mass32;
-    DevBuf<uint8_t> skip;
+    DevBuf<uint8_t> skip, bucket;
+    DevBuf<int32_t> tile_hist, dest, n_eff;
+    bool sorted_valid = false;    // the SoA streams are in radial-bucket order and `dest` maps catalogue -> slot
     // morphology
     DevBuf<Task> tasks;
     DevBuf<int32_t> task_counter;
@@ -105,6 +107,7 @@ struct cpg_ctx {
     int opt_shells_per_pass = 0;
     int64_t opt_large_halo_min = 0;
     int opt_cluster_size = 0;
+    int opt_radial_order = 1;
     cpg_timing timing = {};
 };
 
@@ -147,6 +150,7 @@ GatherParams gather_view(cpg_ctx *c, float L_BOX)
     G.n_obj = c->n_obj; G.n_idx = c->n_idx; G.L_BOX = L_BOX;
     G.dx = c->g_dx.p; G.dy = c->g_dy.p; G.dz = c->g_dz.p; G.m = c->g_m.p;
     G.vx = c->g_vx.p; G.vy = c->g_vy.p; G.vz = c->g_vz.p;
+    G.dest = c->sorted_valid ? c->dest.p : nullptr;
     return G;
 }
 
@@ -179,13 +183,33 @@ struct Timer {
     }
 };
 
-// Gather positions (+ statistics); requires centres on the device.  Launch count is added to timing.
-int run_gather(cpg_ctx *c, float L_BOX)
+// Gather positions and masses; requires centres (and, for the radial ordering, r200 / rr) on the device.
+// sort_R > 0: write every object's particles in radial-bucket order of the sort_R shell radii and fill
+// n_eff (cpg_gather.cuh "Radial ordering"); keep_dest: also record catalogue entry -> slot (velocity gather).
+int run_gather(cpg_ctx *c, float L_BOX, int sort_R = 0, bool keep_dest = false)
 {
     const int64_t n = c->n_idx;
     CPG_TRY(c->g_dx.ensure(c->n_pad)); CPG_TRY(c->g_dy.ensure(c->n_pad));
     CPG_TRY(c->g_dz.ensure(c->n_pad)); CPG_TRY(c->g_m.ensure(c->n_pad));
-    if (n > 0) {
+    c->sorted_valid = false;
+    const int nc = (int)c->h_chunks.size();
+    if (sort_R > 0 && n > 0 && nc > 0) {
+        const int B = sort_R + 1;
+        CPG_TRY(c->bucket.ensure(n)); CPG_TRY(c->tile_hist.ensure((size_t)nc * B));
+        CPG_TRY(c->n_eff.ensure((size_t)c->n_obj * sort_R));
+        if (keep_dest) CPG_TRY(c->dest.ensure(n));
+        SortParams P;
+        P.G = gather_view(c, L_BOX);
+        P.chunks = c->chunks.p; P.chunk_first = c->chunk_first.p; P.size = c->size.p;
+        P.r200 = c->r200.p; P.rr = c->rr.p; P.n_chunks = nc; P.R = sort_R;
+        P.bucket = c->bucket.p; P.tile_hist = c->tile_hist.p; P.dest = keep_dest ? c->dest.p : nullptr;
+        P.n_eff = c->n_eff.p;
+        bucket_hist_kernel<<<nc, 256, 0, c->stream>>>(P);
+        bucket_scan_kernel<<<grid_for(c->n_obj, 128, 1 << 30), 128, 0, c->stream>>>(P, c->n_obj);
+        gather_sorted_kernel<<<nc, 256, 0, c->stream>>>(P);
+        c->timing.kernel_launches += 3;
+        c->sorted_valid = keep_dest;
+    } else if (n > 0) {
         gather_pos_kernel<<<grid_for(n, 256, c->sm_count * 32), 256, 0, c->stream>>>(gather_view(c, L_BOX));
         c->timing.kernel_launches++;
     }
@@ -220,7 +244,7 @@ int run_vcenters(cpg_ctx *c, float L_BOX)
     CPG_TRY(c->g_vx.ensure(c->n_pad)); CPG_TRY(c->g_vy.ensure(c->n_pad)); CPG_TRY(c->g_vz.ensure(c->n_pad));
     if (c->n_obj > 0) {
         mass32_kernel<<<grid_for((int64_t)c->n_obj * 32, 128, c->sm_count * 16), 128, 0, c->stream>>>(
-            soa_view(c), c->n_obj, c->mass32.p);
+            gather_view(c, L_BOX), c->n_obj, c->mass32.p);
         if (nc > 0)
             vsum_chunk_kernel<<<nc, 256, 0, c->stream>>>(gather_view(c, L_BOX), soa_view(c), c->chunks.p, nc, c->vpart.p);
         vcenter_final_kernel<<<grid_for(c->n_obj, 128, 1 << 30), 128, 0, c->stream>>>(c->chunk_first.p, c->n_obj,
@@ -359,7 +383,8 @@ CPG_API void cpg_destroy(cpg_ctx *c)
                               &c->n_iter, &c->n_pts, &c->bin_cnt, &c->counts};
     for (auto *b : i32) b->release();
     c->off.release(); c->poff.release(); c->chunks.release(); c->kchunks.release();
-    c->mass32.release(); c->skip.release(); c->tasks.release();
+    c->mass32.release(); c->skip.release(); c->tasks.release(); c->bucket.release();
+    c->tile_hist.release(); c->dest.release(); c->n_eff.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -376,6 +401,8 @@ CPG_API int cpg_set_option(cpg_ctx *c, const char *name, int64_t value)
         c->opt_shells_per_pass = (int)value;
     } else if (!strcmp(name, "large_halo_min")) {
         c->opt_large_halo_min = value;
+    } else if (!strcmp(name, "radial_order")) {
+        c->opt_radial_order = value != 0;
     } else if (!strcmp(name, "cluster_size")) {
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16) {
             set_error("cluster_size must be 0, 1, 2, 4, 8 or 16");
@@ -559,7 +586,10 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     T.mark(1);
 
     // ---- gather (positions, masses, statistics, velocity centres)
-    CPG_TRY(run_gather(c, L_BOX));
+    bool radial = local && c->opt_radial_order && R <= SORT_MAX_B - 1;
+    for (int k = 0; radial && k < R; k++)
+        if (!(r_over_r200[k] > 0.0) || (k > 0 && !(r_over_r200[k] > r_over_r200[k - 1]))) radial = false;
+    CPG_TRY(run_gather(c, L_BOX, radial ? R : 0, radial && use_vel));
     CPG_TRY(run_stats(c));
     if (use_vel) CPG_TRY(run_vcenters(c, L_BOX));
     T.mark(2);
@@ -568,6 +598,7 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     MorphParams P;
     P.soa = soa_view(c);
     P.r200 = c->r200.p; P.rr = c->rr.p; P.skip = c->skip.p;
+    P.n_eff = radial ? c->n_eff.p : nullptr;
     P.tasks = c->tasks.p; P.n_tasks = 0; P.task_counter = c->task_counter.p;
     P.R = R; P.local = local ? 1 : 0; P.SAFE = SAFE;
     P.tol = IT_TOL; P.wall = IT_WALL; P.itmin = IT_MIN;

@@ -31,6 +31,7 @@ struct GatherParams {
     int64_t n_idx;
     float L_BOX;
     double *dx, *dy, *dz, *m, *vx, *vy, *vz;
+    const int32_t *dest;     // (n_idx) slot of catalogue entry j inside its object (radial ordering) or nullptr
 };
 
 __device__ __forceinline__ int find_object(const int64_t *off, int n_obj, int64_t j)
@@ -86,11 +87,14 @@ __global__ void __launch_bounds__(256) gather_vel_kernel(const GatherParams G)
         const int h = find_object(G.off, G.n_obj, j);
         const int64_t first = G.off[h], last = G.off[h + 1];
         const int64_t g = G.idx[j];
-        const int64_t o = G.poff[h] + (j - first);
+        const int64_t o = G.poff[h] + (G.dest ? (int64_t)G.dest[j] : (j - first));
         G.vx[o] = __dsub_rn(G.vxyz[3 * g], G.vcenters[3 * h]);
         G.vy[o] = __dsub_rn(G.vxyz[3 * g + 1], G.vcenters[3 * h + 1]);
         G.vz[o] = __dsub_rn(G.vxyz[3 * g + 2], G.vcenters[3 * h + 2]);
-        if (j == last - 1 && ((last - first) & 1)) { G.vx[o + 1] = 0.0; G.vy[o + 1] = 0.0; G.vz[o + 1] = 0.0; }
+        if (j == last - 1 && ((last - first) & 1)) {
+            const int64_t pad = G.poff[h] + (last - first);
+            G.vx[pad] = 0.0; G.vy[pad] = 0.0; G.vz[pad] = 0.0;
+        }
     }
 }
 
@@ -167,16 +171,16 @@ __global__ void stats_final_kernel(const int32_t *chunk_first /* n_obj+1 */, con
 // helper_class.pyx:98-100: `cdef float mass_total` accumulated sequentially in catalogue order
 // (mass_total = (float)((double)mass_total + m)).  The order is part of the result, so one lane walks the
 // object while the warp streams the masses in coalesced 32-element batches.
-__global__ void __launch_bounds__(128) mass32_kernel(const SoA soa, int n_obj, float *mass32)
+__global__ void __launch_bounds__(128) mass32_kernel(const GatherParams G, int n_obj, float *mass32)
 {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; h < n_obj; h += warps) {
-        const int N = soa.size[h];
-        const double *m = soa.m + soa.poff[h];
+        const int64_t first = G.off[h];
+        const int N = (int)(G.off[h + 1] - first);
         float acc = 0.0f;
         for (int i0 = 0; i0 < N; i0 += 32) {
-            const double mine = (i0 + lane < N) ? m[i0 + lane] : 0.0;
+            const double mine = (i0 + lane < N) ? G.masses[G.idx[first + i0 + lane]] : 0.0;
             const int cntb = min(32, N - i0);
             for (int j = 0; j < cntb; j++) {
                 const double mj = __shfl_sync(0xffffffffu, mine, j);
@@ -197,12 +201,11 @@ __global__ void __launch_bounds__(256) vsum_chunk_kernel(const GatherParams G, c
     const Chunk ck = chunks[c];
     const int N = soa.size[ck.halo];
     const int64_t first = G.off[ck.halo];
-    const int64_t base = soa.poff[ck.halo];
     const int end = min(N, ck.start + CHUNK);
     double v[3] = {0.0, 0.0, 0.0};
     for (int i = ck.start + threadIdx.x; i < end; i += blockDim.x) {
         const int64_t g = G.idx[first + i];
-        const double m = soa.m[base + i];
+        const double m = G.masses[g];
         v[0] = fma(m, G.vxyz[3 * g], v[0]);
         v[1] = fma(m, G.vxyz[3 * g + 1], v[1]);
         v[2] = fma(m, G.vxyz[3 * g + 2], v[2]);
@@ -222,6 +225,154 @@ __global__ void vcenter_final_kernel(const int32_t *chunk_first, int n_obj, cons
     }
     const double M = (double)mass32[h];
     vcenters[3 * h] = s[0] / M; vcenters[3 * h + 1] = s[1] / M; vcenters[3 * h + 2] = s[2] / M;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Radial ordering.  With q, s <= 1 the ellipsoidal radius of the reference satisfies
+//   p0^2 + p1^2/q^2 + p2^2/s^2 >= |x - c|^2,
+// so a particle with |x-c|^2 >= d_k^2 can never be a member of shell k in any Katz iteration.  The gather
+// therefore writes each object's particles bucketed by "first shell k with r^2 < d_k^2 (1+1e-12)" (a stable
+// counting sort, catalogue order kept inside a bucket -> deterministic summation order), and the morphology
+// kernels only stream the prefix n_eff[h][k] = #{r^2 < d_k^2 (1+1e-12)} of shell k.  Results are
+// unchanged (the skipped particles fail the reference's test in every iteration); the work drops from N
+// to n_eff per halo-shell iteration.  Needs ascending radii and R <= 255.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SORT_MAX_B = 256;
+
+struct SortParams {
+    GatherParams G;
+    const Chunk *chunks;
+    const int32_t *chunk_first;   // n_obj + 1
+    const int32_t *size;          // n_obj
+    const double *r200;           // n_obj
+    const double *rr;             // R ascending
+    int32_t n_chunks;
+    int32_t R;
+    uint8_t *bucket;              // (n_idx)
+    int32_t *tile_hist;           // (n_chunks, R+1): counts, then exclusive offsets inside the object
+    int32_t *dest;                // (n_idx) or nullptr
+    int32_t *n_eff;               // (n_obj, R)
+};
+
+__device__ __forceinline__ void load_relative(const GatherParams &G, int h, int64_t first, int64_t j, double &dx,
+                                              double &dy, double &dz, int64_t &g)
+{
+    g = G.idx[j];
+    double x = G.xyz[3 * g], y = G.xyz[3 * g + 1], z = G.xyz[3 * g + 2];
+    if (G.L_BOX != 0.0f) {
+        const int64_t g0 = G.idx[first];
+        pbc_reflect(x, y, z, G.xyz[3 * g0], G.xyz[3 * g0 + 1], G.L_BOX);
+    }
+    dx = __dsub_rn(x, G.centers[3 * h]);
+    dy = __dsub_rn(y, G.centers[3 * h + 1]);
+    dz = __dsub_rn(z, G.centers[3 * h + 2]);
+}
+
+__global__ void __launch_bounds__(256) bucket_hist_kernel(const SortParams P)
+{
+    __shared__ double s_thr[SORT_MAX_B];
+    __shared__ int s_hist[SORT_MAX_B];
+    const Chunk ck = P.chunks[blockIdx.x];
+    const int h = ck.halo, R = P.R, B = R + 1;
+    const int N = P.size[h];
+    const int64_t first = P.G.off[h];
+    const int end = min(N, ck.start + CHUNK);
+    const double r200 = P.r200[h];
+    for (int k = threadIdx.x; k < B; k += blockDim.x) {
+        if (k < R) {
+            const double d = __dmul_rn(r200, P.rr[k]);
+            s_thr[k] = __dmul_rn(__dmul_rn(d, d), 1.000000000001);
+        }
+        s_hist[k] = 0;
+    }
+    __syncthreads();
+    for (int i = ck.start + threadIdx.x; i < end; i += blockDim.x) {
+        double dx, dy, dz;
+        int64_t g;
+        load_relative(P.G, h, first, first + i, dx, dy, dz, g);
+        const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        int lo = 0, hi = R;   // smallest k with r2 < thr[k]; R if none
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (r2 < s_thr[mid]) hi = mid; else lo = mid + 1;
+        }
+        P.bucket[first + i] = (uint8_t)lo;
+        atomicAdd(&s_hist[lo], 1);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < B; k += blockDim.x) P.tile_hist[(size_t)blockIdx.x * B + k] = s_hist[k];
+}
+
+// Exclusive offsets of every (chunk, bucket) inside its object, bucket-major, and the prefix lengths.
+__global__ void bucket_scan_kernel(const SortParams P, int n_obj)
+{
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= n_obj) return;
+    const int R = P.R, B = R + 1;
+    const int c0 = P.chunk_first[h], c1 = P.chunk_first[h + 1];
+    int running = 0;
+    for (int b = 0; b < B; b++) {
+        for (int c = c0; c < c1; c++) {
+            const int t = P.tile_hist[(size_t)c * B + b];
+            P.tile_hist[(size_t)c * B + b] = running;
+            running += t;
+        }
+        if (b < R) P.n_eff[(size_t)h * R + b] = running;
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_sorted_kernel(const SortParams P)
+{
+    __shared__ int s_wh[8][SORT_MAX_B];
+    const Chunk ck = P.chunks[blockIdx.x];
+    const int h = ck.halo, B = P.R + 1;
+    const int N = P.size[h];
+    const int64_t first = P.G.off[h], pbase = P.G.poff[h];
+    const int end = min(N, ck.start + CHUNK);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 8 * SORT_MAX_B; i += blockDim.x) (&s_wh[0][0])[i] = 0;
+    __syncthreads();
+    // every warp owns a contiguous eighth of the chunk, so that "earlier warp" == "earlier in the catalogue"
+    const int w_lo = ck.start + warp * (CHUNK / 8), w_hi = min(end, w_lo + CHUNK / 8);
+    for (int i0 = w_lo; i0 < w_hi; i0 += 32) {
+        const int i = i0 + lane;
+        const int b = (i < w_hi) ? (int)P.bucket[first + i] : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        if (b >= 0 && lane == __ffs(peers) - 1) s_wh[warp][b] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < B) {
+        int run = P.tile_hist[(size_t)blockIdx.x * B + threadIdx.x];
+        for (int w = 0; w < 8; w++) {
+            const int t = s_wh[w][threadIdx.x];
+            s_wh[w][threadIdx.x] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+    for (int i0 = w_lo; i0 < w_hi; i0 += 32) {
+        const int i = i0 + lane;
+        const int b = (i < w_hi) ? (int)P.bucket[first + i] : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        int rank = 0;
+        if (b >= 0) rank = s_wh[warp][b] + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+        if (b >= 0 && lane == __ffs(peers) - 1) s_wh[warp][b] += __popc(peers);
+        __syncwarp();
+        if (b >= 0) {
+            double dx, dy, dz;
+            int64_t g;
+            load_relative(P.G, h, first, first + i, dx, dy, dz, g);
+            const int64_t o = pbase + rank;
+            P.G.dx[o] = dx; P.G.dy[o] = dy; P.G.dz[o] = dz;
+            P.G.m[o] = P.G.masses[g];
+            if (P.dest) P.dest[first + i] = rank;
+        }
+    }
+    if (threadIdx.x == 0 && end == N && (N & 1)) {   // pad element of an odd-sized object
+        P.G.dx[pbase + N] = 1e150; P.G.dy[pbase + N] = 1e150; P.G.dz[pbase + N] = 1e150; P.G.m[pbase + N] = 0.0;
+    }
 }
 
 }  // namespace cpg

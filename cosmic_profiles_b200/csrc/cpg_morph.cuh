@@ -68,12 +68,12 @@ __device__ __forceinline__ void accumulate(double (&acc)[7], int &cnt, bool sel,
 // r2 = ((dx*dx + dy*dy) + dz*dz) with every operation rounded separately.
 template <int S, bool SHELL, bool REDUCED, bool VDISP>
 __device__ __forceinline__ void pass0_particle(const Particle &p, const double *frames, unsigned amask,
-                                               double (&acc)[S][7], int (&cnt)[S])
+                                               const int *np, int tile, double (&acc)[S][7], int (&cnt)[S])
 {
     const double r2 = __dadd_rn(__dadd_rn(p.xx, p.yy), p.zz);
 #pragma unroll
     for (int s = 0; s < S; s++) {
-        if (amask & (1u << s)) {
+        if ((amask & (1u << s)) && tile < np[s]) {
             const double *F = frames + s * F_SLOTS;
             bool sel = r2 < F[F_D2];
             if (SHELL)
@@ -87,11 +87,12 @@ __device__ __forceinline__ void pass0_particle(const Particle &p, const double *
 // (shape_profs_algos.pyx:247-260 / :122-143) fused with the next tensor accumulation.
 template <int S, bool SHELL, bool REDUCED, bool VDISP, int NP>
 __device__ __forceinline__ void passk_particles(const Particle (&p)[NP], const double *frames, unsigned amask,
-                                                double (&acc)[S][7], int (&cnt)[S])
+                                                const int *np, int tile, double (&acc)[S][7], int (&cnt)[S])
 {
 #pragma unroll
     for (int s = 0; s < S; s++) {
-        if (amask & (1u << s)) {
+        // np[s]: pairs in the radial prefix of shell s; `tile` (first pair of this warp's batch) is warp-uniform
+        if ((amask & (1u << s)) && tile < np[s]) {
             const double2 *F2 = reinterpret_cast<const double2 *>(frames + s * F_SLOTS);
             const double2 f0 = F2[0], f1 = F2[1], f2 = F2[2], f3 = F2[3];
             // f0=(Axx,Ayy) f1=(Azz,Axy) f2=(Axz,Ayz) f3=(d2,thr)
@@ -243,10 +244,12 @@ __device__ __forceinline__ void load_pair(const SoA &soa, int64_t base, int i2, 
     }
 }
 
-// One full pass of `nthreads` cooperating threads (thread `tid`) over the object's particle pairs.
+// One full pass of `nthreads` cooperating threads (thread `tid`, lane `lane` of its warp) over the object's
+// particle pairs.  np[s] = pairs in the radial prefix of shell s, npairs = max over the active shells.
 template <int S, bool SHELL, bool REDUCED, bool VDISP, bool FIRST>
-__device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npairs, int tid, int nthreads,
-                                         const double *frames, unsigned amask, double (&acc)[S][7], int (&cnt)[S])
+__device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npairs, int tid, int nthreads, int lane,
+                                         const double *frames, const int *np, unsigned amask, double (&acc)[S][7],
+                                         int (&cnt)[S])
 {
 #pragma unroll
     for (int s = 0; s < S; s++) {
@@ -261,19 +264,29 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
             Particle p[4];
             load_pair<VDISP>(soa, base, i2, p[0], p[1]);
             load_pair<VDISP>(soa, base, i2 + nthreads, p[2], p[3]);
-            passk_particles<S, SHELL, REDUCED, VDISP, 4>(p, frames, amask, acc, cnt);
+            passk_particles<S, SHELL, REDUCED, VDISP, 4>(p, frames, amask, np, i2 - lane, acc, cnt);
         }
     }
     for (; i2 < npairs; i2 += nthreads) {
         Particle p[2];
         load_pair<VDISP>(soa, base, i2, p[0], p[1]);
         if (FIRST) {
-            pass0_particle<S, SHELL, REDUCED, VDISP>(p[0], frames, amask, acc, cnt);
-            pass0_particle<S, SHELL, REDUCED, VDISP>(p[1], frames, amask, acc, cnt);
+            pass0_particle<S, SHELL, REDUCED, VDISP>(p[0], frames, amask, np, i2 - lane, acc, cnt);
+            pass0_particle<S, SHELL, REDUCED, VDISP>(p[1], frames, amask, np, i2 - lane, acc, cnt);
         } else {
-            passk_particles<S, SHELL, REDUCED, VDISP, 2>(p, frames, amask, acc, cnt);
+            passk_particles<S, SHELL, REDUCED, VDISP, 2>(p, frames, amask, np, i2 - lane, acc, cnt);
         }
     }
+}
+
+// Pair counts of the radial prefixes of a task's shells -> shared ints; returns nothing, the caller takes
+// max over active shells with active_npairs().
+__device__ __forceinline__ int active_npairs(const int *np, unsigned amask, int S)
+{
+    int n = 0;
+    for (int s = 0; s < S; s++)
+        if (amask & (1u << s)) n = max(n, np[s]);
+    return n;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -287,8 +300,10 @@ template <int S, bool SHELL, bool REDUCED, bool VDISP>
 __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) morph_warp_kernel(const MorphParams P)
 {
     __shared__ __align__(16) double s_frames[WARP_KERNEL_WARPS][S * F_SLOTS];
+    __shared__ int s_np[WARP_KERNEL_WARPS][S];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *frames = s_frames[warp];
+    int *np = s_np[warp];
     const int ls = lane & (S - 1);
 
     for (;;) {
@@ -304,7 +319,6 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) morph_warp_kernel(cons
             continue;   // shape_profs_algos.pyx:1024-1029: outputs stay zero, counters stay -1
         const int N = P.soa.size[halo];
         const int64_t base = P.soa.poff[halo];
-        const int npairs = (N + 1) >> 1;
 
         KatzState st;
         st.q = 1.0; st.s = 1.0; st.iteration = 1;
@@ -317,13 +331,16 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) morph_warp_kernel(cons
             frames[ls * F_SLOTS + F_D2] = __dmul_rn(st.d, st.d);
             const double in = __dsub_rn(st.d, st.delta);
             frames[ls * F_SLOTS + F0_IN2] = __dmul_rn(in, in);
+            const int ne = (P.n_eff && st.active) ? P.n_eff[out_idx] : N;
+            np[ls] = (ne + 1) >> 1;
         }
         __syncwarp();
         unsigned amask = __ballot_sync(0xffffffffu, st.active && lane < S);
 
         double acc[S][7];
         int cnt[S];
-        run_pass<S, SHELL, REDUCED, VDISP, true>(P.soa, base, npairs, lane, 32, frames, amask, acc, cnt);
+        run_pass<S, SHELL, REDUCED, VDISP, true>(P.soa, base, active_npairs(np, amask, S), lane, 32, lane, frames, np,
+                                                 amask, acc, cnt);
         while (true) {
             // warp reduction, then every lane keeps the sums of the shell it serves
             double tot[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -346,7 +363,8 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) morph_warp_kernel(cons
             amask = __ballot_sync(0xffffffffu, st.active && lane < S);
             if (amask == 0)
                 break;
-            run_pass<S, SHELL, REDUCED, VDISP, false>(P.soa, base, npairs, lane, 32, frames, amask, acc, cnt);
+            run_pass<S, SHELL, REDUCED, VDISP, false>(P.soa, base, active_npairs(np, amask, S), lane, 32, lane, frames,
+                                                      np, amask, acc, cnt);
         }
     }
 }
@@ -368,11 +386,13 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     __shared__ __align__(16) double s_frames[NW][S * F_SLOTS];   // warp-private frames (no CTA barrier to publish)
     __shared__ double s_part[2][NW][S][8];                      // per-warp partial sums
     __shared__ double s_cta[2][S][8];                           // per-CTA partial sums, read by the cluster
+    __shared__ int s_np[NW][S];
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *frames = s_frames[warp];
+    int *np = s_np[warp];
     const int ls = lane & (S - 1);
 
     const int t = blockIdx.x / C;
@@ -382,7 +402,6 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
         return;   // uniform over the cluster
     const int N = P.soa.size[halo];
     const int64_t base = P.soa.poff[halo];
-    const int npairs = (N + 1) >> 1;
     const int tid = rank * (NW * 32) + threadIdx.x, nthreads = C * NW * 32;
 
     KatzState st;
@@ -395,6 +414,8 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
         frames[ls * F_SLOTS + F_D2] = __dmul_rn(st.d, st.d);
         const double in = __dsub_rn(st.d, st.delta);
         frames[ls * F_SLOTS + F0_IN2] = __dmul_rn(in, in);
+        const int ne = (P.n_eff && st.active) ? P.n_eff[out_idx] : N;
+        np[ls] = (ne + 1) >> 1;
     }
     __syncwarp();
     unsigned amask = __ballot_sync(0xffffffffu, st.active && lane < S);
@@ -403,7 +424,8 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     double acc[S][7];
     int cnt[S];
     int buf = 0;
-    run_pass<S, SHELL, REDUCED, VDISP, true>(P.soa, base, npairs, tid, nthreads, frames, amask, acc, cnt);
+    run_pass<S, SHELL, REDUCED, VDISP, true>(P.soa, base, active_npairs(np, amask, S), tid, nthreads, lane, frames, np,
+                                             amask, acc, cnt);
     while (true) {
 #pragma unroll
         for (int s = 0; s < S; s++) {
@@ -453,7 +475,8 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
         buf ^= 1;
         if (amask == 0)
             break;
-        run_pass<S, SHELL, REDUCED, VDISP, false>(P.soa, base, npairs, tid, nthreads, frames, amask, acc, cnt);
+        run_pass<S, SHELL, REDUCED, VDISP, false>(P.soa, base, active_npairs(np, amask, S), tid, nthreads, lane, frames,
+                                                  np, amask, acc, cnt);
     }
     if (C > 1)
         cluster.sync();   // nobody leaves while a peer may still read its shared memory

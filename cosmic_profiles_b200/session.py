@@ -9,6 +9,7 @@ _contexts = {}
 # Public knobs ------------------------------------------------------------------------------------
 devices = None          # list of CUDA device ordinals to shard objects over; None = [current default 0]
 options = {}            # forwarded to cpg_set_option on every context (e.g. {"shells_per_pass": 4})
+DEFAULT_OPTIONS = {"shells_per_pass": 0, "large_halo_min": 0, "cluster_size": 0, "radial_order": 1}
 
 
 def get_context(device=0):
@@ -17,7 +18,7 @@ def get_context(device=0):
         if ctx is None:
             ctx = _lib.Context(device)
             _contexts[device] = ctx
-        for k, v in options.items():
+        for k, v in dict(DEFAULT_OPTIONS, **options).items():
             ctx.set_option(k, v)
         return ctx
 

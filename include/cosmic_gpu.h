@@ -129,6 +129,8 @@ CPG_API int cpg_get_timing(cpg_ctx *ctx, cpg_timing *out);
  *   "shells_per_pass"  1,2,4 or 0=auto   how many shells of one object share one read of its particles
  *   "large_halo_min"   particles from which a thread-block cluster works on one object
  *   "cluster_size"     CTAs per cluster for large objects (1,2,4,8,16; 0=auto)
+ *   "radial_order"     1 (default): gather every object in radial-bucket order and let shell k stream only
+ *                      the particles with |x-c| < d_k (they are the only possible members); 0: catalogue order
  */
 CPG_API int cpg_set_option(cpg_ctx *ctx, const char *name, int64_t value);
 
