@@ -301,9 +301,15 @@ def main():
         ctx.set_catalogue(cat["idx_cat"], cat["obj_size"])
 
     def shapes():
+        # a step always redoes the catalogue gather ("includes the on-device gather"); the
+        # global-shape call of the same step then reuses it, as a getShapeCatLocal + getShapeCatGlobal
+        # sequence on one catalogue would
+        ctx.set_option("invalidate_gather", 1)
         out_l, nit_l, _, _, _ = ctx.shape(cat["centers"], cat["r200"], RR, True, 0.0, 0.0, *k, False, False, False)
+        nit_l = nit_l.copy()   # a view into the context's page-locked result scratch
         t_l = ctx.timing()
         out_g, nit_g, _, _, _ = ctx.shape(cat["centers"], cat["r200"], None, False, SAFE, 0.0, *k, False, False, False)
+        nit_g = nit_g.copy()
         t_g = ctx.timing()
         return nit_l, nit_g, t_l, t_g
 
@@ -320,6 +326,11 @@ def main():
     pi_local = float((nit_l.clip(0).sum(1) * sizes).sum())
     pi_global = float((nit_g.clip(0)[:, 0] * sizes).sum())
     pi_step = pi_local + pi_global
+    try:   # particles the local-shape kernels really stream (radial prefixes), for the roofline discussion
+        n_eff = ctx.prefix_lengths(len(RR)).astype(np.int64)
+        visited_local = float((n_eff * nit_l.clip(0)).sum())
+    except Exception:
+        visited_local = pi_local
     clocks = ClockSampler(local_rank)
     barrier()
     clocks.start()
@@ -358,12 +369,13 @@ def main():
     # ---- reduce over ranks: time = max, work = sum -------------------------------------------------
     vals = torch.tensor([dev_ms / a.steps, wall_ms / a.steps, e2e_ms, kern_local_ms / a.steps], dtype=torch.float64,
                         device="cuda")
-    work = torch.tensor([pi_step, pi_local, float(launches), float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+    work = torch.tensor([pi_step, pi_local, float(launches), float(h2d), float(d2h), visited_local], dtype=torch.float64,
+                        device="cuda")
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(work, op=dist.ReduceOp.SUM)
     step_ms, wall_step_ms, e2e_step_ms, kern_ms = [float(x) for x in vals.tolist()]
-    pi_all, pi_local_all, launches_all, h2d_all, d2h_all = [float(x) for x in work.tolist()]
+    pi_all, pi_local_all, launches_all, h2d_all, d2h_all, visited_all = [float(x) for x in work.tolist()]
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -393,7 +405,9 @@ def main():
                              "kernel": "morph_warp_kernel/morph_cluster_kernel (local shapes)",
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                              "algorithmic_bytes_per_launch_set": pi_local_all / world * BYTES_PER_PI,
-                             "kernel_ms": kern_ms, "frac_of_8TBps_nominal": achieved / 8000.0},
+                             "kernel_ms": kern_ms, "frac_of_8TBps_nominal": achieved / 8000.0,
+                             "streamed_particle_iterations": visited_all / world,
+                             "streamed_GBps": visited_all / world * BYTES_PER_PI / (kern_ms * 1e-3) / 1e9},
                 "cpu_baseline": cpu, "clocks": clk, "breakdown_ms_per_step_rank0": {k_: round(v_, 3) for k_, v_ in brk.items()},
                 "particle_iterations_per_step": pi_all, "particles_per_gpu": n_part}
         print(json.dumps(line), flush=True)

@@ -28,7 +28,7 @@ class Timing(ctypes.Structure):
 
 EXPORTS = ["cpg_device_count", "cpg_last_error", "cpg_version", "cpg_create", "cpg_destroy", "cpg_set_particles",
            "cpg_set_catalogue", "cpg_shape", "cpg_dens_sph", "cpg_dens_ell", "cpg_dens_kernel", "cpg_obj_masses",
-           "cpg_get_timing", "cpg_set_option"]
+           "cpg_get_timing", "cpg_set_option", "cpg_host_alloc", "cpg_host_free", "cpg_get_prefix_lengths"]
 
 
 def load():
@@ -58,8 +58,12 @@ def load():
     L.cpg_obj_masses.argtypes = [vp, _D]
     L.cpg_get_timing.argtypes = [vp, ctypes.POINTER(Timing)]
     L.cpg_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int64]
+    L.cpg_host_alloc.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
+    L.cpg_host_free.argtypes = [vp]
+    L.cpg_host_free.restype = None
+    L.cpg_get_prefix_lengths.argtypes = [vp, _I, ctypes.c_int32]
     for f in EXPORTS:
-        if f not in ("cpg_last_error", "cpg_version", "cpg_destroy"):
+        if f not in ("cpg_last_error", "cpg_version", "cpg_destroy", "cpg_host_free"):
             getattr(L, f).restype = ctypes.c_int
     _lib = L
     return L
@@ -90,6 +94,30 @@ def i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
+class PinnedBuffer:
+    """Grow-only page-locked host scratch (cpg_host_alloc) handed out as numpy views."""
+
+    def __init__(self):
+        self.ptr = ctypes.c_void_p()
+        self.cap = 0
+
+    def view(self, shape, dtype):
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        if nbytes > self.cap:
+            self.release()
+            cap = max(nbytes, 1 << 16)
+            _check(load().cpg_host_alloc(cap, ctypes.byref(self.ptr)), "cpg_host_alloc")
+            self.cap = cap
+        buf = (ctypes.c_char * max(nbytes, 1)).from_address(self.ptr.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def release(self):
+        if self.ptr:
+            load().cpg_host_free(self.ptr)
+            self.ptr = ctypes.c_void_p()
+            self.cap = 0
+
+
 class Context:
     """One CUDA device with a resident snapshot + catalogue (cpg_ctx)."""
 
@@ -100,11 +128,14 @@ class Context:
         self.device = int(device)
         self.n_obj = 0
         self.have_vel = False
+        self._pin = [PinnedBuffer() for _ in range(3)]
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             self._L.cpg_destroy(self._h)
             self._h = ctypes.c_void_p()
+            for b in self._pin:
+                b.release()
 
     def __del__(self):
         try:
@@ -140,9 +171,11 @@ class Context:
         r200 = f64(r200)
         rr = f64(r_over_r200) if local else None
         R = int(rr.shape[0]) if local else 1
-        out = np.zeros((n, R, 12))
-        nit = np.full((n, R), -1, dtype=np.int32)
-        npt = np.full((n, R), -1, dtype=np.int32)
+        # results land in page-locked scratch owned by this context: the returned out/nit/npt are views that
+        # stay valid until the next shape() call (the drop-in drivers copy out of them right away)
+        out = self._pin[0].view((n, R, 12), np.float64)
+        nit = self._pin[1].view((n, R), np.int32)
+        npt = self._pin[2].view((n, R), np.int32)
         m = np.zeros(n)
         vc = np.zeros((n, 3))
         _check(self._L.cpg_shape(self._h, _dp(centers), _dp(r200), _dp(rr), R, int(bool(local)), float(SAFE),
@@ -179,6 +212,11 @@ class Context:
         m = np.zeros(self.n_obj)
         _check(self._L.cpg_obj_masses(self._h, _dp(m)), "cpg_obj_masses")
         return m
+
+    def prefix_lengths(self, R):
+        ne = np.zeros((self.n_obj, R), dtype=np.int32)
+        _check(self._L.cpg_get_prefix_lengths(self._h, _ip(ne), int(R)), "cpg_get_prefix_lengths")
+        return ne
 
     def timing(self):
         t = Timing()

@@ -95,6 +95,21 @@ struct cpg_ctx {
     DevBuf<uint8_t> skip, bucket;
     DevBuf<int32_t> tile_hist, dest, n_eff;
     bool sorted_valid = false;    // the SoA streams are in radial-bucket order and `dest` maps catalogue -> slot
+    // what the gathered SoA currently holds (skip the gather when a call asks for the same thing again)
+    uint64_t snapshot_version = 0, catalogue_version = 0;
+    struct {
+        bool valid = false, stats = false, vel = false;
+        uint64_t snap = 0, cat = 0;
+        float L_BOX = 0.f;
+        int sort_R = 0;
+        std::vector<double> centers, r200, rr;
+    } have;
+    struct {
+        bool valid = false;
+        uint64_t cat = 0;
+        int S = 0, R = 0, nw = 0, ncl = 0, cluster_size = 1;
+        int64_t large_min = 0;
+    } task_key;
     // morphology
     DevBuf<Task> tasks;
     DevBuf<int32_t> task_counter;
@@ -185,10 +200,22 @@ struct Timer {
 
 // Gather positions and masses; requires centres (and, for the radial ordering, r200 / rr) on the device.
 // sort_R > 0: write every object's particles in radial-bucket order of the sort_R shell radii and fill
-// n_eff (cpg_gather.cuh "Radial ordering"); keep_dest: also record catalogue entry -> slot (velocity gather).
-int run_gather(cpg_ctx *c, float L_BOX, int sort_R = 0, bool keep_dest = false)
+// n_eff (cpg_gather.cuh "Radial ordering").  Skipped when the SoA already holds exactly this (same snapshot,
+// catalogue, centres, L_BOX and -- if an ordering is requested -- the same radii): the order of the
+// particles inside an object never matters to a kernel that does not use n_eff.
+int run_gather(cpg_ctx *c, const double *h_centers, const double *h_r200, const double *h_rr, float L_BOX,
+               int sort_R = 0)
 {
     const int64_t n = c->n_idx;
+    const size_t n3 = (size_t)c->n_obj * 3;
+    auto &H = c->have;
+    bool same = H.valid && H.snap == c->snapshot_version && H.cat == c->catalogue_version && H.L_BOX == L_BOX &&
+                H.centers.size() == n3 && !memcmp(H.centers.data(), h_centers, n3 * sizeof(double));
+    if (same && sort_R > 0)
+        same = H.sort_R == sort_R && H.rr.size() == (size_t)sort_R && !memcmp(H.rr.data(), h_rr, sort_R * sizeof(double)) &&
+               H.r200.size() == (size_t)c->n_obj && !memcmp(H.r200.data(), h_r200, c->n_obj * sizeof(double));
+    if (same) return CPG_OK;
+    H.valid = false; H.stats = false; H.vel = false;
     CPG_TRY(c->g_dx.ensure(c->n_pad)); CPG_TRY(c->g_dy.ensure(c->n_pad));
     CPG_TRY(c->g_dz.ensure(c->n_pad)); CPG_TRY(c->g_m.ensure(c->n_pad));
     c->sorted_valid = false;
@@ -197,29 +224,38 @@ int run_gather(cpg_ctx *c, float L_BOX, int sort_R = 0, bool keep_dest = false)
         const int B = sort_R + 1;
         CPG_TRY(c->bucket.ensure(n)); CPG_TRY(c->tile_hist.ensure((size_t)nc * B));
         CPG_TRY(c->n_eff.ensure((size_t)c->n_obj * sort_R));
-        if (keep_dest) CPG_TRY(c->dest.ensure(n));
+        CPG_TRY(c->dest.ensure(n));
         SortParams P;
         P.G = gather_view(c, L_BOX);
         P.chunks = c->chunks.p; P.chunk_first = c->chunk_first.p; P.size = c->size.p;
         P.r200 = c->r200.p; P.rr = c->rr.p; P.n_chunks = nc; P.R = sort_R;
-        P.bucket = c->bucket.p; P.tile_hist = c->tile_hist.p; P.dest = keep_dest ? c->dest.p : nullptr;
+        P.bucket = c->bucket.p; P.tile_hist = c->tile_hist.p; P.dest = c->dest.p;
         P.n_eff = c->n_eff.p;
         bucket_hist_kernel<<<nc, 256, 0, c->stream>>>(P);
         bucket_scan_kernel<<<grid_for(c->n_obj, 128, 1 << 30), 128, 0, c->stream>>>(P, c->n_obj);
-        gather_sorted_kernel<<<nc, 256, 0, c->stream>>>(P);
+        bucket_rank_kernel<<<nc, 256, 0, c->stream>>>(P);
         c->timing.kernel_launches += 3;
-        c->sorted_valid = keep_dest;
-    } else if (n > 0) {
+        c->sorted_valid = true;
+    }
+    if (n > 0) {
         gather_pos_kernel<<<grid_for(n, 256, c->sm_count * 32), 256, 0, c->stream>>>(gather_view(c, L_BOX));
         c->timing.kernel_launches++;
     }
     CPG_CUDA(cudaGetLastError());
     c->mass_stream_valid = true;
+    H.valid = true; H.snap = c->snapshot_version; H.cat = c->catalogue_version; H.L_BOX = L_BOX;
+    H.sort_R = sort_R;
+    H.centers.assign(h_centers, h_centers + n3);
+    if (sort_R > 0) {
+        H.rr.assign(h_rr, h_rr + sort_R);
+        H.r200.assign(h_r200, h_r200 + c->n_obj);
+    }
     return CPG_OK;
 }
 
 int run_stats(cpg_ctx *c)
 {
+    if (c->have.valid && c->have.stats) return CPG_OK;
     const int nc = (int)c->h_chunks.size();
     CPG_TRY(c->part_mass.ensure(nc)); CPG_TRY(c->part_flag.ensure(nc));
     CPG_TRY(c->obj_mass.ensure(c->n_obj)); CPG_TRY(c->skip.ensure(c->n_obj));
@@ -233,11 +269,13 @@ int run_stats(cpg_ctx *c)
         c->timing.kernel_launches++;
     }
     CPG_CUDA(cudaGetLastError());
+    c->have.stats = c->have.valid;
     return CPG_OK;
 }
 
 int run_vcenters(cpg_ctx *c, float L_BOX)
 {
+    if (c->have.valid && c->have.vel) return CPG_OK;
     const int nc = (int)c->h_chunks.size();
     CPG_TRY(c->mass32.ensure(c->n_obj)); CPG_TRY(c->vpart.ensure((size_t)nc * 3));
     CPG_TRY(c->vcenters.ensure((size_t)c->n_obj * 3));
@@ -255,6 +293,7 @@ int run_vcenters(cpg_ctx *c, float L_BOX)
         c->timing.kernel_launches += 4;
     }
     CPG_CUDA(cudaGetLastError());
+    c->have.vel = c->have.valid;
     return CPG_OK;
 }
 
@@ -401,6 +440,8 @@ CPG_API int cpg_set_option(cpg_ctx *c, const char *name, int64_t value)
         c->opt_shells_per_pass = (int)value;
     } else if (!strcmp(name, "large_halo_min")) {
         c->opt_large_halo_min = value;
+    } else if (!strcmp(name, "invalidate_gather")) {
+        c->have.valid = false;   // one-shot: the next compute call redoes the catalogue gather
     } else if (!strcmp(name, "radial_order")) {
         c->opt_radial_order = value != 0;
     } else if (!strcmp(name, "cluster_size")) {
@@ -435,6 +476,8 @@ CPG_API int cpg_set_particles(cpg_ctx *c, const double *xyz, const double *vxyz,
     CPG_CUDA(cudaStreamSynchronize(c->stream));
     c->n_part = n_part;
     c->mass_stream_valid = false;
+    c->snapshot_version++;
+    c->have.valid = false;
     return CPG_OK;
 }
 
@@ -510,6 +553,9 @@ CPG_API int cpg_set_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx,
     c->n_pad = poff[n_obj];
     c->n_obj = n_obj;
     c->mass_stream_valid = false;
+    c->catalogue_version++;
+    c->have.valid = false;
+    c->task_key.valid = false;
     return CPG_OK;
 }
 
@@ -552,32 +598,39 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     if (S > R) S = pow2_floor(R);
     int64_t large_min = c->opt_large_halo_min > 0 ? c->opt_large_halo_min : (int64_t)131072;
     if (c->opt_large_halo_min == 0 && n_units < warp_slots / 2) large_min = 8192;   // few units: spread each over CTAs
-    std::vector<Task> warp_tasks, cl_tasks;
-    int64_t largest = 0;
-    for (int oi = 0; oi < n; oi++) {
-        const int h = c->order[oi];
-        const int64_t N = c->h_size[h];
-        largest = std::max(largest, N);
-        std::vector<Task> &dst = (N >= large_min) ? cl_tasks : warp_tasks;
-        for (int k0 = 0; k0 < R; k0 += S)
-            dst.push_back(Task{h, (int16_t)k0, (int16_t)std::min(S, R - k0)});
-    }
-    int cluster_size = c->opt_cluster_size;
-    if (cluster_size == 0) {
-        cluster_size = 1;
-        if (!cl_tasks.empty()) {
-            // enough CTAs to cover the GPU about twice, bounded by the largest object (>= 32k particles per CTA)
-            const int64_t want = (2 * (int64_t)c->sm_count + (int64_t)cl_tasks.size() - 1) / (int64_t)cl_tasks.size();
-            const int64_t by_size = std::max<int64_t>(1, largest / 32768);
-            cluster_size = pow2_floor(std::max<int64_t>(1, std::min<int64_t>(std::min(want, by_size), 16)));
+    auto &TK = c->task_key;
+    if (!(TK.valid && TK.cat == c->catalogue_version && TK.S == S && TK.R == R && TK.large_min == large_min &&
+          (c->opt_cluster_size == 0 || c->opt_cluster_size == TK.cluster_size))) {
+        std::vector<Task> warp_tasks, cl_tasks;
+        int64_t largest = 0;
+        for (int oi = 0; oi < n; oi++) {
+            const int h = c->order[oi];
+            const int64_t N = c->h_size[h];
+            largest = std::max(largest, N);
+            std::vector<Task> &dst = (N >= large_min) ? cl_tasks : warp_tasks;
+            for (int k0 = 0; k0 < R; k0 += S)
+                dst.push_back(Task{h, (int16_t)k0, (int16_t)std::min(S, R - k0)});
         }
+        int cluster_size = c->opt_cluster_size;
+        if (cluster_size == 0) {
+            cluster_size = 1;
+            if (!cl_tasks.empty()) {
+                // enough CTAs to cover the GPU about twice, bounded by the largest object (>= 32k particles per CTA)
+                const int64_t want = (2 * (int64_t)c->sm_count + (int64_t)cl_tasks.size() - 1) / (int64_t)cl_tasks.size();
+                const int64_t by_size = std::max<int64_t>(1, largest / 32768);
+                cluster_size = pow2_floor(std::max<int64_t>(1, std::min<int64_t>(std::min(want, by_size), 16)));
+            }
+        }
+        TK.nw = (int)warp_tasks.size(); TK.ncl = (int)cl_tasks.size(); TK.cluster_size = cluster_size;
+        warp_tasks.insert(warp_tasks.end(), cl_tasks.begin(), cl_tasks.end());
+        CPG_TRY(c->tasks.ensure(warp_tasks.size()));
+        CPG_CUDA(cudaMemcpyAsync(c->tasks.p, warp_tasks.data(), sizeof(Task) * warp_tasks.size(), cudaMemcpyHostToDevice,
+                                 c->stream));
+        CPG_CUDA(cudaStreamSynchronize(c->stream));   // warp_tasks is a local
+        c->timing.h2d_bytes += (int64_t)(sizeof(Task) * warp_tasks.size());
+        TK.valid = true; TK.cat = c->catalogue_version; TK.S = S; TK.R = R; TK.large_min = large_min;
     }
-    const int nw = (int)warp_tasks.size(), ncl = (int)cl_tasks.size();
-    warp_tasks.insert(warp_tasks.end(), cl_tasks.begin(), cl_tasks.end());
-    CPG_TRY(c->tasks.ensure(warp_tasks.size()));
-    CPG_CUDA(cudaMemcpyAsync(c->tasks.p, warp_tasks.data(), sizeof(Task) * warp_tasks.size(), cudaMemcpyHostToDevice,
-                             c->stream));
-    c->timing.h2d_bytes += (int64_t)(sizeof(Task) * warp_tasks.size());
+    const int nw = TK.nw, ncl = TK.ncl, cluster_size = TK.cluster_size;
     CPG_TRY(c->out12.ensure(nR * 12)); CPG_TRY(c->n_iter.ensure(nR)); CPG_TRY(c->n_pts.ensure(nR));
     CPG_CUDA(cudaMemsetAsync(c->out12.p, 0, sizeof(double) * 12 * nR, c->stream));
     CPG_CUDA(cudaMemsetAsync(c->n_iter.p, 0xff, sizeof(int32_t) * nR, c->stream));
@@ -589,7 +642,7 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     bool radial = local && c->opt_radial_order && R <= SORT_MAX_B - 1;
     for (int k = 0; radial && k < R; k++)
         if (!(r_over_r200[k] > 0.0) || (k > 0 && !(r_over_r200[k] > r_over_r200[k - 1]))) radial = false;
-    CPG_TRY(run_gather(c, L_BOX, radial ? R : 0, radial && use_vel));
+    CPG_TRY(run_gather(c, centers, r200, r_over_r200, L_BOX, radial ? R : 0));
     CPG_TRY(run_stats(c));
     if (use_vel) CPG_TRY(run_vcenters(c, L_BOX));
     T.mark(2);
@@ -598,7 +651,7 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     MorphParams P;
     P.soa = soa_view(c);
     P.r200 = c->r200.p; P.rr = c->rr.p; P.skip = c->skip.p;
-    P.n_eff = radial ? c->n_eff.p : nullptr;
+    P.n_eff = radial ? c->n_eff.p : nullptr;   // run_gather guarantees n_eff matches these radii when radial
     P.tasks = c->tasks.p; P.n_tasks = 0; P.task_counter = c->task_counter.p;
     P.R = R; P.local = local ? 1 : 0; P.SAFE = SAFE;
     P.tol = IT_TOL; P.wall = IT_WALL; P.itmin = IT_MIN;
@@ -630,6 +683,11 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     c->timing.kernel_ms = Timer::ms(c->ev[2], c->ev[3]);
     c->timing.d2h_ms = Timer::ms(c->ev[3], c->ev[4]);
     return CPG_OK;
+}
+
+static int dens_gather(cpg_ctx *c, const double *centers, float L_BOX)
+{
+    return run_gather(c, centers, nullptr, nullptr, L_BOX, 0);
 }
 
 static int dens_common_begin(cpg_ctx *c, Timer &T, const double *centers, const double *r200, float L_BOX)
@@ -680,7 +738,7 @@ CPG_API int cpg_dens_sph(cpg_ctx *c, const double *centers, const double *r200, 
     CPG_TRY(c->bin_mass.ensure((size_t)nc * R)); CPG_TRY(c->bin_cnt.ensure((size_t)nc * R));
     CPG_TRY(c->dens.ensure(nR)); CPG_TRY(c->counts.ensure(nR));
     T.mark(1);
-    CPG_TRY(run_gather(c, L_BOX));
+    CPG_TRY(dens_gather(c, centers, L_BOX));
     T.mark(2);
     DensParams D = {};
     D.soa = soa_view(c); D.chunks = c->chunks.p; D.n_chunks = nc; D.R = R; D.r200 = c->r200.p; D.edges = c->d_edges.p;
@@ -726,7 +784,7 @@ CPG_API int cpg_dens_ell(cpg_ctx *c, const double *centers, const double *a, con
     CPG_TRY(c->bin_mass.ensure((size_t)nc * R)); CPG_TRY(c->bin_cnt.ensure((size_t)nc * R));
     CPG_TRY(c->dens.ensure(nR)); CPG_TRY(c->counts.ensure(nR));
     T.mark(1);
-    CPG_TRY(run_gather(c, L_BOX));
+    CPG_TRY(dens_gather(c, centers, L_BOX));
     T.mark(2);
     DensParams D = {};
     D.soa = soa_view(c); D.chunks = c->chunks.p; D.n_chunks = nc; D.R = R;
@@ -766,7 +824,7 @@ CPG_API int cpg_dens_kernel(cpg_ctx *c, const double *centers, const double *r20
     CPG_TRY(c->bin_mass.ensure((size_t)nc * R));
     CPG_TRY(c->dens.ensure(nR));
     T.mark(1);
-    CPG_TRY(run_gather(c, L_BOX));
+    CPG_TRY(dens_gather(c, centers, L_BOX));
     T.mark(2);
     DensParams D = {};
     D.soa = soa_view(c); D.chunks = c->kchunks.p; D.n_chunks = nc; D.R = R; D.r200 = c->r200.p; D.edges = c->d_edges.p;
@@ -790,13 +848,48 @@ CPG_API int cpg_obj_masses(cpg_ctx *c, double *obj_mass)
     if (n > 0 && !obj_mass) return CPG_ERR_ARGUMENT;
     Timer T(c);
     if (n == 0) return CPG_OK;
-    if (!c->mass_stream_valid) {
+    if (!c->have.valid) {
+        std::vector<double> zeros((size_t)n * 3, 0.0);
         CPG_TRY(c->centers.ensure((size_t)n * 3));
         CPG_CUDA(cudaMemsetAsync(c->centers.p, 0, sizeof(double) * 3 * n, c->stream));
-        CPG_TRY(run_gather(c, 0.0f));
+        CPG_TRY(run_gather(c, zeros.data(), nullptr, nullptr, 0.0f, 0));
     }
     CPG_TRY(run_stats(c));
     CPG_CUDA(cudaMemcpyAsync(obj_mass, c->obj_mass.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CPG_CUDA(cudaStreamSynchronize(c->stream));
+    return CPG_OK;
+}
+
+CPG_API int cpg_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return CPG_ERR_ARGUMENT;
+    *out = nullptr;
+    if (cpg_device_count() <= 0) {
+        set_error("cpg_host_alloc: no CUDA device");
+        return CPG_ERR_NO_DEVICE;
+    }
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        set_error("cudaHostAlloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return CPG_ERR_NOMEM;
+    }
+    return CPG_OK;
+}
+
+CPG_API void cpg_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+CPG_API int cpg_get_prefix_lengths(cpg_ctx *c, int32_t *n_eff, int32_t R)
+{
+    CPG_TRY(use_device(c));
+    if (!n_eff || !c->have.valid || c->have.sort_R != R || R <= 0) {
+        set_error("cpg_get_prefix_lengths: the resident gather holds no radial ordering for R=%d", (int)R);
+        return CPG_ERR_STATE;
+    }
+    CPG_CUDA(cudaMemcpyAsync(n_eff, c->n_eff.p, sizeof(int32_t) * (size_t)c->n_obj * R, cudaMemcpyDeviceToHost, c->stream));
     CPG_CUDA(cudaStreamSynchronize(c->stream));
     return CPG_OK;
 }

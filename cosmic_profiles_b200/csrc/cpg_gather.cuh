@@ -68,13 +68,14 @@ __global__ void __launch_bounds__(256) gather_pos_kernel(const GatherParams G)
             const int64_t g0 = G.idx[first];
             pbc_reflect(x, y, z, G.xyz[3 * g0], G.xyz[3 * g0 + 1], G.L_BOX);
         }
-        const int64_t o = G.poff[h] + (j - first);
+        const int64_t o = G.poff[h] + (G.dest ? (int64_t)G.dest[j] : (j - first));
         G.dx[o] = __dsub_rn(x, G.centers[3 * h]);
         G.dy[o] = __dsub_rn(y, G.centers[3 * h + 1]);
         G.dz[o] = __dsub_rn(z, G.centers[3 * h + 2]);
         G.m[o] = G.masses[g];
         if (j == last - 1 && ((last - first) & 1)) {   // pad element of an odd-sized object
-            G.dx[o + 1] = 1e150; G.dy[o + 1] = 1e150; G.dz[o + 1] = 1e150; G.m[o + 1] = 0.0;
+            const int64_t pad = G.poff[h] + (last - first);
+            G.dx[pad] = 1e150; G.dy[pad] = 1e150; G.dz[pad] = 1e150; G.m[pad] = 0.0;
         }
     }
 }
@@ -321,13 +322,15 @@ __global__ void bucket_scan_kernel(const SortParams P, int n_obj)
     }
 }
 
-__global__ void __launch_bounds__(256) gather_sorted_kernel(const SortParams P)
+// Stable rank of every catalogue entry inside its object's bucket order -> dest[j].  Only the one-byte bucket
+// ids are read here; the data movement itself is the fully parallel gather_pos_kernel (G.dest = dest).
+__global__ void __launch_bounds__(256) bucket_rank_kernel(const SortParams P)
 {
     __shared__ int s_wh[8][SORT_MAX_B];
     const Chunk ck = P.chunks[blockIdx.x];
     const int h = ck.halo, B = P.R + 1;
     const int N = P.size[h];
-    const int64_t first = P.G.off[h], pbase = P.G.poff[h];
+    const int64_t first = P.G.off[h];
     const int end = min(N, ck.start + CHUNK);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 8 * SORT_MAX_B; i += blockDim.x) (&s_wh[0][0])[i] = 0;
@@ -360,18 +363,7 @@ __global__ void __launch_bounds__(256) gather_sorted_kernel(const SortParams P)
         __syncwarp();
         if (b >= 0 && lane == __ffs(peers) - 1) s_wh[warp][b] += __popc(peers);
         __syncwarp();
-        if (b >= 0) {
-            double dx, dy, dz;
-            int64_t g;
-            load_relative(P.G, h, first, first + i, dx, dy, dz, g);
-            const int64_t o = pbase + rank;
-            P.G.dx[o] = dx; P.G.dy[o] = dy; P.G.dz[o] = dz;
-            P.G.m[o] = P.G.masses[g];
-            if (P.dest) P.dest[first + i] = rank;
-        }
-    }
-    if (threadIdx.x == 0 && end == N && (N & 1)) {   // pad element of an odd-sized object
-        P.G.dx[pbase + N] = 1e150; P.G.dy[pbase + N] = 1e150; P.G.dz[pbase + N] = 1e150; P.G.m[pbase + N] = 0.0;
+        if (b >= 0) P.dest[first + i] = rank;
     }
 }
 

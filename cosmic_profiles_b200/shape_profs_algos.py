@@ -26,9 +26,10 @@ def _run_one(device, xyz, vxyz, masses, idx_cat, obj_size, cen, r200, rr, local,
     ctx = _session.get_context(device)
     ctx.set_particles(xyz, vxyz, masses)
     ctx.set_catalogue(idx_cat, obj_size)
-    res = ctx.shape(cen, r200, rr, local, SAFE, L_BOX, IT_TOL, IT_WALL, IT_MIN, reduced, shell_based,
-                    vxyz is not None)
-    return res + (ctx.timing(),)
+    # out/nit/npt are views into the context's page-locked scratch, valid until its next shape() call;
+    # every caller below copies out of them before touching the context again
+    return ctx.shape(cen, r200, rr, local, SAFE, L_BOX, IT_TOL, IT_WALL, IT_MIN, reduced, shell_based,
+                     vxyz is not None) + (ctx.timing(),)
 
 
 def _morph(xyz, vxyz, masses, r200, idx_cat, obj_size, L_BOX, r_over_r200, IT_TOL, IT_WALL, IT_MIN, CENTER, SAFE,
@@ -50,6 +51,7 @@ def _morph(xyz, vxyz, masses, r200, idx_cat, obj_size, L_BOX, r_over_r200, IT_TO
     args = (rr, local, SAFE, L_BOX, IT_TOL, IT_WALL, IT_MIN, reduced, shell_based)
     if len(devs) == 1 or n < 2 * len(devs):
         out, nit, npt, m, vc, tim = _run_one(devs[0], xyz, vxyz, masses, idx_cat, obj_size, cen, r200, *args)
+        nit, npt = nit.copy(), npt.copy()
         timings = [tim]
     else:
         # objects are independent: shard them, one host thread per device, disjoint output slices
@@ -96,7 +98,7 @@ def _morph(xyz, vxyz, masses, r200, idx_cat, obj_size, L_BOX, r_over_r200, IT_TO
         major, inter, minor = major[:, 0], inter[:, 0], minor[:, 0]
         nit, npt = nit[:, 0], npt[:, 0]
     last_info.clear()
-    last_info.update(n_iter=nit, n_pts=npt, vcenters=vc, timing=timings, raw=out)
+    last_info.update(n_iter=nit, n_pts=npt, vcenters=vc, timing=timings)
     return d, q, s, minor, inter, major, cen_out, m
 
 

@@ -18,6 +18,7 @@
 #ifndef COSMIC_GPU_H
 #define COSMIC_GPU_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -122,6 +123,16 @@ CPG_API int cpg_dens_kernel(cpg_ctx *ctx, const double *centers, const double *r
  * (dens_profs_algos.pyx:45-47). */
 CPG_API int cpg_obj_masses(cpg_ctx *ctx, double *obj_mass);
 
+/* Page-locked host buffers for results (device->host copies into pageable memory run at a fraction of the
+ * PCIe rate).  No counterpart in the reference, whose drivers np.zeros() their outputs
+ * (shape_profs_algos.pyx:560-572). */
+CPG_API int cpg_host_alloc(size_t bytes, void **out);
+CPG_API void cpg_host_free(void *p);
+
+/* Radial-prefix lengths n_eff (n_obj,R) of the most recent local cpg_shape call (diagnostics: how many
+ * particles shell k actually streams per Katz iteration; see cpg_gather.cuh "Radial ordering"). */
+CPG_API int cpg_get_prefix_lengths(cpg_ctx *ctx, int32_t *n_eff, int32_t R);
+
 /* Timing breakdown of the most recent compute call on this context. */
 CPG_API int cpg_get_timing(cpg_ctx *ctx, cpg_timing *out);
 
@@ -129,6 +140,8 @@ CPG_API int cpg_get_timing(cpg_ctx *ctx, cpg_timing *out);
  *   "shells_per_pass"  1,2,4 or 0=auto   how many shells of one object share one read of its particles
  *   "large_halo_min"   particles from which a thread-block cluster works on one object
  *   "cluster_size"     CTAs per cluster for large objects (1,2,4,8,16; 0=auto)
+ *   "invalidate_gather" (any value) one-shot: forget the resident gathered catalogue, so that the next compute
+ *                      call redoes the gather even if snapshot, catalogue, centres and L_BOX are unchanged
  *   "radial_order"     1 (default): gather every object in radial-bucket order and let shell k stream only
  *                      the particles with |x-c| < d_k (they are the only possible members); 0: catalogue order
  */
