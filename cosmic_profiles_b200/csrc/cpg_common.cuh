@@ -81,34 +81,53 @@ __device__ __forceinline__ void jacobi_rotate(double &app, double &aqq, double &
                                               double *vp, double *vq)
 {
     if (apq != 0.0) {
-        const double theta = (aqq - app) / (2.0 * apq);
-        double t = 1.0 / (fabs(theta) + sqrt(theta * theta + 1.0));   // |theta| = inf -> t = 0
-        t = theta < 0.0 ? -t : t;
-        const double c = rsqrt(t * t + 1.0), s = t * c;
-        app -= t * apq;
-        aqq += t * apq;
+        // tan of the rotation angle, smaller root: t = apq / (tau + sign(tau) * hypot(tau, apq)), tau = (aqq-app)/2
+        const double tau = 0.5 * (aqq - app);
+        const double r = sqrt(fma(tau, tau, apq * apq));
+        const double t = apq / (tau + copysign(r, tau));
+        const double c = rsqrt(fma(t, t, 1.0)), s = t * c;
+        app = fma(-t, apq, app);
+        aqq = fma(t, apq, aqq);
         apq = 0.0;
         const double x = arp, y = arq;
         arp = c * x - s * y;
         arq = s * x + c * y;
 #pragma unroll
-        for (int r = 0; r < 3; r++) {
-            const double a = vp[r], b = vq[r];
-            vp[r] = c * a - s * b;
-            vq[r] = s * a + c * b;
+        for (int r3 = 0; r3 < 3; r3++) {
+            const double a = vp[r3], b = vq[r3];
+            vp[r3] = c * a - s * b;
+            vq[r3] = s * a + c * b;
         }
     }
 }
 
+// a: symmetric input (a00 a01 a02 a11 a12 a22).  v (in/out): on entry an orthonormal basis that is expected
+// to nearly diagonalise `a` (the eigenvectors of the previous Katz iteration, or the identity); on exit the
+// eigenvectors sorted by ascending eigenvalue.  Working on V^T a V starts the cyclic Jacobi sweeps close to
+// convergence (quadratic), typically 2-3 sweeps instead of 5-6.
 __device__ __forceinline__ void eigh3(double a00, double a01, double a02, double a11, double a12, double a22,
                                       double w[3], double v[9])
 {
-    double v0[3] = {1.0, 0.0, 0.0}, v1[3] = {0.0, 1.0, 0.0}, v2[3] = {0.0, 0.0, 1.0};
-    for (int sweep = 0; sweep < 60; sweep++) {
+    double v0[3] = {v[0], v[1], v[2]}, v1[3] = {v[3], v[4], v[5]}, v2[3] = {v[6], v[7], v[8]};
+    {
+        // b_k = a * v_k, then a' = V^T a V
+        double b0[3], b1[3], b2[3];
+#define CPG_MATVEC(b, x)                                        \
+        b[0] = fma(a02, x[2], fma(a01, x[1], a00 * x[0]));      \
+        b[1] = fma(a12, x[2], fma(a11, x[1], a01 * x[0]));      \
+        b[2] = fma(a22, x[2], fma(a12, x[1], a02 * x[0]));
+        CPG_MATVEC(b0, v0) CPG_MATVEC(b1, v1) CPG_MATVEC(b2, v2)
+#undef CPG_MATVEC
+#define CPG_DOT(x, y) fma(x[2], y[2], fma(x[1], y[1], x[0] * y[0]))
+        a00 = CPG_DOT(v0, b0); a01 = CPG_DOT(v0, b1); a02 = CPG_DOT(v0, b2);
+        a11 = CPG_DOT(v1, b1); a12 = CPG_DOT(v1, b2); a22 = CPG_DOT(v2, b2);
+#undef CPG_DOT
+    }
+    for (int sweep = 0; sweep < 40; sweep++) {
         const double off = a01 * a01 + a02 * a02 + a12 * a12;
         const double dia = a00 * a00 + a11 * a11 + a22 * a22;
-        if (!(off > 1e-40 * dia))
-            break;   // converged, or NaN input
+        if (!(off > 1e-33 * dia))
+            break;   // off-diagonal below 3e-17 of the diagonal (eigenvectors exact to rounding), or NaN input
         jacobi_rotate(a00, a11, a01, a02, a12, v0, v1);
         jacobi_rotate(a00, a22, a02, a01, a12, v0, v2);
         jacobi_rotate(a11, a22, a12, a01, a02, v1, v2);
@@ -124,8 +143,48 @@ __device__ __forceinline__ void eigh3(double a00, double a01, double a02, double
     CPG_CSWAP(a00, a11, v0, v1)
 #undef CPG_CSWAP
     w[0] = a00; w[1] = a11; w[2] = a22;
+    // re-orthonormalise cheaply (one Gram-Schmidt pass keeps the warm-started basis orthonormal to rounding
+    // over many Katz iterations): v2 unit, v1 orthogonal to v2, v0 = v1 x v2
+    {
+        double n = rsqrt(fma(v2[2], v2[2], fma(v2[1], v2[1], v2[0] * v2[0])));
+        v2[0] *= n; v2[1] *= n; v2[2] *= n;
+        const double d = fma(v1[2], v2[2], fma(v1[1], v2[1], v1[0] * v2[0]));
+        v1[0] = fma(-d, v2[0], v1[0]); v1[1] = fma(-d, v2[1], v1[1]); v1[2] = fma(-d, v2[2], v1[2]);
+        n = rsqrt(fma(v1[2], v1[2], fma(v1[1], v1[1], v1[0] * v1[0])));
+        v1[0] *= n; v1[1] *= n; v1[2] *= n;
+        const double c0 = v1[1] * v2[2] - v1[2] * v2[1], c1 = v1[2] * v2[0] - v1[0] * v2[2],
+                     c2 = v1[0] * v2[1] - v1[1] * v2[0];
+        const double sgn = fma(c2, v0[2], fma(c1, v0[1], c0 * v0[0])) < 0.0 ? -1.0 : 1.0;
+        v0[0] = sgn * c0; v0[1] = sgn * c1; v0[2] = sgn * c2;
+    }
 #pragma unroll
     for (int r = 0; r < 3; r++) { v[r] = v0[r]; v[3 + r] = v1[r]; v[6 + r] = v2[r]; }
+}
+
+// Sum NV = 8, 16 or 32 per-lane values over the warp with the halving exchange: after log2 steps lane l holds
+// the warp total of value (l mod NV).  31 shuffles for 32 values instead of 160 with one butterfly each;
+// the summation tree is fixed, so the result is deterministic.
+template <int NV>
+__device__ __forceinline__ double warp_sum_transpose(double (&val)[NV], int lane)
+{
+    static_assert(NV == 8 || NV == 16 || NV == 32, "NV");
+    // lanes that differ in a bit >= log2(NV) hold the same value index: plain butterfly over those bits
+#pragma unroll
+    for (int o = 16; o >= NV; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < NV; j++) val[j] += __shfl_xor_sync(0xffffffffu, val[j], o);
+    }
+#pragma unroll
+    for (int n = NV / 2; n >= 1; n >>= 1) {
+        const bool upper = (lane & n) != 0;
+#pragma unroll
+        for (int j = 0; j < n; j++) {
+            const double send = upper ? val[j] : val[j + n];
+            const double keep = upper ? val[j + n] : val[j];
+            val[j] = keep + __shfl_xor_sync(0xffffffffu, send, n);
+        }
+    }
+    return val[0];
 }
 
 }  // namespace cpg

@@ -33,8 +33,11 @@ enum {
     F_THR,                                          // inner-ellipsoid threshold: 1 (shell), -1 (first shell: disabled)
     F_BXX, F_BYY, F_BZZ, F_BXY, F_BXZ, F_BYZ,       // B = R^T diag(1/(d-delta)^2, 1/(q d-delta)^2, 1/(s d-delta)^2) R
     F0_IN2,                                         // pass 0 only: (d-delta)^2
-    F_SLOTS = 16
+    F_PAD,
+    F_V,                                            // 9 slots: eigenvector basis of the previous iteration
+    F_SLOTS = 26                                    // (even: rows stay 16-byte aligned for the double2 loads)
 };
+static_assert(F_V == 16 && F_SLOTS % 2 == 0, "frame layout");
 
 struct Particle {              // one particle as seen by the accumulators
     double xx, yy, zz, xy, xz, yz;   // products of the centre-relative position
@@ -140,7 +143,8 @@ struct KatzState {
 // the global/shared stores; all lanes of a shell compute identical values.
 template <bool SHELL>
 __device__ __forceinline__ void katz_step(KatzState &st, const double (&tot)[7], int pts, const MorphParams &P,
-                                          double *frame, bool frame_writer, size_t out_idx, bool out_writer)
+                                          const double (&vprev)[9], double *frame, bool frame_writer, size_t out_idx,
+                                          bool out_writer)
 {
     if (!st.active)
         return;
@@ -154,6 +158,8 @@ __device__ __forceinline__ void katz_step(KatzState &st, const double (&tot)[7],
     }
     const double im = 1.0 / tot[6];
     double w[3], v[9];
+#pragma unroll
+    for (int r = 0; r < 9; r++) v[r] = vprev[r];   // warm start: basis of the previous iteration
     eigh3(tot[0] * im, tot[1] * im, tot[2] * im, tot[3] * im, tot[4] * im, tot[5] * im, w, v);
     if (!(w[2] > 0.0)) {
         // all-zero or NaN tensor (coincident points, a particle exactly at the centre in reduced mode): the
@@ -185,6 +191,8 @@ __device__ __forceinline__ void katz_step(KatzState &st, const double (&tot)[7],
         return;
     }
     if (frame_writer) {
+#pragma unroll
+        for (int r = 0; r < 9; r++) frame[F_V + r] = v[r];
         // v[6..8] major (e2), v[3..5] intermediate (e1), v[0..2] minor (e0)
         const double iq2 = 1.0 / (st.q * st.q), is2 = 1.0 / (st.s * st.s);
         quad_form(frame + F_AXX, v, 1.0, iq2, is2);
@@ -296,6 +304,50 @@ __device__ __forceinline__ int active_npairs(const int *np, unsigned amask, int 
 // ------------------------------------------------------------------------------------------------
 constexpr int WARP_KERNEL_WARPS = 4;
 
+// Lane <-> shell mapping shared by both kernels.  The transposed warp reduction leaves the total of value
+// (l mod 8S) in lane l; value 8s+c is component c (Sxx,Sxy,Sxz,Syy,Syz,Szz,M,count) of shell s.  So the lanes
+// [8s, 8s+8) (and their images modulo 8S) serve shell s, and lane 8s is the one that writes its frame.
+template <int S>
+struct LaneMap {
+    static constexpr int NV = 8 * S;
+    int ls;        // shell served by this lane
+    bool writer;   // this lane publishes frames / results of shell ls
+    __device__ __forceinline__ explicit LaneMap(int lane) : ls((lane & (NV - 1)) >> 3), writer(lane < NV && (lane & 7) == 0) {}
+    __device__ static __forceinline__ unsigned active_mask(bool active_writer)
+    {
+        const unsigned b = __ballot_sync(0xffffffffu, active_writer);
+        unsigned m = 0;
+#pragma unroll
+        for (int s = 0; s < S; s++) m |= ((b >> (8 * s)) & 1u) << s;
+        return m;
+    }
+};
+
+template <int S>
+__device__ __forceinline__ void init_frames(double *frames, int *np, const LaneMap<S> &L, const KatzState &st, int ne)
+{
+    if (L.writer) {
+        double *F = frames + L.ls * F_SLOTS;
+        F[F_D2] = __dmul_rn(st.d, st.d);
+        const double in = __dsub_rn(st.d, st.delta);
+        F[F0_IN2] = __dmul_rn(in, in);
+#pragma unroll
+        for (int r = 0; r < 9; r++) F[F_V + r] = (r == 0 || r == 4 || r == 8) ? 1.0 : 0.0;
+        np[L.ls] = (ne + 1) >> 1;
+    }
+}
+
+template <int S>
+__device__ __forceinline__ void pack_values(const double (&acc)[S][7], const int (&cnt)[S], double (&val)[8 * S])
+{
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+#pragma unroll
+        for (int c = 0; c < 7; c++) val[8 * s + c] = acc[s][c];
+        val[8 * s + 7] = (double)cnt[s];   // exact below 2^53
+    }
+}
+
 template <int S, bool SHELL, bool REDUCED, bool VDISP>
 __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) morph_warp_kernel(const MorphParams P)
 {
@@ -304,7 +356,8 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) morph_warp_kernel(cons
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *frames = s_frames[warp];
     int *np = s_np[warp];
-    const int ls = lane & (S - 1);
+    const LaneMap<S> L(lane);
+    const int ls = L.ls;
 
     for (;;) {
         int t = 0;
@@ -327,40 +380,28 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) morph_warp_kernel(cons
         shell_geometry(P, halo, k, st.d, st.delta);
         const size_t out_idx = (size_t)halo * P.R + k;
         __syncwarp();
-        if (lane < S) {
-            frames[ls * F_SLOTS + F_D2] = __dmul_rn(st.d, st.d);
-            const double in = __dsub_rn(st.d, st.delta);
-            frames[ls * F_SLOTS + F0_IN2] = __dmul_rn(in, in);
-            const int ne = (P.n_eff && st.active) ? P.n_eff[out_idx] : N;
-            np[ls] = (ne + 1) >> 1;
-        }
+        init_frames<S>(frames, np, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N);
         __syncwarp();
-        unsigned amask = __ballot_sync(0xffffffffu, st.active && lane < S);
+        unsigned amask = LaneMap<S>::active_mask(st.active && L.writer);
 
         double acc[S][7];
         int cnt[S];
         run_pass<S, SHELL, REDUCED, VDISP, true>(P.soa, base, active_npairs(np, amask, S), lane, 32, lane, frames, np,
                                                  amask, acc, cnt);
         while (true) {
-            // warp reduction, then every lane keeps the sums of the shell it serves
-            double tot[7] = {0, 0, 0, 0, 0, 0, 0};
-            int pts = 0;
+            double val[8 * S];
+            pack_values<S>(acc, cnt, val);
+            const double mine = warp_sum_transpose<8 * S>(val, lane);
+            double tot[7], vprev[9];
 #pragma unroll
-            for (int s = 0; s < S; s++) {
-                if (amask & (1u << s)) {
+            for (int c = 0; c < 7; c++) tot[c] = __shfl_sync(0xffffffffu, mine, (lane & ~7) + c);
+            const int pts = (int)__shfl_sync(0xffffffffu, mine, (lane & ~7) + 7);
 #pragma unroll
-                    for (int c = 0; c < 7; c++) {
-                        const double r = warp_sum(acc[s][c]);
-                        tot[c] = (ls == s) ? r : tot[c];
-                    }
-                    const int n = warp_sum_int(cnt[s]);
-                    pts = (ls == s) ? n : pts;
-                }
-            }
+            for (int r = 0; r < 9; r++) vprev[r] = frames[ls * F_SLOTS + F_V + r];
             __syncwarp();
-            katz_step<SHELL>(st, tot, pts, P, frames + ls * F_SLOTS, lane < S, out_idx, lane < S);
+            katz_step<SHELL>(st, tot, pts, P, vprev, frames + ls * F_SLOTS, L.writer, out_idx, L.writer);
             __syncwarp();
-            amask = __ballot_sync(0xffffffffu, st.active && lane < S);
+            amask = LaneMap<S>::active_mask(st.active && L.writer);
             if (amask == 0)
                 break;
             run_pass<S, SHELL, REDUCED, VDISP, false>(P.soa, base, active_npairs(np, amask, S), lane, 32, lane, frames,
@@ -382,10 +423,10 @@ constexpr int CLUSTER_KERNEL_WARPS = 8;
 template <int S, bool SHELL, bool REDUCED, bool VDISP>
 __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kernel(const MorphParams P)
 {
-    constexpr int NW = CLUSTER_KERNEL_WARPS;
+    constexpr int NW = CLUSTER_KERNEL_WARPS, NV = 8 * S;
     __shared__ __align__(16) double s_frames[NW][S * F_SLOTS];   // warp-private frames (no CTA barrier to publish)
-    __shared__ double s_part[2][NW][S][8];                      // per-warp partial sums
-    __shared__ double s_cta[2][S][8];                           // per-CTA partial sums, read by the cluster
+    __shared__ double s_part[2][NW][NV];                        // per-warp partial sums
+    __shared__ double s_cta[2][NV];                             // per-CTA partial sums, read by the cluster
     __shared__ int s_np[NW][S];
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
@@ -393,7 +434,8 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *frames = s_frames[warp];
     int *np = s_np[warp];
-    const int ls = lane & (S - 1);
+    const LaneMap<S> L(lane);
+    const int ls = L.ls;
 
     const int t = blockIdx.x / C;
     const Task tk = P.tasks[t];
@@ -410,16 +452,10 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     const int k = tk.shell0 + (st.active ? ls : 0);
     shell_geometry(P, halo, k, st.d, st.delta);
     const size_t out_idx = (size_t)halo * P.R + k;
-    if (lane < S) {
-        frames[ls * F_SLOTS + F_D2] = __dmul_rn(st.d, st.d);
-        const double in = __dsub_rn(st.d, st.delta);
-        frames[ls * F_SLOTS + F0_IN2] = __dmul_rn(in, in);
-        const int ne = (P.n_eff && st.active) ? P.n_eff[out_idx] : N;
-        np[ls] = (ne + 1) >> 1;
-    }
+    init_frames<S>(frames, np, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N);
     __syncwarp();
-    unsigned amask = __ballot_sync(0xffffffffu, st.active && lane < S);
-    const bool out_writer = (rank == 0 && warp == 0 && lane < S);
+    unsigned amask = LaneMap<S>::active_mask(st.active && L.writer);
+    const bool out_writer = (rank == 0 && warp == 0 && L.writer);
 
     double acc[S][7];
     int cnt[S];
@@ -427,51 +463,42 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     run_pass<S, SHELL, REDUCED, VDISP, true>(P.soa, base, active_npairs(np, amask, S), tid, nthreads, lane, frames, np,
                                              amask, acc, cnt);
     while (true) {
-#pragma unroll
-        for (int s = 0; s < S; s++) {
-            if (amask & (1u << s)) {
-#pragma unroll
-                for (int c = 0; c < 7; c++) {
-                    const double r = warp_sum(acc[s][c]);
-                    if (lane == 0) s_part[buf][warp][s][c] = r;
-                }
-                const int n = warp_sum_int(cnt[s]);
-                if (lane == 0) s_part[buf][warp][s][7] = (double)n;   // exact below 2^53
-            }
+        {
+            double val[NV];
+            pack_values<S>(acc, cnt, val);
+            const double mine = warp_sum_transpose<NV>(val, lane);
+            if (lane < NV) s_part[buf][warp][lane] = mine;
         }
         __syncthreads();
-        double tot[7] = {0, 0, 0, 0, 0, 0, 0};
+        double tot[7] = {0, 0, 0, 0, 0, 0, 0}, vprev[9];
         double ptsd = 0.0;
         if (C == 1) {
-            if (st.active) {
 #pragma unroll
-                for (int w = 0; w < NW; w++) {
+            for (int w = 0; w < NW; w++) {
 #pragma unroll
-                    for (int c = 0; c < 7; c++) tot[c] += s_part[buf][w][ls][c];
-                    ptsd += s_part[buf][w][ls][7];
-                }
+                for (int c = 0; c < 7; c++) tot[c] += s_part[buf][w][8 * ls + c];
+                ptsd += s_part[buf][w][8 * ls + 7];
             }
         } else {
-            if (threadIdx.x < S * 8) {
-                const int s = threadIdx.x >> 3, c = threadIdx.x & 7;
+            if (threadIdx.x < NV) {
                 double v = 0.0;
-                if (amask & (1u << s))
-                    for (int w = 0; w < NW; w++) v += s_part[buf][w][s][c];
-                s_cta[buf][s][c] = v;
+                for (int w = 0; w < NW; w++) v += s_part[buf][w][threadIdx.x];
+                s_cta[buf][threadIdx.x] = v;
             }
             cluster.sync();
-            if (st.active) {
-                for (int r = 0; r < C; r++) {
-                    const double *remote = cluster.map_shared_rank(&s_cta[buf][ls][0], r);
+            for (int r = 0; r < C; r++) {
+                const double *remote = cluster.map_shared_rank(&s_cta[buf][8 * ls], r);
 #pragma unroll
-                    for (int c = 0; c < 7; c++) tot[c] += remote[c];
-                    ptsd += remote[7];
-                }
+                for (int c = 0; c < 7; c++) tot[c] += remote[c];
+                ptsd += remote[7];
             }
         }
-        katz_step<SHELL>(st, tot, (int)ptsd, P, frames + ls * F_SLOTS, lane < S, out_idx, out_writer);
+#pragma unroll
+        for (int r = 0; r < 9; r++) vprev[r] = frames[ls * F_SLOTS + F_V + r];
         __syncwarp();
-        amask = __ballot_sync(0xffffffffu, st.active && lane < S);
+        katz_step<SHELL>(st, tot, (int)ptsd, P, vprev, frames + ls * F_SLOTS, L.writer, out_idx, out_writer);
+        __syncwarp();
+        amask = LaneMap<S>::active_mask(st.active && L.writer);
         buf ^= 1;
         if (amask == 0)
             break;
