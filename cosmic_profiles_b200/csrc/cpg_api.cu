@@ -302,19 +302,23 @@ int launch_morph(cpg_ctx *c, MorphParams P, int n_warp_tasks, int n_cluster_task
 {
     if (n_warp_tasks > 0) {
         auto kern = morph_warp_kernel<S, SHELL, REDUCED, VDISP>;
+        const int smem = WARP_KERNEL_WARPS * RingCfg<VDISP>::WARP_BYTES;
+        CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int per_sm = 0;
-        CPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARP_KERNEL_WARPS * 32, 0));
+        CPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARP_KERNEL_WARPS * 32, smem));
         if (per_sm < 1) per_sm = 1;
         const int grid = std::min((n_warp_tasks + WARP_KERNEL_WARPS - 1) / WARP_KERNEL_WARPS, c->sm_count * per_sm);
         MorphParams Pw = P;
         Pw.n_tasks = n_warp_tasks;
-        kern<<<grid, WARP_KERNEL_WARPS * 32, 0, c->stream>>>(Pw);
+        kern<<<grid, WARP_KERNEL_WARPS * 32, smem, c->stream>>>(Pw);
         c->timing.kernel_launches++;
         c->timing.hot_kernel_launches++;
         CPG_CUDA(cudaGetLastError());
     }
     if (n_cluster_tasks > 0) {
         auto kern = morph_cluster_kernel<S, SHELL, REDUCED, VDISP>;
+        const int smem = CLUSTER_KERNEL_WARPS * RingCfg<VDISP>::WARP_BYTES;
+        CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         if (cluster_size > 8)
             CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         MorphParams Pc = P;
@@ -323,7 +327,7 @@ int launch_morph(cpg_ctx *c, MorphParams P, int n_warp_tasks, int n_cluster_task
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)n_cluster_tasks * cluster_size);
         cfg.blockDim = dim3(CLUSTER_KERNEL_WARPS * 32);
-        cfg.dynamicSmemBytes = 0;
+        cfg.dynamicSmemBytes = smem;
         cfg.stream = c->stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;

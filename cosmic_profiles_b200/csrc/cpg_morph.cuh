@@ -49,34 +49,37 @@ template <bool REDUCED, bool VDISP>
 __device__ __forceinline__ void accumulate(double (&acc)[7], int &cnt, bool sel, double v, const Particle &p)
 {
     // weight: m (non-reduced) or m / r_ell^2 (reduced, helper_class.pyx:54); the common 1/mass_tot factor
-    // is applied once per iteration after the reduction (it only rescales the tensor).
-    double w = REDUCED ? p.m / v : p.m;
-    w = sel ? w : 0.0;
-    if (VDISP) {
+    // is applied once per iteration after the reduction (it only rescales the tensor).  Written as a guarded
+    // block so that ptxas predicates the seven fp64 updates instead of selecting a zero weight: a particle
+    // outside the ellipsoid costs issue slots but no fp64 pipe time.
+    if (sel) {
+        const double w = REDUCED ? p.m / v : p.m;
+        if (VDISP) {
 #pragma unroll
-        for (int c = 0; c < 6; c++) acc[c] = fma(w, p.t[c], acc[c]);
-    } else {
-        acc[0] = fma(w, p.xx, acc[0]);
-        acc[1] = fma(w, p.xy, acc[1]);
-        acc[2] = fma(w, p.xz, acc[2]);
-        acc[3] = fma(w, p.yy, acc[3]);
-        acc[4] = fma(w, p.yz, acc[4]);
-        acc[5] = fma(w, p.zz, acc[5]);
+            for (int c = 0; c < 6; c++) acc[c] = fma(w, p.t[c], acc[c]);
+        } else {
+            acc[0] = fma(w, p.xx, acc[0]);
+            acc[1] = fma(w, p.xy, acc[1]);
+            acc[2] = fma(w, p.xz, acc[2]);
+            acc[3] = fma(w, p.yy, acc[3]);
+            acc[4] = fma(w, p.yz, acc[4]);
+            acc[5] = fma(w, p.zz, acc[5]);
+        }
+        acc[6] += p.m;
+        cnt += 1;
     }
-    acc[6] += REDUCED ? (sel ? p.m : 0.0) : w;
-    cnt += sel ? 1 : 0;
 }
 
 // Pass 0: spherical start (shape_profs_algos.pyx:206-212 / :81-87), exact reference arithmetic:
 // r2 = ((dx*dx + dy*dy) + dz*dz) with every operation rounded separately.
 template <int S, bool SHELL, bool REDUCED, bool VDISP>
-__device__ __forceinline__ void pass0_particle(const Particle &p, const double *frames, unsigned amask,
-                                               const int *np, int tile, double (&acc)[S][7], int (&cnt)[S])
+__device__ __forceinline__ void pass0_particle(const Particle &p, const double *frames, unsigned smask,
+                                               double (&acc)[S][7], int (&cnt)[S])
 {
     const double r2 = __dadd_rn(__dadd_rn(p.xx, p.yy), p.zz);
 #pragma unroll
     for (int s = 0; s < S; s++) {
-        if ((amask & (1u << s)) && tile < np[s]) {
+        if (smask & (1u << s)) {
             const double *F = frames + s * F_SLOTS;
             bool sel = r2 < F[F_D2];
             if (SHELL)
@@ -89,30 +92,35 @@ __device__ __forceinline__ void pass0_particle(const Particle &p, const double *
 // Pass k>=1: membership in the ellipsoid (shell) of the previous eigen-decomposition
 // (shape_profs_algos.pyx:247-260 / :122-143) fused with the next tensor accumulation.
 template <int S, bool SHELL, bool REDUCED, bool VDISP, int NP>
-__device__ __forceinline__ void passk_particles(const Particle (&p)[NP], const double *frames, unsigned amask,
-                                                const int *np, int tile, double (&acc)[S][7], int (&cnt)[S])
+__device__ __forceinline__ void passk_particles(const Particle (&p)[NP], const double *frames, unsigned smask,
+                                                double (&acc)[S][7], int (&cnt)[S])
 {
 #pragma unroll
     for (int s = 0; s < S; s++) {
-        // np[s]: pairs in the radial prefix of shell s; `tile` (first pair of this warp's batch) is warp-uniform
-        if ((amask & (1u << s)) && tile < np[s]) {
+        // smask: shells that are still iterating AND whose radial prefix reaches this tile (warp-uniform)
+        if (smask & (1u << s)) {
             const double2 *F2 = reinterpret_cast<const double2 *>(frames + s * F_SLOTS);
             const double2 f0 = F2[0], f1 = F2[1], f2 = F2[2], f3 = F2[3];
             // f0=(Axx,Ayy) f1=(Azz,Axy) f2=(Axz,Ayz) f3=(d2,thr)
             double2 f4, f5, f6;
             if (SHELL) { f4 = F2[4]; f5 = F2[5]; f6 = F2[6]; }   // (Bxx,Byy) (Bzz,Bxy) (Bxz,Byz)
+            double v[NP];
+            bool sel[NP];
+#pragma unroll
+            for (int j = 0; j < NP; j++)   // NP independent chains: keep the fp64 pipe busy
+                v[j] = fma(f2.y, p[j].yz, fma(f2.x, p[j].xz, fma(f1.y, p[j].xy,
+                       fma(f1.x, p[j].zz, fma(f0.y, p[j].yy, f0.x * p[j].xx)))));
 #pragma unroll
             for (int j = 0; j < NP; j++) {
-                const double v = fma(f2.y, p[j].yz, fma(f2.x, p[j].xz, fma(f1.y, p[j].xy,
-                                 fma(f1.x, p[j].zz, fma(f0.y, p[j].yy, f0.x * p[j].xx)))));
-                bool sel = v < f3.x;
+                sel[j] = v[j] < f3.x;
                 if (SHELL) {
                     const double u = fma(f6.y, p[j].yz, fma(f6.x, p[j].xz, fma(f5.y, p[j].xy,
                                      fma(f5.x, p[j].zz, fma(f4.y, p[j].yy, f4.x * p[j].xx)))));
-                    sel = sel && (u >= f3.y);
+                    sel[j] = sel[j] && (u >= f3.y);
                 }
-                accumulate<REDUCED, VDISP>(acc[s], cnt[s], sel, v, p[j]);
             }
+#pragma unroll
+            for (int j = 0; j < NP; j++) accumulate<REDUCED, VDISP>(acc[s], cnt[s], sel[j], v[j], p[j]);
         }
     }
 }
@@ -224,40 +232,152 @@ __device__ __forceinline__ void shell_geometry(const MorphParams &P, int halo, i
     }
 }
 
-__device__ __forceinline__ void make_products(double x, double y, double z, double (&o)[6])
+__device__ __forceinline__ void make_particle(double x, double y, double z, double m, Particle &p)
 {
-    o[0] = __dmul_rn(x, x); o[1] = __dmul_rn(y, y); o[2] = __dmul_rn(z, z);
-    o[3] = x * y; o[4] = x * z; o[5] = y * z;
+    p.xx = __dmul_rn(x, x); p.yy = __dmul_rn(y, y); p.zz = __dmul_rn(z, z);   // exact squares: pass 0 needs them
+    p.xy = x * y; p.xz = x * z; p.yz = y * z;
+    p.m = m;
 }
 
-template <bool VDISP>
-__device__ __forceinline__ void load_pair(const SoA &soa, int64_t base, int i2, Particle &a, Particle &b)
+__device__ __forceinline__ void make_tensor_products(double u, double v, double w, Particle &p)
 {
-    const double2 x = reinterpret_cast<const double2 *>(soa.dx + base)[i2];
-    const double2 y = reinterpret_cast<const double2 *>(soa.dy + base)[i2];
-    const double2 z = reinterpret_cast<const double2 *>(soa.dz + base)[i2];
-    const double2 m = reinterpret_cast<const double2 *>(soa.m + base)[i2];
-    double pa[6], pb[6];
-    make_products(x.x, y.x, z.x, pa);
-    make_products(x.y, y.y, z.y, pb);
-    a.xx = pa[0]; a.yy = pa[1]; a.zz = pa[2]; a.xy = pa[3]; a.xz = pa[4]; a.yz = pa[5]; a.m = m.x;
-    b.xx = pb[0]; b.yy = pb[1]; b.zz = pb[2]; b.xy = pb[3]; b.xz = pb[4]; b.yz = pb[5]; b.m = m.y;
+    // component order of accumulate(): xx, xy, xz, yy, yz, zz
+    p.t[0] = u * u; p.t[1] = u * v; p.t[2] = u * w; p.t[3] = v * v; p.t[4] = v * w; p.t[5] = w * w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Particle streaming: TMA bulk copies (cp.async.bulk global -> shared, completion on an mbarrier) into a
+// per-warp ring of RING_STAGES tiles.  A tile is TILE_PAIRS consecutive particle pairs of every stream
+// (1 KB per stream); lane l consumes pairs l and l+32 of the tile with conflict-free 16-byte LDS.  One
+// elected lane issues the copies RING_STAGES tiles ahead, so the warp never waits on global-memory latency
+// with registers tied up, and an object whose radial prefix fits in the ring (<= 512 particles per warp)
+// is loaded once and stays resident in shared memory for all Katz iterations of the task.
+// ------------------------------------------------------------------------------------------------
+constexpr int TILE_PAIRS = 64;
+constexpr int RING_MAX_STAGES = 4;
+
+template <bool VDISP>
+struct RingCfg {
+    static constexpr int NSTREAM = VDISP ? 7 : 4;
+    static constexpr int STAGES = VDISP ? 2 : 4;   // 16 KB (positions) / 14 KB (with velocities) per warp
+    static constexpr int STREAM_BYTES = TILE_PAIRS * 16;
+    static constexpr int STAGE_BYTES = NSTREAM * STREAM_BYTES;
+    static constexpr int WARP_BYTES = STAGES * STAGE_BYTES;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct WarpRing {
+    unsigned char *buf;   // this warp's RING_STAGES tiles in shared memory
+    uint64_t *bar;        // one mbarrier per stage
+    uint32_t seq;         // tiles issued so far by this warp (stage = seq % STAGES, parity = (seq / STAGES) & 1)
+    uint32_t res_seq;     // first sequence number of the resident tiles of the current task
+    bool res_loaded;      // resident tiles are in place
+};
+
+__device__ __forceinline__ void ring_init(WarpRing &r, unsigned char *buf, uint64_t *bar, int lane)
+{
+    r.buf = buf; r.bar = bar; r.seq = 0; r.res_seq = 0; r.res_loaded = false;
+    if (lane == 0) {
+        for (int s = 0; s < RING_MAX_STAGES; s++) mbar_init(bar + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+}
+
+// Issue the bulk copies of tile `t` (pairs [64 t, 64 t + n)) of every stream into ring slot `seq`.
+template <bool VDISP>
+__device__ __forceinline__ void ring_issue(const WarpRing &r, uint32_t seq, const SoA &soa, int64_t base, int t, int npairs)
+{
+    using C = RingCfg<VDISP>;
+    const uint32_t stage = seq % C::STAGES;
+    const uint32_t bytes = (uint32_t)min(TILE_PAIRS, npairs - t * TILE_PAIRS) * 16u;
+    unsigned char *dst = r.buf + stage * C::STAGE_BYTES;
+    uint64_t *bar = r.bar + stage;
+    const int64_t o = base + (int64_t)t * (2 * TILE_PAIRS);
+    mbar_expect_tx(bar, bytes * C::NSTREAM);
+    bulk_g2s(dst + 0 * C::STREAM_BYTES, soa.dx + o, bytes, bar);
+    bulk_g2s(dst + 1 * C::STREAM_BYTES, soa.dy + o, bytes, bar);
+    bulk_g2s(dst + 2 * C::STREAM_BYTES, soa.dz + o, bytes, bar);
+    bulk_g2s(dst + 3 * C::STREAM_BYTES, soa.m + o, bytes, bar);
     if (VDISP) {
-        const double2 u = reinterpret_cast<const double2 *>(soa.vx + base)[i2];
-        const double2 v = reinterpret_cast<const double2 *>(soa.vy + base)[i2];
-        const double2 w = reinterpret_cast<const double2 *>(soa.vz + base)[i2];
-        // tensor component order of accumulate(): xx, xy, xz, yy, yz, zz
-        a.t[0] = u.x * u.x; a.t[1] = u.x * v.x; a.t[2] = u.x * w.x; a.t[3] = v.x * v.x; a.t[4] = v.x * w.x; a.t[5] = w.x * w.x;
-        b.t[0] = u.y * u.y; b.t[1] = u.y * v.y; b.t[2] = u.y * w.y; b.t[3] = v.y * v.y; b.t[4] = v.y * w.y; b.t[5] = w.y * w.y;
+        bulk_g2s(dst + 4 * C::STREAM_BYTES, soa.vx + o, bytes, bar);
+        bulk_g2s(dst + 5 * C::STREAM_BYTES, soa.vy + o, bytes, bar);
+        bulk_g2s(dst + 6 * C::STREAM_BYTES, soa.vz + o, bytes, bar);
     }
 }
 
-// One full pass of `nthreads` cooperating threads (thread `tid`, lane `lane` of its warp) over the object's
-// particle pairs.  np[s] = pairs in the radial prefix of shell s, npairs = max over the active shells.
+// The two particles of pair `pi` of the tile in ring slot `seq` (this lane consumes pairs lane and lane+32).
+template <bool VDISP>
+__device__ __forceinline__ void ring_read_pair(const WarpRing &r, uint32_t seq, int pi, int pairs_in_tile, Particle &a,
+                                               Particle &b)
+{
+    using C = RingCfg<VDISP>;
+    const unsigned char *src = r.buf + (seq % C::STAGES) * C::STAGE_BYTES;
+    double2 x, y, z, m;
+    if (pi < pairs_in_tile) {
+        x = reinterpret_cast<const double2 *>(src + 0 * C::STREAM_BYTES)[pi];
+        y = reinterpret_cast<const double2 *>(src + 1 * C::STREAM_BYTES)[pi];
+        z = reinterpret_cast<const double2 *>(src + 2 * C::STREAM_BYTES)[pi];
+        m = reinterpret_cast<const double2 *>(src + 3 * C::STREAM_BYTES)[pi];
+    } else {   // beyond the prefix: the same never-selected sentinel the gather pads odd objects with
+        x = y = z = make_double2(1e150, 1e150);
+        m = make_double2(0.0, 0.0);
+    }
+    make_particle(x.x, y.x, z.x, m.x, a);
+    make_particle(x.y, y.y, z.y, m.y, b);
+    if (VDISP) {
+        double2 u = make_double2(0.0, 0.0), v = u, w = u;
+        if (pi < pairs_in_tile) {
+            u = reinterpret_cast<const double2 *>(src + 4 * C::STREAM_BYTES)[pi];
+            v = reinterpret_cast<const double2 *>(src + 5 * C::STREAM_BYTES)[pi];
+            w = reinterpret_cast<const double2 *>(src + 6 * C::STREAM_BYTES)[pi];
+        }
+        make_tensor_products(u.x, v.x, w.x, a);
+        make_tensor_products(u.y, v.y, w.y, b);
+    }
+}
+
+// One full pass over the object's radial prefix.  This warp consumes tiles tile0, tile0+tstride, ... of the
+// `npairs` pairs that the still-active shells need; npr[s] = pairs in the prefix of shell s.
+// resident: every tile this warp will ever need for the task fits in its ring -> loaded by the first pass,
+// re-read from shared memory by all later ones.
 template <int S, bool SHELL, bool REDUCED, bool VDISP, bool FIRST>
-__device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npairs, int tid, int nthreads, int lane,
-                                         const double *frames, const int *np, unsigned amask, double (&acc)[S][7],
-                                         int (&cnt)[S])
+__device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npairs, int tile0, int tstride, int lane,
+                                         WarpRing &ring, bool resident, int npairs_task, const double *frames,
+                                         const int (&npr)[S], unsigned amask, double (&acc)[S][7], int (&cnt)[S])
 {
 #pragma unroll
     for (int s = 0; s < S; s++) {
@@ -265,35 +385,76 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
 #pragma unroll
         for (int k = 0; k < 7; k++) acc[s][k] = 0.0;
     }
-    int i2 = tid;
-    if (!FIRST && !VDISP) {
-        // two pairs in flight per thread: more loads outstanding, frame registers reused over 4 particles
-        for (; i2 + nthreads < npairs; i2 += 2 * nthreads) {
+    constexpr int RING_STAGES = RingCfg<VDISP>::STAGES;
+    const int ntiles = (npairs + TILE_PAIRS - 1) / TILE_PAIRS;
+    const int nmine = tile0 < ntiles ? (ntiles - tile0 + tstride - 1) / tstride : 0;
+    const bool reuse = resident && ring.res_loaded;
+    const int npairs_load = resident ? npairs_task : npairs;
+    uint32_t seq0 = reuse ? ring.res_seq : ring.seq;
+    int issue_n = nmine;
+    if (resident && !reuse) {   // first pass of a resident task: bring in everything the task will ever need
+        const int nt_task = (npairs_task + TILE_PAIRS - 1) / TILE_PAIRS;
+        issue_n = tile0 < nt_task ? (nt_task - tile0 + tstride - 1) / tstride : 0;
+    }
+    if (!reuse && lane == 0)
+        for (int j = 0; j < min(issue_n, RING_STAGES); j++)
+            ring_issue<VDISP>(ring, seq0 + j, soa, base, tile0 + j * tstride, npairs_load);
+    for (int j = 0; j < nmine; j++) {
+        const int t = tile0 + j * tstride;
+        const uint32_t seq = seq0 + j;
+        if (!reuse) mbar_wait(ring.bar + seq % RING_STAGES, (seq / RING_STAGES) & 1u);
+        const int pairs_in_tile = min(TILE_PAIRS, npairs - t * TILE_PAIRS);
+        unsigned smask = 0;
+#pragma unroll
+        for (int s = 0; s < S; s++)
+            if (t * TILE_PAIRS < npr[s]) smask |= 1u << s;
+        smask &= amask;
+        if (FIRST || VDISP) {
+            // two particles at a time (pass 0 is cheap; the dispersion variant carries 13 doubles per particle)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                Particle p[2];
+                ring_read_pair<VDISP>(ring, seq, lane + 32 * h, pairs_in_tile, p[0], p[1]);
+                if (FIRST) {
+                    pass0_particle<S, SHELL, REDUCED, VDISP>(p[0], frames, smask, acc, cnt);
+                    pass0_particle<S, SHELL, REDUCED, VDISP>(p[1], frames, smask, acc, cnt);
+                } else {
+                    passk_particles<S, SHELL, REDUCED, VDISP, 2>(p, frames, smask, acc, cnt);
+                }
+            }
+        } else {
             Particle p[4];
-            load_pair<VDISP>(soa, base, i2, p[0], p[1]);
-            load_pair<VDISP>(soa, base, i2 + nthreads, p[2], p[3]);
-            passk_particles<S, SHELL, REDUCED, VDISP, 4>(p, frames, amask, np, i2 - lane, acc, cnt);
+            ring_read_pair<VDISP>(ring, seq, lane, pairs_in_tile, p[0], p[1]);
+            ring_read_pair<VDISP>(ring, seq, lane + 32, pairs_in_tile, p[2], p[3]);
+            passk_particles<S, SHELL, REDUCED, VDISP, 4>(p, frames, smask, acc, cnt);
+        }
+        if (!resident && j + RING_STAGES < nmine) {
+            __syncwarp();   // every lane has taken its data out of this slot
+            if (lane == 0)
+                ring_issue<VDISP>(ring, seq + RING_STAGES, soa, base, t + RING_STAGES * tstride, npairs_load);
         }
     }
-    for (; i2 < npairs; i2 += nthreads) {
-        Particle p[2];
-        load_pair<VDISP>(soa, base, i2, p[0], p[1]);
-        if (FIRST) {
-            pass0_particle<S, SHELL, REDUCED, VDISP>(p[0], frames, amask, np, i2 - lane, acc, cnt);
-            pass0_particle<S, SHELL, REDUCED, VDISP>(p[1], frames, amask, np, i2 - lane, acc, cnt);
+    if (!reuse) {
+        if (resident) {
+            // the barriers of resident tiles beyond the first pass's active range have not been waited on yet
+            for (int j = nmine; j < issue_n; j++)
+                mbar_wait(ring.bar + (seq0 + j) % RING_STAGES, ((seq0 + j) / RING_STAGES) & 1u);
+            ring.res_seq = seq0;
+            ring.res_loaded = true;
+            ring.seq = seq0 + issue_n;
         } else {
-            passk_particles<S, SHELL, REDUCED, VDISP, 2>(p, frames, amask, np, i2 - lane, acc, cnt);
+            ring.seq = seq0 + nmine;
         }
     }
 }
 
-// Pair counts of the radial prefixes of a task's shells -> shared ints; returns nothing, the caller takes
-// max over active shells with active_npairs().
-__device__ __forceinline__ int active_npairs(const int *np, unsigned amask, int S)
+template <int S>
+__device__ __forceinline__ int active_npairs(const int (&npr)[S], unsigned amask)
 {
     int n = 0;
+#pragma unroll
     for (int s = 0; s < S; s++)
-        if (amask & (1u << s)) n = max(n, np[s]);
+        if (amask & (1u << s)) n = max(n, npr[s]);
     return n;
 }
 
@@ -351,13 +512,17 @@ __device__ __forceinline__ void pack_values(const double (&acc)[S][7], const int
 template <int S, bool SHELL, bool REDUCED, bool VDISP>
 __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) morph_warp_kernel(const MorphParams P)
 {
+    extern __shared__ __align__(128) unsigned char s_ring_w[];   // WARP_KERNEL_WARPS rings
     __shared__ __align__(16) double s_frames[WARP_KERNEL_WARPS][S * F_SLOTS];
+    __shared__ __align__(8) uint64_t s_bar[WARP_KERNEL_WARPS][RING_MAX_STAGES];
     __shared__ int s_np[WARP_KERNEL_WARPS][S];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *frames = s_frames[warp];
     int *np = s_np[warp];
     const LaneMap<S> L(lane);
     const int ls = L.ls;
+    WarpRing ring;
+    ring_init(ring, s_ring_w + warp * RingCfg<VDISP>::WARP_BYTES, s_bar[warp], lane);
 
     for (;;) {
         int t = 0;
@@ -383,11 +548,17 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) morph_warp_kernel(cons
         init_frames<S>(frames, np, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N);
         __syncwarp();
         unsigned amask = LaneMap<S>::active_mask(st.active && L.writer);
+        int npr[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) npr[s] = np[s];
+        const int npairs_task = active_npairs<S>(npr, amask);
+        const bool resident = (npairs_task + TILE_PAIRS - 1) / TILE_PAIRS <= RingCfg<VDISP>::STAGES;
+        ring.res_loaded = false;
 
         double acc[S][7];
         int cnt[S];
-        run_pass<S, SHELL, REDUCED, VDISP, true>(P.soa, base, active_npairs(np, amask, S), lane, 32, lane, frames, np,
-                                                 amask, acc, cnt);
+        run_pass<S, SHELL, REDUCED, VDISP, true>(P.soa, base, npairs_task, 0, 1, lane, ring, resident, npairs_task, frames,
+                                                 npr, amask, acc, cnt);
         while (true) {
             double val[8 * S];
             pack_values<S>(acc, cnt, val);
@@ -404,8 +575,8 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) morph_warp_kernel(cons
             amask = LaneMap<S>::active_mask(st.active && L.writer);
             if (amask == 0)
                 break;
-            run_pass<S, SHELL, REDUCED, VDISP, false>(P.soa, base, active_npairs(np, amask, S), lane, 32, lane, frames,
-                                                      np, amask, acc, cnt);
+            run_pass<S, SHELL, REDUCED, VDISP, false>(P.soa, base, active_npairs<S>(npr, amask), 0, 1, lane, ring, resident,
+                                                      npairs_task, frames, npr, amask, acc, cnt);
         }
     }
 }
@@ -424,7 +595,9 @@ template <int S, bool SHELL, bool REDUCED, bool VDISP>
 __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kernel(const MorphParams P)
 {
     constexpr int NW = CLUSTER_KERNEL_WARPS, NV = 8 * S;
+    extern __shared__ __align__(128) unsigned char s_ring_c[];     // NW rings
     __shared__ __align__(16) double s_frames[NW][S * F_SLOTS];   // warp-private frames (no CTA barrier to publish)
+    __shared__ __align__(8) uint64_t s_bar[NW][RING_MAX_STAGES];
     __shared__ double s_part[2][NW][NV];                        // per-warp partial sums
     __shared__ double s_cta[2][NV];                             // per-CTA partial sums, read by the cluster
     __shared__ int s_np[NW][S];
@@ -444,7 +617,9 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
         return;   // uniform over the cluster
     const int N = P.soa.size[halo];
     const int64_t base = P.soa.poff[halo];
-    const int tid = rank * (NW * 32) + threadIdx.x, nthreads = C * NW * 32;
+    const int tile0 = rank * NW + warp, tstride = C * NW;   // 64-pair tiles dealt round-robin to the cluster's warps
+    WarpRing ring;
+    ring_init(ring, s_ring_c + warp * RingCfg<VDISP>::WARP_BYTES, s_bar[warp], lane);
 
     KatzState st;
     st.q = 1.0; st.s = 1.0; st.iteration = 1;
@@ -456,12 +631,18 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     __syncwarp();
     unsigned amask = LaneMap<S>::active_mask(st.active && L.writer);
     const bool out_writer = (rank == 0 && warp == 0 && L.writer);
+    int npr[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) npr[s] = np[s];
+    const int npairs_task = active_npairs<S>(npr, amask);
+    const int nt_task = (npairs_task + TILE_PAIRS - 1) / TILE_PAIRS;
+    const bool resident = (tile0 < nt_task ? (nt_task - tile0 + tstride - 1) / tstride : 0) <= RingCfg<VDISP>::STAGES;
 
     double acc[S][7];
     int cnt[S];
     int buf = 0;
-    run_pass<S, SHELL, REDUCED, VDISP, true>(P.soa, base, active_npairs(np, amask, S), tid, nthreads, lane, frames, np,
-                                             amask, acc, cnt);
+    run_pass<S, SHELL, REDUCED, VDISP, true>(P.soa, base, npairs_task, tile0, tstride, lane, ring, resident, npairs_task,
+                                             frames, npr, amask, acc, cnt);
     while (true) {
         {
             double val[NV];
@@ -502,8 +683,8 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
         buf ^= 1;
         if (amask == 0)
             break;
-        run_pass<S, SHELL, REDUCED, VDISP, false>(P.soa, base, active_npairs(np, amask, S), tid, nthreads, lane, frames,
-                                                  np, amask, acc, cnt);
+        run_pass<S, SHELL, REDUCED, VDISP, false>(P.soa, base, active_npairs<S>(npr, amask), tile0, tstride, lane, ring,
+                                                  resident, npairs_task, frames, npr, amask, acc, cnt);
     }
     if (C > 1)
         cluster.sync();   // nobody leaves while a peer may still read its shared memory
