@@ -243,6 +243,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=3.0e6, help="particles in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=20260101)
+    ap.add_argument("--opt", action="append", default=[], help="scheduling tunable name=value (cpg_set_option)")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
 
@@ -294,6 +295,9 @@ def main():
         % (rank, a.halos, n_part, n_part * 32 / 1e9, time.perf_counter() - t0))
 
     ctx = _lib.Context(local_rank)
+    for kv in a.opt:
+        name, val = kv.split("=")
+        ctx.set_option(name, int(val))
     k = (KATZ["IT_TOL"], KATZ["IT_WALL"], KATZ["IT_MIN"])
 
     def upload():

@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcosmicgpu.so")
+LIB_PATH = os.environ.get("COSMICGPU_LIB", os.path.join(HERE, "libcosmicgpu.so"))
 
 _D = ctypes.POINTER(ctypes.c_double)
 _I = ctypes.POINTER(ctypes.c_int32)

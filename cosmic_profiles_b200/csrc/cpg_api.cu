@@ -67,8 +67,9 @@ using namespace cpg;
 struct cpg_ctx {
     int device = 0;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: large-object kernel, concurrent with the warp kernel
     cudaEvent_t ev[6] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // snapshot
     DevBuf<double> xyz, vxyz, masses;
     int64_t n_part = 0;
@@ -300,6 +301,39 @@ int run_vcenters(cpg_ctx *c, float L_BOX)
 template <int S, bool SHELL, bool REDUCED, bool VDISP>
 int launch_morph(cpg_ctx *c, MorphParams P, int n_warp_tasks, int n_cluster_tasks, int cluster_size)
 {
+    // The few large objects (cluster kernel) and the many small ones (warp kernel) are independent: run the two
+    // kernels concurrently (fork/join on a second stream) so that each fills the other's tail.
+    const bool both = n_warp_tasks > 0 && n_cluster_tasks > 0;
+    cudaStream_t cl_stream = both ? c->stream2 : c->stream;
+    if (both) {
+        CPG_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+        CPG_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    }
+    if (n_cluster_tasks > 0) {
+        auto kern = morph_cluster_kernel<S, SHELL, REDUCED, VDISP>;
+        const int smem = CLUSTER_KERNEL_WARPS * RingCfg<VDISP>::WARP_BYTES;
+        CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        if (cluster_size > 8)
+            CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        MorphParams Pc = P;
+        Pc.tasks = P.tasks + n_warp_tasks;   // cluster tasks are stored behind the warp tasks
+        Pc.n_tasks = n_cluster_tasks;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)n_cluster_tasks * cluster_size);
+        cfg.blockDim = dim3(CLUSTER_KERNEL_WARPS * 32);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = cl_stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cluster_size;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CPG_CUDA(cudaLaunchKernelEx(&cfg, kern, Pc));
+        c->timing.kernel_launches++;
+        c->timing.hot_kernel_launches++;
+    }
     if (n_warp_tasks > 0) {
         auto kern = morph_warp_kernel<S, SHELL, REDUCED, VDISP>;
         const int smem = WARP_KERNEL_WARPS * RingCfg<VDISP>::WARP_BYTES;
@@ -315,30 +349,9 @@ int launch_morph(cpg_ctx *c, MorphParams P, int n_warp_tasks, int n_cluster_task
         c->timing.hot_kernel_launches++;
         CPG_CUDA(cudaGetLastError());
     }
-    if (n_cluster_tasks > 0) {
-        auto kern = morph_cluster_kernel<S, SHELL, REDUCED, VDISP>;
-        const int smem = CLUSTER_KERNEL_WARPS * RingCfg<VDISP>::WARP_BYTES;
-        CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        if (cluster_size > 8)
-            CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-        MorphParams Pc = P;
-        Pc.tasks = P.tasks + n_warp_tasks;   // cluster tasks are stored behind the warp tasks
-        Pc.n_tasks = n_cluster_tasks;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)n_cluster_tasks * cluster_size);
-        cfg.blockDim = dim3(CLUSTER_KERNEL_WARPS * 32);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = c->stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = cluster_size;
-        at[0].val.clusterDim.y = 1;
-        at[0].val.clusterDim.z = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
-        CPG_CUDA(cudaLaunchKernelEx(&cfg, kern, Pc));
-        c->timing.kernel_launches++;
-        c->timing.hot_kernel_launches++;
+    if (both) {
+        CPG_CUDA(cudaEventRecord(c->ev_join, c->stream2));
+        CPG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     }
     return CPG_OK;
 }
@@ -407,7 +420,10 @@ CPG_API int cpg_create(int device, cpg_ctx **out)
     }
     c->sm_count = prop.multiProcessorCount;
     CPG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CPG_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
     for (auto &e : c->ev) CPG_CUDA(cudaEventCreate(&e));
+    CPG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CPG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     *out = c;
     return CPG_OK;
 }
@@ -429,6 +445,9 @@ CPG_API void cpg_destroy(cpg_ctx *c)
     c->mass32.release(); c->skip.release(); c->tasks.release(); c->bucket.release();
     c->tile_hist.release(); c->dest.release(); c->n_eff.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

@@ -52,6 +52,27 @@ __device__ __forceinline__ void accumulate(double (&acc)[7], int &cnt, bool sel,
     // is applied once per iteration after the reduction (it only rescales the tensor).  Written as a guarded
     // block so that ptxas predicates the seven fp64 updates instead of selecting a zero weight: a particle
     // outside the ellipsoid costs issue slots but no fp64 pipe time.
+#ifdef CPG_ACC_SELECT
+    {
+        double w = REDUCED ? p.m / v : p.m;
+        w = sel ? w : 0.0;
+        const double mm = sel ? p.m : 0.0;
+        if (VDISP) {
+#pragma unroll
+            for (int c = 0; c < 6; c++) acc[c] = fma(w, p.t[c], acc[c]);
+        } else {
+            acc[0] = fma(w, p.xx, acc[0]);
+            acc[1] = fma(w, p.xy, acc[1]);
+            acc[2] = fma(w, p.xz, acc[2]);
+            acc[3] = fma(w, p.yy, acc[3]);
+            acc[4] = fma(w, p.yz, acc[4]);
+            acc[5] = fma(w, p.zz, acc[5]);
+        }
+        acc[6] += mm;
+        cnt += sel ? 1 : 0;
+    }
+    return;
+#endif
     if (sel) {
         const double w = REDUCED ? p.m / v : p.m;
         if (VDISP) {
@@ -272,12 +293,12 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar_s, uint32_t bytes)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
 }
 
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait(uint32_t bar_s, uint32_t parity)
 {
     asm volatile(
         "{\n"
@@ -287,20 +308,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}\n" ::"r"(bar_s), "r"(parity) : "memory");
 }
 
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_s, const void *src, uint32_t bytes, uint32_t bar_s)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+    // a CTA-local shared address is a valid shared::cluster address of the executing CTA
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s),
+                 "l"(src), "r"(bytes), "r"(bar_s)
                  : "memory");
 }
 
 struct WarpRing {
-    unsigned char *buf;   // this warp's RING_STAGES tiles in shared memory
+    unsigned char *buf;   // this warp's tiles in shared memory
     uint64_t *bar;        // one mbarrier per stage
+    uint32_t buf_s, bar_s;   // the same two as 32-bit shared-window addresses (computed once)
     uint32_t seq;         // tiles issued so far by this warp (stage = seq % STAGES, parity = (seq / STAGES) & 1)
     uint32_t res_seq;     // first sequence number of the resident tiles of the current task
     bool res_loaded;      // resident tiles are in place
@@ -309,6 +331,7 @@ struct WarpRing {
 __device__ __forceinline__ void ring_init(WarpRing &r, unsigned char *buf, uint64_t *bar, int lane)
 {
     r.buf = buf; r.bar = bar; r.seq = 0; r.res_seq = 0; r.res_loaded = false;
+    r.buf_s = smem_u32(buf); r.bar_s = smem_u32(bar);
     if (lane == 0) {
         for (int s = 0; s < RING_MAX_STAGES; s++) mbar_init(bar + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -324,8 +347,8 @@ __device__ __forceinline__ void ring_issue(const WarpRing &r, uint32_t seq, cons
     using C = RingCfg<VDISP>;
     const uint32_t stage = seq % C::STAGES;
     const uint32_t bytes = (uint32_t)min(TILE_PAIRS, npairs - t * TILE_PAIRS) * 16u;
-    unsigned char *dst = r.buf + stage * C::STAGE_BYTES;
-    uint64_t *bar = r.bar + stage;
+    const uint32_t dst = r.buf_s + stage * C::STAGE_BYTES;
+    const uint32_t bar = r.bar_s + stage * 8u;
     const int64_t o = base + (int64_t)t * (2 * TILE_PAIRS);
     mbar_expect_tx(bar, bytes * C::NSTREAM);
     bulk_g2s(dst + 0 * C::STREAM_BYTES, soa.dx + o, bytes, bar);
@@ -341,33 +364,39 @@ __device__ __forceinline__ void ring_issue(const WarpRing &r, uint32_t seq, cons
 
 // The two particles of pair `pi` of the tile in ring slot `seq` (this lane consumes pairs lane and lane+32).
 template <bool VDISP>
-__device__ __forceinline__ void ring_read_pair(const WarpRing &r, uint32_t seq, int pi, int pairs_in_tile, Particle &a,
-                                               Particle &b)
+__device__ __forceinline__ void ring_read_pair(const WarpRing &r, uint32_t seq, int pi, Particle &a, Particle &b)
 {
     using C = RingCfg<VDISP>;
     const unsigned char *src = r.buf + (seq % C::STAGES) * C::STAGE_BYTES;
-    double2 x, y, z, m;
-    if (pi < pairs_in_tile) {
-        x = reinterpret_cast<const double2 *>(src + 0 * C::STREAM_BYTES)[pi];
-        y = reinterpret_cast<const double2 *>(src + 1 * C::STREAM_BYTES)[pi];
-        z = reinterpret_cast<const double2 *>(src + 2 * C::STREAM_BYTES)[pi];
-        m = reinterpret_cast<const double2 *>(src + 3 * C::STREAM_BYTES)[pi];
-    } else {   // beyond the prefix: the same never-selected sentinel the gather pads odd objects with
-        x = y = z = make_double2(1e150, 1e150);
-        m = make_double2(0.0, 0.0);
-    }
+    const double2 x = reinterpret_cast<const double2 *>(src + 0 * C::STREAM_BYTES)[pi];
+    const double2 y = reinterpret_cast<const double2 *>(src + 1 * C::STREAM_BYTES)[pi];
+    const double2 z = reinterpret_cast<const double2 *>(src + 2 * C::STREAM_BYTES)[pi];
+    const double2 m = reinterpret_cast<const double2 *>(src + 3 * C::STREAM_BYTES)[pi];
     make_particle(x.x, y.x, z.x, m.x, a);
     make_particle(x.y, y.y, z.y, m.y, b);
     if (VDISP) {
-        double2 u = make_double2(0.0, 0.0), v = u, w = u;
-        if (pi < pairs_in_tile) {
-            u = reinterpret_cast<const double2 *>(src + 4 * C::STREAM_BYTES)[pi];
-            v = reinterpret_cast<const double2 *>(src + 5 * C::STREAM_BYTES)[pi];
-            w = reinterpret_cast<const double2 *>(src + 6 * C::STREAM_BYTES)[pi];
-        }
+        const double2 u = reinterpret_cast<const double2 *>(src + 4 * C::STREAM_BYTES)[pi];
+        const double2 v = reinterpret_cast<const double2 *>(src + 5 * C::STREAM_BYTES)[pi];
+        const double2 w = reinterpret_cast<const double2 *>(src + 6 * C::STREAM_BYTES)[pi];
         make_tensor_products(u.x, v.x, w.x, a);
         make_tensor_products(u.y, v.y, w.y, b);
     }
+}
+
+// The bulk copy of a partial tile leaves the tail of the slot untouched: fill it with the never-selected
+// sentinel the gather pads odd objects with, so that the compute loop needs no per-lane bounds checks.
+template <bool VDISP>
+__device__ __forceinline__ void ring_fill_tail(const WarpRing &r, uint32_t seq, int lane, int pairs_in_tile)
+{
+    using C = RingCfg<VDISP>;
+    unsigned char *dst = r.buf + (seq % C::STAGES) * C::STAGE_BYTES;
+    for (int pi = pairs_in_tile + lane; pi < TILE_PAIRS; pi += 32) {
+#pragma unroll
+        for (int st = 0; st < C::NSTREAM; st++)
+            reinterpret_cast<double2 *>(dst + st * C::STREAM_BYTES)[pi] =
+                (st < 3) ? make_double2(1e150, 1e150) : make_double2(0.0, 0.0);
+    }
+    __syncwarp();
 }
 
 // One full pass over the object's radial prefix.  This warp consumes tiles tile0, tile0+tstride, ... of the
@@ -402,19 +431,27 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
     for (int j = 0; j < nmine; j++) {
         const int t = tile0 + j * tstride;
         const uint32_t seq = seq0 + j;
-        if (!reuse) mbar_wait(ring.bar + seq % RING_STAGES, (seq / RING_STAGES) & 1u);
-        const int pairs_in_tile = min(TILE_PAIRS, npairs - t * TILE_PAIRS);
+        if (!reuse) {
+            mbar_wait(ring.bar_s + (seq % RING_STAGES) * 8u, (seq / RING_STAGES) & 1u);
+            // only the last tile of the loaded range can be partial (particles past the active prefix but
+            // inside the loaded range are real particles that fail every membership test)
+            const int loaded = min(TILE_PAIRS, npairs_load - t * TILE_PAIRS);
+            if (loaded < TILE_PAIRS) ring_fill_tail<VDISP>(ring, seq, lane, loaded);
+        }
         unsigned smask = 0;
 #pragma unroll
         for (int s = 0; s < S; s++)
             if (t * TILE_PAIRS < npr[s]) smask |= 1u << s;
         smask &= amask;
-        if (FIRST || VDISP) {
+#ifndef CPG_NP2
+#define CPG_NP2 0
+#endif
+        if (FIRST || VDISP || CPG_NP2) {
             // two particles at a time (pass 0 is cheap; the dispersion variant carries 13 doubles per particle)
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 Particle p[2];
-                ring_read_pair<VDISP>(ring, seq, lane + 32 * h, pairs_in_tile, p[0], p[1]);
+                ring_read_pair<VDISP>(ring, seq, lane + 32 * h, p[0], p[1]);
                 if (FIRST) {
                     pass0_particle<S, SHELL, REDUCED, VDISP>(p[0], frames, smask, acc, cnt);
                     pass0_particle<S, SHELL, REDUCED, VDISP>(p[1], frames, smask, acc, cnt);
@@ -424,8 +461,8 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
             }
         } else {
             Particle p[4];
-            ring_read_pair<VDISP>(ring, seq, lane, pairs_in_tile, p[0], p[1]);
-            ring_read_pair<VDISP>(ring, seq, lane + 32, pairs_in_tile, p[2], p[3]);
+            ring_read_pair<VDISP>(ring, seq, lane, p[0], p[1]);
+            ring_read_pair<VDISP>(ring, seq, lane + 32, p[2], p[3]);
             passk_particles<S, SHELL, REDUCED, VDISP, 4>(p, frames, smask, acc, cnt);
         }
         if (!resident && j + RING_STAGES < nmine) {
@@ -438,7 +475,7 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
         if (resident) {
             // the barriers of resident tiles beyond the first pass's active range have not been waited on yet
             for (int j = nmine; j < issue_n; j++)
-                mbar_wait(ring.bar + (seq0 + j) % RING_STAGES, ((seq0 + j) / RING_STAGES) & 1u);
+                mbar_wait(ring.bar_s + ((seq0 + j) % RING_STAGES) * 8u, ((seq0 + j) / RING_STAGES) & 1u);
             ring.res_seq = seq0;
             ring.res_loaded = true;
             ring.seq = seq0 + issue_n;
@@ -464,6 +501,9 @@ __device__ __forceinline__ int active_npairs(const int (&npr)[S], unsigned amask
 // warps pulling tasks (sorted largest first) from an atomic queue.
 // ------------------------------------------------------------------------------------------------
 constexpr int WARP_KERNEL_WARPS = 4;
+#ifndef CPG_WARP_MINB
+#define CPG_WARP_MINB 3   // resident CTAs per SM the register allocator must leave room for
+#endif
 
 // Lane <-> shell mapping shared by both kernels.  The transposed warp reduction leaves the total of value
 // (l mod 8S) in lane l; value 8s+c is component c (Sxx,Sxy,Sxz,Syy,Syz,Szz,M,count) of shell s.  So the lanes
@@ -510,7 +550,7 @@ __device__ __forceinline__ void pack_values(const double (&acc)[S][7], const int
 }
 
 template <int S, bool SHELL, bool REDUCED, bool VDISP>
-__global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32) morph_warp_kernel(const MorphParams P)
+__global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_warp_kernel(const MorphParams P)
 {
     extern __shared__ __align__(128) unsigned char s_ring_w[];   // WARP_KERNEL_WARPS rings
     __shared__ __align__(16) double s_frames[WARP_KERNEL_WARPS][S * F_SLOTS];
