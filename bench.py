@@ -231,6 +231,27 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ------------------------------------------------------------------------------------ rank reduction
+
+def reduce_over_ranks(times_ms, work, world, device):
+    """Multi-GPU bookkeeping (no data-path collective exists): every time-like entry is the MAX over ranks,
+    every work-like entry the SUM.  Uses whatever torch.distributed backend is initialised (nccl on the GPU
+    box, gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(times_ms), dtype=torch.float64, device=device)
+    w = torch.tensor(list(work), dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    return [float(x) for x in t.tolist()], [float(x) for x in w.tolist()]
+
+
+def rank_seed(seed, rank):
+    """Each rank samples its own catalogue of the per-GPU size (weak scaling)."""
+    return seed + 1000 * rank
+
+
 # --------------------------------------------------------------------------------------------- main
 
 def main():
@@ -288,8 +309,8 @@ def main():
     from cosmic_profiles_b200 import _lib
 
     t0 = time.perf_counter()
-    tab = halo_table(a.halos, a.seed + 1000 * rank)
-    cat = generate_on_device(tab, a.seed + 1000 * rank, local_rank)
+    tab = halo_table(a.halos, rank_seed(a.seed, rank))
+    cat = generate_on_device(tab, rank_seed(a.seed, rank), local_rank)
     n_part = int(cat["obj_size"].sum())
     log("[rank %d] catalogue: %d objects, %d particles (%.2f GB x,y,z,m), generated in %.1f s"
         % (rank, a.halos, n_part, n_part * 32 / 1e9, time.perf_counter() - t0))
@@ -371,15 +392,9 @@ def main():
     d2h = int(t_l["d2h_bytes"] + t_g["d2h_bytes"])
 
     # ---- reduce over ranks: time = max, work = sum -------------------------------------------------
-    vals = torch.tensor([dev_ms / a.steps, wall_ms / a.steps, e2e_ms, kern_local_ms / a.steps], dtype=torch.float64,
-                        device="cuda")
-    work = torch.tensor([pi_step, pi_local, float(launches), float(h2d), float(d2h), visited_local], dtype=torch.float64,
-                        device="cuda")
-    if world > 1:
-        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-        dist.all_reduce(work, op=dist.ReduceOp.SUM)
-    step_ms, wall_step_ms, e2e_step_ms, kern_ms = [float(x) for x in vals.tolist()]
-    pi_all, pi_local_all, launches_all, h2d_all, d2h_all, visited_all = [float(x) for x in work.tolist()]
+    (step_ms, wall_step_ms, e2e_step_ms, kern_ms), (pi_all, pi_local_all, launches_all, h2d_all, d2h_all, visited_all) = \
+        reduce_over_ranks([dev_ms / a.steps, wall_ms / a.steps, e2e_ms, kern_local_ms / a.steps],
+                          [pi_step, pi_local, float(launches), float(h2d), float(d2h), visited_local], world, "cuda")
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
