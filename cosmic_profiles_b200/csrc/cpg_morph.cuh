@@ -32,8 +32,8 @@ enum {
     F_D2,                                           // d^2
     F_THR,                                          // inner-ellipsoid threshold: 1 (shell), -1 (first shell: disabled)
     F_BXX, F_BYY, F_BZZ, F_BXY, F_BXZ, F_BYZ,       // B = R^T diag(1/(d-delta)^2, 1/(q d-delta)^2, 1/(s d-delta)^2) R
-    F0_IN2,                                         // pass 0 only: (d-delta)^2
-    F_PAD,
+    F_PAD0,
+    F_PAD1,
     F_V,                                            // 9 slots: eigenvector basis of the previous iteration
     F_SLOTS = 26                                    // (even: rows stay 16-byte aligned for the double2 loads)
 };
@@ -91,25 +91,10 @@ __device__ __forceinline__ void accumulate(double (&acc)[7], int &cnt, bool sel,
     }
 }
 
-// Pass 0: spherical start (shape_profs_algos.pyx:206-212 / :81-87), exact reference arithmetic:
-// r2 = ((dx*dx + dy*dy) + dz*dz) with every operation rounded separately.
-template <int S, bool SHELL, bool REDUCED, bool VDISP>
-__device__ __forceinline__ void pass0_particle(const Particle &p, const double *frames, unsigned smask,
-                                               double (&acc)[S][7], int (&cnt)[S])
-{
-    const double r2 = __dadd_rn(__dadd_rn(p.xx, p.yy), p.zz);
-#pragma unroll
-    for (int s = 0; s < S; s++) {
-        if (smask & (1u << s)) {
-            const double *F = frames + s * F_SLOTS;
-            bool sel = r2 < F[F_D2];
-            if (SHELL)
-                sel = sel && (r2 >= F[F0_IN2]);
-            accumulate<REDUCED, VDISP>(acc[s], cnt[s], sel, r2, p);
-        }
-    }
-}
-
+// Pass 0 (spherical start, shape_profs_algos.pyx:206-212 / :81-87) runs through the same code with A = B = I
+// and thr = (d-delta)^2: the fma chain below then evaluates ((xx + yy) + zz) + 0 + 0 + 0 with xx, yy, zz
+// the exactly rounded squares, i.e. bit for bit the reference's r2 -- no separate code path (the kernels
+// are instruction-cache bound enough as it is).
 // Pass k>=1: membership in the ellipsoid (shell) of the previous eigen-decomposition
 // (shape_profs_algos.pyx:247-260 / :122-143) fused with the next tensor accumulation.
 template <int S, bool SHELL, bool REDUCED, bool VDISP, int NP>
@@ -403,7 +388,7 @@ __device__ __forceinline__ void ring_fill_tail(const WarpRing &r, uint32_t seq, 
 // `npairs` pairs that the still-active shells need; npr[s] = pairs in the prefix of shell s.
 // resident: every tile this warp will ever need for the task fits in its ring -> loaded by the first pass,
 // re-read from shared memory by all later ones.
-template <int S, bool SHELL, bool REDUCED, bool VDISP, bool FIRST>
+template <int S, bool SHELL, bool REDUCED, bool VDISP>
 __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npairs, int tile0, int tstride, int lane,
                                          WarpRing &ring, bool resident, int npairs_task, const double *frames,
                                          const int (&npr)[S], unsigned amask, double (&acc)[S][7], int (&cnt)[S])
@@ -443,21 +428,13 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
         for (int s = 0; s < S; s++)
             if (t * TILE_PAIRS < npr[s]) smask |= 1u << s;
         smask &= amask;
-#ifndef CPG_NP2
-#define CPG_NP2 0
-#endif
-        if (FIRST || VDISP || CPG_NP2) {
-            // two particles at a time (pass 0 is cheap; the dispersion variant carries 13 doubles per particle)
+        if (VDISP) {
+            // two particles at a time: the dispersion variant carries 13 doubles per particle
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 Particle p[2];
                 ring_read_pair<VDISP>(ring, seq, lane + 32 * h, p[0], p[1]);
-                if (FIRST) {
-                    pass0_particle<S, SHELL, REDUCED, VDISP>(p[0], frames, smask, acc, cnt);
-                    pass0_particle<S, SHELL, REDUCED, VDISP>(p[1], frames, smask, acc, cnt);
-                } else {
-                    passk_particles<S, SHELL, REDUCED, VDISP, 2>(p, frames, smask, acc, cnt);
-                }
+                passk_particles<S, SHELL, REDUCED, VDISP, 2>(p, frames, smask, acc, cnt);
             }
         } else {
             Particle p[4];
@@ -531,7 +508,9 @@ __device__ __forceinline__ void init_frames(double *frames, int *np, const LaneM
         double *F = frames + L.ls * F_SLOTS;
         F[F_D2] = __dmul_rn(st.d, st.d);
         const double in = __dsub_rn(st.d, st.delta);
-        F[F0_IN2] = __dmul_rn(in, in);
+        F[F_THR] = __dmul_rn(in, in);   // pass 0: r2 >= (d-delta)^2 (shell variant; 0 for the first shell)
+#pragma unroll
+        for (int r = 0; r < 6; r++) F[F_AXX + r] = F[F_BXX + r] = (r < 3) ? 1.0 : 0.0;   // A = B = I
 #pragma unroll
         for (int r = 0; r < 9; r++) F[F_V + r] = (r == 0 || r == 4 || r == 8) ? 1.0 : 0.0;
         np[L.ls] = (ne + 1) >> 1;
@@ -597,7 +576,7 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
 
         double acc[S][7];
         int cnt[S];
-        run_pass<S, SHELL, REDUCED, VDISP, true>(P.soa, base, npairs_task, 0, 1, lane, ring, resident, npairs_task, frames,
+        run_pass<S, SHELL, REDUCED, VDISP>(P.soa, base, npairs_task, 0, 1, lane, ring, resident, npairs_task, frames,
                                                  npr, amask, acc, cnt);
         while (true) {
             double val[8 * S];
@@ -615,7 +594,7 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
             amask = LaneMap<S>::active_mask(st.active && L.writer);
             if (amask == 0)
                 break;
-            run_pass<S, SHELL, REDUCED, VDISP, false>(P.soa, base, active_npairs<S>(npr, amask), 0, 1, lane, ring, resident,
+            run_pass<S, SHELL, REDUCED, VDISP>(P.soa, base, active_npairs<S>(npr, amask), 0, 1, lane, ring, resident,
                                                       npairs_task, frames, npr, amask, acc, cnt);
         }
     }
@@ -681,7 +660,7 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     double acc[S][7];
     int cnt[S];
     int buf = 0;
-    run_pass<S, SHELL, REDUCED, VDISP, true>(P.soa, base, npairs_task, tile0, tstride, lane, ring, resident, npairs_task,
+    run_pass<S, SHELL, REDUCED, VDISP>(P.soa, base, npairs_task, tile0, tstride, lane, ring, resident, npairs_task,
                                              frames, npr, amask, acc, cnt);
     while (true) {
         {
@@ -723,7 +702,7 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
         buf ^= 1;
         if (amask == 0)
             break;
-        run_pass<S, SHELL, REDUCED, VDISP, false>(P.soa, base, active_npairs<S>(npr, amask), tile0, tstride, lane, ring,
+        run_pass<S, SHELL, REDUCED, VDISP>(P.soa, base, active_npairs<S>(npr, amask), tile0, tstride, lane, ring,
                                                   resident, npairs_task, frames, npr, amask, acc, cnt);
     }
     if (C > 1)
