@@ -35,7 +35,7 @@ struct DevBuf {
     {
         if (n <= cap && p) return CPG_OK;
         release();
-        const size_t want = n ? n : 1;
+        const size_t want = (n ? n : 1) + (16 + sizeof(T) - 1) / sizeof(T);   // 16 bytes of slack (small_upload pads)
         cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
         if (e != cudaSuccess) {
             p = nullptr;
@@ -70,6 +70,11 @@ struct cpg_ctx {
     cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: large-object kernel, concurrent with the warp kernel
     cudaEvent_t ev[6] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // page-locked, device-mapped staging for the small per-call inputs (centres, radii, task list): they are
+    // pulled by a copy kernel instead of queueing on the host->device copy engine behind another context's
+    // multi-GB snapshot upload
+    unsigned char *stage = nullptr;
+    size_t stage_cap = 0, stage_used = 0;
     // snapshot
     DevBuf<double> xyz, vxyz, masses;
     int64_t n_part = 0;
@@ -136,6 +141,51 @@ int use_device(cpg_ctx *c)
         return CPG_ERR_ARGUMENT;
     }
     CPG_CUDA(cudaSetDevice(c->device));
+    return CPG_OK;
+}
+
+// Large host->device transfers are issued in pieces: the copy engine serves streams copy by copy, so a small
+// upload of another context (centres, radii) is not stuck behind a multi-GB transfer for tens of ms.
+int upload_chunked(void *dst, const void *src, size_t bytes, cudaStream_t stream)
+{
+    const size_t piece = (size_t)32 << 20;
+    for (size_t o = 0; o < bytes; o += piece) {
+        const size_t nb = std::min(piece, bytes - o);
+        CPG_CUDA(cudaMemcpyAsync((char *)dst + o, (const char *)src + o, nb, cudaMemcpyHostToDevice, stream));
+    }
+    return CPG_OK;
+}
+
+__global__ void stage_copy_kernel(const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t n16)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) dst[i] = src[i];
+}
+
+int grid_for(int64_t n, int block, int cap);
+
+// Host -> device copy of a small array through the mapped staging buffer (dst must be 16-byte aligned, which
+// every cudaMalloc'ed buffer is; the tail is padded inside the staging area, so dst needs 16-byte slack:
+// DevBuf allocations are rounded up accordingly).
+int small_upload(cpg_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    const size_t padded = (bytes + 15) & ~(size_t)15;
+    if (c->stage_used + padded > c->stage_cap) {
+        // grow: wait for earlier staged copies, then reallocate
+        CPG_CUDA(cudaStreamSynchronize(c->stream));
+        const size_t want = std::max<size_t>((c->stage_used + padded) * 2, (size_t)4 << 20);
+        if (c->stage) cudaFreeHost(c->stage);
+        c->stage = nullptr; c->stage_cap = 0; c->stage_used = 0;
+        CPG_CUDA(cudaHostAlloc((void **)&c->stage, want, cudaHostAllocMapped | cudaHostAllocPortable));
+        c->stage_cap = want;
+    }
+    unsigned char *h = c->stage + c->stage_used;
+    memcpy(h, src, bytes);
+    if (padded > bytes) memset(h + bytes, 0, padded - bytes);
+    c->stage_used += padded;
+    const size_t n16 = padded / 16;
+    stage_copy_kernel<<<grid_for((int64_t)n16, 256, c->sm_count * 4), 256, 0, c->stream>>>((const uint4 *)h, (uint4 *)dst, n16);
+    CPG_CUDA(cudaGetLastError());
     return CPG_OK;
 }
 
@@ -447,6 +497,7 @@ CPG_API void cpg_destroy(cpg_ctx *c)
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stage) cudaFreeHost(c->stage);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -489,12 +540,12 @@ CPG_API int cpg_set_particles(cpg_ctx *c, const double *xyz, const double *vxyz,
     }
     CPG_TRY(c->xyz.ensure((size_t)n_part * 3));
     CPG_TRY(c->masses.ensure((size_t)n_part));
-    CPG_CUDA(cudaMemcpyAsync(c->xyz.p, xyz, sizeof(double) * 3 * n_part, cudaMemcpyHostToDevice, c->stream));
-    CPG_CUDA(cudaMemcpyAsync(c->masses.p, masses, sizeof(double) * n_part, cudaMemcpyHostToDevice, c->stream));
+    CPG_TRY(upload_chunked(c->xyz.p, xyz, sizeof(double) * 3 * n_part, c->stream));
+    CPG_TRY(upload_chunked(c->masses.p, masses, sizeof(double) * n_part, c->stream));
     c->have_vel = vxyz != nullptr;
     if (vxyz) {
         CPG_TRY(c->vxyz.ensure((size_t)n_part * 3));
-        CPG_CUDA(cudaMemcpyAsync(c->vxyz.p, vxyz, sizeof(double) * 3 * n_part, cudaMemcpyHostToDevice, c->stream));
+        CPG_TRY(upload_chunked(c->vxyz.p, vxyz, sizeof(double) * 3 * n_part, c->stream));
     }
     CPG_CUDA(cudaStreamSynchronize(c->stream));
     c->n_part = n_part;
@@ -541,7 +592,7 @@ CPG_API int cpg_set_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx,
     CPG_TRY(c->chunks.ensure(c->h_chunks.size())); CPG_TRY(c->kchunks.ensure(c->h_kchunks.size()));
     CPG_TRY(c->chunk_first.ensure(n_obj + 1)); CPG_TRY(c->kchunk_first.ensure(n_obj + 1));
     CPG_TRY(c->task_counter.ensure(4));
-    if (n_idx) CPG_CUDA(cudaMemcpyAsync(c->idx.p, idx_cat, sizeof(int32_t) * n_idx, cudaMemcpyHostToDevice, c->stream));
+    if (n_idx) CPG_TRY(upload_chunked(c->idx.p, idx_cat, sizeof(int32_t) * n_idx, c->stream));
     if (n_obj) CPG_CUDA(cudaMemcpyAsync(c->size.p, obj_size, sizeof(int32_t) * n_obj, cudaMemcpyHostToDevice, c->stream));
     CPG_CUDA(cudaMemcpyAsync(c->off.p, off.data(), sizeof(int64_t) * (n_obj + 1), cudaMemcpyHostToDevice, c->stream));
     CPG_CUDA(cudaMemcpyAsync(c->poff.p, poff.data(), sizeof(int64_t) * (n_obj + 1), cudaMemcpyHostToDevice, c->stream));
@@ -604,9 +655,10 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     const size_t nR = (size_t)n * R;
     T.mark(0);
     CPG_TRY(c->centers.ensure((size_t)n * 3)); CPG_TRY(c->r200.ensure(n)); CPG_TRY(c->rr.ensure(R));
-    CPG_CUDA(cudaMemcpyAsync(c->centers.p, centers, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
-    CPG_CUDA(cudaMemcpyAsync(c->r200.p, r200, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
-    if (local) CPG_CUDA(cudaMemcpyAsync(c->rr.p, r_over_r200, sizeof(double) * R, cudaMemcpyHostToDevice, c->stream));
+    c->stage_used = 0;
+    CPG_TRY(small_upload(c, c->centers.p, centers, sizeof(double) * 3 * n));
+    CPG_TRY(small_upload(c, c->r200.p, r200, sizeof(double) * n));
+    if (local) CPG_TRY(small_upload(c, c->rr.p, r_over_r200, sizeof(double) * R));
     c->timing.h2d_bytes = (int64_t)sizeof(double) * (4 * (int64_t)n + (local ? R : 0));
 
     // ---- task list: objects largest first; S shells of one object per task
@@ -647,9 +699,7 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
         TK.nw = (int)warp_tasks.size(); TK.ncl = (int)cl_tasks.size(); TK.cluster_size = cluster_size;
         warp_tasks.insert(warp_tasks.end(), cl_tasks.begin(), cl_tasks.end());
         CPG_TRY(c->tasks.ensure(warp_tasks.size()));
-        CPG_CUDA(cudaMemcpyAsync(c->tasks.p, warp_tasks.data(), sizeof(Task) * warp_tasks.size(), cudaMemcpyHostToDevice,
-                                 c->stream));
-        CPG_CUDA(cudaStreamSynchronize(c->stream));   // warp_tasks is a local
+        CPG_TRY(small_upload(c, c->tasks.p, warp_tasks.data(), sizeof(Task) * warp_tasks.size()));
         c->timing.h2d_bytes += (int64_t)(sizeof(Task) * warp_tasks.size());
         TK.valid = true; TK.cat = c->catalogue_version; TK.S = S; TK.R = R; TK.large_min = large_min;
     }
@@ -718,8 +768,9 @@ static int dens_common_begin(cpg_ctx *c, Timer &T, const double *centers, const 
     const int n = c->n_obj;
     T.mark(0);
     CPG_TRY(c->centers.ensure((size_t)n * 3)); CPG_TRY(c->r200.ensure(n));
-    CPG_CUDA(cudaMemcpyAsync(c->centers.p, centers, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
-    if (r200) CPG_CUDA(cudaMemcpyAsync(c->r200.p, r200, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    c->stage_used = 0;
+    CPG_TRY(small_upload(c, c->centers.p, centers, sizeof(double) * 3 * n));
+    if (r200) CPG_TRY(small_upload(c, c->r200.p, r200, sizeof(double) * n));
     c->timing.h2d_bytes = (int64_t)sizeof(double) * (r200 ? 4 : 3) * n;
     return CPG_OK;
 }
