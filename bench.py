@@ -454,6 +454,13 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:   # DRAM bytes of the two local-shape kernels from the committed ncu capture of this workload
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if int(tr.get("workload_halos", -1)) == a.halos:
+                traffic = float(tr["dram_bytes_per_local_shape_launch_set"])
+        except Exception:
+            pass
         achieved = pi_local_all / world * BYTES_PER_PI / (kern_ms * 1e-3) / 1e9   # per GPU, GB/s
         line = {"metric": METRIC, "value": pi_all / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
@@ -466,7 +473,8 @@ def main():
                         "serial_value": pi_all / (e2e_serial_step_ms * 1e-3)},
                 "gpu_launches": int(launches_all),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": None,
+                             "frac": achieved / peak, "traffic": traffic,
+                             "traffic_source": "profiles/r1_traffic.json (ncu --set full, same workload)" if traffic else None,
                              "kernel": "morph_warp_kernel/morph_cluster_kernel (local shapes)",
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                              "algorithmic_bytes_per_launch_set": pi_local_all / world * BYTES_PER_PI,
