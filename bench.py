@@ -142,13 +142,26 @@ def reference_sample_inputs(cat, pick):
     return xyz, m, np.arange(len(sel), dtype=np.int32), sizes, np.ascontiguousarray(cat["r200"][pick])
 
 
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1; the reference arm must use every host core.  Set the variable
+    (for a libgomp that is not loaded yet) and the ICV of an already loaded libgomp."""
+    cores = len(os.sched_getaffinity(0))
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)
+    except Exception:
+        pass
+    return cores
+
+
 def time_reference(cat, pick, steps, warmup):
     """Time the reference's own drivers (compiled from /root/reference into oracle/_ref; falls back to the
     C port of the oracle if that build is absent) on the sampled objects.  Returns (PI/s, info)."""
     from oracle import cp_oracle as O
     from oracle import ref_loader
     xyz, m, idx, sizes, r200 = reference_sample_inputs(cat, pick)
-    cores = len(os.sched_getaffinity(0))
+    cores = use_all_host_cores()
     k = (KATZ["IT_TOL"], KATZ["IT_WALL"], KATZ["IT_MIN"])
     # particle-iterations of the sample, from the oracle's integer outputs (same algorithm, same counts)
     _, (nit_l, _, _, _) = O.morph(xyz, None, m, r200, idx, sizes, 0.0, RR, *k, "com", False, False, True)
@@ -280,7 +293,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        os.environ.setdefault("OMP_NUM_THREADS", str(len(os.sched_getaffinity(0))))
+        use_all_host_cores()
         import torch
         tab = halo_table(a.halos, a.seed)
         if torch.cuda.is_available():
@@ -442,7 +455,6 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        os.environ.setdefault("OMP_NUM_THREADS", str(len(os.sched_getaffinity(0))))
         pick = stratified_sample(sizes, a.cpu_budget)
         v, info = time_reference(cat, pick, 1, 0)
         cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
