@@ -662,17 +662,23 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     c->timing.h2d_bytes = (int64_t)sizeof(double) * (4 * (int64_t)n + (local ? R : 0));
 
     // ---- task list: objects largest first; S shells of one object per task
-    const int warp_slots = c->sm_count * 16;
-    int64_t n_units = (int64_t)n * R;
+    const int warp_slots = c->sm_count * 12;   // resident warps of the warp kernel (3 CTAs x 4 warps per SM)
+    const int64_t n_units = (int64_t)n * R;
     int S = c->opt_shells_per_pass;
     if (S == 0) {
+        // S shells share one read of the particles.  Worth it when there are still plenty of tasks to fill the
+        // GPU afterwards, or when the objects are so large that streaming them dominates (cluster teams then
+        // supply the parallelism).
+        const int64_t mean_size = c->n_idx / std::max(1, n);
         S = 1;
-        if (R >= 2 && n_units / 2 >= 4 * (int64_t)warp_slots) S = 2;
-        if (R >= 4 && n_units / 4 >= 4 * (int64_t)warp_slots) S = 4;
+        if (R >= 2 && (n_units / 2 >= 4 * (int64_t)warp_slots || mean_size >= 200000)) S = 2;
+        if (R >= 4 && (n_units / 4 >= 4 * (int64_t)warp_slots || mean_size >= 200000)) S = 4;
     }
     if (S > R) S = pow2_floor(R);
     int64_t large_min = c->opt_large_halo_min > 0 ? c->opt_large_halo_min : (int64_t)131072;
-    if (c->opt_large_halo_min == 0 && n_units < warp_slots / 2) large_min = 8192;   // few units: spread each over CTAs
+    // few tasks: a warp per task would leave the GPU to a handful of long-running warps (non-converging shells
+    // iterate up to IT_WALL times); give every task of a non-tiny object a CTA / cluster instead
+    if (c->opt_large_halo_min == 0 && (n_units + S - 1) / S < 8 * (int64_t)warp_slots) large_min = 4096;
     auto &TK = c->task_key;
     if (!(TK.valid && TK.cat == c->catalogue_version && TK.S == S && TK.R == R && TK.large_min == large_min &&
           (c->opt_cluster_size == 0 || c->opt_cluster_size == TK.cluster_size))) {

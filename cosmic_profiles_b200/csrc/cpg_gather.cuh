@@ -171,7 +171,39 @@ __global__ void stats_final_kernel(const int32_t *chunk_first /* n_obj+1 */, con
 
 // helper_class.pyx:98-100: `cdef float mass_total` accumulated sequentially in catalogue order
 // (mass_total = (float)((double)mass_total + m)).  The order is part of the result, so one lane walks the
-// object while the warp streams the masses in coalesced 32-element batches.
+// object while the warp streams the masses in coalesced 32-element batches.  Objects whose members all have
+// the same mass (every dark-matter-only snapshot) take a closed-form route: inside one fp32 binade the
+// accumulator is a multiple of its ulp, so every step adds the same rounded increment and a whole binade is
+// advanced in O(1) -- bit-identical to the sequential loop, including its saturation once m < ulp/2.
+__device__ __forceinline__ float f32_step(float acc, double m) { return (float)__dadd_rn((double)acc, m); }
+
+__device__ float mass32_equal(double m, int N)
+{
+    float acc = 0.0f;
+    int i = 0;
+    while (i < N) {
+        const float next = f32_step(acc, m);
+        if (next == acc) break;                       // saturated: no later addition changes the sum
+        const float inc = next - acc;                 // exact: both are multiples of ulp(acc)'s grid or acc == 0
+        int e;
+        frexpf(acc, &e);                              // acc in [2^(e-1), 2^e)
+        const float top = ldexpf(1.0f, e);
+        // the increment is constant while acc stays in this binade AND acc + m is rounded on this binade's grid
+        // AND no tie-to-even case occurs (then the increment alternates with the parity of acc)
+        const double u = (double)ldexpf(1.0f, e - 24);          // ulp of the binade
+        const double frac = m / u - floor(m / u);
+        const bool constant = acc > 0.0f && frac != 0.5 && f32_step(next, m) - next == inc;
+        if (!constant) { acc = next; i++; continue; }
+        // steps k = 1..n with acc + k*inc + (m - inc) still below `top` behave identically
+        long long n = (long long)floor(((double)top - (double)acc - m) / (double)inc);
+        if (n < 1) { acc = next; i++; continue; }
+        if (n > N - i) n = N - i;
+        acc = (float)((double)acc + (double)n * (double)inc);   // exact: a multiple of u below top
+        i += (int)n;
+    }
+    return acc;
+}
+
 __global__ void __launch_bounds__(128) mass32_kernel(const GatherParams G, int n_obj, float *mass32)
 {
     const int lane = threadIdx.x & 31;
@@ -179,13 +211,22 @@ __global__ void __launch_bounds__(128) mass32_kernel(const GatherParams G, int n
     for (int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; h < n_obj; h += warps) {
         const int64_t first = G.off[h];
         const int N = (int)(G.off[h + 1] - first);
+        if (N == 0) {
+            if (lane == 0) mass32[h] = 0.0f;
+            continue;
+        }
+        const double m0 = G.masses[G.idx[first]];
+        bool same = true;
+        for (int i = lane; i < N; i += 32) same = same && (G.masses[G.idx[first + i]] == m0);
+        same = __all_sync(0xffffffffu, same);
         float acc = 0.0f;
-        for (int i0 = 0; i0 < N; i0 += 32) {
-            const double mine = (i0 + lane < N) ? G.masses[G.idx[first + i0 + lane]] : 0.0;
-            const int cntb = min(32, N - i0);
-            for (int j = 0; j < cntb; j++) {
-                const double mj = __shfl_sync(0xffffffffu, mine, j);
-                acc = (float)__dadd_rn((double)acc, mj);
+        if (same && m0 > 0.0) {
+            acc = mass32_equal(m0, N);   // uniform across the warp
+        } else {
+            for (int i0 = 0; i0 < N; i0 += 32) {
+                const double mine = (i0 + lane < N) ? G.masses[G.idx[first + i0 + lane]] : 0.0;
+                const int cntb = min(32, N - i0);
+                for (int j = 0; j < cntb; j++) acc = f32_step(acc, __shfl_sync(0xffffffffu, mine, j));
             }
         }
         if (lane == 0) mass32[h] = acc;

@@ -1,0 +1,167 @@
+#!/usr/bin/env python3
+"""Timings of the BASELINE.json configurations that are NOT the bench line (configs[0], [2], [3]-flavour, [4]),
+on one B200, written to profiles/r1_other_configs.json.  Parity for these flavours is covered by
+tests/test_gpu_configs.py and tests/test_gpu_parity.py; this script only measures.
+
+    python profiles/other_configs.py [--quick]
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from cosmic_profiles_b200 import _lib  # noqa: E402
+
+K = (1e-2, 100, 10)
+quick = "--quick" in sys.argv
+out = {}
+
+
+def timed(fn, n=3):
+    fn()
+    t = []
+    for _ in range(n):
+        t0 = time.perf_counter()
+        r = fn()
+        t.append((time.perf_counter() - t0) * 1e3)
+    return min(t), r
+
+
+def catalogue(sizes, seed, profile="einasto", vel=False):
+    tab = bench.halo_table(len(sizes), seed)
+    tab["sizes"] = np.asarray(sizes, dtype=np.int64)
+    tab["r_vir"] = tab["r_vir"] * 0 + 0.3 * (tab["sizes"] / 1e4) ** (1 / 3.0)
+    if profile != "einasto":
+        from cosmic_profiles_b200.mock import _radius_sampler
+        tab["u"], tab["cdf"] = _radius_sampler(profile, 5.0)
+    cat = bench.generate_on_device(tab, seed, 0)
+    if vel:
+        rng = np.random.default_rng(seed)
+        cat["vxyz"] = np.ascontiguousarray(rng.normal(size=cat["xyz"].shape) * np.array([300.0, 200.0, 100.0]))
+    return cat
+
+
+ctx = _lib.Context(0)
+
+# ---- configs[0]: 100 NFW halos x 1e4, 20 shells, reduced, E1 and S1 -------------------------------------
+cat = catalogue([10000] * 100, 1, "nfw")
+ctx.set_particles(cat["xyz"], None, cat["masses"]); ctx.set_catalogue(cat["idx_cat"], cat["obj_size"])
+rr20 = np.logspace(-1.5, 0, 20)
+for shell in (False, True):
+    def run():
+        ctx.set_option("invalidate_gather", 1)
+        o, nit, _, _, _ = ctx.shape(cat["centers"], cat["r200"], rr20, True, 0.0, 0.0, *K, True, shell, False)
+        return nit.copy(), ctx.timing()
+    ms, (nit, tim) = timed(run)
+    pi = float((nit.clip(0).sum(1) * cat["obj_size"]).sum())
+    out["config0_100x1e4_R20_reduced_%s" % ("S1" if shell else "E1")] = dict(
+        wall_ms=ms, kernel_ms=tim["kernel_ms"], gather_ms=tim["gather_ms"], particle_iterations=pi,
+        PI_per_s_kernel=pi / (tim["kernel_ms"] * 1e-3), halo_shells_per_s=2000 / (ms * 1e-3))
+
+# ---- configs[2]: densities on the configs[1] catalogue ---------------------------------------------------
+nh = 2000 if quick else 10000
+tab = bench.halo_table(nh, 20260101)
+cat = bench.generate_on_device(tab, 20260101, 0)
+npart = int(cat["obj_size"].sum())
+ctx.set_particles(cat["xyz"], None, cat["masses"]); ctx.set_catalogue(cat["idx_cat"], cat["obj_size"])
+rb = np.logspace(-2, 0, 50)
+from cosmic_profiles_b200 import dens_profs_algos as D  # noqa: E402
+edges = D.sph_bin_edges(rb)
+
+
+def sph():
+    ctx.set_option("invalidate_gather", 1)
+    d, c = ctx.dens_sph(cat["centers"], cat["r200"], edges, 0.0)
+    return ctx.timing()
+
+
+ms, tim = timed(sph)
+out["config2_dens_sph_R50"] = dict(halos=nh, particles=npart, wall_ms=ms, kernel_ms=tim["kernel_ms"], gather_ms=tim["gather_ms"],
+                                   GBps_kernel=npart * 32 / (tim["kernel_ms"] * 1e-3) / 1e9,
+                                   halo_bins_per_s=nh * 50 / (ms * 1e-3))
+
+
+def kde():
+    d = ctx.dens_kernel(cat["centers"], cat["r200"], rb, 0.0)
+    return ctx.timing()
+
+
+ms, tim = timed(kde, 2)
+out["config2_dens_kernel_R50"] = dict(halos=nh, particles=npart, wall_ms=ms, kernel_ms=tim["kernel_ms"],
+                                      evaluations_per_s=npart * 50 / (tim["kernel_ms"] * 1e-3))
+# ellipsoidal binning needs the local shape profile first (default 70-shell config), then scipy interpolation
+o, nit, _, _, _ = ctx.shape(cat["centers"], cat["r200"], bench.RR, True, 0.0, 0.0, *K, False, False, False)
+o = o.copy()
+o[o == 0.0] = np.nan
+d_, q_, s_ = o[:, :, 0], o[:, :, 1], o[:, :, 2]
+t0 = time.perf_counter()
+ai, bi, ci, mj, it, mn = D.interpolate_shapes(cat["r200"], rb, d_, d_ * q_, d_ * s_, o[:, :, 3:6], o[:, :, 6:9], o[:, :, 9:12])
+interp_s = time.perf_counter() - t0
+
+
+def ell():
+    d, c = ctx.dens_ell(cat["centers"], ai, bi, ci, mj, it, mn, 0.0)
+    return ctx.timing()
+
+
+ms, tim = timed(ell, 2)
+out["config2_dens_ell_R50"] = dict(halos=nh, particles=npart, wall_ms=ms, kernel_ms=tim["kernel_ms"],
+                                   host_scipy_interp_s=interp_s,
+                                   particle_bin_tests_per_s=npart * 50 / (tim["kernel_ms"] * 1e-3))
+
+# ---- configs[3] flavour: velocity-dispersion local + global on the same catalogue (one GPU's share) ----
+nv = 500 if quick else 3000
+tabv = bench.halo_table(nv, 5)
+catv = bench.generate_on_device(tabv, 5, 0)
+rng = np.random.default_rng(5)
+vx = np.ascontiguousarray(rng.normal(size=catv["xyz"].shape) * np.array([300.0, 200.0, 100.0]))
+
+
+def vd():
+    ctx.set_option("invalidate_gather", 1)
+    o, nit, _, _, _ = ctx.shape(catv["centers"], catv["r200"], bench.RR, True, 0.0, 0.0, *K, False, False, True)
+    return nit.copy(), ctx.timing()
+
+
+# Gadget MassTable-style constant particle mass (BASELINE configs[3]); with unequal masses the sequential fp32
+# mass normaliser of calcCoM cannot take the closed-form route and dominates the gather (see "unequal" entry)
+mconst = np.full(catv["masses"].shape, 0.0123456789)
+for label, mm in (("", mconst), ("_unequal_masses", catv["masses"])):
+    ctx.set_particles(catv["xyz"], vx, mm); ctx.set_catalogue(catv["idx_cat"], catv["obj_size"])
+    ms, (nit, tim) = timed(lambda: vd(), 2)
+    pi = float((nit.clip(0).sum(1) * catv["obj_size"]).sum())
+    out["config3_vdisp_local_R70" + label] = dict(halos=nv, particles=int(catv["obj_size"].sum()), wall_ms=ms,
+                                                  kernel_ms=tim["kernel_ms"], gather_ms=tim["gather_ms"], particle_iterations=pi,
+                                                  PI_per_s_kernel=pi / (tim["kernel_ms"] * 1e-3),
+                                                  algorithmic_GBps_56B=pi * 56 / (tim["kernel_ms"] * 1e-3) / 1e9)
+
+
+# ---- configs[4]: one large halo, 50 shells, shell-based non-reduced (cluster / DSMEM path) -------------
+nbig = 10_000_000 if quick else 100_000_000
+catb = catalogue([nbig], 9, "nfw")
+ctx.set_particles(catb["xyz"], None, catb["masses"]); ctx.set_catalogue(catb["idx_cat"], catb["obj_size"])
+rr50 = np.logspace(-2, 0, 50)
+for opts in ({}, {"shells_per_pass": 4, "cluster_size": 16}, {"shells_per_pass": 2, "cluster_size": 8}):
+    for kk in ("shells_per_pass", "cluster_size", "large_halo_min"):
+        ctx.set_option(kk, opts.get(kk, 0))
+
+    def big():
+        ctx.set_option("invalidate_gather", 1)
+        o, nit, npt, _, _ = ctx.shape(catb["centers"], catb["r200"], rr50, True, 0.0, 0.0, *K, False, True, False)
+        return nit.copy(), ctx.timing()
+    ms, (nit, tim) = timed(big, 2)
+    pi = float(nit.clip(0).sum() * nbig)
+    ne = ctx.prefix_lengths(50).astype(np.int64)
+    out["config4_single_halo_%g_R50_S1shell_%s" % (nbig, "auto" if not opts else "S%dC%d" % (opts["shells_per_pass"], opts["cluster_size"]))] = dict(
+        wall_ms=ms, kernel_ms=tim["kernel_ms"], gather_ms=tim["gather_ms"], iterations=nit.ravel().tolist(),
+        particle_iterations=pi, PI_per_s_kernel=pi / (tim["kernel_ms"] * 1e-3),
+        algorithmic_GBps=pi * 32 / (tim["kernel_ms"] * 1e-3) / 1e9,
+        streamed_GBps=float((ne * nit.clip(0)).sum()) * 32 / (tim["kernel_ms"] * 1e-3) / 1e9)
+
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "r1_other_configs.json"), "w"), indent=1)
+print(json.dumps(out, indent=1))

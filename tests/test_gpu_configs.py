@@ -128,3 +128,25 @@ def test_large_rigid_motion_invariance(gpu, large):
     dots = np.abs(np.sum(major0 * rot[5][same], axis=-1))
     gap = 1 - base[1][same] ** 2
     assert (1 - dots[gap > 1e-3]).max() < 1e-12
+
+
+def test_velocity_centres_equal_mass_closed_form(gpu):
+    """Dark-matter-only snapshots (all masses equal) take the closed-form route of the sequential fp32 mass
+    normaliser of helper_class.calcCoM (cpg_gather.cuh: mass32_equal); it must agree with the oracle's literal
+    sequential loop, including for an object large enough that fp32 accumulation visibly drifts."""
+    from cosmic_profiles_b200.mock import make_catalogue
+    from oracle import cp_oracle as O
+    S, sess = gpu
+    cat = make_catalogue([300000, 70000, 5000, 1234, 77], seed=21, equal_mass=True, with_velocities=True)
+    cen = O.centres(cat["xyz"], cat["masses"], cat["idx_cat"], cat["obj_size"], 0.0, "com", True)
+    ref, (nit, npt, vc, _) = O.morph(cat["xyz"], cat["vxyz"], cat["masses"], cat["r200"], cat["idx_cat"], cat["obj_size"],
+                                     0.0, None, 1e-2, 100, 10, "com", False, False, False, SAFE=6.0, centers=cen)
+    got = S.calcMorphGlobalVelDisp(cat["xyz"], cat["vxyz"], cat["masses"], cat["r200"], cat["idx_cat"], cat["obj_size"],
+                                   0.0, 1e-2, 100, 10, "com", 6.0, False, centers=cen)
+    # the fp32 normaliser differs from the fp64 mass by ~1e-7..1e-5 relative here; the closed form must hit it
+    m64 = np.array([cat["masses"][0] * n for n in cat["obj_size"]])
+    drift = np.abs(np.linalg.norm(vc, axis=1) / np.linalg.norm(S.last_info["vcenters"], axis=1) - 1)
+    assert drift.max() < 1e-13, drift
+    P.assert_ints(S.last_info["n_iter"], nit, "vglobal equal-mass n_iter")
+    P.assert_shape_tuple(got, ref, "vglobal equal-mass")
+    assert m64.shape == (5,)
