@@ -28,7 +28,7 @@ class Timing(ctypes.Structure):
 
 EXPORTS = ["cpg_device_count", "cpg_last_error", "cpg_version", "cpg_create", "cpg_destroy", "cpg_set_particles",
            "cpg_set_catalogue", "cpg_shape", "cpg_dens_sph", "cpg_dens_ell", "cpg_dens_kernel", "cpg_obj_masses",
-           "cpg_get_timing", "cpg_set_option", "cpg_host_alloc", "cpg_host_free", "cpg_get_prefix_lengths"]
+           "cpg_get_timing", "cpg_set_option", "cpg_host_alloc", "cpg_host_free", "cpg_get_prefix_lengths", "cpg_centers"]
 
 
 def load():
@@ -62,6 +62,7 @@ def load():
     L.cpg_host_free.argtypes = [vp]
     L.cpg_host_free.restype = None
     L.cpg_get_prefix_lengths.argtypes = [vp, _I, ctypes.c_int32]
+    L.cpg_centers.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_double, _D, _D]
     for f in EXPORTS:
         if f not in ("cpg_last_error", "cpg_version", "cpg_destroy", "cpg_host_free"):
             getattr(L, f).restype = ctypes.c_int
@@ -212,6 +213,13 @@ class Context:
         m = np.zeros(self.n_obj)
         _check(self._L.cpg_obj_masses(self._h, _dp(m)), "cpg_obj_masses")
         return m
+
+    def centers(self, mode, shape_path, L_BOX, ref_points=None):
+        cen = np.zeros((self.n_obj, 3))
+        ref = None if ref_points is None else f64(ref_points)
+        _check(self._L.cpg_centers(self._h, int(mode), int(bool(shape_path)), float(L_BOX), _dp(ref), _dp(cen)),
+               "cpg_centers")
+        return cen
 
     def prefix_lengths(self, R):
         ne = np.zeros((self.n_obj, R), dtype=np.int32)

@@ -16,6 +16,28 @@ def _reference_points(n):
     return rng.choice(np.arange(n), (min(50, n),), replace=False)
 
 
+_choice_cache = {}
+
+
+def reference_points(xyz, idx_cat, obj_size):
+    """The reference point respectPBCNoRef / calcCoM average from <= 50 seeded random members of every object
+    (python_routines.py:512-514, :540-542).  Needed by the device centre finder when L_BOX != 0, where the
+    reference point decides which particles are translated by +-L_BOX."""
+    off = np.concatenate(([0], np.cumsum(np.asarray(obj_size, dtype=np.int64))))
+    ref = np.zeros((len(obj_size), 3), dtype=np.float64)
+    for p in range(len(obj_size)):
+        n = int(obj_size[p])
+        if n == 0:
+            continue
+        choose = _choice_cache.get(n)
+        if choose is None:
+            choose = _reference_points(n)
+            if len(_choice_cache) < 100000:
+                _choice_cache[n] = choose
+        ref[p] = np.average(xyz[idx_cat[off[p]:off[p + 1]][choose]], axis=0)
+    return ref
+
+
 def respect_pbc_noref(xyz, L_BOX):
     if L_BOX == 0.0:
         return xyz

@@ -11,6 +11,7 @@
 #include <numeric>
 #include <vector>
 
+#include "cpg_centers.cuh"
 #include "cpg_dens.cuh"
 #include "cpg_gather.cuh"
 #include "cpg_morph.cuh"
@@ -99,7 +100,8 @@ struct cpg_ctx {
     DevBuf<int32_t> part_flag;
     DevBuf<float> mass32;
     DevBuf<uint8_t> skip, bucket;
-    DevBuf<int32_t> tile_hist, dest, n_eff;
+    DevBuf<int32_t> tile_hist, dest, n_eff, cidxA, cidxB;
+    DevBuf<double> cref;
     bool sorted_valid = false;    // the SoA streams are in radial-bucket order and `dest` maps catalogue -> slot
     // what the gathered SoA currently holds (skip the gather when a call asks for the same thing again)
     uint64_t snapshot_version = 0, catalogue_version = 0;
@@ -493,7 +495,8 @@ CPG_API void cpg_destroy(cpg_ctx *c)
     for (auto *b : i32) b->release();
     c->off.release(); c->poff.release(); c->chunks.release(); c->kchunks.release();
     c->mass32.release(); c->skip.release(); c->tasks.release(); c->bucket.release();
-    c->tile_hist.release(); c->dest.release(); c->n_eff.release();
+    c->tile_hist.release(); c->dest.release(); c->n_eff.release(); c->cidxA.release(); c->cidxB.release();
+    c->cref.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -937,6 +940,46 @@ CPG_API int cpg_obj_masses(cpg_ctx *c, double *obj_mass)
     CPG_TRY(run_stats(c));
     CPG_CUDA(cudaMemcpyAsync(obj_mass, c->obj_mass.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     CPG_CUDA(cudaStreamSynchronize(c->stream));
+    return CPG_OK;
+}
+
+CPG_API int cpg_centers(cpg_ctx *c, int32_t mode, int32_t shape_path, double L_BOX, const double *ref_points,
+                        double *centers_out)
+{
+    CPG_TRY(use_device(c));
+    const int n = c->n_obj;
+    if ((n > 0 && !centers_out) || (mode != 0 && mode != 1) || (L_BOX != 0.0 && !ref_points)) {
+        set_error("cpg_centers: bad arguments (L_BOX != 0 needs the reference points of respectPBCNoRef)");
+        return CPG_ERR_ARGUMENT;
+    }
+    Timer T(c);
+    if (n == 0) return CPG_OK;
+    T.mark(0);
+    c->stage_used = 0;
+    CPG_TRY(c->centers.ensure((size_t)n * 3));
+    if (ref_points) {
+        CPG_TRY(c->cref.ensure((size_t)n * 3));
+        CPG_TRY(small_upload(c, c->cref.p, ref_points, sizeof(double) * 3 * n));
+    }
+    if (mode == 1) { CPG_TRY(c->cidxA.ensure(c->n_idx)); CPG_TRY(c->cidxB.ensure(c->n_idx)); }
+    T.mark(1);
+    T.mark(2);
+    CenterParams P;
+    P.G = gather_view(c, 0.0f);
+    P.size = c->size.p; P.ref = ref_points ? c->cref.p : nullptr; P.L_BOX = L_BOX;
+    P.mode = mode; P.shape_path = shape_path;
+    P.idxA = c->cidxA.p; P.idxB = c->cidxB.p; P.centers = c->centers.p;
+    centers_kernel<<<n, 256, 0, c->stream>>>(P);
+    c->timing.kernel_launches++; c->timing.hot_kernel_launches++;
+    CPG_CUDA(cudaGetLastError());
+    T.mark(3);
+    CPG_CUDA(cudaMemcpyAsync(centers_out, c->centers.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    T.mark(4);
+    CPG_CUDA(cudaStreamSynchronize(c->stream));
+    c->have.valid = false;   // c->centers was overwritten: the resident gather no longer matches it
+    c->timing.h2d_ms = Timer::ms(c->ev[0], c->ev[1]);
+    c->timing.kernel_ms = Timer::ms(c->ev[2], c->ev[3]);
+    c->timing.d2h_ms = Timer::ms(c->ev[3], c->ev[4]);
     return CPG_OK;
 }
 

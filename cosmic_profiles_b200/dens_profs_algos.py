@@ -25,12 +25,23 @@ def _context(xyz, masses, idx_cat, obj_size):
     return ctx
 
 
+def _centres(ctx, xyz, masses, idx_cat, obj_size, L_BOX, CENTER, centers):
+    """Density paths: calcMode starts from rad = 1000 (dens_profs_algos.pyx:42)."""
+    if centers is not None:
+        return _lib.f64(centers)
+    if _session.gpu_centers:
+        ref = _centers.reference_points(xyz, idx_cat, obj_size) if L_BOX != 0.0 else None
+        return ctx.centers(1 if CENTER == 'mode' else 0, False, L_BOX, ref)
+    return _centers.compute_centers(xyz, masses, idx_cat, obj_size, L_BOX, CENTER, False)
+
+
 def calcMassesCenters(xyz, masses, idx_cat, obj_size, L_BOX, CENTER):
     xyz, masses, idx_cat, obj_size = _prep(xyz, masses, idx_cat, obj_size)
-    cen = _centers.compute_centers(xyz, masses, idx_cat, obj_size, L_BOX, CENTER, shape_path=False)
     if len(obj_size) == 0:
-        return _centers.recentre(cen, L_BOX), np.zeros(0)
-    m = _context(xyz, masses, idx_cat, obj_size).obj_masses()
+        return np.zeros((0, 3)), np.zeros(0)
+    ctx = _context(xyz, masses, idx_cat, obj_size)
+    cen = _centres(ctx, xyz, masses, idx_cat, obj_size, L_BOX, CENTER, None)
+    m = ctx.obj_masses()
     return _centers.recentre(cen, L_BOX), m
 
 
@@ -50,9 +61,8 @@ def calcDensProfsSphDirectBinning(xyz, masses, r200s, r_over_r200, idx_cat, obj_
     R = len(r_over_r200)
     if len(obj_size) == 0:
         return np.zeros((0, R), dtype=np.float64)
-    cen = _centers.compute_centers(xyz, masses, idx_cat, obj_size, L_BOX, CENTER, False) if centers is None \
-        else _lib.f64(centers)
     ctx = _context(xyz, masses, idx_cat, obj_size)
+    cen = _centres(ctx, xyz, masses, idx_cat, obj_size, L_BOX, CENTER, centers)
     dens, cnt = ctx.dens_sph(cen, r200s, sph_bin_edges(r_over_r200), L_BOX)
     last_info.clear()
     last_info.update(counts=cnt, timing=[ctx.timing()])
@@ -91,9 +101,8 @@ def calcDensProfsEllDirectBinning(xyz, masses, r200s, r_over_r200, a, b, c, majo
     major, inter, minor = (_lib.f64(np.asarray(v)) for v in (major, inter, minor))
     assert a.shape[0] == b.shape[0] and b.shape[0] == c.shape[0]
     ai, bi, ci, mj, it, mn = interpolate_shapes(r200s, r_over_r200, a, b, c, major, inter, minor)
-    cen = _centers.compute_centers(xyz, masses, idx_cat, obj_size, L_BOX, CENTER, False) if centers is None \
-        else _lib.f64(centers)
     ctx = _context(xyz, masses, idx_cat, obj_size)
+    cen = _centres(ctx, xyz, masses, idx_cat, obj_size, L_BOX, CENTER, centers)
     dens, cnt = ctx.dens_ell(cen, ai, bi, ci, mj, it, mn, L_BOX)
     last_info.clear()
     last_info.update(counts=cnt, timing=[ctx.timing()])
@@ -105,9 +114,8 @@ def calcDensProfsKernelBased(xyz, masses, r200s, r_over_r200, idx_cat, obj_size,
     R = len(r_over_r200)
     if len(obj_size) == 0:
         return np.zeros((0, R), dtype=np.float64)
-    cen = _centers.compute_centers(xyz, masses, idx_cat, obj_size, L_BOX, CENTER, False) if centers is None \
-        else _lib.f64(centers)
     ctx = _context(xyz, masses, idx_cat, obj_size)
+    cen = _centres(ctx, xyz, masses, idx_cat, obj_size, L_BOX, CENTER, centers)
     dens = ctx.dens_kernel(cen, r200s, r_over_r200, L_BOX)
     last_info.clear()
     last_info.update(timing=[ctx.timing()])

@@ -22,14 +22,18 @@ def _nan0(a):
 
 
 def _run_one(device, xyz, vxyz, masses, idx_cat, obj_size, cen, r200, rr, local, SAFE, L_BOX, IT_TOL, IT_WALL,
-             IT_MIN, reduced, shell_based):
+             IT_MIN, reduced, shell_based, CENTER="com"):
+    """Returns (out, nit, npt, m, vc, centres, timing)."""
     ctx = _session.get_context(device)
     ctx.set_particles(xyz, vxyz, masses)
     ctx.set_catalogue(idx_cat, obj_size)
+    if cen is None:   # centres on the device (shape path: calcMode starts from the bounding-box extent)
+        ref = _centers.reference_points(xyz, idx_cat, obj_size) if L_BOX != 0.0 else None
+        cen = ctx.centers(1 if CENTER == 'mode' else 0, True, L_BOX, ref)
     # out/nit/npt are views into the context's page-locked scratch, valid until its next shape() call;
     # every caller below copies out of them before touching the context again
     return ctx.shape(cen, r200, rr, local, SAFE, L_BOX, IT_TOL, IT_WALL, IT_MIN, reduced, shell_based,
-                     vxyz is not None) + (ctx.timing(),)
+                     vxyz is not None) + (cen, ctx.timing())
 
 
 def _morph(xyz, vxyz, masses, r200, idx_cat, obj_size, L_BOX, r_over_r200, IT_TOL, IT_WALL, IT_MIN, CENTER, SAFE,
@@ -43,14 +47,16 @@ def _morph(xyz, vxyz, masses, r200, idx_cat, obj_size, L_BOX, r_over_r200, IT_TO
     rr = _lib.f64(np.asarray(r_over_r200)) if local else None
     n = int(obj_size.shape[0])
     R = int(rr.shape[0]) if local else 1
-    if centers is None:
-        cen = _centers.compute_centers(xyz, masses, idx_cat, obj_size, L_BOX, CENTER, shape_path=True)
-    else:
+    if centers is not None:
         cen = _lib.f64(centers)
+    elif _session.gpu_centers:
+        cen = None          # computed on the device by every shard (cpg_centers)
+    else:
+        cen = _centers.compute_centers(xyz, masses, idx_cat, obj_size, L_BOX, CENTER, shape_path=True)
     devs = _session.devices or [0]
-    args = (rr, local, SAFE, L_BOX, IT_TOL, IT_WALL, IT_MIN, reduced, shell_based)
+    args = (rr, local, SAFE, L_BOX, IT_TOL, IT_WALL, IT_MIN, reduced, shell_based, CENTER)
     if len(devs) == 1 or n < 2 * len(devs):
-        out, nit, npt, m, vc, tim = _run_one(devs[0], xyz, vxyz, masses, idx_cat, obj_size, cen, r200, *args)
+        out, nit, npt, m, vc, cen, tim = _run_one(devs[0], xyz, vxyz, masses, idx_cat, obj_size, cen, r200, *args)
         nit, npt = nit.copy(), npt.copy()
         timings = [tim]
     else:
@@ -61,6 +67,7 @@ def _morph(xyz, vxyz, masses, r200, idx_cat, obj_size, L_BOX, r_over_r200, IT_TO
         npt = np.full((n, R), -1, dtype=np.int32)
         m = np.zeros(n)
         vc = np.zeros((n, 3))
+        cen_all = np.zeros((n, 3))
         timings = [None] * len(devs)
         errors = []
 
@@ -73,9 +80,9 @@ def _morph(xyz, vxyz, masses, r200, idx_cat, obj_size, L_BOX, r_over_r200, IT_TO
                 # ship only this shard's particles; the shard catalogue becomes 0..n_sub-1
                 local_idx = np.arange(len(sub_idx), dtype=np.int32)
                 res = _run_one(devs[k], xyz[sub_idx], None if vxyz is None else vxyz[sub_idx], masses[sub_idx],
-                               local_idx, sub_size, cen[objs], r200[objs], *args)
-                out[objs], nit[objs], npt[objs], m[objs], vc[objs] = res[:5]
-                timings[k] = res[5]
+                               local_idx, sub_size, None if cen is None else cen[objs], r200[objs], *args)
+                out[objs], nit[objs], npt[objs], m[objs], vc[objs], cen_all[objs] = res[:6]
+                timings[k] = res[6]
             except Exception as e:   # surfaced below, in the caller's thread
                 errors.append(e)
 
@@ -86,6 +93,7 @@ def _morph(xyz, vxyz, masses, r200, idx_cat, obj_size, L_BOX, r_over_r200, IT_TO
             t.join()
         if errors:
             raise errors[0]
+        cen = cen_all
     d = _nan0(out[:, :, 0])
     q = _nan0(out[:, :, 1])
     s = _nan0(out[:, :, 2])

@@ -123,6 +123,16 @@ CPG_API int cpg_dens_kernel(cpg_ctx *ctx, const double *centers, const double *r
  * (dens_profs_algos.pyx:45-47). */
 CPG_API int cpg_obj_masses(cpg_ctx *ctx, double *obj_mass);
 
+/* Object centres.  Replaces the serial Python centre loops of the drivers
+ * (shape_profs_algos.pyx:586-591, dens_profs_algos.pyx:39-44, :96-101) and python_routines.calcCoM (:530-547),
+ * calcMode (:287-306), respectPBCNoRef (:499-528).  mode 0 = 'com', 1 = 'mode'; shape_path selects the initial
+ * radius of calcMode (1: bounding-box extent, :589; 0: 1000, dens_profs_algos.pyx:42).  ref_points (n_obj,3):
+ * the reference points respectPBCNoRef / calcCoM average from 50 seeded random members -- required when
+ * L_BOX != 0 (they decide which particles are translated), optional otherwise.  centers_out (n_obj,3) is the
+ * centre BEFORE recentreObject; an empty object yields NaN like the reference's division by zero. */
+CPG_API int cpg_centers(cpg_ctx *ctx, int32_t mode, int32_t shape_path, double L_BOX, const double *ref_points,
+                        double *centers_out);
+
 /* Page-locked host buffers for results (device->host copies into pageable memory run at a fraction of the
  * PCIe rate).  No counterpart in the reference, whose drivers np.zeros() their outputs
  * (shape_profs_algos.pyx:560-572). */

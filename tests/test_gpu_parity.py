@@ -226,3 +226,29 @@ def test_edge_cases(gpu):
     with pytest.raises(CosmicGpuError):
         S.calcMorphLocal(X, M, R2, bad, Z, 0.0, rr, 1e-2, 100, 10, "com", False, False,
                          centers=np.zeros((4, 3)))
+
+
+@pytest.mark.parametrize("kind", ["main", "pbc"])
+def test_device_centres(gpu, kind):
+    """cpg_centers ('com' and shrinking-sphere 'mode', shape-path and density-path start radii, periodic box)
+    against the reference's numpy centre finding (golden calcMassesCenters + the oracle's restatement)."""
+    from cosmic_profiles_b200 import centers as C
+    from cosmic_profiles_b200 import session as sess_mod
+    from oracle import cp_oracle as O
+    S, D, sess = gpu
+    z, meta, cat = P.load_golden(kind)
+    X, M, R2, I, Z = _args(cat)
+    L = meta["L_BOX"]
+    ctx = sess_mod.get_context(0)
+    ctx.set_particles(X, None, M)
+    ctx.set_catalogue(I, Z)
+    ref = C.reference_points(X, I, Z) if L != 0.0 else None
+    for center in ("com", "mode"):
+        for shape_path in (True, False):
+            want = O.centres(X, M, I, Z, L, center, shape_path)
+            got = ctx.centers(1 if center == "mode" else 0, shape_path, L, ref)
+            assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), (center, shape_path)
+        # the public density-path driver (recentred centres + masses) against the compiled reference
+        cen, m = D.calcMassesCenters(X, M, I, Z, L, center)
+        P.assert_close(cen, z["masses_centers_%s/centers" % center], "centers " + center, rtol=1e-12)
+        P.assert_close(m, z["masses_centers_%s/m" % center], "m", rtol=1e-12)

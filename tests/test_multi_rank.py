@@ -51,13 +51,15 @@ def test_shim_sharding_matches_unsharded(monkeypatch):
     calls = []
 
     def fake_run_one(device, xyz, vxyz, masses, idx_cat, obj_size, cen, r200, rr, local, SAFE, L_BOX, IT_TOL, IT_WALL,
-                     IT_MIN, reduced, shell_based):
+                     IT_MIN, reduced, shell_based, CENTER="com"):
         calls.append((device, len(obj_size)))
+        if cen is None:   # what cpg_centers would do on the shard
+            cen = O.centres(xyz, masses, idx_cat, obj_size, L_BOX, CENTER, True)
         _, (nit, npt, vc, out) = O.morph(xyz, vxyz, masses, r200, idx_cat, obj_size, L_BOX, rr, IT_TOL, IT_WALL, IT_MIN,
                                          "com", reduced, shell_based, local, SAFE=SAFE, centers=cen)
         m = np.array([masses[idx_cat[a:b]].sum() for a, b in zip(np.cumsum(obj_size) - obj_size, np.cumsum(obj_size))])
         R = out.shape[1]
-        return out, nit.reshape(len(obj_size), R), npt.reshape(len(obj_size), R), m, vc, {"kernel_ms": 0.0}
+        return out, nit.reshape(len(obj_size), R), npt.reshape(len(obj_size), R), m, vc, cen, {"kernel_ms": 0.0}
 
     monkeypatch.setattr(S, "_run_one", fake_run_one)
     cat = make_catalogue([900, 300, 1500, 700, 1100, 450, 2000], seed=4, with_velocities=True, shuffle_particles=True)
