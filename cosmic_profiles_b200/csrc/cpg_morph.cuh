@@ -68,7 +68,7 @@ __device__ __forceinline__ void accumulate(double (&acc)[7], int &cnt, bool sel,
             acc[4] = fma(w, p.yz, acc[4]);
             acc[5] = fma(w, p.zz, acc[5]);
         }
-        acc[6] += mm;
+        (void)mm;
         cnt += sel ? 1 : 0;
     }
     return;
@@ -86,8 +86,24 @@ __device__ __forceinline__ void accumulate(double (&acc)[7], int &cnt, bool sel,
             acc[4] = fma(w, p.yz, acc[4]);
             acc[5] = fma(w, p.zz, acc[5]);
         }
-        acc[6] += p.m;
-        cnt += 1;
+        cnt += 1;   // (no mass sum: the reference's 1/mass_tot only rescales the tensor, helper_class.pyx:52)
+    }
+}
+
+// A particle that is certainly inside the ellipsoid (see run_pass: inner radial prefix): no test at all.
+template <bool VDISP>
+__device__ __forceinline__ void accumulate_inside(double (&acc)[7], const Particle &p)
+{
+    if (VDISP) {
+#pragma unroll
+        for (int c = 0; c < 6; c++) acc[c] = fma(p.m, p.t[c], acc[c]);
+    } else {
+        acc[0] = fma(p.m, p.xx, acc[0]);
+        acc[1] = fma(p.m, p.xy, acc[1]);
+        acc[2] = fma(p.m, p.xz, acc[2]);
+        acc[3] = fma(p.m, p.yy, acc[3]);
+        acc[4] = fma(p.m, p.yz, acc[4]);
+        acc[5] = fma(p.m, p.zz, acc[5]);
     }
 }
 
@@ -99,10 +115,18 @@ __device__ __forceinline__ void accumulate(double (&acc)[7], int &cnt, bool sel,
 // (shape_profs_algos.pyx:247-260 / :122-143) fused with the next tensor accumulation.
 template <int S, bool SHELL, bool REDUCED, bool VDISP, int NP>
 __device__ __forceinline__ void passk_particles(const Particle (&p)[NP], const double *frames, unsigned smask,
-                                                double (&acc)[S][7], int (&cnt)[S])
+                                                unsigned inmask, double (&acc)[S][7], int (&cnt)[S])
 {
 #pragma unroll
     for (int s = 0; s < S; s++) {
+        // inmask: this whole tile lies in the shell's inner prefix |x-c| < s*d (1-1e-9): with q, s <= 1 the
+        // ellipsoidal radius obeys r_ell^2 <= |x-c|^2 / s^2 < d^2, every particle is a member, nothing to test
+        if (!SHELL && !REDUCED && (inmask & (1u << s))) {
+#pragma unroll
+            for (int j = 0; j < NP; j++) accumulate_inside<VDISP>(acc[s], p[j]);
+            cnt[s] += NP;
+            continue;
+        }
         // smask: shells that are still iterating AND whose radial prefix reaches this tile (warp-uniform)
         if (smask & (1u << s)) {
             const double2 *F2 = reinterpret_cast<const double2 *>(frames + s * F_SLOTS);
@@ -143,6 +167,25 @@ __device__ __forceinline__ void quad_form(double *A, const double (&v)[9], doubl
     A[5] = 2.0 * (w2 * e2[1] * e2[2] + w1 * e1[1] * e1[2] + w0 * e0[1] * e0[2]);
 }
 
+// Inner radial prefix of a shell: the particles of the buckets j with rr[j] <= s * rr[k] * (1 - 1e-9) lie at
+// |x-c| < s*d_k and are members of shell k's ellipsoid whatever its orientation.  rr: the R shell radii (shared
+// memory copy), neff: this object's prefix lengths (shared memory copy); both null when there is no ordering.
+struct InnerPrefix {
+    const double *rr;
+    const int *neff;
+    __device__ __forceinline__ int pairs_inside(int k, double s) const
+    {
+        if (!rr) return 0;
+        const double lim = s * rr[k] * (1.0 - 1e-9);
+        int lo = -1, hi = k;   // rr[lo] <= lim < rr[hi]   (rr ascending, rr[k] > lim)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (rr[mid] <= lim) lo = mid; else hi = mid;
+        }
+        return lo >= 0 ? neff[lo] >> 1 : 0;   // whole pairs only
+    }
+};
+
 // Per halo-shell iteration state, replicated in every lane that serves the shell.
 struct KatzState {
     double q, s;        // current axis ratios
@@ -158,7 +201,7 @@ struct KatzState {
 template <bool SHELL>
 __device__ __forceinline__ void katz_step(KatzState &st, const double (&tot)[7], int pts, const MorphParams &P,
                                           const double (&vprev)[9], double *frame, bool frame_writer, size_t out_idx,
-                                          bool out_writer)
+                                          bool out_writer, const InnerPrefix &ip, int k, int *nin_slot)
 {
     if (!st.active)
         return;
@@ -170,7 +213,7 @@ __device__ __forceinline__ void katz_step(KatzState &st, const double (&tot)[7],
         st.active = false;
         return;
     }
-    const double im = 1.0 / tot[6];
+    const double im = 1.0 / (tot[0] + tot[3] + tot[5]);   // any positive scale does: only ratios are consumed
     double w[3], v[9];
 #pragma unroll
     for (int r = 0; r < 9; r++) v[r] = vprev[r];   // warm start: basis of the previous iteration
@@ -221,6 +264,7 @@ __device__ __forceinline__ void katz_step(KatzState &st, const double (&tot)[7],
             }
             frame[F_THR] = first ? -1.0 : 1.0;
         }
+        *nin_slot = ip.pairs_inside(k, st.s);
     }
     st.iteration += 1;
 }
@@ -260,6 +304,7 @@ __device__ __forceinline__ void make_tensor_products(double u, double v, double 
 // is loaded once and stays resident in shared memory for all Katz iterations of the task.
 // ------------------------------------------------------------------------------------------------
 constexpr int TILE_PAIRS = 64;
+constexpr int MAX_SORT_R = 256;   // == SORT_MAX_B of cpg_gather.cuh: radial ordering exists for R <= 255
 constexpr int RING_MAX_STAGES = 4;
 
 template <bool VDISP>
@@ -391,8 +436,12 @@ __device__ __forceinline__ void ring_fill_tail(const WarpRing &r, uint32_t seq, 
 template <int S, bool SHELL, bool REDUCED, bool VDISP>
 __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npairs, int tile0, int tstride, int lane,
                                          WarpRing &ring, bool resident, int npairs_task, const double *frames,
-                                         const int (&npr)[S], unsigned amask, double (&acc)[S][7], int (&cnt)[S])
+                                         const int (&npr)[S], const int *nin, unsigned amask, double (&acc)[S][7],
+                                         int (&cnt)[S])
 {
+    int ninr[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) ninr[s] = nin[s];
 #pragma unroll
     for (int s = 0; s < S; s++) {
         cnt[s] = 0;
@@ -428,19 +477,26 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
         for (int s = 0; s < S; s++)
             if (t * TILE_PAIRS < npr[s]) smask |= 1u << s;
         smask &= amask;
+        unsigned inmask = 0;
+        if (!SHELL && !REDUCED) {
+#pragma unroll
+            for (int s = 0; s < S; s++)
+                if ((t + 1) * TILE_PAIRS <= ninr[s]) inmask |= 1u << s;
+            inmask &= amask;
+        }
         if (VDISP) {
             // two particles at a time: the dispersion variant carries 13 doubles per particle
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 Particle p[2];
                 ring_read_pair<VDISP>(ring, seq, lane + 32 * h, p[0], p[1]);
-                passk_particles<S, SHELL, REDUCED, VDISP, 2>(p, frames, smask, acc, cnt);
+                passk_particles<S, SHELL, REDUCED, VDISP, 2>(p, frames, smask, inmask, acc, cnt);
             }
         } else {
             Particle p[4];
             ring_read_pair<VDISP>(ring, seq, lane, p[0], p[1]);
             ring_read_pair<VDISP>(ring, seq, lane + 32, p[2], p[3]);
-            passk_particles<S, SHELL, REDUCED, VDISP, 4>(p, frames, smask, acc, cnt);
+            passk_particles<S, SHELL, REDUCED, VDISP, 4>(p, frames, smask, inmask, acc, cnt);
         }
         if (!resident && j + RING_STAGES < nmine) {
             __syncwarp();   // every lane has taken its data out of this slot
@@ -502,9 +558,11 @@ struct LaneMap {
 };
 
 template <int S>
-__device__ __forceinline__ void init_frames(double *frames, int *np, const LaneMap<S> &L, const KatzState &st, int ne)
+__device__ __forceinline__ void init_frames(double *frames, int *np, int *nin, const LaneMap<S> &L, const KatzState &st,
+                                            int ne, const InnerPrefix &ip, int k)
 {
     if (L.writer) {
+        nin[L.ls] = st.active ? ip.pairs_inside(k, 1.0) : 0;   // pass 0: the sphere of radius d
         double *F = frames + L.ls * F_SLOTS;
         F[F_D2] = __dmul_rn(st.d, st.d);
         const double in = __dsub_rn(st.d, st.delta);
@@ -534,14 +592,24 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
     extern __shared__ __align__(128) unsigned char s_ring_w[];   // WARP_KERNEL_WARPS rings
     __shared__ __align__(16) double s_frames[WARP_KERNEL_WARPS][S * F_SLOTS];
     __shared__ __align__(8) uint64_t s_bar[WARP_KERNEL_WARPS][RING_MAX_STAGES];
-    __shared__ int s_np[WARP_KERNEL_WARPS][S];
+    __shared__ int s_np[WARP_KERNEL_WARPS][S], s_nin[WARP_KERNEL_WARPS][S];
+    __shared__ double s_rr[MAX_SORT_R];                       // shell radii (inner-prefix lookup)
+    __shared__ int s_neff[WARP_KERNEL_WARPS][MAX_SORT_R];      // prefix lengths of the warp's current object
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *frames = s_frames[warp];
-    int *np = s_np[warp];
+    int *np = s_np[warp], *nin = s_nin[warp];
     const LaneMap<S> L(lane);
     const int ls = L.ls;
     WarpRing ring;
     ring_init(ring, s_ring_w + warp * RingCfg<VDISP>::WARP_BYTES, s_bar[warp], lane);
+    const bool use_inner = !SHELL && !REDUCED && P.n_eff != nullptr;
+    if (use_inner) {
+        for (int j = threadIdx.x; j < P.R; j += blockDim.x) s_rr[j] = P.rr[j];
+        __syncthreads();
+    }
+    InnerPrefix ip;
+    ip.rr = use_inner ? s_rr : nullptr;
+    ip.neff = s_neff[warp];
 
     for (;;) {
         int t = 0;
@@ -564,7 +632,11 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
         shell_geometry(P, halo, k, st.d, st.delta);
         const size_t out_idx = (size_t)halo * P.R + k;
         __syncwarp();
-        init_frames<S>(frames, np, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N);
+        if (use_inner) {   // the object's prefix lengths up to the task's last shell
+            for (int j = lane; j < tk.shell0 + tk.nshell; j += 32) s_neff[warp][j] = P.n_eff[(size_t)halo * P.R + j];
+            __syncwarp();
+        }
+        init_frames<S>(frames, np, nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
         __syncwarp();
         unsigned amask = LaneMap<S>::active_mask(st.active && L.writer);
         int npr[S];
@@ -577,7 +649,7 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
         double acc[S][7];
         int cnt[S];
         run_pass<S, SHELL, REDUCED, VDISP>(P.soa, base, npairs_task, 0, 1, lane, ring, resident, npairs_task, frames,
-                                                 npr, amask, acc, cnt);
+                                           npr, nin, amask, acc, cnt);
         while (true) {
             double val[8 * S];
             pack_values<S>(acc, cnt, val);
@@ -589,13 +661,13 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
 #pragma unroll
             for (int r = 0; r < 9; r++) vprev[r] = frames[ls * F_SLOTS + F_V + r];
             __syncwarp();
-            katz_step<SHELL>(st, tot, pts, P, vprev, frames + ls * F_SLOTS, L.writer, out_idx, L.writer);
+            katz_step<SHELL>(st, tot, pts, P, vprev, frames + ls * F_SLOTS, L.writer, out_idx, L.writer, ip, k, nin + ls);
             __syncwarp();
             amask = LaneMap<S>::active_mask(st.active && L.writer);
             if (amask == 0)
                 break;
             run_pass<S, SHELL, REDUCED, VDISP>(P.soa, base, active_npairs<S>(npr, amask), 0, 1, lane, ring, resident,
-                                                      npairs_task, frames, npr, amask, acc, cnt);
+                                               npairs_task, frames, npr, nin, amask, acc, cnt);
         }
     }
 }
@@ -619,13 +691,15 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     __shared__ __align__(8) uint64_t s_bar[NW][RING_MAX_STAGES];
     __shared__ double s_part[2][NW][NV];                        // per-warp partial sums
     __shared__ double s_cta[2][NV];                             // per-CTA partial sums, read by the cluster
-    __shared__ int s_np[NW][S];
+    __shared__ int s_np[NW][S], s_nin[NW][S];
+    __shared__ double s_rr[MAX_SORT_R];
+    __shared__ int s_neff[MAX_SORT_R];
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *frames = s_frames[warp];
-    int *np = s_np[warp];
+    int *np = s_np[warp], *nin = s_nin[warp];
     const LaneMap<S> L(lane);
     const int ls = L.ls;
 
@@ -646,7 +720,18 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     const int k = tk.shell0 + (st.active ? ls : 0);
     shell_geometry(P, halo, k, st.d, st.delta);
     const size_t out_idx = (size_t)halo * P.R + k;
-    init_frames<S>(frames, np, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N);
+    const bool use_inner = !SHELL && !REDUCED && P.n_eff != nullptr;
+    if (use_inner) {
+        for (int j = threadIdx.x; j < P.R; j += blockDim.x) {
+            s_rr[j] = P.rr[j];
+            s_neff[j] = P.n_eff[(size_t)halo * P.R + j];
+        }
+        __syncthreads();
+    }
+    InnerPrefix ip;
+    ip.rr = use_inner ? s_rr : nullptr;
+    ip.neff = s_neff;
+    init_frames<S>(frames, np, nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
     __syncwarp();
     unsigned amask = LaneMap<S>::active_mask(st.active && L.writer);
     const bool out_writer = (rank == 0 && warp == 0 && L.writer);
@@ -661,7 +746,7 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     int cnt[S];
     int buf = 0;
     run_pass<S, SHELL, REDUCED, VDISP>(P.soa, base, npairs_task, tile0, tstride, lane, ring, resident, npairs_task,
-                                             frames, npr, amask, acc, cnt);
+                                       frames, npr, nin, amask, acc, cnt);
     while (true) {
         {
             double val[NV];
@@ -696,14 +781,15 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
 #pragma unroll
         for (int r = 0; r < 9; r++) vprev[r] = frames[ls * F_SLOTS + F_V + r];
         __syncwarp();
-        katz_step<SHELL>(st, tot, (int)ptsd, P, vprev, frames + ls * F_SLOTS, L.writer, out_idx, out_writer);
+        katz_step<SHELL>(st, tot, (int)ptsd, P, vprev, frames + ls * F_SLOTS, L.writer, out_idx, out_writer, ip, k,
+                         nin + ls);
         __syncwarp();
         amask = LaneMap<S>::active_mask(st.active && L.writer);
         buf ^= 1;
         if (amask == 0)
             break;
         run_pass<S, SHELL, REDUCED, VDISP>(P.soa, base, active_npairs<S>(npr, amask), tile0, tstride, lane, ring,
-                                                  resident, npairs_task, frames, npr, amask, acc, cnt);
+                                           resident, npairs_task, frames, npr, nin, amask, acc, cnt);
     }
     if (C > 1)
         cluster.sync();   // nobody leaves while a peer may still read its shared memory
