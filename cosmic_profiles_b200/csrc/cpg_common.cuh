@@ -77,15 +77,46 @@ __device__ __forceinline__ int warp_sum_int(int v)
 // zheevr call (cython_helpers/helper_class.pyx:123-164).  Eigenvalues ascending in w[0..2]; v[3*k+r] is
 // component r of the eigenvector of w[k] (unit length to ~1e-16, sign arbitrary like LAPACK's).
 // ---------------------------------------------------------------------------------------------------
+// Reciprocal and reciprocal square root to ~1 ulp from the SFU seed (MUFU.RCP64H / MUFU.RSQ64H, 2^-20ish)
+// and two Newton steps -- a handful of DFMAs instead of the IEEE-exact division / sqrt sequences with their
+// out-of-line special-case paths (the eigen-solve is instruction- and I-cache-bound).  Arguments are finite,
+// non-zero and far from the under/overflow thresholds (the tensor is trace-normalised first).
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    return fma(y, e, y);
+}
+
 __device__ __forceinline__ void jacobi_rotate(double &app, double &aqq, double &apq, double &arp, double &arq,
                                               double *vp, double *vq)
 {
     if (apq != 0.0) {
-        // tan of the rotation angle, smaller root: t = apq / (tau + sign(tau) * hypot(tau, apq)), tau = (aqq-app)/2
+        // tan of the rotation angle, smaller root: t = apq / (tau + sign(tau) * hypot(tau, apq)), tau = (aqq-app)/2.
+        // (c, s) = (1, t) / sqrt(1 + t^2) is a rotation to rounding whatever the accuracy of t.
         const double tau = 0.5 * (aqq - app);
-        const double r = sqrt(fma(tau, tau, apq * apq));
-        const double t = apq / (tau + copysign(r, tau));
-        const double c = rsqrt(fma(t, t, 1.0)), s = t * c;
+        const double h = fma(tau, tau, apq * apq);
+        if (!(h > 1e-290)) {   // both the gap and the coupling vanish below 1e-145 of the trace: nothing to rotate
+            apq = 0.0;
+            return;
+        }
+        const double r = h * fast_rsqrt(h);
+        const double t = apq * fast_rcp(tau + copysign(r, tau));
+        const double c = fast_rsqrt(fma(t, t, 1.0)), s = t * c;
         app = fma(-t, apq, app);
         aqq = fma(t, apq, aqq);
         apq = 0.0;
@@ -146,11 +177,11 @@ __device__ __forceinline__ void eigh3(double a00, double a01, double a02, double
     // re-orthonormalise cheaply (one Gram-Schmidt pass keeps the warm-started basis orthonormal to rounding
     // over many Katz iterations): v2 unit, v1 orthogonal to v2, v0 = v1 x v2
     {
-        double n = rsqrt(fma(v2[2], v2[2], fma(v2[1], v2[1], v2[0] * v2[0])));
+        double n = fast_rsqrt(fma(v2[2], v2[2], fma(v2[1], v2[1], v2[0] * v2[0])));
         v2[0] *= n; v2[1] *= n; v2[2] *= n;
         const double d = fma(v1[2], v2[2], fma(v1[1], v2[1], v1[0] * v2[0]));
         v1[0] = fma(-d, v2[0], v1[0]); v1[1] = fma(-d, v2[1], v1[1]); v1[2] = fma(-d, v2[2], v1[2]);
-        n = rsqrt(fma(v1[2], v1[2], fma(v1[1], v1[1], v1[0] * v1[0])));
+        n = fast_rsqrt(fma(v1[2], v1[2], fma(v1[1], v1[1], v1[0] * v1[0])));
         v1[0] *= n; v1[1] *= n; v1[2] *= n;
         const double c0 = v1[1] * v2[2] - v1[2] * v2[1], c1 = v1[2] * v2[0] - v1[0] * v2[2],
                      c2 = v1[0] * v2[1] - v1[1] * v2[0];

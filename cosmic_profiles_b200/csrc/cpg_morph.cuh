@@ -213,7 +213,7 @@ __device__ __forceinline__ void katz_step(KatzState &st, const double (&tot)[7],
         st.active = false;
         return;
     }
-    const double im = 1.0 / (tot[0] + tot[3] + tot[5]);   // any positive scale does: only ratios are consumed
+    const double im = fast_rcp(tot[0] + tot[3] + tot[5]);   // any positive scale does: only ratios are consumed
     double w[3], v[9];
 #pragma unroll
     for (int r = 0; r < 9; r++) v[r] = vprev[r];   // warm start: basis of the previous iteration
