@@ -131,6 +131,7 @@ struct cpg_ctx {
     int64_t opt_large_halo_min = 0;
     int opt_cluster_size = 0;
     int opt_radial_order = 1;
+    int opt_groups = 0;   // 0 auto, 1 one group of S shells per warp task, 2 two groups
     cpg_timing timing = {};
 };
 
@@ -350,7 +351,7 @@ int run_vcenters(cpg_ctx *c, float L_BOX)
     return CPG_OK;
 }
 
-template <int S, bool SHELL, bool REDUCED, bool VDISP>
+template <int S, int G, bool SHELL, bool REDUCED, bool VDISP>
 int launch_morph(cpg_ctx *c, MorphParams P, int n_warp_tasks, int n_cluster_tasks, int cluster_size)
 {
     // The few large objects (cluster kernel) and the many small ones (warp kernel) are independent: run the two
@@ -387,7 +388,7 @@ int launch_morph(cpg_ctx *c, MorphParams P, int n_warp_tasks, int n_cluster_task
         c->timing.hot_kernel_launches++;
     }
     if (n_warp_tasks > 0) {
-        auto kern = morph_warp_kernel<S, SHELL, REDUCED, VDISP>;
+        auto kern = morph_warp_kernel<S, G, SHELL, REDUCED, VDISP>;
         const int smem = WARP_KERNEL_WARPS * RingCfg<VDISP>::WARP_BYTES;
         CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int per_sm = 0;
@@ -408,11 +409,11 @@ int launch_morph(cpg_ctx *c, MorphParams P, int n_warp_tasks, int n_cluster_task
     return CPG_OK;
 }
 
-template <int S>
+template <int S, int G>
 int dispatch_morph(cpg_ctx *c, const MorphParams &P, bool shell, bool reduced, bool vdisp, int nw, int ncl, int cs)
 {
 #define CPG_CASE(SH, RE, VD) \
-    if (shell == SH && reduced == RE && vdisp == VD) return launch_morph<S, SH, RE, VD>(c, P, nw, ncl, cs);
+    if (shell == SH && reduced == RE && vdisp == VD) return launch_morph<S, G, SH, RE, VD>(c, P, nw, ncl, cs);
     CPG_CASE(false, false, false) CPG_CASE(false, true, false) CPG_CASE(true, false, false) CPG_CASE(true, true, false)
     CPG_CASE(false, false, true) CPG_CASE(false, true, true) CPG_CASE(true, false, true) CPG_CASE(true, true, true)
 #undef CPG_CASE
@@ -519,6 +520,12 @@ CPG_API int cpg_set_option(cpg_ctx *c, const char *name, int64_t value)
         c->opt_large_halo_min = value;
     } else if (!strcmp(name, "invalidate_gather")) {
         c->have.valid = false;   // one-shot: the next compute call redoes the catalogue gather
+    } else if (!strcmp(name, "shell_groups")) {
+        if (value < 0 || value > 2) {
+            set_error("shell_groups must be 0, 1 or 2");
+            return CPG_ERR_ARGUMENT;
+        }
+        c->opt_groups = (int)value;
     } else if (!strcmp(name, "radial_order")) {
         c->opt_radial_order = value != 0;
     } else if (!strcmp(name, "cluster_size")) {
@@ -682,8 +689,14 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     // few tasks: a warp per task would leave the GPU to a handful of long-running warps (non-converging shells
     // iterate up to IT_WALL times); give every task of a non-tiny object a CTA / cluster instead
     if (c->opt_large_halo_min == 0 && (n_units + S - 1) / S < 8 * (int64_t)warp_slots) large_min = 4096;
+    // the warp kernel passes over two groups of 4 shells per task when there are tasks to spare: the per-iteration
+    // reduction + eigen-solve + bookkeeping (40 % of its time at 4 shells per task) is then shared by 8 shells
+    // (measured on configs[1]: 41 ms against 29 ms with one group -- fewer, longer tasks, fewer of them resident in
+    // shared memory -- so two groups are only taken when asked for)
+    int G = 1;
+    if (S == 4 && c->opt_groups == 2 && R >= 8) G = 2;
     auto &TK = c->task_key;
-    if (!(TK.valid && TK.cat == c->catalogue_version && TK.S == S && TK.R == R && TK.large_min == large_min &&
+    if (!(TK.valid && TK.cat == c->catalogue_version && TK.S == S * 16 + G && TK.R == R && TK.large_min == large_min &&
           (c->opt_cluster_size == 0 || c->opt_cluster_size == TK.cluster_size))) {
         std::vector<Task> warp_tasks, cl_tasks;
         int64_t largest = 0;
@@ -691,9 +704,11 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
             const int h = c->order[oi];
             const int64_t N = c->h_size[h];
             largest = std::max(largest, N);
-            std::vector<Task> &dst = (N >= large_min) ? cl_tasks : warp_tasks;
-            for (int k0 = 0; k0 < R; k0 += S)
-                dst.push_back(Task{h, (int16_t)k0, (int16_t)std::min(S, R - k0)});
+            const bool big = N >= large_min;
+            std::vector<Task> &dst = big ? cl_tasks : warp_tasks;
+            const int step = big ? S : S * G;
+            for (int k0 = 0; k0 < R; k0 += step)
+                dst.push_back(Task{h, (int16_t)k0, (int16_t)std::min(step, R - k0)});
         }
         int cluster_size = c->opt_cluster_size;
         if (cluster_size == 0) {
@@ -710,7 +725,7 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
         CPG_TRY(c->tasks.ensure(warp_tasks.size()));
         CPG_TRY(small_upload(c, c->tasks.p, warp_tasks.data(), sizeof(Task) * warp_tasks.size()));
         c->timing.h2d_bytes += (int64_t)(sizeof(Task) * warp_tasks.size());
-        TK.valid = true; TK.cat = c->catalogue_version; TK.S = S; TK.R = R; TK.large_min = large_min;
+        TK.valid = true; TK.cat = c->catalogue_version; TK.S = S * 16 + G; TK.R = R; TK.large_min = large_min;
     }
     const int nw = TK.nw, ncl = TK.ncl, cluster_size = TK.cluster_size;
     CPG_TRY(c->out12.ensure(nR * 12)); CPG_TRY(c->n_iter.ensure(nR)); CPG_TRY(c->n_pts.ensure(nR));
@@ -739,9 +754,10 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     P.tol = IT_TOL; P.wall = IT_WALL; P.itmin = IT_MIN;
     P.out12 = c->out12.p; P.n_iter = c->n_iter.p; P.n_pts = c->n_pts.p;
     int rc;
-    if (S == 4) rc = dispatch_morph<4>(c, P, shell_based != 0, reduced != 0, use_vel != 0, nw, ncl, cluster_size);
-    else if (S == 2) rc = dispatch_morph<2>(c, P, shell_based != 0, reduced != 0, use_vel != 0, nw, ncl, cluster_size);
-    else rc = dispatch_morph<1>(c, P, shell_based != 0, reduced != 0, use_vel != 0, nw, ncl, cluster_size);
+    if (S == 4 && G == 2) rc = dispatch_morph<4, 2>(c, P, shell_based != 0, reduced != 0, use_vel != 0, nw, ncl, cluster_size);
+    else if (S == 4) rc = dispatch_morph<4, 1>(c, P, shell_based != 0, reduced != 0, use_vel != 0, nw, ncl, cluster_size);
+    else if (S == 2) rc = dispatch_morph<2, 1>(c, P, shell_based != 0, reduced != 0, use_vel != 0, nw, ncl, cluster_size);
+    else rc = dispatch_morph<1, 1>(c, P, shell_based != 0, reduced != 0, use_vel != 0, nw, ncl, cluster_size);
     CPG_TRY(rc);
     T.mark(3);
 

@@ -507,8 +507,11 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
     if (!reuse) {
         if (resident) {
             // the barriers of resident tiles beyond the first pass's active range have not been waited on yet
-            for (int j = nmine; j < issue_n; j++)
+            for (int j = nmine; j < issue_n; j++) {
                 mbar_wait(ring.bar_s + ((seq0 + j) % RING_STAGES) * 8u, ((seq0 + j) / RING_STAGES) & 1u);
+                const int loaded = min(TILE_PAIRS, npairs_load - (tile0 + j * tstride) * TILE_PAIRS);
+                if (loaded < TILE_PAIRS) ring_fill_tail<VDISP>(ring, seq0 + j, lane, loaded);
+            }
             ring.res_seq = seq0;
             ring.res_loaded = true;
             ring.seq = seq0 + issue_n;
@@ -541,24 +544,31 @@ constexpr int WARP_KERNEL_WARPS = 4;
 // Lane <-> shell mapping shared by both kernels.  The transposed warp reduction leaves the total of value
 // (l mod 8S) in lane l; value 8s+c is component c (Sxx,Sxy,Sxz,Syy,Syz,Szz,M,count) of shell s.  So the lanes
 // [8s, 8s+8) (and their images modulo 8S) serve shell s, and lane 8s is the one that writes its frame.
-template <int S>
+template <int S, int G = 1>
 struct LaneMap {
+    // G == 1: S shells per task, the transposed reduction leaves value (l mod 8S) in lane l, lanes [8s,8s+8) serve
+    //         shell s.  G == 2 (S == 4): two groups of 4 shells are passed over one after the other, their sums
+    //         sit in two registers, and lanes [4s,4s+4) serve shell s of the 8.
+    static_assert(G == 1 || (G == 2 && S == 4), "two groups only for S == 4");
     static constexpr int NV = 8 * S;
+    static constexpr int NS = S * G;
     int ls;        // shell served by this lane
     bool writer;   // this lane publishes frames / results of shell ls
-    __device__ __forceinline__ explicit LaneMap(int lane) : ls((lane & (NV - 1)) >> 3), writer(lane < NV && (lane & 7) == 0) {}
+    __device__ __forceinline__ explicit LaneMap(int lane)
+        : ls(G == 1 ? ((lane & (NV - 1)) >> 3) : (lane >> 2)),
+          writer(G == 1 ? (lane < NV && (lane & 7) == 0) : ((lane & 3) == 0)) {}
     __device__ static __forceinline__ unsigned active_mask(bool active_writer)
     {
         const unsigned b = __ballot_sync(0xffffffffu, active_writer);
         unsigned m = 0;
 #pragma unroll
-        for (int s = 0; s < S; s++) m |= ((b >> (8 * s)) & 1u) << s;
+        for (int s = 0; s < NS; s++) m |= ((b >> ((G == 1 ? 8 : 4) * s)) & 1u) << s;
         return m;
     }
 };
 
-template <int S>
-__device__ __forceinline__ void init_frames(double *frames, int *np, int *nin, const LaneMap<S> &L, const KatzState &st,
+template <class LM>
+__device__ __forceinline__ void init_frames(double *frames, int *np, int *nin, const LM &L, const KatzState &st,
                                             int ne, const InnerPrefix &ip, int k)
 {
     if (L.writer) {
@@ -586,19 +596,21 @@ __device__ __forceinline__ void pack_values(const double (&acc)[S][7], const int
     }
 }
 
-template <int S, bool SHELL, bool REDUCED, bool VDISP>
+template <int S, int G, bool SHELL, bool REDUCED, bool VDISP>
 __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_warp_kernel(const MorphParams P)
 {
+    using LM = LaneMap<S, G>;
+    constexpr int NS = S * G;   // shells per task; they are passed over in G groups of S
     extern __shared__ __align__(128) unsigned char s_ring_w[];   // WARP_KERNEL_WARPS rings
-    __shared__ __align__(16) double s_frames[WARP_KERNEL_WARPS][S * F_SLOTS];
+    __shared__ __align__(16) double s_frames[WARP_KERNEL_WARPS][NS * F_SLOTS];
     __shared__ __align__(8) uint64_t s_bar[WARP_KERNEL_WARPS][RING_MAX_STAGES];
-    __shared__ int s_np[WARP_KERNEL_WARPS][S], s_nin[WARP_KERNEL_WARPS][S];
+    __shared__ int s_np[WARP_KERNEL_WARPS][NS], s_nin[WARP_KERNEL_WARPS][NS];
     __shared__ double s_rr[MAX_SORT_R];                       // shell radii (inner-prefix lookup)
     __shared__ int s_neff[WARP_KERNEL_WARPS][MAX_SORT_R];      // prefix lengths of the warp's current object
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *frames = s_frames[warp];
     int *np = s_np[warp], *nin = s_nin[warp];
-    const LaneMap<S> L(lane);
+    const LM L(lane);
     const int ls = L.ls;
     WarpRing ring;
     ring_init(ring, s_ring_w + warp * RingCfg<VDISP>::WARP_BYTES, s_bar[warp], lane);
@@ -636,38 +648,63 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
             for (int j = lane; j < tk.shell0 + tk.nshell; j += 32) s_neff[warp][j] = P.n_eff[(size_t)halo * P.R + j];
             __syncwarp();
         }
-        init_frames<S>(frames, np, nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
+        init_frames(frames, np, nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
         __syncwarp();
-        unsigned amask = LaneMap<S>::active_mask(st.active && L.writer);
-        int npr[S];
+        unsigned amask = LM::active_mask(st.active && L.writer);
+        int npr[G][S];
+        int npairs_task = 0;
 #pragma unroll
-        for (int s = 0; s < S; s++) npr[s] = np[s];
-        const int npairs_task = active_npairs<S>(npr, amask);
+        for (int g = 0; g < G; g++) {
+#pragma unroll
+            for (int s = 0; s < S; s++) npr[g][s] = np[g * S + s];
+            npairs_task = max(npairs_task, active_npairs<S>(npr[g], (amask >> (g * S)) & ((1u << S) - 1u)));
+        }
         const bool resident = (npairs_task + TILE_PAIRS - 1) / TILE_PAIRS <= RingCfg<VDISP>::STAGES;
         ring.res_loaded = false;
 
-        double acc[S][7];
-        int cnt[S];
-        run_pass<S, SHELL, REDUCED, VDISP>(P.soa, base, npairs_task, 0, 1, lane, ring, resident, npairs_task, frames,
-                                           npr, nin, amask, acc, cnt);
         while (true) {
-            double val[8 * S];
-            pack_values<S>(acc, cnt, val);
-            const double mine = warp_sum_transpose<8 * S>(val, lane);
-            double tot[7], vprev[9];
+            // one pass per group of S shells; every group leaves its 8S sums transposed in one register
+            double mine[G];
 #pragma unroll
-            for (int c = 0; c < 7; c++) tot[c] = __shfl_sync(0xffffffffu, mine, (lane & ~7) + c);
-            const int pts = (int)__shfl_sync(0xffffffffu, mine, (lane & ~7) + 7);
+            for (int g = 0; g < G; g++) {
+                const unsigned am = (amask >> (g * S)) & ((1u << S) - 1u);
+                mine[g] = 0.0;
+                if (am) {
+                    double acc[S][7];
+                    int cnt[S];
+                    run_pass<S, SHELL, REDUCED, VDISP>(P.soa, base, active_npairs<S>(npr[g], am), 0, 1, lane, ring, resident,
+                                                       npairs_task, frames + g * S * F_SLOTS, npr[g], nin + g * S, am, acc,
+                                                       cnt);
+                    double val[8 * S];
+                    pack_values<S>(acc, cnt, val);
+                    mine[g] = warp_sum_transpose<8 * S>(val, lane);
+                }
+            }
+            double tot[7], vprev[9];
+            int pts;
+            if (G == 1) {
+#pragma unroll
+                for (int c = 0; c < 7; c++) tot[c] = __shfl_sync(0xffffffffu, mine[0], (lane & ~7) + c);
+                pts = (int)__shfl_sync(0xffffffffu, mine[0], (lane & ~7) + 7);
+            } else {
+                const int src = (ls & (S - 1)) * 8;
+                const bool hi = ls >= S;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const double a = __shfl_sync(0xffffffffu, mine[0], src + c);
+                    const double b = __shfl_sync(0xffffffffu, mine[G - 1], src + c);
+                    const double v = hi ? b : a;
+                    if (c < 7) tot[c] = v; else pts = (int)v;
+                }
+            }
 #pragma unroll
             for (int r = 0; r < 9; r++) vprev[r] = frames[ls * F_SLOTS + F_V + r];
             __syncwarp();
             katz_step<SHELL>(st, tot, pts, P, vprev, frames + ls * F_SLOTS, L.writer, out_idx, L.writer, ip, k, nin + ls);
             __syncwarp();
-            amask = LaneMap<S>::active_mask(st.active && L.writer);
+            amask = LM::active_mask(st.active && L.writer);
             if (amask == 0)
                 break;
-            run_pass<S, SHELL, REDUCED, VDISP>(P.soa, base, active_npairs<S>(npr, amask), 0, 1, lane, ring, resident,
-                                               npairs_task, frames, npr, nin, amask, acc, cnt);
         }
     }
 }
@@ -731,7 +768,7 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     InnerPrefix ip;
     ip.rr = use_inner ? s_rr : nullptr;
     ip.neff = s_neff;
-    init_frames<S>(frames, np, nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
+    init_frames(frames, np, nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
     __syncwarp();
     unsigned amask = LaneMap<S>::active_mask(st.active && L.writer);
     const bool out_writer = (rank == 0 && warp == 0 && L.writer);

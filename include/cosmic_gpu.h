@@ -148,6 +148,8 @@ CPG_API int cpg_get_timing(cpg_ctx *ctx, cpg_timing *out);
 
 /* Tunables (scheduling only; results do not depend on them beyond fp64 summation order):
  *   "shells_per_pass"  1,2,4 or 0=auto   how many shells of one object share one read of its particles
+ *   "shell_groups"     1 (default, also 0) or 2 groups of 4 shells per warp task: the groups are passed over one after
+ *                      the other and share one reduction / eigen-solve step per Katz iteration (slower on configs[1])
  *   "large_halo_min"   particles from which a thread-block cluster works on one object
  *   "cluster_size"     CTAs per cluster for large objects (1,2,4,8,16; 0=auto)
  *   "invalidate_gather" (any value) one-shot: forget the resident gathered catalogue, so that the next compute

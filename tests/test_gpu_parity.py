@@ -124,10 +124,12 @@ SCHED = [dict(shells_per_pass=1, large_halo_min=1 << 40, cluster_size=0),     # 
          dict(shells_per_pass=4, large_halo_min=5000, cluster_size=16),
          dict(shells_per_pass=0, large_halo_min=0, cluster_size=0),           # auto
          dict(shells_per_pass=4, large_halo_min=1 << 40, cluster_size=0, radial_order=0),   # catalogue order
-         dict(shells_per_pass=2, large_halo_min=3000, cluster_size=2, radial_order=0)]
+         dict(shells_per_pass=2, large_halo_min=3000, cluster_size=2, radial_order=0),
+         dict(shells_per_pass=4, shell_groups=2, large_halo_min=1 << 40, cluster_size=0),   # 8 shells per warp task
+         dict(shells_per_pass=4, shell_groups=2, large_halo_min=8000, cluster_size=2, radial_order=0)]
 
 
-@pytest.mark.parametrize("sched", SCHED, ids=lambda s: "S%d_L%d_C%d_R%d" % (s["shells_per_pass"], min(s["large_halo_min"], 99999), s["cluster_size"], s.get("radial_order", 1)))
+@pytest.mark.parametrize("sched", SCHED, ids=lambda s: "S%d_L%d_C%d_R%d_G%d" % (s["shells_per_pass"], min(s["large_halo_min"], 99999), s["cluster_size"], s.get("radial_order", 1), s.get("shell_groups", 0)))
 def test_oracle_shapes_all_schedules(gpu, big, sched):
     S, D, sess = gpu
     cat, rr, cen, _ = big
@@ -151,8 +153,8 @@ def test_oracle_shapes_all_schedules(gpu, big, sched):
         sess.options.clear()
 
 
-@pytest.mark.parametrize("sched", [SCHED[2], SCHED[5], SCHED[8], SCHED[10]],
-                         ids=["warpS4", "clusterS2C4", "auto", "clusterS2C2_catalogue_order"])
+@pytest.mark.parametrize("sched", [SCHED[2], SCHED[5], SCHED[8], SCHED[10], SCHED[11]],
+                         ids=["warpS4", "clusterS2C4", "auto", "clusterS2C2_catalogue_order", "warpS4G2"])
 def test_oracle_velocity_dispersion(gpu, big, sched):
     S, D, sess = gpu
     cat, rr, cen, _ = big
