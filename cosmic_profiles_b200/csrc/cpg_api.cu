@@ -273,7 +273,8 @@ int run_gather(cpg_ctx *c, const double *h_centers, const double *h_r200, const 
     CPG_TRY(c->g_dx.ensure(c->n_pad)); CPG_TRY(c->g_dy.ensure(c->n_pad));
     CPG_TRY(c->g_dz.ensure(c->n_pad)); CPG_TRY(c->g_m.ensure(c->n_pad));
     c->sorted_valid = false;
-    const int nc = (int)c->h_chunks.size();
+    const int nc = (int)c->h_kchunks.size();   // ordering works on 2048-particle chunks (== KDE_CHUNK)
+    static_assert(SORT_CHUNK == KDE_CHUNK, "the ordering kernels reuse the 2048-particle chunk list");
     if (sort_R > 0 && n > 0 && nc > 0) {
         const int B = sort_R + 1;
         CPG_TRY(c->bucket.ensure(n)); CPG_TRY(c->tile_hist.ensure((size_t)nc * B));
@@ -281,17 +282,18 @@ int run_gather(cpg_ctx *c, const double *h_centers, const double *h_r200, const 
         CPG_TRY(c->dest.ensure(n));
         SortParams P;
         P.G = gather_view(c, L_BOX);
-        P.chunks = c->chunks.p; P.chunk_first = c->chunk_first.p; P.size = c->size.p;
+        P.chunks = c->kchunks.p; P.chunk_first = c->kchunk_first.p; P.size = c->size.p;
         P.r200 = c->r200.p; P.rr = c->rr.p; P.n_chunks = nc; P.R = sort_R;
         P.bucket = c->bucket.p; P.tile_hist = c->tile_hist.p; P.dest = c->dest.p;
         P.n_eff = c->n_eff.p;
+        CPG_CUDA(cudaFuncSetAttribute(gather_bucketed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)GATHER_BUCKETED_SMEM));
         bucket_hist_kernel<<<nc, 256, 0, c->stream>>>(P);
-        bucket_scan_kernel<<<grid_for(c->n_obj, 128, 1 << 30), 128, 0, c->stream>>>(P, c->n_obj);
-        bucket_rank_kernel<<<nc, 256, 0, c->stream>>>(P);
+        bucket_scan_kernel<<<grid_for((int64_t)c->n_obj * 32, 128, 1 << 30), 128, 0, c->stream>>>(P, c->n_obj);
+        gather_bucketed_kernel<<<nc, 256, GATHER_BUCKETED_SMEM, c->stream>>>(P);
         c->timing.kernel_launches += 3;
         c->sorted_valid = true;
-    }
-    if (n > 0) {
+    } else if (n > 0) {
         gather_pos_kernel<<<grid_for(n, 256, c->sm_count * 32), 256, 0, c->stream>>>(gather_view(c, L_BOX));
         c->timing.kernel_launches++;
     }

@@ -310,6 +310,8 @@ __device__ __forceinline__ void load_relative(const GatherParams &G, int h, int6
     dz = __dsub_rn(z, G.centers[3 * h + 2]);
 }
 
+constexpr int SORT_CHUNK = 2048;   // particles per CTA of the ordering kernels (8 per thread)
+
 __global__ void __launch_bounds__(256) bucket_hist_kernel(const SortParams P)
 {
     __shared__ double s_thr[SORT_MAX_B];
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(256) bucket_hist_kernel(const SortParams P)
     const int h = ck.halo, R = P.R, B = R + 1;
     const int N = P.size[h];
     const int64_t first = P.G.off[h];
-    const int end = min(N, ck.start + CHUNK);
+    const int end = min(N, ck.start + SORT_CHUNK);
     const double r200 = P.r200[h];
     for (int k = threadIdx.x; k < B; k += blockDim.x) {
         if (k < R) {
@@ -345,67 +347,128 @@ __global__ void __launch_bounds__(256) bucket_hist_kernel(const SortParams P)
     for (int k = threadIdx.x; k < B; k += blockDim.x) P.tile_hist[(size_t)blockIdx.x * B + k] = s_hist[k];
 }
 
-// Exclusive offsets of every (chunk, bucket) inside its object, bucket-major, and the prefix lengths.
-__global__ void bucket_scan_kernel(const SortParams P, int n_obj)
+// Exclusive offsets of every (chunk, bucket) inside its object, bucket-major then chunk order (= stable), and
+// the prefix lengths n_eff.  A warp per object, lanes over buckets.
+__global__ void __launch_bounds__(128) bucket_scan_kernel(const SortParams P, int n_obj)
 {
-    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (h >= n_obj) return;
     const int R = P.R, B = R + 1;
     const int c0 = P.chunk_first[h], c1 = P.chunk_first[h + 1];
-    int running = 0;
-    for (int b = 0; b < B; b++) {
-        for (int c = c0; c < c1; c++) {
-            const int t = P.tile_hist[(size_t)c * B + b];
-            P.tile_hist[(size_t)c * B + b] = running;
-            running += t;
+    int carry = 0;
+    for (int b0 = 0; b0 < B; b0 += 32) {
+        const int b = b0 + lane;
+        int tot = 0;
+        if (b < B)
+            for (int c = c0; c < c1; c++) tot += P.tile_hist[(size_t)c * B + b];
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
-        if (b < R) P.n_eff[(size_t)h * R + b] = running;
+        int run = carry + incl - tot;
+        if (b < B) {
+            for (int c = c0; c < c1; c++) {
+                const int t = P.tile_hist[(size_t)c * B + b];
+                P.tile_hist[(size_t)c * B + b] = run;
+                run += t;
+            }
+            if (b < R) P.n_eff[(size_t)h * R + b] = carry + incl;
+        }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
     }
 }
 
-// Stable rank of every catalogue entry inside its object's bucket order -> dest[j].  Only the one-byte bucket
-// ids are read here; the data movement itself is the fully parallel gather_pos_kernel (G.dest = dest).
-__global__ void __launch_bounds__(256) bucket_rank_kernel(const SortParams P)
+// Stable bucket ordering of one chunk + the gather itself.  The chunk's particles are staged in shared memory
+// in bucket order, so that the global stores are runs of consecutive addresses (one run per bucket present
+// in the chunk) instead of 4 isolated 8-byte stores per particle.
+__global__ void __launch_bounds__(256) gather_bucketed_kernel(const SortParams P)
 {
-    __shared__ int s_wh[8][SORT_MAX_B];
+    extern __shared__ __align__(16) unsigned char s_gb[];
+    double *sx = reinterpret_cast<double *>(s_gb), *sy = sx + SORT_CHUNK, *sz = sy + SORT_CHUNK, *sm = sz + SORT_CHUNK;
+    int *sdest = reinterpret_cast<int *>(sm + SORT_CHUNK);
+    int(*s_wh)[SORT_MAX_B] = reinterpret_cast<int(*)[SORT_MAX_B]>(sdest + SORT_CHUNK);
+    int *s_bstart = &s_wh[8][0];
     const Chunk ck = P.chunks[blockIdx.x];
     const int h = ck.halo, B = P.R + 1;
     const int N = P.size[h];
-    const int64_t first = P.G.off[h];
-    const int end = min(N, ck.start + CHUNK);
+    const int64_t first = P.G.off[h], pbase = P.G.poff[h];
+    const int end = min(N, ck.start + SORT_CHUNK);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 8 * SORT_MAX_B; i += blockDim.x) (&s_wh[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < 9 * SORT_MAX_B; i += blockDim.x) (&s_wh[0][0])[i] = 0;
     __syncthreads();
     // every warp owns a contiguous eighth of the chunk, so that "earlier warp" == "earlier in the catalogue"
-    const int w_lo = ck.start + warp * (CHUNK / 8), w_hi = min(end, w_lo + CHUNK / 8);
-    for (int i0 = w_lo; i0 < w_hi; i0 += 32) {
-        const int i = i0 + lane;
-        const int b = (i < w_hi) ? (int)P.bucket[first + i] : -1;
-        const unsigned peers = __match_any_sync(0xffffffffu, b);
-        if (b >= 0 && lane == __ffs(peers) - 1) s_wh[warp][b] += __popc(peers);
+    constexpr int PER_WARP = SORT_CHUNK / 8, ROUNDS = PER_WARP / 32;
+    const int w_lo = ck.start + warp * PER_WARP;
+    int bk[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        const int i = w_lo + r * 32 + lane;
+        bk[r] = (i < end) ? (int)P.bucket[first + i] : -1;
+        const unsigned peers = __match_any_sync(0xffffffffu, bk[r]);
+        if (bk[r] >= 0 && lane == __ffs(peers) - 1) s_wh[warp][bk[r]] += __popc(peers);
         __syncwarp();
     }
     __syncthreads();
-    if ((int)threadIdx.x < B) {
-        int run = P.tile_hist[(size_t)blockIdx.x * B + threadIdx.x];
+    if ((int)threadIdx.x < B) {   // per bucket: exclusive prefix over the warps, total into s_bstart
+        int run = 0;
         for (int w = 0; w < 8; w++) {
             const int t = s_wh[w][threadIdx.x];
             s_wh[w][threadIdx.x] = run;
             run += t;
         }
+        s_bstart[threadIdx.x] = run;
     }
     __syncthreads();
-    for (int i0 = w_lo; i0 < w_hi; i0 += 32) {
-        const int i = i0 + lane;
-        const int b = (i < w_hi) ? (int)P.bucket[first + i] : -1;
+    if (threadIdx.x == 0) {   // exclusive scan of the bucket totals: where each bucket starts inside the chunk
+        int run = 0;
+        for (int k = 0; k < B; k++) {
+            const int t = s_bstart[k];
+            s_bstart[k] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+    int lp[ROUNDS], gd[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        const int b = bk[r];
         const unsigned peers = __match_any_sync(0xffffffffu, b);
-        int rank = 0;
-        if (b >= 0) rank = s_wh[warp][b] + __popc(peers & ((1u << lane) - 1u));
+        int rin = 0;
+        if (b >= 0) rin = s_wh[warp][b] + __popc(peers & ((1u << lane) - 1u));
         __syncwarp();
         if (b >= 0 && lane == __ffs(peers) - 1) s_wh[warp][b] += __popc(peers);
         __syncwarp();
-        if (b >= 0) P.dest[first + i] = rank;
+        lp[r] = b >= 0 ? s_bstart[b] + rin : -1;
+        gd[r] = b >= 0 ? P.tile_hist[(size_t)blockIdx.x * B + b] + rin : 0;
+    }
+    // the data movement itself: 8 independent gathers per thread in flight
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        if (lp[r] >= 0) {
+            const int i = w_lo + r * 32 + lane;
+            double dx, dy, dz;
+            int64_t g;
+            load_relative(P.G, h, first, first + i, dx, dy, dz, g);
+            sx[lp[r]] = dx; sy[lp[r]] = dy; sz[lp[r]] = dz;
+            sm[lp[r]] = P.G.masses[g];
+            sdest[lp[r]] = gd[r];
+            if (P.dest) P.dest[first + i] = gd[r];
+        }
+    }
+    __syncthreads();
+    const int n = end - ck.start;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const int64_t o = pbase + sdest[j];
+        P.G.dx[o] = sx[j]; P.G.dy[o] = sy[j]; P.G.dz[o] = sz[j]; P.G.m[o] = sm[j];
+    }
+    if (threadIdx.x == 0 && end == N && (N & 1)) {   // pad element of an odd-sized object
+        P.G.dx[pbase + N] = 1e150; P.G.dy[pbase + N] = 1e150; P.G.dz[pbase + N] = 1e150; P.G.m[pbase + N] = 0.0;
     }
 }
+
+constexpr size_t GATHER_BUCKETED_SMEM = (size_t)SORT_CHUNK * (4 * sizeof(double) + sizeof(int)) + 9 * SORT_MAX_B * sizeof(int);
 
 }  // namespace cpg
