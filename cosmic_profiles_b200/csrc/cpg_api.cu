@@ -100,7 +100,7 @@ struct cpg_ctx {
     DevBuf<int32_t> part_flag;
     DevBuf<float> mass32;
     DevBuf<uint8_t> skip, bucket;
-    DevBuf<int32_t> tile_hist, dest, n_eff, cidxA, cidxB;
+    DevBuf<int32_t> tile_hist, dest, n_eff, cidxA, cidxB, d_order;
     DevBuf<double> cref;
     bool sorted_valid = false;    // the SoA streams are in radial-bucket order and `dest` maps catalogue -> slot
     // what the gathered SoA currently holds (skip the gather when a call asks for the same thing again)
@@ -498,7 +498,7 @@ CPG_API void cpg_destroy(cpg_ctx *c)
     for (auto *b : i32) b->release();
     c->off.release(); c->poff.release(); c->chunks.release(); c->kchunks.release();
     c->mass32.release(); c->skip.release(); c->tasks.release(); c->bucket.release();
-    c->tile_hist.release(); c->dest.release(); c->n_eff.release(); c->cidxA.release(); c->cidxB.release();
+    c->tile_hist.release(); c->dest.release(); c->n_eff.release(); c->cidxA.release(); c->cidxB.release(); c->d_order.release();
     c->cref.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -604,6 +604,9 @@ CPG_API int cpg_set_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx,
     CPG_TRY(c->chunks.ensure(c->h_chunks.size())); CPG_TRY(c->kchunks.ensure(c->h_kchunks.size()));
     CPG_TRY(c->chunk_first.ensure(n_obj + 1)); CPG_TRY(c->kchunk_first.ensure(n_obj + 1));
     CPG_TRY(c->task_counter.ensure(4));
+    CPG_TRY(c->d_order.ensure(n_obj));
+    if (n_obj)
+        CPG_CUDA(cudaMemcpyAsync(c->d_order.p, c->order.data(), sizeof(int32_t) * n_obj, cudaMemcpyHostToDevice, c->stream));
     if (n_idx) CPG_TRY(upload_chunked(c->idx.p, idx_cat, sizeof(int32_t) * n_idx, c->stream));
     if (n_obj) CPG_CUDA(cudaMemcpyAsync(c->size.p, obj_size, sizeof(int32_t) * n_obj, cudaMemcpyHostToDevice, c->stream));
     CPG_CUDA(cudaMemcpyAsync(c->off.p, off.data(), sizeof(int64_t) * (n_obj + 1), cudaMemcpyHostToDevice, c->stream));
@@ -984,7 +987,7 @@ CPG_API int cpg_centers(cpg_ctx *c, int32_t mode, int32_t shape_path, double L_B
     T.mark(2);
     CenterParams P;
     P.G = gather_view(c, 0.0f);
-    P.size = c->size.p; P.ref = ref_points ? c->cref.p : nullptr; P.L_BOX = L_BOX;
+    P.size = c->size.p; P.order = c->d_order.p; P.ref = ref_points ? c->cref.p : nullptr; P.L_BOX = L_BOX;
     P.mode = mode; P.shape_path = shape_path;
     P.idxA = c->cidxA.p; P.idxB = c->cidxB.p; P.centers = c->centers.p;
     centers_kernel<<<n, 256, 0, c->stream>>>(P);

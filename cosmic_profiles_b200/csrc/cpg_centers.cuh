@@ -15,6 +15,7 @@ namespace cpg {
 struct CenterParams {
     GatherParams G;            // xyz, masses, idx, off, n_obj, L_BOX (as double below)
     const int32_t *size;
+    const int32_t *order;      // objects largest first: block b works on object order[b] (the big ones start first)
     const double *ref;         // (n_obj,3) reference points of respectPBCNoRef / calcCoM, or nullptr (L_BOX == 0)
     double L_BOX;
     int32_t mode;              // 0: centre of mass, 1: shrinking-sphere mode
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(256) centers_kernel(const CenterParams P)
     __shared__ double scratch[8 * 6 + 6];
     __shared__ int s_scan[8];
     __shared__ int s_total;
-    const int h = blockIdx.x;
+    const int h = P.order[blockIdx.x];
     const int N = P.size[h];
     const int64_t first = P.G.off[h];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
