@@ -115,11 +115,15 @@ struct cpg_ctx {
     struct {
         bool valid = false;
         uint64_t cat = 0;
-        int S = 0, R = 0, nw = 0, ncl = 0, cluster_size = 1;
+        int S = 0, R = 0, nw = 0, ncl = 0, ngrid = 0, cluster_size = 1;
+        int64_t grid_min = 0;
         int64_t large_min = 0;
     } task_key;
     // morphology
     DevBuf<Task> tasks;
+    DevBuf<GridState> grid_states;
+    DevBuf<double> grid_partials;
+    int64_t opt_grid_halo_min = 0;
     DevBuf<int32_t> task_counter;
     DevBuf<double> out12;
     DevBuf<int32_t> n_iter, n_pts;
@@ -422,6 +426,61 @@ int dispatch_morph(cpg_ctx *c, const MorphParams &P, bool shell, bool reduced, b
     return CPG_ERR_ARGUMENT;
 }
 
+// Kernel 3 driver: tasks (object, S shells) of huge objects, one after the other; per Katz iteration one pass
+// over the whole grid + one step warp.  The host looks at the task's active mask every few iterations.
+template <int S, bool SHELL, bool REDUCED, bool VDISP>
+int launch_grid(cpg_ctx *c, MorphParams P, int first_task, int n_tasks)
+{
+    auto pass = grid_pass_kernel<S, SHELL, REDUCED, VDISP>;
+    const int smem = GRID_KERNEL_WARPS * RingCfg<VDISP>::WARP_BYTES;
+    CPG_CUDA(cudaFuncSetAttribute(pass, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int per_sm = 0;
+    CPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pass, GRID_KERNEL_WARPS * 32, smem));
+    const int n_cta = c->sm_count * std::max(1, per_sm);
+    CPG_TRY(c->grid_states.ensure(n_tasks));
+    CPG_TRY(c->grid_partials.ensure((size_t)n_cta * 8 * S));
+    const Task *tasks = P.tasks + first_task;
+    grid_init_kernel<S><<<n_tasks, 32, 0, c->stream>>>(P, tasks, c->grid_states.p, n_tasks);
+    c->timing.kernel_launches++;
+    unsigned *h_amask = nullptr;
+    CPG_CUDA(cudaHostAlloc((void **)&h_amask, sizeof(unsigned), cudaHostAllocDefault));
+    int rc = CPG_OK;
+    for (int t = 0; t < n_tasks && rc == CPG_OK; t++) {
+        GridState *gs = c->grid_states.p + t;
+        int done = 0;
+        while (done <= P.wall + 1) {
+            const int batch = std::min(8, P.wall + 2 - done);
+            for (int i = 0; i < batch; i++) {
+                pass<<<n_cta, GRID_KERNEL_WARPS * 32, smem, c->stream>>>(P, gs, c->grid_partials.p);
+                grid_step_kernel<S, SHELL><<<1, 32, 0, c->stream>>>(P, gs, c->grid_partials.p, n_cta);
+            }
+            c->timing.kernel_launches += 2 * batch;
+            c->timing.hot_kernel_launches += batch;
+            done += batch;
+            if (cudaMemcpyAsync(h_amask, &gs->amask, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+                cudaStreamSynchronize(c->stream) != cudaSuccess) {
+                set_error("grid morphology path failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = CPG_ERR_CUDA;
+                break;
+            }
+            if (*h_amask == 0) break;
+        }
+    }
+    cudaFreeHost(h_amask);
+    return rc;
+}
+
+template <int S>
+int dispatch_grid(cpg_ctx *c, const MorphParams &P, bool shell, bool reduced, bool vdisp, int first_task, int n_tasks)
+{
+#define CPG_CASE(SH, RE, VD) \
+    if (shell == SH && reduced == RE && vdisp == VD) return launch_grid<S, SH, RE, VD>(c, P, first_task, n_tasks);
+    CPG_CASE(false, false, false) CPG_CASE(false, true, false) CPG_CASE(true, false, false) CPG_CASE(true, true, false)
+    CPG_CASE(false, false, true) CPG_CASE(false, true, true) CPG_CASE(true, false, true) CPG_CASE(true, true, true)
+#undef CPG_CASE
+    return CPG_ERR_ARGUMENT;
+}
+
 int pow2_floor(int64_t v)
 {
     int p = 1;
@@ -498,6 +557,7 @@ CPG_API void cpg_destroy(cpg_ctx *c)
     for (auto *b : i32) b->release();
     c->off.release(); c->poff.release(); c->chunks.release(); c->kchunks.release();
     c->mass32.release(); c->skip.release(); c->tasks.release(); c->bucket.release();
+    c->grid_states.release(); c->grid_partials.release();
     c->tile_hist.release(); c->dest.release(); c->n_eff.release(); c->cidxA.release(); c->cidxB.release(); c->d_order.release();
     c->cref.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -518,6 +578,8 @@ CPG_API int cpg_set_option(cpg_ctx *c, const char *name, int64_t value)
             return CPG_ERR_ARGUMENT;
         }
         c->opt_shells_per_pass = (int)value;
+    } else if (!strcmp(name, "grid_halo_min")) {
+        c->opt_grid_halo_min = value;
     } else if (!strcmp(name, "large_halo_min")) {
         c->opt_large_halo_min = value;
     } else if (!strcmp(name, "invalidate_gather")) {
@@ -700,14 +762,20 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     // shared memory -- so two groups are only taken when asked for)
     int G = 1;
     if (S == 4 && c->opt_groups == 2 && R >= 8) G = 2;
+    // objects of millions of particles: one launch over the whole grid per Katz iteration (kernel 3)
+    const int64_t grid_min = c->opt_grid_halo_min > 0 ? c->opt_grid_halo_min : ((int64_t)1 << 22);
     auto &TK = c->task_key;
     if (!(TK.valid && TK.cat == c->catalogue_version && TK.S == S * 16 + G && TK.R == R && TK.large_min == large_min &&
-          (c->opt_cluster_size == 0 || c->opt_cluster_size == TK.cluster_size))) {
-        std::vector<Task> warp_tasks, cl_tasks;
+          TK.grid_min == grid_min && (c->opt_cluster_size == 0 || c->opt_cluster_size == TK.cluster_size))) {
+        std::vector<Task> warp_tasks, cl_tasks, grid_tasks;
         int64_t largest = 0;
         for (int oi = 0; oi < n; oi++) {
             const int h = c->order[oi];
             const int64_t N = c->h_size[h];
+            if (N >= grid_min) {
+                for (int k0 = 0; k0 < R; k0 += S) grid_tasks.push_back(Task{h, (int16_t)k0, (int16_t)std::min(S, R - k0)});
+                continue;
+            }
             largest = std::max(largest, N);
             const bool big = N >= large_min;
             std::vector<Task> &dst = big ? cl_tasks : warp_tasks;
@@ -726,13 +794,15 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
             }
         }
         TK.nw = (int)warp_tasks.size(); TK.ncl = (int)cl_tasks.size(); TK.cluster_size = cluster_size;
+        TK.ngrid = (int)grid_tasks.size(); TK.grid_min = grid_min;
         warp_tasks.insert(warp_tasks.end(), cl_tasks.begin(), cl_tasks.end());
+        warp_tasks.insert(warp_tasks.end(), grid_tasks.begin(), grid_tasks.end());   // layout: warp | cluster | grid
         CPG_TRY(c->tasks.ensure(warp_tasks.size()));
         CPG_TRY(small_upload(c, c->tasks.p, warp_tasks.data(), sizeof(Task) * warp_tasks.size()));
         c->timing.h2d_bytes += (int64_t)(sizeof(Task) * warp_tasks.size());
         TK.valid = true; TK.cat = c->catalogue_version; TK.S = S * 16 + G; TK.R = R; TK.large_min = large_min;
     }
-    const int nw = TK.nw, ncl = TK.ncl, cluster_size = TK.cluster_size;
+    const int nw = TK.nw, ncl = TK.ncl, ngrid = TK.ngrid, cluster_size = TK.cluster_size;
     CPG_TRY(c->out12.ensure(nR * 12)); CPG_TRY(c->n_iter.ensure(nR)); CPG_TRY(c->n_pts.ensure(nR));
     CPG_CUDA(cudaMemsetAsync(c->out12.p, 0, sizeof(double) * 12 * nR, c->stream));
     CPG_CUDA(cudaMemsetAsync(c->n_iter.p, 0xff, sizeof(int32_t) * nR, c->stream));
@@ -758,6 +828,13 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     P.R = R; P.local = local ? 1 : 0; P.SAFE = SAFE;
     P.tol = IT_TOL; P.wall = IT_WALL; P.itmin = IT_MIN;
     P.out12 = c->out12.p; P.n_iter = c->n_iter.p; P.n_pts = c->n_pts.p;
+    if (ngrid > 0) {
+        int rcg;
+        if (S == 4) rcg = dispatch_grid<4>(c, P, shell_based != 0, reduced != 0, use_vel != 0, nw + ncl, ngrid);
+        else if (S == 2) rcg = dispatch_grid<2>(c, P, shell_based != 0, reduced != 0, use_vel != 0, nw + ncl, ngrid);
+        else rcg = dispatch_grid<1>(c, P, shell_based != 0, reduced != 0, use_vel != 0, nw + ncl, ngrid);
+        CPG_TRY(rcg);
+    }
     int rc;
     if (S == 4 && G == 2) rc = dispatch_morph<4, 2>(c, P, shell_based != 0, reduced != 0, use_vel != 0, nw, ncl, cluster_size);
     else if (S == 4) rc = dispatch_morph<4, 1>(c, P, shell_based != 0, reduced != 0, use_vel != 0, nw, ncl, cluster_size);

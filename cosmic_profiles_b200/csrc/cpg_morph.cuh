@@ -832,4 +832,121 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
         cluster.sync();   // nobody leaves while a peer may still read its shared memory
 }
 
+// ------------------------------------------------------------------------------------------------
+// Kernel 3: the whole GRID per task, for objects of millions of particles (BASELINE configs[4]: one 1e8-particle
+// halo).  A cluster of 16 CTAs is the most one task can get from kernel 2, and a handful of such tasks leaves
+// most of the GPU waiting for the slowest one.  Here every Katz iteration of a task is one launch of
+// grid_pass_kernel over all SMs (each CTA publishes its 8S partial sums) followed by grid_step_kernel (one
+// warp: fixed-order sum over the CTAs, eigen-solve, convergence test, next frames).  The iteration state
+// lives in global memory between the launches; launches of a converged task return at once.
+// ------------------------------------------------------------------------------------------------
+struct GridState {
+    double frames[4 * F_SLOTS];
+    double q[4], s[4], d[4], delta[4];
+    int iteration[4], active[4], np[4], nin[4];
+    unsigned amask;
+    int halo, shell0, nshell;
+};
+
+template <int S>
+__global__ void grid_init_kernel(const MorphParams P, const Task *tasks, GridState *states, int n_tasks)
+{
+    const int t = blockIdx.x;
+    if (t >= n_tasks) return;
+    const int lane = threadIdx.x & 31;
+    const Task tk = tasks[t];
+    GridState *gs = states + t;
+    const LaneMap<S> L(lane);
+    const int ls = L.ls, halo = tk.halo;
+    const bool dead = P.skip[halo] || (P.local && P.r200[halo] == 0.0);
+    KatzState st;
+    st.q = 1.0; st.s = 1.0; st.iteration = 1;
+    st.active = !dead && ls < tk.nshell;
+    const int k = tk.shell0 + (ls < tk.nshell ? ls : 0);
+    shell_geometry(P, halo, k, st.d, st.delta);
+    const size_t out_idx = (size_t)halo * P.R + k;
+    InnerPrefix ip;
+    ip.rr = (!P.n_eff) ? nullptr : P.rr;
+    ip.neff = P.n_eff ? P.n_eff + (size_t)halo * P.R : nullptr;
+    init_frames(gs->frames, gs->np, gs->nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : P.soa.size[halo], ip, k);
+    if (L.writer) {
+        gs->q[ls] = 1.0; gs->s[ls] = 1.0; gs->d[ls] = st.d; gs->delta[ls] = st.delta;
+        gs->iteration[ls] = 1; gs->active[ls] = st.active ? 1 : 0;
+    }
+    const unsigned amask = LaneMap<S>::active_mask(st.active && L.writer);
+    if (lane == 0) { gs->amask = amask; gs->halo = halo; gs->shell0 = tk.shell0; gs->nshell = tk.nshell; }
+}
+
+constexpr int GRID_KERNEL_WARPS = 8;
+
+template <int S, bool SHELL, bool REDUCED, bool VDISP>
+__global__ void __launch_bounds__(GRID_KERNEL_WARPS * 32) grid_pass_kernel(const MorphParams P, const GridState *gs,
+                                                                          double *partials /* [gridDim.x][8S] */)
+{
+    constexpr int NW = GRID_KERNEL_WARPS, NV = 8 * S;
+    extern __shared__ __align__(128) unsigned char s_ring_g[];
+    __shared__ __align__(16) double s_frames[S * F_SLOTS];
+    __shared__ __align__(8) uint64_t s_bar[NW][RING_MAX_STAGES];
+    __shared__ double s_part[NW][NV];
+    __shared__ int s_nin[S];
+    const unsigned amask = gs->amask;
+    if (amask == 0) return;   // converged (uniform over the grid)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < S * F_SLOTS; i += blockDim.x) s_frames[i] = gs->frames[i];
+    if (threadIdx.x < S) s_nin[threadIdx.x] = (!SHELL && !REDUCED) ? gs->nin[threadIdx.x] : 0;
+    WarpRing ring;
+    ring_init(ring, s_ring_g + warp * RingCfg<VDISP>::WARP_BYTES, s_bar[warp], lane);
+    __syncthreads();
+    int npr[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) npr[s] = gs->np[s];
+    const int halo = gs->halo;
+    double acc[S][7];
+    int cnt[S];
+    run_pass<S, SHELL, REDUCED, VDISP>(P.soa, P.soa.poff[halo], active_npairs<S>(npr, amask), blockIdx.x * NW + warp,
+                                       gridDim.x * NW, lane, ring, false, 0, s_frames, npr, s_nin, amask, acc, cnt);
+    double val[NV];
+    pack_values<S>(acc, cnt, val);
+    const double mine = warp_sum_transpose<NV>(val, lane);
+    if (lane < NV) s_part[warp][lane] = mine;
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double v = 0.0;
+        for (int w = 0; w < NW; w++) v += s_part[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * NV + threadIdx.x] = v;
+    }
+}
+
+template <int S, bool SHELL>
+__global__ void grid_step_kernel(const MorphParams P, GridState *gs, const double *partials, int n_cta)
+{
+    constexpr int NV = 8 * S;
+    if (gs->amask == 0) return;
+    const int lane = threadIdx.x & 31;
+    const LaneMap<S> L(lane);
+    const int ls = L.ls;
+    double mine = 0.0;
+    for (int b = 0; b < n_cta; b++) mine += partials[(size_t)b * NV + (lane & (NV - 1))];   // fixed order
+    double tot[7], vprev[9];
+#pragma unroll
+    for (int c = 0; c < 7; c++) tot[c] = __shfl_sync(0xffffffffu, mine, (lane & ~7) + c);
+    const int pts = (int)__shfl_sync(0xffffffffu, mine, (lane & ~7) + 7);
+    KatzState st;
+    st.q = gs->q[ls]; st.s = gs->s[ls]; st.d = gs->d[ls]; st.delta = gs->delta[ls];
+    st.iteration = gs->iteration[ls]; st.active = gs->active[ls] != 0;
+    const int k = gs->shell0 + (ls < gs->nshell ? ls : 0);
+    const size_t out_idx = (size_t)gs->halo * P.R + k;
+#pragma unroll
+    for (int r = 0; r < 9; r++) vprev[r] = gs->frames[ls * F_SLOTS + F_V + r];
+    InnerPrefix ip;
+    ip.rr = (!P.n_eff) ? nullptr : P.rr;
+    ip.neff = P.n_eff ? P.n_eff + (size_t)gs->halo * P.R : nullptr;
+    __syncwarp();
+    katz_step<SHELL>(st, tot, pts, P, vprev, gs->frames + ls * F_SLOTS, L.writer, out_idx, L.writer, ip, k, gs->nin + ls);
+    __syncwarp();
+    if (L.writer) { gs->q[ls] = st.q; gs->s[ls] = st.s; gs->iteration[ls] = st.iteration; gs->active[ls] = st.active ? 1 : 0; }
+    const unsigned amask = LaneMap<S>::active_mask(st.active && L.writer);
+    if (lane == 0) gs->amask = amask;
+}
+
 }  // namespace cpg

@@ -151,6 +151,8 @@ CPG_API int cpg_get_timing(cpg_ctx *ctx, cpg_timing *out);
  *   "shell_groups"     1 (default, also 0) or 2 groups of 4 shells per warp task: the groups are passed over one after
  *                      the other and share one reduction / eigen-solve step per Katz iteration (slower on configs[1])
  *   "large_halo_min"   particles from which a thread-block cluster works on one object
+ *   "grid_halo_min"    particles from which every Katz iteration of an object is one launch over the whole grid
+ *                      (default 2^22)
  *   "cluster_size"     CTAs per cluster for large objects (1,2,4,8,16; 0=auto)
  *   "invalidate_gather" (any value) one-shot: forget the resident gathered catalogue, so that the next compute
  *                      call redoes the gather even if snapshot, catalogue, centres and L_BOX are unchanged

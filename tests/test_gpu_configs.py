@@ -39,7 +39,7 @@ def test_config1_like(gpu):
         P.assert_shape_tuple(got, ref, "config1 shell=%d" % shell)
 
 
-@pytest.mark.parametrize("cluster", [0, 16])
+@pytest.mark.parametrize("cluster", [0, 16, -1])
 def test_config5_like_large_halo(gpu, cluster):
     """configs[4] flavour: one large halo, shell-based non-reduced profile on the cluster/DSMEM path."""
     from cosmic_profiles_b200.mock import make_catalogue
@@ -51,8 +51,10 @@ def test_config5_like_large_halo(gpu, cluster):
     ref, (nit, npt, _, _) = O.morph(cat["xyz"], None, cat["masses"], cat["r200"], cat["idx_cat"], cat["obj_size"], 0.0,
                                     rr, 1e-2, 100, 10, "com", False, True, True, centers=cen)
     sess.options.clear()
-    if cluster:
+    if cluster > 0:
         sess.options.update(cluster_size=cluster, large_halo_min=1)
+    elif cluster < 0:   # the whole-grid-per-iteration path that objects of >= 2^22 particles take
+        sess.options.update(grid_halo_min=100000)
     try:
         got = S.calcMorphLocal(*_args(cat), 0.0, rr, 1e-2, 100, 10, "com", False, True, centers=cen)
     finally:

@@ -126,10 +126,12 @@ SCHED = [dict(shells_per_pass=1, large_halo_min=1 << 40, cluster_size=0),     # 
          dict(shells_per_pass=4, large_halo_min=1 << 40, cluster_size=0, radial_order=0),   # catalogue order
          dict(shells_per_pass=2, large_halo_min=3000, cluster_size=2, radial_order=0),
          dict(shells_per_pass=4, shell_groups=2, large_halo_min=1 << 40, cluster_size=0),   # 8 shells per warp task
-         dict(shells_per_pass=4, shell_groups=2, large_halo_min=8000, cluster_size=2, radial_order=0)]
+         dict(shells_per_pass=4, shell_groups=2, large_halo_min=8000, cluster_size=2, radial_order=0),
+         dict(shells_per_pass=4, large_halo_min=1 << 40, cluster_size=0, grid_halo_min=2000),   # grid-per-iteration path
+         dict(shells_per_pass=2, large_halo_min=1 << 40, cluster_size=0, grid_halo_min=6000, radial_order=0)]
 
 
-@pytest.mark.parametrize("sched", SCHED, ids=lambda s: "S%d_L%d_C%d_R%d_G%d" % (s["shells_per_pass"], min(s["large_halo_min"], 99999), s["cluster_size"], s.get("radial_order", 1), s.get("shell_groups", 0)))
+@pytest.mark.parametrize("sched", SCHED, ids=lambda s: "S%d_L%d_C%d_R%d_G%d_grid%d" % (s["shells_per_pass"], min(s["large_halo_min"], 99999), s["cluster_size"], s.get("radial_order", 1), s.get("shell_groups", 0), s.get("grid_halo_min", 0)))
 def test_oracle_shapes_all_schedules(gpu, big, sched):
     S, D, sess = gpu
     cat, rr, cen, _ = big
@@ -153,8 +155,8 @@ def test_oracle_shapes_all_schedules(gpu, big, sched):
         sess.options.clear()
 
 
-@pytest.mark.parametrize("sched", [SCHED[2], SCHED[5], SCHED[8], SCHED[10], SCHED[11]],
-                         ids=["warpS4", "clusterS2C4", "auto", "clusterS2C2_catalogue_order", "warpS4G2"])
+@pytest.mark.parametrize("sched", [SCHED[2], SCHED[5], SCHED[8], SCHED[10], SCHED[11], SCHED[13]],
+                         ids=["warpS4", "clusterS2C4", "auto", "clusterS2C2_catalogue_order", "warpS4G2", "gridS4"])
 def test_oracle_velocity_dispersion(gpu, big, sched):
     S, D, sess = gpu
     cat, rr, cen, _ = big
