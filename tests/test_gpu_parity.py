@@ -256,3 +256,32 @@ def test_device_centres(gpu, kind):
         cen, m = D.calcMassesCenters(X, M, I, Z, L, center)
         P.assert_close(cen, z["masses_centers_%s/centers" % center], "centers " + center, rtol=1e-12)
         P.assert_close(m, z["masses_centers_%s/m" % center], "m", rtol=1e-12)
+
+
+def test_unusual_radii_and_limits(gpu, big):
+    """Shell lists the radial ordering cannot use (non-ascending, a single shell, more than 255 shells), a tight
+    IT_WALL and a large IT_MIN: same integers and values as the oracle."""
+    from oracle import cp_oracle as O
+    S, D, sess = gpu
+    cat, _, cen, _ = big
+    X, M, R2, I, Z = _args(cat)
+    cases = [
+        (np.array([0.5, 0.1, 1.0, 0.3]), 1e-2, 100, 10),            # not ascending
+        (np.array([0.7]), 1e-2, 100, 10),                             # one shell
+        (np.logspace(-1.2, 0, 300), 1e-2, 100, 10),                   # R > 255
+        (np.logspace(-1.5, 0, 9), 1e-3, 4, 10),                       # IT_WALL hit by most shells
+        (np.logspace(-1.5, 0, 9), 1e-2, 100, 2500),                   # IT_MIN rejects the inner shells
+    ]
+    sub = slice(3, 12)   # a few mid-size objects keep the R=300 case cheap for the CPU oracle
+    off = cat["offsets"]
+    idx = I[off[3]:off[12]]
+    for rr, tol, wall, itmin in cases:
+        for shell in (False, True):
+            ref, (nit, npt, _, _) = O.morph(X, None, M, R2[sub], idx, Z[sub], 0.0, rr, tol, wall, itmin, "com", False,
+                                            shell, True, centers=cen[sub])
+            got = S.calcMorphLocal(X, M, R2[sub], idx, Z[sub], 0.0, rr, tol, wall, itmin, "com", False, shell,
+                                   centers=cen[sub])
+            tag = "R=%d tol=%g wall=%d itmin=%d shell=%d" % (len(rr), tol, wall, itmin, shell)
+            P.assert_ints(S.last_info["n_iter"], nit, tag + " n_iter")
+            P.assert_ints(S.last_info["n_pts"], npt, tag + " n_pts")
+            P.assert_shape_tuple(got, ref, tag)
