@@ -96,7 +96,7 @@ struct cpg_ctx {
     DevBuf<double> g_dx, g_dy, g_dz, g_m, g_vx, g_vy, g_vz;
     bool mass_stream_valid = false;
     // per-object scratch
-    DevBuf<double> centers, vcenters, r200, rr, obj_mass, part_mass, vpart;
+    DevBuf<double> centers, vcenters, r200, rr, obj_mass, part_mass, vpart, part_mm, obj_eqm;
     DevBuf<int32_t> part_flag;
     DevBuf<float> mass32;
     DevBuf<uint8_t> skip, bucket;
@@ -317,15 +317,17 @@ int run_stats(cpg_ctx *c)
 {
     if (c->have.valid && c->have.stats) return CPG_OK;
     const int nc = (int)c->h_chunks.size();
-    CPG_TRY(c->part_mass.ensure(nc)); CPG_TRY(c->part_flag.ensure(nc));
-    CPG_TRY(c->obj_mass.ensure(c->n_obj)); CPG_TRY(c->skip.ensure(c->n_obj));
+    CPG_TRY(c->part_mass.ensure(nc)); CPG_TRY(c->part_flag.ensure(nc)); CPG_TRY(c->part_mm.ensure((size_t)2 * nc));
+    CPG_TRY(c->obj_mass.ensure(c->n_obj)); CPG_TRY(c->skip.ensure(c->n_obj)); CPG_TRY(c->obj_eqm.ensure(c->n_obj));
     if (nc > 0) {
-        stats_chunk_kernel<<<nc, 256, 0, c->stream>>>(soa_view(c), c->chunks.p, nc, c->part_mass.p, c->part_flag.p);
+        stats_chunk_kernel<<<nc, 256, 0, c->stream>>>(soa_view(c), c->chunks.p, nc, c->part_mass.p, c->part_flag.p,
+                                                     c->part_mm.p);
         c->timing.kernel_launches++;
     }
     if (c->n_obj > 0) {
         stats_final_kernel<<<grid_for(c->n_obj, 128, 1 << 30), 128, 0, c->stream>>>(
-            c->chunk_first.p, c->size.p, c->n_obj, c->part_mass.p, c->part_flag.p, c->obj_mass.p, c->skip.p);
+            c->chunk_first.p, c->size.p, c->n_obj, c->part_mass.p, c->part_flag.p, c->part_mm.p, c->obj_mass.p, c->skip.p,
+            c->obj_eqm.p);
         c->timing.kernel_launches++;
     }
     CPG_CUDA(cudaGetLastError());
@@ -342,7 +344,7 @@ int run_vcenters(cpg_ctx *c, float L_BOX)
     CPG_TRY(c->g_vx.ensure(c->n_pad)); CPG_TRY(c->g_vy.ensure(c->n_pad)); CPG_TRY(c->g_vz.ensure(c->n_pad));
     if (c->n_obj > 0) {
         mass32_kernel<<<grid_for((int64_t)c->n_obj * 32, 128, c->sm_count * 16), 128, 0, c->stream>>>(
-            gather_view(c, L_BOX), c->n_obj, c->mass32.p);
+            gather_view(c, L_BOX), c->n_obj, c->obj_eqm.p, c->mass32.p);
         if (nc > 0)
             vsum_chunk_kernel<<<nc, 256, 0, c->stream>>>(gather_view(c, L_BOX), soa_view(c), c->chunks.p, nc, c->vpart.p);
         vcenter_final_kernel<<<grid_for(c->n_obj, 128, 1 << 30), 128, 0, c->stream>>>(c->chunk_first.p, c->n_obj,
@@ -549,7 +551,7 @@ CPG_API void cpg_destroy(cpg_ctx *c)
     cudaStreamSynchronize(c->stream);
     DevBuf<double> *dbl[] = {&c->xyz, &c->vxyz, &c->masses, &c->g_dx, &c->g_dy, &c->g_dz, &c->g_m, &c->g_vx, &c->g_vy,
                              &c->g_vz, &c->centers, &c->vcenters, &c->r200, &c->rr, &c->obj_mass, &c->part_mass,
-                             &c->vpart, &c->out12, &c->d_a, &c->d_b, &c->d_c, &c->d_major, &c->d_inter, &c->d_minor,
+                             &c->vpart, &c->part_mm, &c->obj_eqm, &c->out12, &c->d_a, &c->d_b, &c->d_c, &c->d_major, &c->d_inter, &c->d_minor,
                              &c->d_edges, &c->dens, &c->bin_mass};
     for (auto *b : dbl) b->release();
     DevBuf<int32_t> *i32[] = {&c->idx, &c->size, &c->chunk_first, &c->kchunk_first, &c->part_flag, &c->task_counter,

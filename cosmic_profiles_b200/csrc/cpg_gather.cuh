@@ -121,9 +121,10 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double *scratch /* [8
 // Per-chunk partial statistics: mass, "some particle differs from particle 0" flag (the only thing the
 // reference consumes of calcLocalSpread is ==0, i.e. an empty or fully coincident cloud).
 __global__ void __launch_bounds__(256) stats_chunk_kernel(const SoA soa, const Chunk *chunks, int n_chunks,
-                                                          double *part_mass, int32_t *part_spread)
+                                                          double *part_mass, int32_t *part_spread, double *part_mminmax)
 {
     __shared__ double scratch[8 * 1];
+    __shared__ double s_mm[8][2];
     __shared__ int s_flag;
     const int c = blockIdx.x;
     if (c >= n_chunks) return;
@@ -135,33 +136,45 @@ __global__ void __launch_bounds__(256) stats_chunk_kernel(const SoA soa, const C
     __syncthreads();
     const double x0 = soa.dx[base], y0 = soa.dy[base], z0 = soa.dz[base];
     double v[1] = {0.0};
+    double mlo = 1e300, mhi = -1e300;
     int differs = 0;
     for (int i = ck.start + threadIdx.x; i < end; i += blockDim.x) {
-        v[0] += soa.m[base + i];
+        const double m = soa.m[base + i];
+        v[0] += m;
+        mlo = fmin(mlo, m); mhi = fmax(mhi, m);
         differs |= (soa.dx[base + i] != x0) | (soa.dy[base + i] != y0) | (soa.dz[base + i] != z0);
     }
     if (differs) s_flag = 1;
+    for (int o = 16; o > 0; o >>= 1) {
+        mlo = fmin(mlo, __shfl_xor_sync(0xffffffffu, mlo, o));
+        mhi = fmax(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_mm[threadIdx.x >> 5][0] = mlo; s_mm[threadIdx.x >> 5][1] = mhi; }
     block_sum<1>(v, scratch);
     if (threadIdx.x == 0) {
         part_mass[c] = v[0];
         part_spread[c] = s_flag;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) { mlo = fmin(mlo, s_mm[w][0]); mhi = fmax(mhi, s_mm[w][1]); }
+        part_mminmax[2 * c] = mlo; part_mminmax[2 * c + 1] = mhi;
     }
 }
 
 // Combine the chunk partials of every object in chunk order.
 __global__ void stats_final_kernel(const int32_t *chunk_first /* n_obj+1 */, const int32_t *size, int n_obj,
-                                   const double *part_mass, const int32_t *part_spread, double *obj_mass,
-                                   uint8_t *skip)
+                                   const double *part_mass, const int32_t *part_spread, const double *part_mminmax,
+                                   double *obj_mass, uint8_t *skip, double *obj_equal_mass)
 {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= n_obj) return;
-    double m = 0.0;
+    double m = 0.0, mlo = 1e300, mhi = -1e300;
     int spread = 0;
     for (int c = chunk_first[h]; c < chunk_first[h + 1]; c++) {
         m += part_mass[c];
         spread |= part_spread[c];
+        mlo = fmin(mlo, part_mminmax[2 * c]); mhi = fmax(mhi, part_mminmax[2 * c + 1]);
     }
     obj_mass[h] = m;
+    obj_equal_mass[h] = (mlo == mhi && mlo > 0.0) ? mlo : 0.0;   // > 0: every member has exactly this mass
     // The reference leaves an object untouched when calcLocalSpread(xyz) == 0 (helper_class.pyx:62-80 with
     // fp32 accumulators): in practice only an empty object gets there -- for coincident points the fp32
     // rounding of the mean already makes the spread non-zero.  `spread` is kept for diagnostics.
@@ -204,7 +217,8 @@ __device__ float mass32_equal(double m, int N)
     return acc;
 }
 
-__global__ void __launch_bounds__(128) mass32_kernel(const GatherParams G, int n_obj, float *mass32)
+__global__ void __launch_bounds__(128) mass32_kernel(const GatherParams G, int n_obj, const double *obj_equal_mass,
+                                                     float *mass32)
 {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
@@ -215,18 +229,53 @@ __global__ void __launch_bounds__(128) mass32_kernel(const GatherParams G, int n
             if (lane == 0) mass32[h] = 0.0f;
             continue;
         }
-        const double m0 = G.masses[G.idx[first]];
-        bool same = true;
-        for (int i = lane; i < N; i += 32) same = same && (G.masses[G.idx[first + i]] == m0);
-        same = __all_sync(0xffffffffu, same);
+        const double m0 = obj_equal_mass[h];   // from the per-chunk min/max of the statistics kernels
+        const bool same = m0 > 0.0;
         float acc = 0.0f;
-        if (same && m0 > 0.0) {
+        if (same) {
             acc = mass32_equal(m0, N);   // uniform across the warp
         } else {
-            for (int i0 = 0; i0 < N; i0 += 32) {
-                const double mine = (i0 + lane < N) ? G.masses[G.idx[first + i0 + lane]] : 0.0;
-                const int cntb = min(32, N - i0);
-                for (int j = 0; j < cntb; j++) acc = f32_step(acc, __shfl_sync(0xffffffffu, mine, j));
+            // Unequal masses: 32 members at a time.  While the accumulator stays inside one fp32 binade it is a
+            // multiple k*u of that binade's ulp, and adding m rounds to k*u + rne(m'/u)*u with m' = m rounded on the
+            // fp64 grid of the binade -- independent of k unless m'/u is an exact tie.  So a block whose members
+            // all avoid ties and whose sum keeps the accumulator below the top of the binade is added with ONE
+            // integer warp reduction, bit-identically to the sequential loop (checked on the host against the
+            // literal loop for wide dynamic ranges, dyadic masses and occasional giants); any other block (binade
+            // crossings, ties, the very first ones) falls back to the literal sequential additions.
+            constexpr int PF = 8;   // blocks fetched ahead: the catalogue gather has ~1 us of latency per dependent pair
+            for (int s0 = 0; s0 < N; s0 += 32 * PF) {
+                double pre[PF];
+#pragma unroll
+                for (int b = 0; b < PF; b++) {
+                    const int i = s0 + 32 * b + lane;
+                    pre[b] = (i < N) ? G.masses[G.idx[first + i]] : 0.0;
+                }
+#pragma unroll
+                for (int b = 0; b < PF; b++) {
+                    const int i0 = s0 + 32 * b;
+                    if (i0 >= N) break;
+                    const double mine = pre[b];
+                    const int cntb = min(32, N - i0);
+                    int e;
+                    frexpf(acc, &e);   // acc in [2^(e-1), 2^e)
+                    const double top = ldexp(1.0, e), base = ldexp(1.0, e - 1), u = ldexp(1.0, e - 24);
+                    const double mr = __dsub_rn(__dadd_rn(base, mine), base);
+                    const double t = mr / u, fl = floor(t);
+                    const bool lane_ok = (mine >= 0.0) && (mine < base) && (t - fl != 0.5);
+                    long long q = lane_ok ? (long long)rint(t) : 0;
+                    double mmax = mine;
+                    const bool ok = acc > 0.0f && __all_sync(0xffffffffu, lane_ok);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        q += __shfl_xor_sync(0xffffffffu, q, o);
+                        mmax = fmax(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
+                    }
+                    if (ok && (double)acc + (double)q * u + mmax < top) {
+                        acc = (float)((double)acc + (double)q * u);   // exact: a multiple of u below the top
+                    } else {
+                        for (int j = 0; j < cntb; j++) acc = f32_step(acc, __shfl_sync(0xffffffffu, mine, j));
+                    }
+                }
             }
         }
         if (lane == 0) mass32[h] = acc;
