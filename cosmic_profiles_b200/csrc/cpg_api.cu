@@ -1066,10 +1066,29 @@ CPG_API int cpg_centers(cpg_ctx *c, int32_t mode, int32_t shape_path, double L_B
     T.mark(2);
     CenterParams P;
     P.G = gather_view(c, 0.0f);
-    P.size = c->size.p; P.order = c->d_order.p; P.ref = ref_points ? c->cref.p : nullptr; P.L_BOX = L_BOX;
+    P.size = c->size.p; P.order = c->d_order.p; P.first_obj = 0; P.ref = ref_points ? c->cref.p : nullptr; P.L_BOX = L_BOX;
     P.mode = mode; P.shape_path = shape_path;
     P.idxA = c->cidxA.p; P.idxB = c->cidxB.p; P.centers = c->centers.p;
-    centers_kernel<<<n, 256, 0, c->stream>>>(P);
+    // 'mode' on large objects: a cluster of 8 CTAs each (objects are listed largest first)
+    int n_big = 0;
+    if (mode == 1)
+        while (n_big < n && c->h_size[c->order[n_big]] >= 32768) n_big++;
+    if (n_big > 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)n_big * 8);
+        cfg.blockDim = dim3(256);
+        cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 8; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        CPG_CUDA(cudaLaunchKernelEx(&cfg, centers_mode_cluster_kernel, P));
+        c->timing.kernel_launches++; c->timing.hot_kernel_launches++;
+    }
+    if (n > n_big) {
+        P.first_obj = n_big;
+        centers_kernel<<<n - n_big, 256, 0, c->stream>>>(P);
+    }
     c->timing.kernel_launches++; c->timing.hot_kernel_launches++;
     CPG_CUDA(cudaGetLastError());
     T.mark(3);

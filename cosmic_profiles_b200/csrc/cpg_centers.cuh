@@ -8,6 +8,8 @@
 // One CTA per object; every sum is a fixed-order block reduction (deterministic).  Results agree with the
 // reference's numpy arithmetic to ~1e-15 relative (different summation order), far inside the 1e-9 gate.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "cpg_gather.cuh"
 
 namespace cpg {
@@ -15,7 +17,8 @@ namespace cpg {
 struct CenterParams {
     GatherParams G;            // xyz, masses, idx, off, n_obj, L_BOX (as double below)
     const int32_t *size;
-    const int32_t *order;      // objects largest first: block b works on object order[b] (the big ones start first)
+    const int32_t *order;      // objects largest first: block b works on object order[first_obj + b / cluster size]
+    int32_t first_obj;         // offset into `order` (the cluster launch takes the head of the list, the CTA launch the rest)
     const double *ref;         // (n_obj,3) reference points of respectPBCNoRef / calcCoM, or nullptr (L_BOX == 0)
     double L_BOX;
     int32_t mode;              // 0: centre of mass, 1: shrinking-sphere mode
@@ -67,7 +70,7 @@ __global__ void __launch_bounds__(256) centers_kernel(const CenterParams P)
     __shared__ double scratch[8 * 6 + 6];
     __shared__ int s_scan[8];
     __shared__ int s_total;
-    const int h = P.order[blockIdx.x];
+    const int h = P.order[P.first_obj + blockIdx.x];
     const int N = P.size[h];
     const int64_t first = P.G.off[h];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -177,6 +180,128 @@ __global__ void __launch_bounds__(256) centers_kernel(const CenterParams P)
         __syncthreads();
     }
     if (tid == 0) { P.centers[3 * h] = 0.0; P.centers[3 * h + 1] = 0.0; P.centers[3 * h + 2] = 0.0; }
+}
+
+// calcMode for large objects: a thread-block cluster per object.  CTA r owns the r-th slice of the object's
+// members and compacts the survivors of its slice in place (slice-local index lists), the partial sums and
+// counts are exchanged through distributed shared memory in rank order (deterministic), two cluster barriers
+// per shrinking step.  Same arithmetic as centers_kernel.
+__global__ void __launch_bounds__(256) centers_mode_cluster_kernel(const CenterParams P)
+{
+    namespace cg = cooperative_groups;
+    __shared__ double scratch[8 * 6 + 6];
+    __shared__ double s_pub[2][8];   // published partial sums (double-buffered)
+    __shared__ int s_cnt[2];
+    __shared__ int s_scan[8];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    const int h = P.order[P.first_obj + blockIdx.x / C];
+    const int N = P.size[h];
+    const int64_t first = P.G.off[h];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double ref[3] = {0.0, 0.0, 0.0};
+    if (P.ref) { ref[0] = P.ref[3 * h]; ref[1] = P.ref[3 * h + 1]; ref[2] = P.ref[3 * h + 2]; }
+    const int lo = (int)((int64_t)N * rank / C), hi = (int)((int64_t)N * (rank + 1) / C);
+    int *A = P.idxA + first + lo, *B = P.idxB + first + lo;
+    double rad = 1000.0;
+    int buf = 0;
+    if (P.shape_path) {
+        double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+        for (int i = lo + tid; i < hi; i += blockDim.x) {
+            double x, y, z, m;
+            unwrapped(P, first, i, ref, x, y, z, m);
+            mn[0] = fmin(mn[0], x); mx[0] = fmax(mx[0], x);
+            mn[1] = fmin(mn[1], y); mx[1] = fmax(mx[1], y);
+            mn[2] = fmin(mn[2], z); mx[2] = fmax(mx[2], z);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            for (int o = 16; o > 0; o >>= 1) {
+                mn[k] = fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+                mx[k] = fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+            }
+        if (lane == 0)
+            for (int k = 0; k < 3; k++) { scratch[warp * 6 + k] = mn[k]; scratch[warp * 6 + 3 + k] = mx[k]; }
+        __syncthreads();
+        if (tid < 6) {
+            double v = scratch[tid];
+            for (int w = 1; w < 8; w++) v = (tid < 3) ? fmin(v, scratch[w * 6 + tid]) : fmax(v, scratch[w * 6 + tid]);
+            s_pub[buf][tid] = v;
+        }
+        cluster.sync();
+        double ext = 0.0;
+        for (int k = 0; k < 3; k++) {
+            double l = 1e300, u = -1e300;
+            for (int r = 0; r < C; r++) {
+                const double *rp = cluster.map_shared_rank(&s_pub[buf][0], r);
+                l = fmin(l, rp[k]); u = fmax(u, rp[3 + k]);
+            }
+            ext = fmax(ext, u - l);
+        }
+        rad = ext;
+        buf ^= 1;
+    }
+    for (int i = lo + tid; i < hi; i += blockDim.x) A[i - lo] = i;
+    int n_alive = hi - lo;
+    __syncthreads();
+    for (int iter = 0; iter < 4096; iter++) {
+        double v[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int j = tid; j < n_alive; j += blockDim.x) {
+            double x, y, z, m;
+            unwrapped(P, first, A[j], ref, x, y, z, m);
+            v[0] = fma(x, m, v[0]); v[1] = fma(y, m, v[1]); v[2] = fma(z, m, v[2]);
+            v[3] += m;
+        }
+        block_sum_bcast<4>(v, scratch);
+        if (tid < 4) s_pub[buf][tid] = v[tid];
+        cluster.sync();
+        double t[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int r = 0; r < C; r++) {
+            const double *rp = cluster.map_shared_rank(&s_pub[buf][0], r);
+#pragma unroll
+            for (int k = 0; k < 4; k++) t[k] += rp[k];
+        }
+        const double cx = t[0] / t[3], cy = t[1] / t[3], cz = t[2] / t[3];
+        int base = 0;
+        for (int j0 = 0; j0 < n_alive; j0 += blockDim.x) {
+            const int j = j0 + tid;
+            int p = -1;
+            bool keep = false;
+            if (j < n_alive) {
+                p = A[j];
+                double x, y, z, m;
+                unwrapped(P, first, p, ref, x, y, z, m);
+                const double ax = x - cx, ay = y - cy, az = z - cz;
+                keep = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az))) < rad;
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) s_scan[warp] = __popc(bal);
+            __syncthreads();
+            int before = 0, total = 0;
+            for (int w = 0; w < 8; w++) {
+                const int c = s_scan[w];
+                if (w < warp) before += c;
+                total += c;
+            }
+            if (keep) B[base + before + __popc(bal & ((1u << lane) - 1u))] = p;
+            base += total;
+            __syncthreads();
+        }
+        if (tid == 0) s_cnt[buf] = base;
+        cluster.sync();
+        int total_alive = 0;
+        for (int r = 0; r < C; r++) total_alive += *cluster.map_shared_rank(&s_cnt[buf], r);
+        buf ^= 1;
+        if (total_alive < 5) {
+            if (rank == 0 && tid == 0) { P.centers[3 * h] = cx; P.centers[3 * h + 1] = cy; P.centers[3 * h + 2] = cz; }
+            break;
+        }
+        int *tmp = A; A = B; B = tmp;
+        n_alive = base;
+        rad *= 0.83;
+        if (iter == 4095 && rank == 0 && tid == 0) { P.centers[3 * h] = 0.0; P.centers[3 * h + 1] = 0.0; P.centers[3 * h + 2] = 0.0; }
+    }
+    cluster.sync();   // nobody leaves while a peer may still read its shared memory
 }
 
 }  // namespace cpg

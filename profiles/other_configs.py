@@ -94,6 +94,10 @@ def kde():
 ms, tim = timed(kde, 2)
 out["config2_dens_kernel_R50"] = dict(halos=nh, particles=npart, wall_ms=ms, kernel_ms=tim["kernel_ms"],
                                       evaluations_per_s=npart * 50 / (tim["kernel_ms"] * 1e-3))
+# section 8(f) next-1: the centre finding the drivers do before the hot path, on the device
+for label, mode in (("com", 0), ("mode", 1)):
+    ms, tim = timed(lambda: (ctx.centers(mode, True, 0.0, None), ctx.timing())[1])
+    out["centers_%s_configs1_catalogue" % label] = dict(halos=nh, particles=npart, wall_ms=ms, kernel_ms=tim["kernel_ms"])
 # ellipsoidal binning needs the local shape profile first (default 70-shell config), then scipy interpolation
 o, nit, _, _, _ = ctx.shape(cat["centers"], cat["r200"], bench.RR, True, 0.0, 0.0, *K, False, False, False)
 o = o.copy()

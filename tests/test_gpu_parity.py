@@ -285,3 +285,39 @@ def test_unusual_radii_and_limits(gpu, big):
             P.assert_ints(S.last_info["n_iter"], nit, tag + " n_iter")
             P.assert_ints(S.last_info["n_pts"], npt, tag + " n_pts")
             P.assert_shape_tuple(got, ref, tag)
+
+
+def test_device_centres_large_objects(gpu):
+    """Objects above the cluster threshold of cpg_centers (8 CTAs per object, slice-local compaction, partial sums
+    exchanged through distributed shared memory): same 'mode' / 'com' centres as the numpy restatement, with and
+    without a periodic box."""
+    from cosmic_profiles_b200 import centers as C
+    from cosmic_profiles_b200 import session as sess_mod
+    from oracle import cp_oracle as O
+    rng = np.random.default_rng(77)
+    sizes = np.array([40000, 700, 131075, 32768, 32767, 5, 90001], dtype=np.int32)
+    L = 50.0
+    parts = []
+    for n in sizes:
+        c = rng.uniform(0.0, L, 3)
+        r = 0.4 * rng.random(n) ** 2.0           # cuspy: many shrinking steps before fewer than 5 are left
+        u = rng.normal(size=(n, 3))
+        u /= np.linalg.norm(u, axis=1)[:, None]
+        parts.append(c + r[:, None] * u * np.array([1.0, 0.7, 0.5]))
+    X = np.ascontiguousarray(np.concatenate(parts))
+    M = np.ascontiguousarray(rng.uniform(0.5, 1.5, len(X)))
+    I = rng.permutation(len(X)).astype(np.int32)
+    # catalogue order = a permutation of the particle array, objects stay contiguous in idx_cat
+    owner = np.repeat(np.arange(len(sizes)), sizes)
+    I = np.concatenate([rng.permutation(np.flatnonzero(owner == h)) for h in range(len(sizes))]).astype(np.int32)
+    ctx = sess_mod.get_context(0)
+    for box in (0.0, L):
+        Xb = np.ascontiguousarray(np.mod(X, L)) if box else X
+        ctx.set_particles(Xb, None, M)
+        ctx.set_catalogue(I, sizes)
+        ref = C.reference_points(Xb, I, sizes) if box else None
+        for center in ("mode", "com"):
+            for shape_path in (True, False):
+                want = O.centres(Xb, M, I, sizes, box, center, shape_path)
+                got = ctx.centers(1 if center == "mode" else 0, shape_path, box, ref)
+                assert np.abs(got - want).max() <= 1e-11 * max(np.abs(want).max(), 1.0), (box, center, shape_path)
