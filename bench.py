@@ -198,20 +198,57 @@ def time_reference(cat, pick, steps, warmup):
 # ------------------------------------------------------------------------------------------ clocks
 
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU, sampled while the timed regions run (B200_PROFILING.md's clocks
+    line).  Primary source: NVML in-process (the library nvidia-smi itself reads; a sample every 20 ms, so even a
+    200 ms timed region is covered); fallback: an `nvidia-smi -lms 100` child.  Every sample carries its host
+    timestamp; stop(t0, t1) keeps the samples taken inside [t0, t1]."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.device = device
-        self.rows = []
+        self.rows = []       # (t, sm_mhz, sm_max_mhz, [reason names])
         self.proc = None
+        self.source = None
+        self._stop = threading.Event()
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.device
+            if vis:
+                ent = vis.split(",")[self.device].strip()
+                phys = int(ent) if ent.isdigit() else self.device
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                     ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                     ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                        bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.rows.append((time.perf_counter(), sm, mx, [n for n, b in names if bits & b]))
+                    except Exception:
+                        pass
+                    self._stop.wait(0.02)
+            self.source = "nvml"
+            self.th = threading.Thread(target=loop, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -219,29 +256,34 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+            r = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
+                why = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8])
+                       if v.lower().startswith("active")]
+                self.rows.append((time.perf_counter(), float(r[1]), float(r[2]), why))
             except Exception:
                 pass
-        busy = [v for v in sm if v > 0]
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def stop(self, t0=None, t1=None):
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi / NVML unavailable"], "samples": 0}
+        self._stop.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            self.th.join(timeout=1)
+        rows = [r for r in self.rows if (t0 is None or r[0] >= t0) and (t1 is None or r[0] <= t1)]
+        window = "timed regions"
+        if not rows:   # region shorter than the sampling period: fall back to everything seen since start()
+            rows, window = list(self.rows), "whole run (no sample fell inside the timed regions)"
+        sm = [r[1] for r in rows if r[1] > 0]
+        reasons = sorted({n for r in rows for n in r[3]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max((r[2] for r in rows), default=None),
+                "reasons": reasons, "samples": len(rows), "source": self.source, "window": window}
 
 
 # ------------------------------------------------------------------------------------ rank reduction
@@ -371,8 +413,9 @@ def main():
     except Exception:
         visited_local = pi_local
     clocks = ClockSampler(local_rank)
-    barrier()
     clocks.start()
+    barrier()
+    t_clk0 = time.perf_counter()
     dev_ms = 0.0
     brk = {}
     kern_local_ms = 0.0
@@ -390,7 +433,6 @@ def main():
         hot_launches_local += t_l["hot_kernel_launches"]
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - w0)
-    clk = clocks.stop()
 
     # ---- end-to-end timing from pinned host buffers (e2e) ---------------------------------------
     # (1) strictly serial: every step uploads its inputs, computes, reads its results back, then the next
@@ -444,6 +486,7 @@ def main():
         if pipe_ms < e2e_serial_ms:
             e2e_ms, e2e_mode = pipe_ms, "double-buffered (2 contexts, uploads of step i+1 overlap kernels of step i)"
         ctx2.close()
+    clk = clocks.stop(t_clk0, time.perf_counter())   # the resident-input steps and both e2e measurements
     h2d = int(cat["xyz"].nbytes + cat["masses"].nbytes + cat["idx_cat"].nbytes + cat["obj_size"].nbytes
               + 2 * (cat["centers"].nbytes + cat["r200"].nbytes) + RR.nbytes)
     d2h = int(t_l["d2h_bytes"] + t_g["d2h_bytes"])

@@ -101,12 +101,13 @@ struct cpg_ctx {
     DevBuf<float> mass32;
     DevBuf<uint8_t> skip, bucket;
     DevBuf<int32_t> tile_hist, dest, n_eff, cidxA, cidxB, d_order;
-    DevBuf<double> cref;
+    DevBuf<double> cref, ptab;
     bool sorted_valid = false;    // the SoA streams are in radial-bucket order and `dest` maps catalogue -> slot
     // what the gathered SoA currently holds (skip the gather when a call asks for the same thing again)
     uint64_t snapshot_version = 0, catalogue_version = 0;
     struct {
         bool valid = false, stats = false, vel = false;
+        int ptab = 0;   // prefix tensor table: 0 none, 1 positions, 2 velocities
         uint64_t snap = 0, cat = 0;
         float L_BOX = 0.f;
         int sort_R = 0;
@@ -135,6 +136,7 @@ struct cpg_ctx {
     int64_t opt_large_halo_min = 0;
     int opt_cluster_size = 0;
     int opt_radial_order = 1;
+    int opt_prefix_table = 1;
     int opt_groups = 0;   // 0 auto, 1 one group of S shells per warp task, 2 two groups
     cpg_timing timing = {};
 };
@@ -273,7 +275,7 @@ int run_gather(cpg_ctx *c, const double *h_centers, const double *h_r200, const 
         same = H.sort_R == sort_R && H.rr.size() == (size_t)sort_R && !memcmp(H.rr.data(), h_rr, sort_R * sizeof(double)) &&
                H.r200.size() == (size_t)c->n_obj && !memcmp(H.r200.data(), h_r200, c->n_obj * sizeof(double));
     if (same) return CPG_OK;
-    H.valid = false; H.stats = false; H.vel = false;
+    H.valid = false; H.stats = false; H.vel = false; H.ptab = 0;
     CPG_TRY(c->g_dx.ensure(c->n_pad)); CPG_TRY(c->g_dy.ensure(c->n_pad));
     CPG_TRY(c->g_dz.ensure(c->n_pad)); CPG_TRY(c->g_m.ensure(c->n_pad));
     c->sorted_valid = false;
@@ -356,6 +358,25 @@ int run_vcenters(cpg_ctx *c, float L_BOX)
     }
     CPG_CUDA(cudaGetLastError());
     c->have.vel = c->have.valid;
+    return CPG_OK;
+}
+
+// Prefix tensor table of the radially ordered SoA (cpg_gather.cuh): built once per gather, reused by every
+// non-reduced ellipsoid-based cpg_shape call on it.
+int run_ptab(cpg_ctx *c, bool use_vel)
+{
+    const int want = use_vel ? 2 : 1;
+    if (c->have.valid && c->have.ptab == want) return CPG_OK;
+    const int nc = (int)c->h_kchunks.size();
+    CPG_TRY(c->ptab.ensure(((size_t)(c->n_pad >> 7) + (size_t)c->n_obj + 1) * 6));
+    if (nc > 0) {
+        tile_tensor_kernel<<<nc, 256, 0, c->stream>>>(soa_view(c), c->kchunks.p, nc, use_vel ? 1 : 0, c->ptab.p);
+        tile_tensor_scan_kernel<<<grid_for((int64_t)c->n_obj * 32, 128, 1 << 30), 128, 0, c->stream>>>(soa_view(c), c->n_obj,
+                                                                                                     c->ptab.p);
+        c->timing.kernel_launches += 2;
+    }
+    CPG_CUDA(cudaGetLastError());
+    c->have.ptab = c->have.valid ? want : 0;
     return CPG_OK;
 }
 
@@ -560,7 +581,7 @@ CPG_API void cpg_destroy(cpg_ctx *c)
     c->off.release(); c->poff.release(); c->chunks.release(); c->kchunks.release();
     c->mass32.release(); c->skip.release(); c->tasks.release(); c->bucket.release();
     c->grid_states.release(); c->grid_partials.release();
-    c->tile_hist.release(); c->dest.release(); c->n_eff.release(); c->cidxA.release(); c->cidxB.release(); c->d_order.release();
+    c->tile_hist.release(); c->dest.release(); c->n_eff.release(); c->cidxA.release(); c->cidxB.release(); c->d_order.release(); c->ptab.release();
     c->cref.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -594,6 +615,8 @@ CPG_API int cpg_set_option(cpg_ctx *c, const char *name, int64_t value)
         c->opt_groups = (int)value;
     } else if (!strcmp(name, "radial_order")) {
         c->opt_radial_order = value != 0;
+    } else if (!strcmp(name, "prefix_table")) {
+        c->opt_prefix_table = value != 0;
     } else if (!strcmp(name, "cluster_size")) {
         if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16) {
             set_error("cluster_size must be 0, 1, 2, 4, 8 or 16");
@@ -819,6 +842,8 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     CPG_TRY(run_gather(c, centers, r200, r_over_r200, L_BOX, radial ? R : 0));
     CPG_TRY(run_stats(c));
     if (use_vel) CPG_TRY(run_vcenters(c, L_BOX));
+    const bool inner = radial && !shell_based && !reduced && c->opt_prefix_table;
+    if (inner) CPG_TRY(run_ptab(c, use_vel != 0));
     T.mark(2);
 
     // ---- the morphology loop
@@ -826,6 +851,7 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     P.soa = soa_view(c);
     P.r200 = c->r200.p; P.rr = c->rr.p; P.skip = c->skip.p;
     P.n_eff = radial ? c->n_eff.p : nullptr;   // run_gather guarantees n_eff matches these radii when radial
+    P.ptab = inner ? c->ptab.p : nullptr;
     P.tasks = c->tasks.p; P.n_tasks = 0; P.task_counter = c->task_counter.p;
     P.R = R; P.local = local ? 1 : 0; P.SAFE = SAFE;
     P.tol = IT_TOL; P.wall = IT_WALL; P.itmin = IT_MIN;

@@ -44,6 +44,8 @@ struct MorphParams {
     const double *r200;        // n_obj
     const double *rr;          // R (local) or unused
     const int32_t *n_eff;      // (n_obj, R) radial-prefix lengths (cpg_gather.cuh) or nullptr = all particles
+    const double *ptab;        // prefix tensor table (cpg_gather.cuh) or nullptr = no inner prefix (shell / reduced /
+                               // no radial order): rows of 6 doubles, row (poff[h] >> 7) + h + t = first 128 (t+1) particles
     const uint8_t *skip;       // n_obj: 1 = per-object early exit (degenerate cloud), shape_profs_algos.pyx:1024
     const Task *tasks;
     int32_t n_tasks;

@@ -520,4 +520,82 @@ __global__ void __launch_bounds__(256) gather_bucketed_kernel(const SortParams P
 
 constexpr size_t GATHER_BUCKETED_SMEM = (size_t)SORT_CHUNK * (4 * sizeof(double) + sizeof(int)) + 9 * SORT_MAX_B * sizeof(int);
 
+// ------------------------------------------------------------------------------------------------
+// Prefix tensor table.  With the particles of an object in radial order, the particles of the whole 128-particle
+// tiles below |x-c| < s*d are members of the shell's ellipsoid whatever its orientation (cpg_morph.cuh, InnerPrefix),
+// and their contribution to the shape tensor is the same in every Katz iteration of every shell of the object.
+// ptab[(toff(h) + t) * 6 + c] = sum over the first 128 (t+1) particles of object h of m * (xx, xy, xz, yy, yz, zz)
+// (positions, or velocities about the velocity centre for the dispersion variant): the morphology kernels stream
+// only the tiles past the inner prefix and add one table row.  toff(h) = (poff[h] >> 7) + h.
+// Two kernels: per-tile sums (a warp per tile, every particle read once), then an in-place scan along each object.
+// ------------------------------------------------------------------------------------------------
+constexpr int PT_TILE = 128;   // == 2 * TILE_PAIRS of cpg_morph.cuh
+
+__device__ __forceinline__ int64_t ptab_row0(const int64_t *poff, int h) { return (poff[h] >> 7) + h; }
+
+__global__ void __launch_bounds__(256) tile_tensor_kernel(const SoA soa, const Chunk *chunks, int n_chunks, int use_vel,
+                                                          double *ptab)
+{
+    const Chunk ck = chunks[blockIdx.x];   // 2048-particle chunks = 16 tiles, two per warp
+    const int h = ck.halo, N = soa.size[h];
+    const int64_t base = soa.poff[h];
+    const int64_t row0 = ptab_row0(soa.poff, h);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double *px = use_vel ? soa.vx : soa.dx, *py = use_vel ? soa.vy : soa.dy, *pz = use_vel ? soa.vz : soa.dz;
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int t = ck.start / PT_TILE + 2 * warp + r;
+        if ((int64_t)(t + 1) * PT_TILE > N) break;   // whole tiles only (warp-uniform)
+        double a[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int64_t o = base + (int64_t)t * PT_TILE + 2 * (lane + 32 * q);
+            const double2 x = *reinterpret_cast<const double2 *>(px + o), y = *reinterpret_cast<const double2 *>(py + o);
+            const double2 z = *reinterpret_cast<const double2 *>(pz + o), m = *reinterpret_cast<const double2 *>(soa.m + o);
+            a[0] = fma(m.x, x.x * x.x, a[0]); a[1] = fma(m.x, x.x * y.x, a[1]); a[2] = fma(m.x, x.x * z.x, a[2]);
+            a[3] = fma(m.x, y.x * y.x, a[3]); a[4] = fma(m.x, y.x * z.x, a[4]); a[5] = fma(m.x, z.x * z.x, a[5]);
+            a[0] = fma(m.y, x.y * x.y, a[0]); a[1] = fma(m.y, x.y * y.y, a[1]); a[2] = fma(m.y, x.y * z.y, a[2]);
+            a[3] = fma(m.y, y.y * y.y, a[3]); a[4] = fma(m.y, y.y * z.y, a[4]); a[5] = fma(m.y, z.y * z.y, a[5]);
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++) a[c] = warp_sum(a[c]);
+        if (lane == 0) {
+            double *row = ptab + (row0 + t) * 6;
+#pragma unroll
+            for (int c = 0; c < 6; c++) row[c] = a[c];
+        }
+    }
+}
+
+// In-place inclusive scan of the tile rows of every object (a warp per object, 32 tiles per step, fixed tree).
+__global__ void __launch_bounds__(128) tile_tensor_scan_kernel(const SoA soa, int n_obj, double *ptab)
+{
+    const int h = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (h >= n_obj) return;
+    const int lane = threadIdx.x & 31;
+    const int nt = soa.size[h] / PT_TILE;
+    double *rows = ptab + ptab_row0(soa.poff, h) * 6;
+    double carry[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int t0 = 0; t0 < nt; t0 += 32) {
+        const int t = t0 + lane;
+        double v[6];
+#pragma unroll
+        for (int c = 0; c < 6; c++) v[c] = t < nt ? rows[(size_t)t * 6 + c] : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int c = 0; c < 6; c++) {
+                const double u = __shfl_up_sync(0xffffffffu, v[c], o);
+                if (lane >= o) v[c] += u;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            v[c] += carry[c];
+            if (t < nt) rows[(size_t)t * 6 + c] = v[c];
+            carry[c] = __shfl_sync(0xffffffffu, v[c], 31);
+        }
+    }
+}
+
 }  // namespace cpg

@@ -90,23 +90,6 @@ __device__ __forceinline__ void accumulate(double (&acc)[7], int &cnt, bool sel,
     }
 }
 
-// A particle that is certainly inside the ellipsoid (see run_pass: inner radial prefix): no test at all.
-template <bool VDISP>
-__device__ __forceinline__ void accumulate_inside(double (&acc)[7], const Particle &p)
-{
-    if (VDISP) {
-#pragma unroll
-        for (int c = 0; c < 6; c++) acc[c] = fma(p.m, p.t[c], acc[c]);
-    } else {
-        acc[0] = fma(p.m, p.xx, acc[0]);
-        acc[1] = fma(p.m, p.xy, acc[1]);
-        acc[2] = fma(p.m, p.xz, acc[2]);
-        acc[3] = fma(p.m, p.yy, acc[3]);
-        acc[4] = fma(p.m, p.yz, acc[4]);
-        acc[5] = fma(p.m, p.zz, acc[5]);
-    }
-}
-
 // Pass 0 (spherical start, shape_profs_algos.pyx:206-212 / :81-87) runs through the same code with A = B = I
 // and thr = (d-delta)^2: the fma chain below then evaluates ((xx + yy) + zz) + 0 + 0 + 0 with xx, yy, zz
 // the exactly rounded squares, i.e. bit for bit the reference's r2 -- no separate code path (the kernels
@@ -115,19 +98,12 @@ __device__ __forceinline__ void accumulate_inside(double (&acc)[7], const Partic
 // (shape_profs_algos.pyx:247-260 / :122-143) fused with the next tensor accumulation.
 template <int S, bool SHELL, bool REDUCED, bool VDISP, int NP>
 __device__ __forceinline__ void passk_particles(const Particle (&p)[NP], const double *frames, unsigned smask,
-                                                unsigned inmask, double (&acc)[S][7], int (&cnt)[S])
+                                                double (&acc)[S][7], int (&cnt)[S])
 {
 #pragma unroll
     for (int s = 0; s < S; s++) {
-        // inmask: this whole tile lies in the shell's inner prefix |x-c| < s*d (1-1e-9): with q, s <= 1 the
-        // ellipsoidal radius obeys r_ell^2 <= |x-c|^2 / s^2 < d^2, every particle is a member, nothing to test
-        if (!SHELL && !REDUCED && (inmask & (1u << s))) {
-#pragma unroll
-            for (int j = 0; j < NP; j++) accumulate_inside<VDISP>(acc[s], p[j]);
-            cnt[s] += NP;
-            continue;
-        }
-        // smask: shells that are still iterating AND whose radial prefix reaches this tile (warp-uniform)
+        // smask: shells that are still iterating, whose radial prefix reaches this tile and whose inner prefix
+        // (served by the prefix tensor table) ends before it (warp-uniform)
         if (smask & (1u << s)) {
             const double2 *F2 = reinterpret_cast<const double2 *>(frames + s * F_SLOTS);
             const double2 f0 = F2[0], f1 = F2[1], f2 = F2[2], f3 = F2[3];
@@ -168,7 +144,9 @@ __device__ __forceinline__ void quad_form(double *A, const double (&v)[9], doubl
 }
 
 // Inner radial prefix of a shell: the particles of the buckets j with rr[j] <= s * rr[k] * (1 - 1e-9) lie at
-// |x-c| < s*d_k and are members of shell k's ellipsoid whatever its orientation.  rr: the R shell radii (shared
+// |x-c| < s*d_k; with q, s <= 1 their ellipsoidal radius obeys r_ell^2 <= |x-c|^2 / s^2 < d_k^2, so they are
+// members of shell k's ellipsoid whatever its orientation.  The whole 128-particle tiles of that prefix are never
+// streamed: their tensor sums are one row of the prefix tensor table (cpg_gather.cuh), added after the reduction.  rr: the R shell radii (shared
 // memory copy), neff: this object's prefix lengths (shared memory copy); both null when there is no ordering.
 struct InnerPrefix {
     const double *rr;
@@ -439,9 +417,13 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
                                          const int (&npr)[S], const int *nin, unsigned amask, double (&acc)[S][7],
                                          int (&cnt)[S])
 {
-    int ninr[S];
+    // tin[s]: whole tiles of shell s's inner prefix -- served by the prefix tensor table, not streamed
+    int tin[S], tlow = 0x7fffffff;
 #pragma unroll
-    for (int s = 0; s < S; s++) ninr[s] = nin[s];
+    for (int s = 0; s < S; s++) {
+        tin[s] = nin[s] / TILE_PAIRS;
+        if (amask & (1u << s)) tlow = min(tlow, tin[s]);
+    }
 #pragma unroll
     for (int s = 0; s < S; s++) {
         cnt[s] = 0;
@@ -449,6 +431,10 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
         for (int k = 0; k < 7; k++) acc[s][k] = 0.0;
     }
     constexpr int RING_STAGES = RingCfg<VDISP>::STAGES;
+    // a resident task keeps all of its tiles in the ring (slot j <-> tile tile0 + j * tstride) and just skips the
+    // ones no shell needs; a streamed pass starts at the first tile some active shell still has to test
+    const int tskip = resident ? 0 : tlow;
+    tile0 += tskip;
     const int ntiles = (npairs + TILE_PAIRS - 1) / TILE_PAIRS;
     const int nmine = tile0 < ntiles ? (ntiles - tile0 + tstride - 1) / tstride : 0;
     const bool reuse = resident && ring.res_loaded;
@@ -475,28 +461,23 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
         unsigned smask = 0;
 #pragma unroll
         for (int s = 0; s < S; s++)
-            if (t * TILE_PAIRS < npr[s]) smask |= 1u << s;
+            if (t * TILE_PAIRS < npr[s] && t >= tin[s]) smask |= 1u << s;
         smask &= amask;
-        unsigned inmask = 0;
-        if (!SHELL && !REDUCED) {
-#pragma unroll
-            for (int s = 0; s < S; s++)
-                if ((t + 1) * TILE_PAIRS <= ninr[s]) inmask |= 1u << s;
-            inmask &= amask;
-        }
-        if (VDISP) {
+        if (smask == 0) {
+            // (resident tasks only)
+        } else if (VDISP) {
             // two particles at a time: the dispersion variant carries 13 doubles per particle
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 Particle p[2];
                 ring_read_pair<VDISP>(ring, seq, lane + 32 * h, p[0], p[1]);
-                passk_particles<S, SHELL, REDUCED, VDISP, 2>(p, frames, smask, inmask, acc, cnt);
+                passk_particles<S, SHELL, REDUCED, VDISP, 2>(p, frames, smask, acc, cnt);
             }
         } else {
             Particle p[4];
             ring_read_pair<VDISP>(ring, seq, lane, p[0], p[1]);
             ring_read_pair<VDISP>(ring, seq, lane + 32, p[2], p[3]);
-            passk_particles<S, SHELL, REDUCED, VDISP, 4>(p, frames, smask, inmask, acc, cnt);
+            passk_particles<S, SHELL, REDUCED, VDISP, 4>(p, frames, smask, acc, cnt);
         }
         if (!resident && j + RING_STAGES < nmine) {
             __syncwarp();   // every lane has taken its data out of this slot
@@ -585,6 +566,16 @@ __device__ __forceinline__ void init_frames(double *frames, int *np, int *nin, c
     }
 }
 
+// What the prefix tensor table contributes to value `comp` (0..5 tensor sums, 7 particle count) of a shell whose
+// inner prefix holds `pairs_in` pairs: the row of its last whole tile.  row0 = table row of the object's tile 0.
+__device__ __forceinline__ double table_term(const double *ptab, int64_t row0, int pairs_in, int comp)
+{
+    const int tin = pairs_in / TILE_PAIRS;
+    if (!ptab || tin == 0) return 0.0;
+    if (comp < 6) return ptab[(row0 + tin - 1) * 6 + comp];
+    return comp == 7 ? (double)(2 * TILE_PAIRS) * (double)tin : 0.0;
+}
+
 template <int S>
 __device__ __forceinline__ void pack_values(const double (&acc)[S][7], const int (&cnt)[S], double (&val)[8 * S])
 {
@@ -614,7 +605,7 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
     const int ls = L.ls;
     WarpRing ring;
     ring_init(ring, s_ring_w + warp * RingCfg<VDISP>::WARP_BYTES, s_bar[warp], lane);
-    const bool use_inner = !SHELL && !REDUCED && P.n_eff != nullptr;
+    const bool use_inner = !SHELL && !REDUCED && P.n_eff != nullptr && P.ptab != nullptr;
     if (use_inner) {
         for (int j = threadIdx.x; j < P.R; j += blockDim.x) s_rr[j] = P.rr[j];
         __syncthreads();
@@ -622,6 +613,7 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
     InnerPrefix ip;
     ip.rr = use_inner ? s_rr : nullptr;
     ip.neff = s_neff[warp];
+    const double *ptab = use_inner ? P.ptab : nullptr;
 
     for (;;) {
         int t = 0;
@@ -661,6 +653,7 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
         }
         const bool resident = (npairs_task + TILE_PAIRS - 1) / TILE_PAIRS <= RingCfg<VDISP>::STAGES;
         ring.res_loaded = false;
+        const int64_t row0 = (base >> 7) + halo;
 
         while (true) {
             // one pass per group of S shells; every group leaves its 8S sums transposed in one register
@@ -670,6 +663,9 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
                 const unsigned am = (amask >> (g * S)) & ((1u << S) - 1u);
                 mine[g] = 0.0;
                 if (am) {
+                    // this lane's value (lane mod 8S) of the reduction = component (lane & 7) of shell (lane mod 8S) / 8:
+                    // fetch what the table adds for the shell's inner prefix now, consume it after the pass
+                    const double tadd = table_term(ptab, row0, nin[g * S + ((lane & (8 * S - 1)) >> 3)], lane & 7);
                     double acc[S][7];
                     int cnt[S];
                     run_pass<S, SHELL, REDUCED, VDISP>(P.soa, base, active_npairs<S>(npr[g], am), 0, 1, lane, ring, resident,
@@ -677,7 +673,7 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
                                                        cnt);
                     double val[8 * S];
                     pack_values<S>(acc, cnt, val);
-                    mine[g] = warp_sum_transpose<8 * S>(val, lane);
+                    mine[g] = warp_sum_transpose<8 * S>(val, lane) + tadd;
                 }
             }
             double tot[7], vprev[9];
@@ -757,7 +753,8 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     const int k = tk.shell0 + (st.active ? ls : 0);
     shell_geometry(P, halo, k, st.d, st.delta);
     const size_t out_idx = (size_t)halo * P.R + k;
-    const bool use_inner = !SHELL && !REDUCED && P.n_eff != nullptr;
+    const bool use_inner = !SHELL && !REDUCED && P.n_eff != nullptr && P.ptab != nullptr;
+    const int64_t row0 = (base >> 7) + halo;
     if (use_inner) {
         for (int j = threadIdx.x; j < P.R; j += blockDim.x) {
             s_rr[j] = P.rr[j];
@@ -777,7 +774,9 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     for (int s = 0; s < S; s++) npr[s] = np[s];
     const int npairs_task = active_npairs<S>(npr, amask);
     const int nt_task = (npairs_task + TILE_PAIRS - 1) / TILE_PAIRS;
-    const bool resident = (tile0 < nt_task ? (nt_task - tile0 + tstride - 1) / tstride : 0) <= RingCfg<VDISP>::STAGES;
+    // uniform over the cluster's warps (a streamed pass deals the tiles from the first one some shell still tests,
+    // a resident one from tile 0: the two dealings must not be mixed inside one task)
+    const bool resident = (nt_task + tstride - 1) / tstride <= RingCfg<VDISP>::STAGES;
 
     double acc[S][7];
     int cnt[S];
@@ -814,6 +813,12 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
                 for (int c = 0; c < 7; c++) tot[c] += remote[c];
                 ptsd += remote[7];
             }
+        }
+        if (use_inner) {   // the inner prefix of the pass just finished comes from the table
+            const int pin = nin[ls];
+#pragma unroll
+            for (int c = 0; c < 6; c++) tot[c] += table_term(P.ptab, row0, pin, c);
+            ptsd += table_term(P.ptab, row0, pin, 7);
         }
 #pragma unroll
         for (int r = 0; r < 9; r++) vprev[r] = frames[ls * F_SLOTS + F_V + r];
@@ -865,8 +870,8 @@ __global__ void grid_init_kernel(const MorphParams P, const Task *tasks, GridSta
     const int k = tk.shell0 + (ls < tk.nshell ? ls : 0);
     shell_geometry(P, halo, k, st.d, st.delta);
     const size_t out_idx = (size_t)halo * P.R + k;
-    InnerPrefix ip;
-    ip.rr = (!P.n_eff) ? nullptr : P.rr;
+    InnerPrefix ip;   // (the host passes ptab only for the non-reduced ellipsoid variant on radially ordered particles)
+    ip.rr = (P.n_eff && P.ptab) ? P.rr : nullptr;
     ip.neff = P.n_eff ? P.n_eff + (size_t)halo * P.R : nullptr;
     init_frames(gs->frames, gs->np, gs->nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : P.soa.size[halo], ip, k);
     if (L.writer) {
@@ -893,7 +898,7 @@ __global__ void __launch_bounds__(GRID_KERNEL_WARPS * 32) grid_pass_kernel(const
     if (amask == 0) return;   // converged (uniform over the grid)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < S * F_SLOTS; i += blockDim.x) s_frames[i] = gs->frames[i];
-    if (threadIdx.x < S) s_nin[threadIdx.x] = (!SHELL && !REDUCED) ? gs->nin[threadIdx.x] : 0;
+    if (threadIdx.x < S) s_nin[threadIdx.x] = (!SHELL && !REDUCED && P.ptab) ? gs->nin[threadIdx.x] : 0;
     WarpRing ring;
     ring_init(ring, s_ring_g + warp * RingCfg<VDISP>::WARP_BYTES, s_bar[warp], lane);
     __syncthreads();
@@ -927,6 +932,8 @@ __global__ void grid_step_kernel(const MorphParams P, GridState *gs, const doubl
     const int ls = L.ls;
     double mine = 0.0;
     for (int b = 0; b < n_cta; b++) mine += partials[(size_t)b * NV + (lane & (NV - 1))];   // fixed order
+    if (!SHELL && P.n_eff && P.ptab)   // inner prefix of the pass just finished
+        mine += table_term(P.ptab, (P.soa.poff[gs->halo] >> 7) + gs->halo, gs->nin[(lane & (NV - 1)) >> 3], lane & 7);
     double tot[7], vprev[9];
 #pragma unroll
     for (int c = 0; c < 7; c++) tot[c] = __shfl_sync(0xffffffffu, mine, (lane & ~7) + c);
@@ -939,7 +946,7 @@ __global__ void grid_step_kernel(const MorphParams P, GridState *gs, const doubl
 #pragma unroll
     for (int r = 0; r < 9; r++) vprev[r] = gs->frames[ls * F_SLOTS + F_V + r];
     InnerPrefix ip;
-    ip.rr = (!P.n_eff) ? nullptr : P.rr;
+    ip.rr = (P.n_eff && P.ptab) ? P.rr : nullptr;
     ip.neff = P.n_eff ? P.n_eff + (size_t)gs->halo * P.R : nullptr;
     __syncwarp();
     katz_step<SHELL>(st, tot, pts, P, vprev, gs->frames + ls * F_SLOTS, L.writer, out_idx, L.writer, ip, k, gs->nin + ls);

@@ -128,10 +128,11 @@ SCHED = [dict(shells_per_pass=1, large_halo_min=1 << 40, cluster_size=0),     # 
          dict(shells_per_pass=4, shell_groups=2, large_halo_min=1 << 40, cluster_size=0),   # 8 shells per warp task
          dict(shells_per_pass=4, shell_groups=2, large_halo_min=8000, cluster_size=2, radial_order=0),
          dict(shells_per_pass=4, large_halo_min=1 << 40, cluster_size=0, grid_halo_min=2000),   # grid-per-iteration path
-         dict(shells_per_pass=2, large_halo_min=1 << 40, cluster_size=0, grid_halo_min=6000, radial_order=0)]
+         dict(shells_per_pass=2, large_halo_min=1 << 40, cluster_size=0, grid_halo_min=6000, radial_order=0),
+         dict(shells_per_pass=4, large_halo_min=4000, cluster_size=2, prefix_table=0)]   # radial order, no prefix table
 
 
-@pytest.mark.parametrize("sched", SCHED, ids=lambda s: "S%d_L%d_C%d_R%d_G%d_grid%d" % (s["shells_per_pass"], min(s["large_halo_min"], 99999), s["cluster_size"], s.get("radial_order", 1), s.get("shell_groups", 0), s.get("grid_halo_min", 0)))
+@pytest.mark.parametrize("sched", SCHED, ids=lambda s: "S%d_L%d_C%d_R%d_G%d_grid%d" % (s["shells_per_pass"], min(s["large_halo_min"], 99999), s["cluster_size"], s.get("radial_order", 1), s.get("shell_groups", 0), s.get("grid_halo_min", 0)) + ("_notable" if s.get("prefix_table", 1) == 0 else ""))
 def test_oracle_shapes_all_schedules(gpu, big, sched):
     S, D, sess = gpu
     cat, rr, cen, _ = big
