@@ -28,7 +28,8 @@ class Timing(ctypes.Structure):
 
 EXPORTS = ["cpg_device_count", "cpg_last_error", "cpg_version", "cpg_create", "cpg_destroy", "cpg_set_particles",
            "cpg_set_catalogue", "cpg_shape", "cpg_dens_sph", "cpg_dens_ell", "cpg_dens_kernel", "cpg_obj_masses",
-           "cpg_get_timing", "cpg_set_option", "cpg_host_alloc", "cpg_host_free", "cpg_get_prefix_lengths", "cpg_centers"]
+           "cpg_get_timing", "cpg_set_option", "cpg_host_alloc", "cpg_host_free", "cpg_get_prefix_lengths", "cpg_centers",
+           "cpg_obj_cat", "cpg_obj_cat_fetch", "cpg_use_obj_cat", "cpg_set_particles_gadget", "cpg_get_particles"]
 
 
 def load():
@@ -63,6 +64,14 @@ def load():
     L.cpg_host_free.restype = None
     L.cpg_get_prefix_lengths.argtypes = [vp, _I, ctypes.c_int32]
     L.cpg_centers.argtypes = [vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_double, _D, _D]
+    L.cpg_obj_cat.argtypes = [vp, _I, _I, _I, _D, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32,
+                              ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int64)]
+    L.cpg_obj_cat_fetch.argtypes = [vp, _I, _D, _I]
+    L.cpg_use_obj_cat.argtypes = [vp]
+    L.cpg_set_particles_gadget.argtypes = [vp, vp, ctypes.c_int32, vp, ctypes.c_int32, vp, ctypes.c_int32, ctypes.c_double,
+                                           ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                           ctypes.c_double]
+    L.cpg_get_particles.argtypes = [vp, _D, _D, _D]
     for f in EXPORTS:
         if f not in ("cpg_last_error", "cpg_version", "cpg_destroy", "cpg_host_free"):
             getattr(L, f).restype = ctypes.c_int
@@ -220,6 +229,61 @@ class Context:
         _check(self._L.cpg_centers(self._h, int(mode), int(bool(shape_path)), float(L_BOX), _dp(ref), _dp(cen)),
                "cpg_centers")
         return cen
+
+    def obj_cat(self, nb_shs, sh_len, fof_sizes, group_r200, min_number_ptcs, fetch_idx=True):
+        """calcObjCat on the device (gadget/gen_catalogues.pyx:39-95): returns (idx_cat or None, obj_r200, obj_size);
+        the result also stays on the device for use_obj_cat()."""
+        nb_shs, sh_len, fof_sizes = i32(nb_shs), i32(sh_len), i32(fof_sizes)
+        group_r200 = f64(group_r200)
+        if not (nb_shs.shape == fof_sizes.shape == group_r200.shape) or nb_shs.ndim != 1 or sh_len.ndim != 1:
+            raise ValueError("nb_shs, fof_sizes, group_r200 must be (N1,) and sh_len (N2,)")
+        n_obj, n_idx = ctypes.c_int32(), ctypes.c_int64()
+        _check(self._L.cpg_obj_cat(self._h, _ip(nb_shs), _ip(sh_len), _ip(fof_sizes), _dp(group_r200), nb_shs.shape[0],
+                                   sh_len.shape[0], int(min_number_ptcs), ctypes.byref(n_obj), ctypes.byref(n_idx)),
+               "cpg_obj_cat")
+        idx = np.empty(n_idx.value, dtype=np.int32) if fetch_idx else None
+        r200 = np.empty(n_obj.value, dtype=np.float64)
+        size = np.empty(n_obj.value, dtype=np.int32)
+        _check(self._L.cpg_obj_cat_fetch(self._h, _ip(idx), _dp(r200), _ip(size)), "cpg_obj_cat_fetch")
+        self._oc_n_obj = int(n_obj.value)
+        return idx, r200, size
+
+    def use_obj_cat(self):
+        """Make the catalogue built by obj_cat() this context's catalogue (device-resident, no idx_cat upload)."""
+        _check(self._L.cpg_use_obj_cat(self._h), "cpg_use_obj_cat")
+        self.n_obj = self._oc_n_obj
+
+    def set_particles_gadget(self, pos, vel, mass, mass_table, length_unit_fac, mass_unit_fac, velocity_unit_fac, time):
+        """Raw snapshot blocks (float32 or float64, as stored on disk) -> fp64 device arrays, with the arithmetic of
+        readgadget.read_field (gadget/readgadget.py:76-124)."""
+        def prep(a, cols):
+            if a is None:
+                return None, 0, None
+            a = np.asarray(a)
+            if a.dtype not in (np.float32, np.float64):
+                a = a.astype(np.float64)
+            a = np.ascontiguousarray(a)
+            if (cols == 3 and (a.ndim != 2 or a.shape[1] != 3)) or (cols == 1 and a.ndim != 1):
+                raise ValueError("positions/velocities must be (N,3), masses (N,)")
+            return a, int(a.dtype == np.float32), ctypes.c_void_p(a.ctypes.data)
+        pos, pf, pp = prep(pos, 3)
+        vel, vf, vp_ = prep(vel, 3)
+        mass, mf, mp = prep(mass, 1)
+        n = pos.shape[0]
+        if (vel is not None and vel.shape[0] != n) or (mass is not None and mass.shape[0] != n):
+            raise ValueError("block lengths differ")
+        _check(self._L.cpg_set_particles_gadget(self._h, pp, pf, vp_, vf, mp, mf, float(mass_table), n,
+                                                float(length_unit_fac), float(mass_unit_fac), float(velocity_unit_fac),
+                                                float(time)), "cpg_set_particles_gadget")
+        self.have_vel = vel is not None
+        self.n_part = n
+
+    def get_particles(self, n_part, with_vel=False):
+        xyz = np.empty((n_part, 3))
+        m = np.empty(n_part)
+        v = np.empty((n_part, 3)) if with_vel else None
+        _check(self._L.cpg_get_particles(self._h, _dp(xyz), _dp(v), _dp(m)), "cpg_get_particles")
+        return xyz, v, m
 
     def prefix_lengths(self, R):
         ne = np.zeros((self.n_obj, R), dtype=np.int32)

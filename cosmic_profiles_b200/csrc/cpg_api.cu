@@ -13,6 +13,7 @@
 
 #include "cpg_centers.cuh"
 #include "cpg_dens.cuh"
+#include "cpg_gadget.cuh"
 #include "cpg_gather.cuh"
 #include "cpg_morph.cuh"
 
@@ -131,6 +132,14 @@ struct cpg_ctx {
     // densities
     DevBuf<double> d_a, d_b, d_c, d_major, d_inter, d_minor, d_edges, dens, bin_mass;
     DevBuf<int32_t> bin_cnt, counts;
+    // Gadget / FoF ingest (cpg_gadget.cuh): group tables, scans, the compacted central-subhalo catalogue
+    DevBuf<int32_t> oc_nb, oc_shlen, oc_fof, oc_size, oc_idx, oc_err;
+    DevBuf<double> oc_r200in, oc_r200;
+    DevBuf<int64_t> oc_shoff, oc_start, oc_passoff, oc_idxoff, oc_cstart, oc_coff;
+    DevBuf<Pair64> oc_tiles;
+    DevBuf<unsigned char> raw_block;   // a snapshot block as stored on disk, before conversion to fp64
+    bool oc_valid = false;
+    int64_t oc_n_pass = 0, oc_n_idx = 0;
     // options
     int opt_shells_per_pass = 0;
     int64_t opt_large_halo_min = 0;
@@ -583,6 +592,10 @@ CPG_API void cpg_destroy(cpg_ctx *c)
     c->grid_states.release(); c->grid_partials.release();
     c->tile_hist.release(); c->dest.release(); c->n_eff.release(); c->cidxA.release(); c->cidxB.release(); c->d_order.release(); c->ptab.release();
     c->cref.release();
+    c->oc_nb.release(); c->oc_shlen.release(); c->oc_fof.release(); c->oc_size.release(); c->oc_idx.release();
+    c->oc_err.release(); c->oc_r200in.release(); c->oc_r200.release(); c->oc_shoff.release(); c->oc_start.release();
+    c->oc_passoff.release(); c->oc_idxoff.release(); c->oc_cstart.release(); c->oc_coff.release();
+    c->oc_tiles.release(); c->raw_block.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -654,13 +667,10 @@ CPG_API int cpg_set_particles(cpg_ctx *c, const double *xyz, const double *vxyz,
     return CPG_OK;
 }
 
-CPG_API int cpg_set_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, const int32_t *obj_size, int32_t n_obj)
+// Catalogue bookkeeping shared by cpg_set_catalogue (idx_cat on the host) and cpg_use_obj_cat (idx_cat already on
+// the device in c->idx: idx_cat == nullptr).
+static int install_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, const int32_t *obj_size, int32_t n_obj)
 {
-    CPG_TRY(use_device(c));
-    if (n_idx < 0 || n_obj < 0 || (n_idx > 0 && !idx_cat) || (n_obj > 0 && !obj_size)) {
-        set_error("cpg_set_catalogue: bad arguments");
-        return CPG_ERR_ARGUMENT;
-    }
     std::vector<int64_t> off(n_obj + 1, 0), poff(n_obj + 1, 0);
     c->h_size.assign(obj_size, obj_size + n_obj);
     c->h_chunks.clear(); c->h_kchunks.clear();
@@ -686,7 +696,8 @@ CPG_API int cpg_set_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx,
     std::iota(c->order.begin(), c->order.end(), 0);
     std::stable_sort(c->order.begin(), c->order.end(), [&](int a, int b) { return obj_size[a] > obj_size[b]; });
 
-    CPG_TRY(c->idx.ensure(n_idx)); CPG_TRY(c->size.ensure(n_obj));
+    if (idx_cat) CPG_TRY(c->idx.ensure(n_idx));
+    CPG_TRY(c->size.ensure(n_obj));
     CPG_TRY(c->off.ensure(n_obj + 1)); CPG_TRY(c->poff.ensure(n_obj + 1));
     CPG_TRY(c->chunks.ensure(c->h_chunks.size())); CPG_TRY(c->kchunks.ensure(c->h_kchunks.size()));
     CPG_TRY(c->chunk_first.ensure(n_obj + 1)); CPG_TRY(c->kchunk_first.ensure(n_obj + 1));
@@ -694,7 +705,7 @@ CPG_API int cpg_set_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx,
     CPG_TRY(c->d_order.ensure(n_obj));
     if (n_obj)
         CPG_CUDA(cudaMemcpyAsync(c->d_order.p, c->order.data(), sizeof(int32_t) * n_obj, cudaMemcpyHostToDevice, c->stream));
-    if (n_idx) CPG_TRY(upload_chunked(c->idx.p, idx_cat, sizeof(int32_t) * n_idx, c->stream));
+    if (n_idx && idx_cat) CPG_TRY(upload_chunked(c->idx.p, idx_cat, sizeof(int32_t) * n_idx, c->stream));
     if (n_obj) CPG_CUDA(cudaMemcpyAsync(c->size.p, obj_size, sizeof(int32_t) * n_obj, cudaMemcpyHostToDevice, c->stream));
     CPG_CUDA(cudaMemcpyAsync(c->off.p, off.data(), sizeof(int64_t) * (n_obj + 1), cudaMemcpyHostToDevice, c->stream));
     CPG_CUDA(cudaMemcpyAsync(c->poff.p, poff.data(), sizeof(int64_t) * (n_obj + 1), cudaMemcpyHostToDevice, c->stream));
@@ -732,6 +743,244 @@ CPG_API int cpg_set_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx,
     c->catalogue_version++;
     c->have.valid = false;
     c->task_key.valid = false;
+    return CPG_OK;
+}
+
+CPG_API int cpg_set_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, const int32_t *obj_size, int32_t n_obj)
+{
+    CPG_TRY(use_device(c));
+    if (n_idx < 0 || n_obj < 0 || (n_idx > 0 && !idx_cat) || (n_obj > 0 && !obj_size)) {
+        set_error("cpg_set_catalogue: bad arguments");
+        return CPG_ERR_ARGUMENT;
+    }
+    return install_catalogue(c, idx_cat, n_idx, obj_size, n_obj);
+}
+
+// ---- Gadget / FoF ingest ----------------------------------------------------------
+
+}  // extern "C"
+
+template <class Load>
+static int device_scan(cpg_ctx *c, Load ld, int64_t n, int64_t *out_a, int64_t *out_b, Pair64 *h_total)
+{
+    const int n_tiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+    CPG_TRY(c->oc_tiles.ensure((size_t)n_tiles + 1));
+    if (n_tiles > 0) {
+        scan_tile_sum_kernel<Load><<<n_tiles, SCAN_THREADS, 0, c->stream>>>(ld, n, c->oc_tiles.p);
+        scan_top_kernel<<<1, SCAN_THREADS, 0, c->stream>>>(c->oc_tiles.p, n_tiles);
+        scan_apply_kernel<Load><<<n_tiles, SCAN_THREADS, 0, c->stream>>>(ld, n, c->oc_tiles.p, out_a, out_b);
+        c->timing.kernel_launches += 3;
+        c->timing.hot_kernel_launches += 3;
+        CPG_CUDA(cudaGetLastError());
+        CPG_CUDA(cudaMemcpyAsync(h_total, c->oc_tiles.p + n_tiles, sizeof(Pair64), cudaMemcpyDeviceToHost, c->stream));
+        CPG_CUDA(cudaStreamSynchronize(c->stream));
+    } else {
+        *h_total = Pair64{0, 0};
+    }
+    return CPG_OK;
+}
+
+extern "C" {
+
+CPG_API int cpg_obj_cat(cpg_ctx *c, const int32_t *nb_shs, const int32_t *sh_len, const int32_t *fof_sizes,
+                        const double *group_r200, int32_t n_fof, int64_t n_sh, int32_t min_number_ptcs,
+                        int32_t *n_obj_out, int64_t *n_idx_out)
+{
+    CPG_TRY(use_device(c));
+    if (n_fof < 0 || n_sh < 0 || !n_obj_out || !n_idx_out || (n_fof > 0 && (!nb_shs || !fof_sizes || !group_r200)) ||
+        (n_sh > 0 && !sh_len)) {
+        set_error("cpg_obj_cat: bad arguments");
+        return CPG_ERR_ARGUMENT;
+    }
+    c->oc_valid = false;
+    Timer T(c);
+    T.mark(0);
+    const size_t n = (size_t)n_fof;
+    CPG_TRY(c->oc_nb.ensure(n)); CPG_TRY(c->oc_fof.ensure(n)); CPG_TRY(c->oc_r200in.ensure(n));
+    CPG_TRY(c->oc_shlen.ensure((size_t)n_sh)); CPG_TRY(c->oc_err.ensure(1));
+    CPG_TRY(c->oc_shoff.ensure(n)); CPG_TRY(c->oc_start.ensure(n)); CPG_TRY(c->oc_passoff.ensure(n));
+    CPG_TRY(c->oc_idxoff.ensure(n));
+    if (n) {
+        CPG_CUDA(cudaMemcpyAsync(c->oc_nb.p, nb_shs, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+        CPG_CUDA(cudaMemcpyAsync(c->oc_fof.p, fof_sizes, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+        CPG_CUDA(cudaMemcpyAsync(c->oc_r200in.p, group_r200, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (n_sh) CPG_CUDA(cudaMemcpyAsync(c->oc_shlen.p, sh_len, sizeof(int32_t) * n_sh, cudaMemcpyHostToDevice, c->stream));
+    CPG_CUDA(cudaMemsetAsync(c->oc_err.p, 0, sizeof(int32_t), c->stream));
+    c->timing.h2d_bytes = (int64_t)(n * 16 + (size_t)n_sh * 4);
+    T.mark(1);
+    T.mark(2);
+    Pair64 tot1, tot2;
+    CPG_TRY(device_scan(c, LoadGroup{c->oc_nb.p, c->oc_fof.p}, n_fof, c->oc_shoff.p, c->oc_start.p, &tot1));
+    CPG_TRY(device_scan(c, LoadPass{c->oc_nb.p, c->oc_shlen.p, c->oc_shoff.p, n_sh, min_number_ptcs}, n_fof,
+                        c->oc_passoff.p, c->oc_idxoff.p, &tot2));
+    const int64_t n_pass = tot2.a, n_idx = tot2.b;
+    if (n_pass > 0x7fffffff) {
+        set_error("cpg_obj_cat: %lld objects do not fit the int32 object count", (long long)n_pass);
+        return CPG_ERR_ARGUMENT;
+    }
+    CPG_TRY(c->oc_cstart.ensure((size_t)n_pass)); CPG_TRY(c->oc_coff.ensure((size_t)n_pass + 1));
+    CPG_TRY(c->oc_size.ensure((size_t)n_pass)); CPG_TRY(c->oc_r200.ensure((size_t)n_pass));
+    CPG_TRY(c->oc_idx.ensure((size_t)n_idx));
+    ObjCatParams P;
+    P.nb_shs = c->oc_nb.p; P.sh_len = c->oc_shlen.p; P.group_r200 = c->oc_r200in.p;
+    P.sh_off = c->oc_shoff.p; P.start = c->oc_start.p; P.pass_off = c->oc_passoff.p; P.idx_off = c->oc_idxoff.p;
+    P.n_fof = n_fof; P.n_sh = n_sh; P.n_part_limit = (int64_t)1 << 31; P.min_ptcs = min_number_ptcs;
+    P.c_start = c->oc_cstart.p; P.c_off = c->oc_coff.p; P.c_size = c->oc_size.p; P.c_r200 = c->oc_r200.p;
+    P.error = c->oc_err.p;
+    objcat_compact_kernel<<<grid_for(std::max<int64_t>(n_fof, 1), 256, 1 << 30), 256, 0, c->stream>>>(P, n_pass, n_idx);
+    c->timing.kernel_launches++;
+    c->timing.hot_kernel_launches++;
+    if (n_idx > 0) {
+        objcat_fill_kernel<<<grid_for(n_idx, 256, c->sm_count * 16), 256, 0, c->stream>>>(c->oc_coff.p, c->oc_cstart.p, n_pass,
+                                                                                         n_idx, c->oc_idx.p);
+        c->timing.kernel_launches++;
+        c->timing.hot_kernel_launches++;
+    }
+    CPG_CUDA(cudaGetLastError());
+    T.mark(3);
+    int32_t err = 0;
+    CPG_CUDA(cudaMemcpyAsync(&err, c->oc_err.p, sizeof err, cudaMemcpyDeviceToHost, c->stream));
+    T.mark(4);
+    CPG_CUDA(cudaStreamSynchronize(c->stream));
+    c->timing.h2d_ms = Timer::ms(c->ev[0], c->ev[1]);
+    c->timing.kernel_ms = Timer::ms(c->ev[2], c->ev[3]);
+    c->timing.d2h_ms = Timer::ms(c->ev[3], c->ev[4]);
+    if (err) {
+        set_error("cpg_obj_cat: a central subhalo reaches past particle 2^31 - 1 (int32 index catalogue, "
+                  "gen_catalogues.pyx:12) or the group tables are inconsistent");
+        return CPG_ERR_ARGUMENT;
+    }
+    c->oc_n_pass = n_pass; c->oc_n_idx = n_idx; c->oc_valid = true;
+    *n_obj_out = (int32_t)n_pass;
+    *n_idx_out = n_idx;
+    (void)tot1;
+    return CPG_OK;
+}
+
+CPG_API int cpg_obj_cat_fetch(cpg_ctx *c, int32_t *idx_cat, double *obj_r200, int32_t *obj_size)
+{
+    CPG_TRY(use_device(c));
+    if (!c->oc_valid) {
+        set_error("cpg_obj_cat_fetch: no catalogue built (call cpg_obj_cat first)");
+        return CPG_ERR_STATE;
+    }
+    const size_t np = (size_t)c->oc_n_pass, ni = (size_t)c->oc_n_idx;
+    if (idx_cat && ni) CPG_CUDA(cudaMemcpyAsync(idx_cat, c->oc_idx.p, sizeof(int32_t) * ni, cudaMemcpyDeviceToHost, c->stream));
+    if (obj_r200 && np) CPG_CUDA(cudaMemcpyAsync(obj_r200, c->oc_r200.p, sizeof(double) * np, cudaMemcpyDeviceToHost, c->stream));
+    if (obj_size && np) CPG_CUDA(cudaMemcpyAsync(obj_size, c->oc_size.p, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, c->stream));
+    CPG_CUDA(cudaStreamSynchronize(c->stream));
+    return CPG_OK;
+}
+
+CPG_API int cpg_use_obj_cat(cpg_ctx *c)
+{
+    CPG_TRY(use_device(c));
+    if (!c->oc_valid) {
+        set_error("cpg_use_obj_cat: no catalogue built (call cpg_obj_cat first)");
+        return CPG_ERR_STATE;
+    }
+    std::vector<int32_t> sizes((size_t)c->oc_n_pass);
+    if (c->oc_n_pass)
+        CPG_CUDA(cudaMemcpyAsync(sizes.data(), c->oc_size.p, sizeof(int32_t) * sizes.size(), cudaMemcpyDeviceToHost, c->stream));
+    CPG_CUDA(cudaStreamSynchronize(c->stream));
+    // the flat catalogue stays where it was built: it becomes the context's idx buffer (no copy, no PCIe traffic)
+    CPG_TRY(c->idx.ensure((size_t)c->oc_n_idx));
+    if (c->oc_n_idx)
+        CPG_CUDA(cudaMemcpyAsync(c->idx.p, c->oc_idx.p, sizeof(int32_t) * (size_t)c->oc_n_idx, cudaMemcpyDeviceToDevice, c->stream));
+    return install_catalogue(c, nullptr, c->oc_n_idx, sizes.data(), (int32_t)c->oc_n_pass);
+}
+
+}  // extern "C"
+
+template <class T>
+static int convert_block(cpg_ctx *c, const void *src, double *dst, int64_t n, const BlockConvert &cv)
+{
+    // staged through a device copy of the raw block in pieces, so that the fp64 result is the only full-size buffer
+    const int64_t piece = (int64_t)16 << 20;   // elements
+    CPG_TRY(c->raw_block.ensure((size_t)std::min(piece, std::max<int64_t>(n, 1)) * sizeof(T)));
+    for (int64_t o = 0; o < n; o += piece) {
+        const int64_t m = std::min(piece, n - o);
+        CPG_CUDA(cudaMemcpyAsync(c->raw_block.p, (const T *)src + o, sizeof(T) * m, cudaMemcpyHostToDevice, c->stream));
+        block_convert_kernel<T><<<grid_for(m, 256, c->sm_count * 16), 256, 0, c->stream>>>((const T *)c->raw_block.p, dst + o, m, cv);
+        c->timing.kernel_launches++;
+    }
+    CPG_CUDA(cudaGetLastError());
+    return CPG_OK;
+}
+
+static int ingest_block(cpg_ctx *c, const void *src, int32_t is_f32, double *dst, int64_t n, double unit_fac, int has_post,
+                        double post_mul)
+{
+    BlockConvert cv;
+    cv.unit_fac = unit_fac; cv.post_mul = post_mul; cv.has_post = has_post;
+    if (is_f32) return convert_block<float>(c, src, dst, n, cv);
+    return convert_block<double>(c, src, dst, n, cv);
+}
+
+extern "C" {
+
+CPG_API int cpg_set_particles_gadget(cpg_ctx *c, const void *pos, int32_t pos_is_f32, const void *vel, int32_t vel_is_f32,
+                                     const void *mass, int32_t mass_is_f32, double mass_table, int64_t n_part,
+                                     double length_unit_fac, double mass_unit_fac, double velocity_unit_fac, double time)
+{
+    CPG_TRY(use_device(c));
+    if (n_part < 0 || (n_part > 0 && !pos) || !(length_unit_fac != 0.0) || !(mass_unit_fac != 0.0) ||
+        (vel && !(velocity_unit_fac != 0.0))) {
+        set_error("cpg_set_particles_gadget: bad arguments");
+        return CPG_ERR_ARGUMENT;
+    }
+    if (!mass && mass_table == 0.0) {   // readgadget.py:109-110: 'Problem reading the block MASS'
+        set_error("cpg_set_particles_gadget: no Masses block and MassTable entry is 0");
+        return CPG_ERR_ARGUMENT;
+    }
+    Timer T(c);
+    T.mark(0);
+    CPG_TRY(c->xyz.ensure((size_t)n_part * 3));
+    CPG_TRY(c->masses.ensure((size_t)n_part));
+    CPG_TRY(ingest_block(c, pos, pos_is_f32, c->xyz.p, n_part * 3, length_unit_fac, 0, 1.0));
+    c->timing.h2d_bytes = n_part * 3 * (pos_is_f32 ? 4 : 8);
+    if (mass) {
+        CPG_TRY(ingest_block(c, mass, mass_is_f32, c->masses.p, n_part, mass_unit_fac, 0, 1.0));
+        c->timing.h2d_bytes += n_part * (mass_is_f32 ? 4 : 8);
+    } else if (n_part > 0) {
+        // np.ones(N, float64) * Masses[ptype] / unit_fac  (readgadget.py:108)
+        block_fill_kernel<<<grid_for(n_part, 256, c->sm_count * 16), 256, 0, c->stream>>>(c->masses.p, n_part,
+                                                                                         (1.0 * mass_table) / mass_unit_fac);
+        c->timing.kernel_launches++;
+    }
+    c->have_vel = vel != nullptr;
+    if (vel) {
+        CPG_TRY(c->vxyz.ensure((size_t)n_part * 3));
+        // array *= np.sqrt(head.time)  (readgadget.py:116)
+        CPG_TRY(ingest_block(c, vel, vel_is_f32, c->vxyz.p, n_part * 3, velocity_unit_fac, 1, sqrt(time)));
+        c->timing.h2d_bytes += n_part * 3 * (vel_is_f32 ? 4 : 8);
+    }
+    T.mark(1);
+    CPG_CUDA(cudaGetLastError());
+    CPG_CUDA(cudaStreamSynchronize(c->stream));
+    c->timing.h2d_ms = Timer::ms(c->ev[0], c->ev[1]);
+    c->n_part = n_part;
+    c->mass_stream_valid = false;
+    c->snapshot_version++;
+    c->have.valid = false;
+    return CPG_OK;
+}
+
+CPG_API int cpg_get_particles(cpg_ctx *c, double *xyz, double *vxyz, double *masses)
+{
+    CPG_TRY(use_device(c));
+    const size_t n = (size_t)c->n_part;
+    if (xyz && n) CPG_CUDA(cudaMemcpyAsync(xyz, c->xyz.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    if (masses && n) CPG_CUDA(cudaMemcpyAsync(masses, c->masses.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (vxyz && n) {
+        if (!c->have_vel) {
+            set_error("cpg_get_particles: no velocities on the device");
+            return CPG_ERR_STATE;
+        }
+        CPG_CUDA(cudaMemcpyAsync(vxyz, c->vxyz.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CPG_CUDA(cudaStreamSynchronize(c->stream));
     return CPG_OK;
 }
 

@@ -32,8 +32,25 @@ def install(target=None):
     return target
 
 
+def install_gadget(targets=None):
+    """Rebind ``calcObjCat`` (gadget/gen_catalogues.pyx:39) where DensShapeProfsGadget.__init__ looks it up: the
+    module globals of shape_profs_classes (:24, call :580) and dens_profs_classes (:10).  targets: modules to patch
+    (default: those two, which must be importable)."""
+    from . import _lib, gen_catalogues
+    _lib.load()
+    if targets is None:
+        import importlib
+        targets = [importlib.import_module(m) for m in gen_catalogues.TARGET_MODULES]
+    for t in targets:
+        key = ("calcObjCat", id(t))
+        if key not in _saved:
+            _saved[key] = (t, getattr(t, "calcObjCat", None))
+        setattr(t, "calcObjCat", gen_catalogues.calcObjCat)
+    return targets
+
+
 def uninstall():
     for n, (target, fn) in list(_saved.items()):
         if fn is not None:
-            setattr(target, n, fn)
+            setattr(target, n[0] if isinstance(n, tuple) else n, fn)
         del _saved[n]

@@ -133,6 +133,42 @@ CPG_API int cpg_obj_masses(cpg_ctx *ctx, double *obj_mass);
 CPG_API int cpg_centers(cpg_ctx *ctx, int32_t mode, int32_t shape_path, double L_BOX, const double *ref_points,
                         double *centers_out);
 
+/*
+ * Gadget / FoF-layout ingest: the two steps DensShapeProfsGadget.__init__ runs on the
+ * host before any driver is called (shape_profs_classes.pyx:571-580).
+ *
+ * cpg_obj_cat: central-subhalo index catalogue from the FoF / SUBFIND group tables.  Replaces calcObjCat and
+ * calcCSHIdxs (gadget/gen_catalogues.pyx:39-95, :12-35).  nb_shs (n_fof) subhalos per group, sh_len (n_sh)
+ * particles per subhalo, fof_sizes (n_fof) particles per group, group_r200 (n_fof).  A group passes when it has a
+ * subhalo and its first one holds >= min_number_ptcs particles (:66-73); its object is the index range
+ * [sum_{q<p} fof_sizes[q], + sh_len[sum_{q<p} nb_shs[q]]) (:80-85).  The result stays on the device;
+ * *n_obj_out / *n_idx_out give the sizes of the arrays cpg_obj_cat_fetch copies out:
+ * idx_cat (n_idx) int32 (may be NULL), obj_r200 (n_obj), obj_size (n_obj) -- calcObjCat's return tuple (:91).
+ * cpg_use_obj_cat makes the device-resident catalogue the context's catalogue (what cpg_set_catalogue does
+ * with host arrays) without the flat index array ever crossing PCIe.
+ */
+CPG_API int cpg_obj_cat(cpg_ctx *ctx, const int32_t *nb_shs, const int32_t *sh_len, const int32_t *fof_sizes,
+                        const double *group_r200, int32_t n_fof, int64_t n_sh, int32_t min_number_ptcs,
+                        int32_t *n_obj_out, int64_t *n_idx_out);
+CPG_API int cpg_obj_cat_fetch(cpg_ctx *ctx, int32_t *idx_cat, double *obj_r200, int32_t *obj_size);
+CPG_API int cpg_use_obj_cat(cpg_ctx *ctx);
+
+/*
+ * Upload the snapshot blocks as stored in the Gadget file and convert them on the device to the fp64 arrays
+ * readgadget.read_block returns (gadget/readgadget.py:76-124, :127-194): pos / vel (n_part,3) and mass (n_part) are
+ * float32 (*_is_f32 != 0) or float64 datasets; array = dataset / unit_fac in the dataset's own precision (NumPy
+ * promotion of a Python-float divisor, :112), velocities then *= sqrt(time) (:116), all widened exactly to fp64
+ * (:169).  mass == NULL: constant MassTable entry, np.ones(N) * mass_table / mass_unit_fac (:108).  vel may be NULL.
+ * unit_fac = internal unit / input unit as computed at readgadget.py:82-85.  Replaces cpg_set_particles for
+ * snapshots that are float32 on disk: 12 instead of 24 bytes per particle and block cross PCIe.
+ * cpg_get_particles copies the converted fp64 arrays back (tests, or callers that also need them on the host).
+ */
+CPG_API int cpg_set_particles_gadget(cpg_ctx *ctx, const void *pos, int32_t pos_is_f32, const void *vel,
+                                     int32_t vel_is_f32, const void *mass, int32_t mass_is_f32, double mass_table,
+                                     int64_t n_part, double length_unit_fac, double mass_unit_fac,
+                                     double velocity_unit_fac, double time);
+CPG_API int cpg_get_particles(cpg_ctx *ctx, double *xyz, double *vxyz, double *masses);
+
 /* Page-locked host buffers for results (device->host copies into pageable memory run at a fraction of the
  * PCIe rate).  No counterpart in the reference, whose drivers np.zeros() their outputs
  * (shape_profs_algos.pyx:560-572). */

@@ -305,3 +305,43 @@ def calcDensProfsKernelBased(xyz, masses, r200s, r_over_r200, idx_cat, obj_size,
                                _p(r200s, D), _p(rr, D), R, ctypes.c_float(L_BOX), _p(dens, D), int(nthreads))
     assert rc == 0
     return dens
+
+
+# ---- Gadget / FoF ingest ---------------------------------------------------
+
+def calcObjCat(nb_shs, sh_len, fof_sizes, group_r200, MIN_NUMBER_PTCS):
+    """gadget/gen_catalogues.pyx:39-95 restated in numpy (pinned against the compiled reference by
+    tests/golden/gadget_golden.npz): group p passes when nb_shs[p] > 0 and the length of its first subhalo,
+    sh_len[sum(nb_shs[:p])], is >= MIN_NUMBER_PTCS (:66-73); its object is the index range starting at
+    sum(fof_sizes[:p]) (:80-85, calcCSHIdxs :29-35).  Returns (obj_cat, obj_r200, obj_size) as :91."""
+    nb_shs = np.asarray(nb_shs, dtype=np.int64)
+    sh_len = np.asarray(sh_len, dtype=np.int64)
+    fof_sizes = np.asarray(fof_sizes, dtype=np.int64)
+    if len(nb_shs) == 0:
+        raise ValueError("zero-size array to reduction operation maximum which has no identity")   # np.max at :76
+    sh_off = np.concatenate(([0], np.cumsum(nb_shs)[:-1]))
+    start = np.concatenate(([0], np.cumsum(fof_sizes)[:-1]))
+    first_len = np.where(nb_shs > 0, sh_len[np.minimum(sh_off, max(len(sh_len) - 1, 0))] if len(sh_len) else 0, 0)
+    ok = (nb_shs > 0) & (first_len >= MIN_NUMBER_PTCS)
+    size = first_len[ok]
+    parts = [np.arange(s0, s0 + n, dtype=np.int64) for s0, n in zip(start[ok], size)]
+    idx = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+    return idx.astype(np.int32), np.asarray(group_r200, dtype=np.float64)[ok], size.astype(np.int32)
+
+
+def read_field_arith(block, dataset, unit_fac, time=1.0, mass_table=0.0, n_part=0):
+    """The arithmetic of readgadget.read_field + read_block on one dataset (gadget/readgadget.py:106-120, :148-169),
+    restated with the very NumPy expressions of the reference (h5py, which only supplies `dataset`, is absent here,
+    so this restatement is the pin: "parity unpinned" against a running reference for this function).
+    block in {"POS ", "VEL ", "MASS"}; dataset None (MASS only) = no Masses dataset, MassTable constant."""
+    if dataset is None:
+        if mass_table == 0.0:
+            raise Exception("Problem reading the block %s" % block)
+        array = np.ones(n_part, np.float64) * mass_table / unit_fac          # :108
+    else:
+        array = dataset[:] / unit_fac                                           # :112
+    if block == "VEL ":
+        array *= np.sqrt(time)                                                  # :116
+    out = np.zeros(array.shape, dtype=np.float64)                              # :164 (float64 destination)
+    out[:] = array                                                              # :169
+    return out

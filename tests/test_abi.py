@@ -72,3 +72,12 @@ def test_lpt_partition_balances():
     idx = np.arange(int(sizes.sum()), dtype=np.int32)
     sub_idx, sub_size = sub_catalogue(idx, sizes, parts[3])
     assert sub_size.sum() == len(sub_idx) == sizes[parts[3]].sum()
+
+
+def test_install_gadget_rebinds_calcObjCat():
+    import cosmic_profiles_b200 as cpb
+    a, b = types.SimpleNamespace(calcObjCat="ref"), types.SimpleNamespace(calcObjCat="ref")
+    cpb.install_gadget([a, b])
+    assert a.calcObjCat is b.calcObjCat and a.calcObjCat.__module__ == "cosmic_profiles_b200.gen_catalogues"
+    cpb.uninstall()
+    assert a.calcObjCat == "ref" and b.calcObjCat == "ref"
