@@ -29,7 +29,7 @@ class Timing(ctypes.Structure):
 EXPORTS = ["cpg_device_count", "cpg_last_error", "cpg_version", "cpg_create", "cpg_destroy", "cpg_set_particles",
            "cpg_set_catalogue", "cpg_shape", "cpg_dens_sph", "cpg_dens_ell", "cpg_dens_kernel", "cpg_obj_masses",
            "cpg_get_timing", "cpg_set_option", "cpg_host_alloc", "cpg_host_free", "cpg_get_prefix_lengths", "cpg_centers",
-           "cpg_obj_cat", "cpg_obj_cat_fetch", "cpg_use_obj_cat", "cpg_set_particles_gadget", "cpg_get_particles"]
+           "cpg_obj_cat", "cpg_obj_cat_fetch", "cpg_use_obj_cat", "cpg_set_particles_gadget", "cpg_get_particles", "cpg_fit_profiles"]
 
 
 def load():
@@ -72,6 +72,8 @@ def load():
                                            ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                            ctypes.c_double]
     L.cpg_get_particles.argtypes = [vp, _D, _D, _D]
+    L.cpg_fit_profiles.argtypes = [vp, _D, _D, _I, _D, _D, _D, _D, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                   ctypes.c_double, ctypes.c_double, _D, _D, _I, _I]
     for f in EXPORTS:
         if f not in ("cpg_last_error", "cpg_version", "cpg_destroy", "cpg_host_free"):
             getattr(L, f).restype = ctypes.c_int
@@ -284,6 +286,21 @@ class Context:
         v = np.empty((n_part, 3)) if with_vel else None
         _check(self._L.cpg_get_particles(self._h, _dp(xyz), _dp(v), _dp(m)), "cpg_get_particles")
         return xyz, v, m
+
+    def fit_profiles(self, radii, lmed, n_valid, avg, x0, lb, ub, profile, xtol=1e-4, ftol=1e-4):
+        """Batched Powell fits (cpg_fit_profiles); returns (best (n,npar), fun, nfev, nit)."""
+        radii, lmed, avg, x0, lb, ub = f64(radii), f64(lmed), f64(avg), f64(x0), f64(lb), f64(ub)
+        n_valid = i32(n_valid)
+        n, R = radii.shape
+        npar = x0.shape[1]
+        best = np.zeros((n, npar))
+        fun = np.zeros(n)
+        nfev = np.zeros(n, dtype=np.int32)
+        nit = np.zeros(n, dtype=np.int32)
+        _check(self._L.cpg_fit_profiles(self._h, _dp(radii), _dp(lmed), _ip(n_valid), _dp(avg), _dp(x0), _dp(lb), _dp(ub),
+                                        n, R, int(profile), float(xtol), float(ftol), _dp(best), _dp(fun), _ip(nfev),
+                                        _ip(nit)), "cpg_fit_profiles")
+        return best, fun, nfev, nit
 
     def prefix_lengths(self, R):
         ne = np.zeros((self.n_obj, R), dtype=np.int32)

@@ -13,6 +13,7 @@
 
 #include "cpg_centers.cuh"
 #include "cpg_dens.cuh"
+#include "cpg_fit.cuh"
 #include "cpg_gadget.cuh"
 #include "cpg_gather.cuh"
 #include "cpg_morph.cuh"
@@ -138,6 +139,8 @@ struct cpg_ctx {
     DevBuf<int64_t> oc_shoff, oc_start, oc_passoff, oc_idxoff, oc_cstart, oc_coff;
     DevBuf<Pair64> oc_tiles;
     DevBuf<unsigned char> raw_block;   // a snapshot block as stored on disk, before conversion to fp64
+    DevBuf<double> fit_radii, fit_lmed, fit_avg, fit_x0, fit_best, fit_fun;
+    DevBuf<int32_t> fit_nvalid, fit_nfev, fit_nit;
     bool oc_valid = false;
     int64_t oc_n_pass = 0, oc_n_idx = 0;
     // options
@@ -596,6 +599,8 @@ CPG_API void cpg_destroy(cpg_ctx *c)
     c->oc_err.release(); c->oc_r200in.release(); c->oc_r200.release(); c->oc_shoff.release(); c->oc_start.release();
     c->oc_passoff.release(); c->oc_idxoff.release(); c->oc_cstart.release(); c->oc_coff.release();
     c->oc_tiles.release(); c->raw_block.release();
+    c->fit_radii.release(); c->fit_lmed.release(); c->fit_avg.release(); c->fit_x0.release(); c->fit_best.release();
+    c->fit_fun.release(); c->fit_nvalid.release(); c->fit_nfev.release(); c->fit_nit.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
@@ -964,6 +969,69 @@ CPG_API int cpg_set_particles_gadget(cpg_ctx *c, const void *pos, int32_t pos_is
     c->mass_stream_valid = false;
     c->snapshot_version++;
     c->have.valid = false;
+    return CPG_OK;
+}
+
+CPG_API int cpg_fit_profiles(cpg_ctx *c, const double *radii, const double *lmed, const int32_t *n_valid, const double *avg,
+                             const double *x0, const double *lb, const double *ub, int32_t n_obj, int32_t R,
+                             int32_t profile, double xtol, double ftol, double *best, double *fun, int32_t *nfev,
+                             int32_t *nit)
+{
+    CPG_TRY(use_device(c));
+    const int npar = profile == FIT_EINASTO ? 3 : (profile == FIT_ABG ? 5 : 2);
+    if (n_obj < 0 || R < 0 || R > FIT_MAX_BINS || profile < 0 || profile > FIT_ABG || !lb || !ub ||
+        (n_obj > 0 && (!radii || !lmed || !n_valid || !avg || !x0 || !best))) {
+        set_error("cpg_fit_profiles: bad arguments (0 <= R <= %d, profile 0..3)", FIT_MAX_BINS);
+        return CPG_ERR_ARGUMENT;
+    }
+    for (int i = 0; i < npar; i++)
+        if (!(lb[i] <= ub[i])) {   // scipy _validate_bounds -> ValueError
+            set_error("cpg_fit_profiles: an upper bound is less than the corresponding lower bound");
+            return CPG_ERR_ARGUMENT;
+        }
+    Timer T(c);
+    if (n_obj == 0) return CPG_OK;
+    const size_t n = (size_t)n_obj, nR = n * (size_t)std::max(R, 1);
+    T.mark(0);
+    CPG_TRY(c->fit_radii.ensure(nR)); CPG_TRY(c->fit_lmed.ensure(nR)); CPG_TRY(c->fit_avg.ensure(n));
+    CPG_TRY(c->fit_x0.ensure(n * npar)); CPG_TRY(c->fit_best.ensure(n * npar)); CPG_TRY(c->fit_fun.ensure(n));
+    CPG_TRY(c->fit_nvalid.ensure(n)); CPG_TRY(c->fit_nfev.ensure(n)); CPG_TRY(c->fit_nit.ensure(n));
+    if (R > 0) {
+        CPG_CUDA(cudaMemcpyAsync(c->fit_radii.p, radii, sizeof(double) * n * R, cudaMemcpyHostToDevice, c->stream));
+        CPG_CUDA(cudaMemcpyAsync(c->fit_lmed.p, lmed, sizeof(double) * n * R, cudaMemcpyHostToDevice, c->stream));
+    }
+    CPG_CUDA(cudaMemcpyAsync(c->fit_avg.p, avg, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    CPG_CUDA(cudaMemcpyAsync(c->fit_x0.p, x0, sizeof(double) * n * npar, cudaMemcpyHostToDevice, c->stream));
+    CPG_CUDA(cudaMemcpyAsync(c->fit_nvalid.p, n_valid, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    c->timing.h2d_bytes = (int64_t)(sizeof(double) * (2 * n * R + n + n * npar) + sizeof(int32_t) * n);
+    T.mark(1);
+    T.mark(2);
+    FitParams Q;
+    Q.radii = c->fit_radii.p; Q.lmed = c->fit_lmed.p; Q.n_valid = c->fit_nvalid.p; Q.avg = c->fit_avg.p; Q.x0 = c->fit_x0.p;
+    for (int i = 0; i < 5; i++) {
+        Q.lb[i] = i < npar ? lb[i] : 0.0;
+        Q.ub[i] = i < npar ? ub[i] : 0.0;
+    }
+    Q.n_obj = n_obj; Q.R = R; Q.profile = profile; Q.xtol = xtol; Q.ftol = ftol;
+    Q.best = c->fit_best.p; Q.fun = c->fit_fun.p; Q.nfev = c->fit_nfev.p; Q.nit = c->fit_nit.p;
+    const int grid = (n_obj + FIT_WARPS - 1) / FIT_WARPS;
+    if (npar == 2) fit_profiles_kernel<2><<<grid, FIT_WARPS * 32, 0, c->stream>>>(Q);
+    else if (npar == 3) fit_profiles_kernel<3><<<grid, FIT_WARPS * 32, 0, c->stream>>>(Q);
+    else fit_profiles_kernel<5><<<grid, FIT_WARPS * 32, 0, c->stream>>>(Q);
+    CPG_CUDA(cudaGetLastError());
+    c->timing.kernel_launches = 1;
+    c->timing.hot_kernel_launches = 1;
+    T.mark(3);
+    CPG_CUDA(cudaMemcpyAsync(best, c->fit_best.p, sizeof(double) * n * npar, cudaMemcpyDeviceToHost, c->stream));
+    if (fun) CPG_CUDA(cudaMemcpyAsync(fun, c->fit_fun.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (nfev) CPG_CUDA(cudaMemcpyAsync(nfev, c->fit_nfev.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (nit) CPG_CUDA(cudaMemcpyAsync(nit, c->fit_nit.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    c->timing.d2h_bytes = (int64_t)(sizeof(double) * (n * npar + n) + 2 * sizeof(int32_t) * n);
+    T.mark(4);
+    CPG_CUDA(cudaStreamSynchronize(c->stream));
+    c->timing.h2d_ms = Timer::ms(c->ev[0], c->ev[1]);
+    c->timing.kernel_ms = Timer::ms(c->ev[2], c->ev[3]);
+    c->timing.d2h_ms = Timer::ms(c->ev[3], c->ev[4]);
     return CPG_OK;
 }
 

@@ -1,0 +1,96 @@
+"""Drop-in for cosmic_profiles.dens_profs.dens_profs_tools.fitDensProfHelper (dens_profs_tools.py:325-359) on the
+device.
+
+The reference fits every object's density profile with scipy.optimize.minimize(method='Powell', bounds=...) in a
+pathos process pool (:347-348), the objective being a Python list comprehension over the bins (:227-230).  Here
+the per-object preparation is the reference's own NumPy arithmetic, vectorised over objects -- NaN bins dropped
+(:254-258), median / np.average(median) (:277), its logarithm (the constant half of every objective term) -- and the
+minimisation itself (scipy 1.18.1's Powell with bounded Forsythe-Malcolm-Moler line searches, restated) runs as one
+warp per object in csrc/cpg_fit.cuh.  Same signature, same (N, n) return array.
+"""
+import numpy as np
+
+from . import session
+from ._lib import CosmicGpuError
+
+PROFILE_ID = {"nfw": 0, "hernquist": 1, "einasto": 2, "alpha_beta_gamma": 3}
+NPARS = {"nfw": 2, "hernquist": 2, "einasto": 3, "alpha_beta_gamma": 5}
+MAX_BINS = 128
+last_info = {}
+
+
+def _bounds(method):
+    """dens_profs_tools.py:262-318: (lb, ub) per parameter; a parameter named in `method` is pinned."""
+    def b(name, lo):
+        return (method[name], method[name]) if name in method else (lo, np.inf)
+    prof = method["profile"]
+    if prof == "einasto":
+        return [(1e-7, np.inf), b("alpha", 1e-10), b("r_s", 1e-5)]
+    if prof == "alpha_beta_gamma":
+        return [(1e-7, np.inf), b("alpha", 1e-5), b("beta", 1e-5), b("gamma", 1e-5), b("r_s", 1e-5)]
+    return [(1e-7, np.inf), b("r_s", 1e-5)]
+
+
+def _initial_guess(prof, r200s):
+    n = len(r200s)
+    if prof == "einasto":
+        x0 = np.tile(np.array([0.1, 0.18, 0.0]), (n, 1))                    # :276
+    elif prof == "alpha_beta_gamma":
+        x0 = np.tile(np.array([0.1, 1.0, 1.0, 1.0, 0.0]), (n, 1))           # :304
+    else:
+        x0 = np.tile(np.array([0.1, 0.0]), (n, 1))                          # :317
+    x0[:, -1] = r200s / 5
+    return x0
+
+
+def prepare(dens_profs, ROverR200, r200s):
+    """Per-object inputs of the objective, with the reference's NumPy operations: R_to_min = ROverR200*r200 (:253),
+    NaN bins removed (:255-256), median/np.average(median) (:277) and np.log of it (:229)."""
+    dens = np.ascontiguousarray(dens_profs, dtype=np.float64)
+    rr = np.asarray(ROverR200, dtype=np.float64)
+    r200s = np.asarray(r200s, dtype=np.float64)
+    n, R = dens.shape
+    keep = ~np.isnan(dens)
+    n_valid = keep.sum(axis=1).astype(np.int32)
+    radii = rr[None, :] * r200s[:, None]
+    med = dens.copy()
+    full = n_valid == R
+    for p in np.flatnonzero(~full):          # objects with NaN bins (empty ellipsoidal shells): squeeze to the front
+        k = keep[p]
+        m = int(n_valid[p])
+        radii[p, :m] = radii[p, k]
+        med[p, :m] = dens[p, k]
+        radii[p, m:] = 0.0
+        med[p, m:] = np.nan
+    avg = np.full(n, np.nan)
+    with np.errstate(all="ignore"):
+        if full.any():
+            avg[full] = med[full].mean(axis=1)            # == np.average(row): same pairwise sum over a contiguous row
+        for p in np.flatnonzero(~full):
+            m = int(n_valid[p])
+            avg[p] = np.average(med[p, :m]) if m > 0 else np.nan
+        lmed = np.log(med / avg[:, None])
+    return np.ascontiguousarray(radii), np.ascontiguousarray(lmed), n_valid, avg
+
+
+def fitDensProfHelper(dens_profs, ROverR200, r200s, method):
+    prof = method["profile"]
+    if prof not in PROFILE_ID:
+        raise KeyError(prof)
+    if method.get("min_method", "Powell") != "Powell":
+        raise CosmicGpuError("only the reference's default minimiser (Powell) runs on the device; got min_method=%r "
+                             "(there is no CPU fallback)" % (method["min_method"],))
+    dens = np.asarray(dens_profs, dtype=np.float64)
+    if dens.ndim != 2 or dens.shape[1] > MAX_BINS:
+        raise ValueError("dens_profs must be (N, r_res) with r_res <= %d" % MAX_BINS)
+    r200s = np.asarray(r200s, dtype=np.float64)
+    radii, lmed, n_valid, avg = prepare(dens, ROverR200, r200s)
+    bnds = _bounds(method)
+    lb = np.array([b[0] for b in bnds], dtype=np.float64)
+    ub = np.array([b[1] for b in bnds], dtype=np.float64)
+    x0 = _initial_guess(prof, r200s)
+    ctx = session.get_context((session.devices or [0])[0])
+    best, fun, nfev, nit = ctx.fit_profiles(radii, lmed, n_valid, avg, x0, lb, ub, PROFILE_ID[prof])
+    last_info.clear()
+    last_info.update(fun=fun, nfev=nfev, nit=nit, timing=ctx.timing())
+    return best

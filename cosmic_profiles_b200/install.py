@@ -32,6 +32,21 @@ def install(target=None):
     return target
 
 
+def install_fits(target=None):
+    """Rebind ``fitDensProfHelper`` (dens_profs/dens_profs_tools.py:325) where fitDensProfs / estConcentrations look
+    it up: a module global of cosmic_base_class (:10, call sites :780, :800)."""
+    from . import _lib, dens_profs_tools
+    _lib.load()
+    if target is None:
+        import importlib
+        target = importlib.import_module("cosmic_profiles.common.cosmic_base_class")
+    key = ("fitDensProfHelper", id(target))
+    if key not in _saved:
+        _saved[key] = (target, getattr(target, "fitDensProfHelper", None))
+    setattr(target, "fitDensProfHelper", dens_profs_tools.fitDensProfHelper)
+    return target
+
+
 def install_gadget(targets=None):
     """Rebind ``calcObjCat`` (gadget/gen_catalogues.pyx:39) where DensShapeProfsGadget.__init__ looks it up: the
     module globals of shape_profs_classes (:24, call :580) and dens_profs_classes (:10).  targets: modules to patch

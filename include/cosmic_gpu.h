@@ -169,6 +169,24 @@ CPG_API int cpg_set_particles_gadget(cpg_ctx *ctx, const void *pos, int32_t pos_
                                      double velocity_unit_fac, double time);
 CPG_API int cpg_get_particles(cpg_ctx *ctx, double *xyz, double *vxyz, double *masses);
 
+/*
+ * Batched density-profile fits.  Replaces fitDensProfHelper / fitDensProf /
+ * toMinimize and the four profile models (dens_profs/dens_profs_tools.py:325-359, :232-323, :227-230, :22-79):
+ * per object, scipy.optimize.minimize(method='Powell', bounds=...) of psi^2 = sum_i (ln med_i - ln model(r_i))^2 / n
+ * (scipy 1.18.1 _minimize_powell + _linesearch_powell + _minimize_scalar_bounded, default options), one warp per
+ * object.  profile 0 nfw, 1 hernquist (rho_s, r_s), 2 einasto (rho_s, alpha, r_s), 3 alpha_beta_gamma
+ * (rho_s, alpha, beta, gamma, r_s).  Inputs as the reference prepares them in NumPy (:254-258, :277):
+ * radii (n_obj,R) = ROverR200 * r200 and lmed (n_obj,R) = log(median / average(median)), NaN bins removed and the
+ * n_valid[p] kept values stored first; avg (n_obj) = average(median); x0 (n_obj,npar) initial guesses; lb / ub
+ * (npar) bounds, ub = +inf where free (every lb finite).  R <= 128.
+ * Outputs: best (n_obj,npar) with best[:,0] multiplied by avg (:320); fun (n_obj) final psi^2, nfev, nit (n_obj)
+ * function evaluations / Powell iterations as scipy counts them (any may be NULL except best).
+ */
+CPG_API int cpg_fit_profiles(cpg_ctx *ctx, const double *radii, const double *lmed, const int32_t *n_valid,
+                             const double *avg, const double *x0, const double *lb, const double *ub, int32_t n_obj,
+                             int32_t R, int32_t profile, double xtol, double ftol, double *best, double *fun,
+                             int32_t *nfev, int32_t *nit);
+
 /* Page-locked host buffers for results (device->host copies into pageable memory run at a fraction of the
  * PCIe rate).  No counterpart in the reference, whose drivers np.zeros() their outputs
  * (shape_profs_algos.pyx:560-572). */

@@ -204,8 +204,8 @@ def linesearch(func, p, xi, tol, lb, ub, fval):
     if b0 != -INF and b1 != INF:
         amin, fret = fminbound(along, b0, b1, xatol=tol / 100)
     else:
-        amin, fret = fminbound(lambda u: along(math.tan(u)), math.atan(b0), math.atan(b1), xatol=tol / 100)
-        amin = math.tan(amin)
+        amin, fret = fminbound(lambda u: along(float(np.tan(u))), float(np.arctan(b0)), float(np.arctan(b1)), xatol=tol / 100)
+        amin = float(np.tan(amin))
     xi = [amin * v for v in xi]
     return fret, [p[i] + xi[i] for i in range(len(p))], xi
 

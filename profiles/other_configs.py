@@ -254,7 +254,70 @@ def sec_gadget():
     g.close()
 
 
-SECTIONS = dict(config0=sec_config0, config2=sec_config2, config3=sec_config3, config4=sec_config4, gadget=sec_gadget)
+def _ref_fit_one(args):
+    import warnings
+    warnings.filterwarnings("ignore")
+    from cosmic_profiles.dens_profs import dens_profs_tools as T
+    rr, method, tup = args
+    return T.fitDensProf(rr, method, tup)[0]
+
+
+def sec_fits():
+    """configs[2]: NFW / Hernquist / Einasto / alpha-beta-gamma fits of the 1e4 spherical direct-binning profiles
+    (bins [10:] as tests/test_densities.py:91-93), device Powell against the reference's fitDensProf on the host."""
+    import multiprocessing as mp
+    import warnings
+    from cosmic_profiles_b200 import dens_profs_algos as D, dens_profs_tools as DT
+    nh = 2000 if quick else 10000
+    tab = bench.halo_table(nh, 20260101)
+    cat = bench.generate_on_device(tab, 20260101, 0)
+    ctx.set_particles(cat["xyz"], None, cat["masses"]); ctx.set_catalogue(cat["idx_cat"], cat["obj_size"])
+    rb = np.logspace(-2, 0, 50)
+    dens, _ = ctx.dens_sph(cat["centers"], cat["r200"], D.sph_bin_edges(rb), 0.0)
+    dens = dens[:, 10:] * 1e10
+    dens[dens == 0.0] = np.nan     # empty inner bins of small objects (log(0)); the reference would fit -inf there
+    rr = rb[10:]
+    ref_ok = False
+    try:
+        from oracle import ref_loader
+        ref_ok = ref_loader.available("pristine")
+        if ref_ok:
+            ref_loader.load("pristine")
+    except Exception:
+        ref_ok = False
+    cores = len(os.sched_getaffinity(0))
+    for prof in ("nfw", "hernquist", "einasto", "alpha_beta_gamma"):
+        method = {"profile": prof}
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            t_prep0 = time.perf_counter()
+            DT.prepare(dens, rr, cat["r200"])
+            prep_ms = (time.perf_counter() - t_prep0) * 1e3
+            ms, best = timed(lambda: DT.fitDensProfHelper(dens, rr, cat["r200"], method), 2)
+        info = DT.last_info
+        entry = dict(objects=nh, bins=int(dens.shape[1]), wall_ms=ms, kernel_ms=info["timing"]["kernel_ms"], host_prepare_ms=prep_ms,
+                     fits_per_s=nh / (ms * 1e-3), mean_nfev=float(info["nfev"].mean()), max_nfev=int(info["nfev"].max()),
+                     evaluations_per_s_kernel=float(info["nfev"].sum()) / (info["timing"]["kernel_ms"] * 1e-3),
+                     finite_rows=int(np.isfinite(best).all(1).sum()))
+        if ref_ok:
+            ns = min(nh, 8 * cores)
+            pick = np.random.default_rng(1).choice(nh, ns, replace=False)
+            jobs = [(rr, method, (dens[i], cat["r200"][i], int(i))) for i in pick]
+            with mp.get_context("fork").Pool(cores) as pool:
+                pool.map(_ref_fit_one, jobs[:cores])          # warm the workers
+                t0 = time.perf_counter()
+                ref = np.array(pool.map(_ref_fit_one, jobs))
+                dt = time.perf_counter() - t0
+            fin = np.isfinite(ref).all(1) & np.isfinite(best[pick]).all(1)
+            rel = np.max(np.abs(best[pick][fin] - ref[fin]) / np.abs(ref[fin]), axis=1)
+            entry.update(reference_fits_per_s=ns / dt, reference_cores=cores, reference_sample=ns,
+                         speedup=(nh / (ms * 1e-3)) / (ns / dt), sample_within_1e9=float((rel < 1e-9).mean()),
+                         sample_within_1e4=float((rel < 1e-4).mean()), sample_max_rel=float(rel.max()),
+                         sample_finite_pattern_equal=bool(np.array_equal(np.isfinite(ref).all(1), np.isfinite(best[pick]).all(1))))
+        out["config2_fit_%s" % prof] = entry
+
+
+SECTIONS = dict(fits=sec_fits, config0=sec_config0, config2=sec_config2, config3=sec_config3, config4=sec_config4, gadget=sec_gadget)
 for name, fn in SECTIONS.items():
     if want(name):
         fn()
