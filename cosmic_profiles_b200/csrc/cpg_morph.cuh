@@ -336,12 +336,14 @@ struct WarpRing {
     bool res_loaded;      // resident tiles are in place
 };
 
-__device__ __forceinline__ void ring_init(WarpRing &r, unsigned char *buf, uint64_t *bar, int lane)
+// arrivals: 1 for the TMA ring (the elected lane's arrive.expect_tx), 32 for the per-lane cp.async ring (every lane's
+// cp.async.mbarrier.arrive.noinc)
+__device__ __forceinline__ void ring_init(WarpRing &r, unsigned char *buf, uint64_t *bar, int lane, uint32_t arrivals = 1)
 {
     r.buf = buf; r.bar = bar; r.seq = 0; r.res_seq = 0; r.res_loaded = false;
     r.buf_s = smem_u32(buf); r.bar_s = smem_u32(bar);
     if (lane == 0) {
-        for (int s = 0; s < RING_MAX_STAGES; s++) mbar_init(bar + s, 1);
+        for (int s = 0; s < RING_MAX_STAGES; s++) mbar_init(bar + s, arrivals);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -368,6 +370,35 @@ __device__ __forceinline__ void ring_issue(const WarpRing &r, uint32_t seq, cons
         bulk_g2s(dst + 5 * C::STREAM_BYTES, soa.vy + o, bytes, bar);
         bulk_g2s(dst + 6 * C::STREAM_BYTES, soa.vz + o, bytes, bar);
     }
+}
+
+// The same tile brought in by the whole warp with 16-byte cp.async (LDGSTS): lane l copies pairs l and l + 32 of every
+// stream, then arrives on the stage's mbarrier once its copies have landed.  8 warp instructions per tile instead of
+// the ~100 the elected-lane TMA issue costs (4 UBLKCP, each behind a uniform-register broadcast loop): used by the
+// warp kernel, whose tasks average fewer than 8 tiles per pass (profiles/README.md, source-page breakdown).
+template <bool VDISP>
+__device__ __forceinline__ void ring_issue_lanes(const WarpRing &r, uint32_t seq, const SoA &soa, int64_t base, int t, int npairs,
+                                                 int lane)
+{
+    using C = RingCfg<VDISP>;
+    const uint32_t stage = seq % C::STAGES;
+    const int n = min(TILE_PAIRS, npairs - t * TILE_PAIRS);
+    const uint32_t dst = r.buf_s + stage * C::STAGE_BYTES;
+    const uint32_t bar = r.bar_s + stage * 8u;
+    const int64_t o = base + (int64_t)t * (2 * TILE_PAIRS);
+    const double *src[7] = {soa.dx, soa.dy, soa.dz, soa.m, soa.vx, soa.vy, soa.vz};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int pi = lane + 32 * h;
+        if (pi < n) {
+#pragma unroll
+            for (int st = 0; st < C::NSTREAM; st++)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + st * C::STREAM_BYTES + pi * 16u),
+                             "l"(src[st] + o + 2 * pi)
+                             : "memory");
+        }
+    }
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 // The two particles of pair `pi` of the tile in ring slot `seq` (this lane consumes pairs lane and lane+32).
@@ -411,7 +442,7 @@ __device__ __forceinline__ void ring_fill_tail(const WarpRing &r, uint32_t seq, 
 // `npairs` pairs that the still-active shells need; npr[s] = pairs in the prefix of shell s.
 // resident: every tile this warp will ever need for the task fits in its ring -> loaded by the first pass,
 // re-read from shared memory by all later ones.
-template <int S, bool SHELL, bool REDUCED, bool VDISP>
+template <int S, bool SHELL, bool REDUCED, bool VDISP, bool LANES = false>
 __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npairs, int tile0, int tstride, int lane,
                                          WarpRing &ring, bool resident, int npairs_task, const double *frames,
                                          const int (&npr)[S], const int *nin, unsigned amask, double (&acc)[S][7],
@@ -445,7 +476,10 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
         const int nt_task = (npairs_task + TILE_PAIRS - 1) / TILE_PAIRS;
         issue_n = tile0 < nt_task ? (nt_task - tile0 + tstride - 1) / tstride : 0;
     }
-    if (!reuse && lane == 0)
+    if (!reuse && LANES) {
+        for (int j = 0; j < min(issue_n, RING_STAGES); j++)
+            ring_issue_lanes<VDISP>(ring, seq0 + j, soa, base, tile0 + j * tstride, npairs_load, lane);
+    } else if (!reuse && lane == 0)
         for (int j = 0; j < min(issue_n, RING_STAGES); j++)
             ring_issue<VDISP>(ring, seq0 + j, soa, base, tile0 + j * tstride, npairs_load);
     for (int j = 0; j < nmine; j++) {
@@ -481,7 +515,9 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
         }
         if (!resident && j + RING_STAGES < nmine) {
             __syncwarp();   // every lane has taken its data out of this slot
-            if (lane == 0)
+            if (LANES)
+                ring_issue_lanes<VDISP>(ring, seq + RING_STAGES, soa, base, t + RING_STAGES * tstride, npairs_load, lane);
+            else if (lane == 0)
                 ring_issue<VDISP>(ring, seq + RING_STAGES, soa, base, t + RING_STAGES * tstride, npairs_load);
         }
     }
@@ -518,6 +554,10 @@ __device__ __forceinline__ int active_npairs(const int (&npr)[S], unsigned amask
 // warps pulling tasks (sorted largest first) from an atomic queue.
 // ------------------------------------------------------------------------------------------------
 constexpr int WARP_KERNEL_WARPS = 4;
+#ifndef CPG_WARP_RING_LANES
+#define CPG_WARP_RING_LANES 1   // 1: per-lane cp.async tile loads in the warp kernel; 0: elected-lane TMA bulk copies
+#endif
+constexpr bool WARP_RING_LANES = CPG_WARP_RING_LANES != 0;
 #ifndef CPG_WARP_MINB
 #define CPG_WARP_MINB 3   // resident CTAs per SM the register allocator must leave room for
 #endif
@@ -604,7 +644,7 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
     const LM L(lane);
     const int ls = L.ls;
     WarpRing ring;
-    ring_init(ring, s_ring_w + warp * RingCfg<VDISP>::WARP_BYTES, s_bar[warp], lane);
+    ring_init(ring, s_ring_w + warp * RingCfg<VDISP>::WARP_BYTES, s_bar[warp], lane, WARP_RING_LANES ? 32u : 1u);
     const bool use_inner = !SHELL && !REDUCED && P.n_eff != nullptr && P.ptab != nullptr;
     if (use_inner) {
         for (int j = threadIdx.x; j < P.R; j += blockDim.x) s_rr[j] = P.rr[j];
@@ -668,7 +708,7 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
                     const double tadd = table_term(ptab, row0, nin[g * S + ((lane & (8 * S - 1)) >> 3)], lane & 7);
                     double acc[S][7];
                     int cnt[S];
-                    run_pass<S, SHELL, REDUCED, VDISP>(P.soa, base, active_npairs<S>(npr[g], am), 0, 1, lane, ring, resident,
+                    run_pass<S, SHELL, REDUCED, VDISP, WARP_RING_LANES>(P.soa, base, active_npairs<S>(npr[g], am), 0, 1, lane, ring, resident,
                                                        npairs_task, frames + g * S * F_SLOTS, npr[g], nin + g * S, am, acc,
                                                        cnt);
                     double val[8 * S];

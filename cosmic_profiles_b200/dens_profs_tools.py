@@ -53,22 +53,18 @@ def prepare(dens_profs, ROverR200, r200s):
     keep = ~np.isnan(dens)
     n_valid = keep.sum(axis=1).astype(np.int32)
     radii = rr[None, :] * r200s[:, None]
-    med = dens.copy()
-    full = n_valid == R
-    for p in np.flatnonzero(~full):          # objects with NaN bins (empty ellipsoidal shells): squeeze to the front
-        k = keep[p]
-        m = int(n_valid[p])
-        radii[p, :m] = radii[p, k]
-        med[p, :m] = dens[p, k]
-        radii[p, m:] = 0.0
-        med[p, m:] = np.nan
+    med = dens
+    if (n_valid < R).any():
+        # objects with NaN bins (empty shells): stable partition, kept bins first, for all rows at once
+        order = np.argsort(~keep, axis=1, kind="stable")
+        radii = np.take_along_axis(radii, order, axis=1)
+        med = np.take_along_axis(dens, order, axis=1)
     avg = np.full(n, np.nan)
     with np.errstate(all="ignore"):
-        if full.any():
-            avg[full] = med[full].mean(axis=1)            # == np.average(row): same pairwise sum over a contiguous row
-        for p in np.flatnonzero(~full):
-            m = int(n_valid[p])
-            avg[p] = np.average(med[p, :m]) if m > 0 else np.nan
+        for m in np.unique(n_valid):          # np.average(row[:m]) == mean over a contiguous row of m values (same pairwise sum)
+            rows = np.flatnonzero(n_valid == m)
+            if m > 0:
+                avg[rows] = np.ascontiguousarray(med[rows, :m]).mean(axis=1)
         lmed = np.log(med / avg[:, None])
     return np.ascontiguousarray(radii), np.ascontiguousarray(lmed), n_valid, avg
 
