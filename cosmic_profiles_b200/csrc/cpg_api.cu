@@ -115,15 +115,18 @@ struct cpg_ctx {
         int sort_R = 0;
         std::vector<double> centers, r200, rr;
     } have;
-    struct {
+    // task lists are cached per (catalogue, R, S, thresholds): a getShapeCatLocal + getShapeCatGlobal sequence
+    // alternates between two of them, and rebuilding + uploading the 1.8e5 tasks of configs[1] costs ~1.5 ms
+    struct TaskKey {
         bool valid = false;
-        uint64_t cat = 0;
+        uint64_t cat = 0, used = 0;
         int S = 0, R = 0, nw = 0, ncl = 0, ngrid = 0, cluster_size = 1;
         int64_t grid_min = 0;
         int64_t large_min = 0;
-    } task_key;
+        DevBuf<Task> tasks;
+    } task_cache[4];
+    uint64_t task_clock = 0;
     // morphology
-    DevBuf<Task> tasks;
     DevBuf<GridState> grid_states;
     DevBuf<double> grid_partials;
     int64_t opt_grid_halo_min = 0;
@@ -256,6 +259,18 @@ __global__ void idx_range_kernel(const int32_t *idx, int64_t n, int32_t *minmax)
         atomicMin(&minmax[0], lo);
         atomicMax(&minmax[1], hi);
     }
+}
+
+// Result arrays of cpg_shape: out12 zeros (what the reference returns for a failed halo-shell), counters -1
+// (= the per-object early exit), work-queue heads 0.
+__global__ void init_results_kernel(double2 *__restrict__ out12, int32_t *__restrict__ n_iter, int32_t *__restrict__ n_pts,
+                                    int32_t *__restrict__ counters, int64_t nR)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = i0; i < nR * 6; i += stride) out12[i] = make_double2(0.0, 0.0);
+    for (int64_t i = i0; i < nR; i += stride) { n_iter[i] = -1; n_pts[i] = -1; }
+    if (i0 < 4) counters[i0] = 0;
 }
 
 struct Timer {
@@ -591,7 +606,8 @@ CPG_API void cpg_destroy(cpg_ctx *c)
                               &c->n_iter, &c->n_pts, &c->bin_cnt, &c->counts};
     for (auto *b : i32) b->release();
     c->off.release(); c->poff.release(); c->chunks.release(); c->kchunks.release();
-    c->mass32.release(); c->skip.release(); c->tasks.release(); c->bucket.release();
+    c->mass32.release(); c->skip.release(); c->bucket.release();
+    for (auto &tk : c->task_cache) tk.tasks.release();
     c->grid_states.release(); c->grid_partials.release();
     c->tile_hist.release(); c->dest.release(); c->n_eff.release(); c->cidxA.release(); c->cidxB.release(); c->d_order.release(); c->ptab.release();
     c->cref.release();
@@ -747,7 +763,7 @@ static int install_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, 
     c->mass_stream_valid = false;
     c->catalogue_version++;
     c->have.valid = false;
-    c->task_key.valid = false;
+    for (auto &tk : c->task_cache) tk.valid = false;
     return CPG_OK;
 }
 
@@ -1106,9 +1122,17 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     if (S == 4 && c->opt_groups == 2 && R >= 8) G = 2;
     // objects of millions of particles: one launch over the whole grid per Katz iteration (kernel 3)
     const int64_t grid_min = c->opt_grid_halo_min > 0 ? c->opt_grid_halo_min : ((int64_t)1 << 22);
-    auto &TK = c->task_key;
-    if (!(TK.valid && TK.cat == c->catalogue_version && TK.S == S * 16 + G && TK.R == R && TK.large_min == large_min &&
-          TK.grid_min == grid_min && (c->opt_cluster_size == 0 || c->opt_cluster_size == TK.cluster_size))) {
+    cpg_ctx::TaskKey *hit = nullptr, *victim = nullptr;
+    for (auto &tk : c->task_cache)
+        if (tk.valid && tk.cat == c->catalogue_version && tk.S == S * 16 + G && tk.R == R && tk.large_min == large_min &&
+            tk.grid_min == grid_min && (c->opt_cluster_size == 0 || c->opt_cluster_size == tk.cluster_size))
+            hit = &tk;
+    for (auto &tk : c->task_cache)   // victim: a free slot, else the least recently used one
+        if (!victim || (victim->valid && (!tk.valid || tk.used < victim->used))) victim = &tk;
+    auto &TK = hit ? *hit : *victim;
+    TK.used = ++c->task_clock;
+    if (!hit) {
+        TK.valid = false;
         std::vector<Task> warp_tasks, cl_tasks, grid_tasks;
         int64_t largest = 0;
         for (int oi = 0; oi < n; oi++) {
@@ -1139,17 +1163,18 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
         TK.ngrid = (int)grid_tasks.size(); TK.grid_min = grid_min;
         warp_tasks.insert(warp_tasks.end(), cl_tasks.begin(), cl_tasks.end());
         warp_tasks.insert(warp_tasks.end(), grid_tasks.begin(), grid_tasks.end());   // layout: warp | cluster | grid
-        CPG_TRY(c->tasks.ensure(warp_tasks.size()));
-        CPG_TRY(small_upload(c, c->tasks.p, warp_tasks.data(), sizeof(Task) * warp_tasks.size()));
+        CPG_TRY(TK.tasks.ensure(warp_tasks.size()));
+        CPG_TRY(small_upload(c, TK.tasks.p, warp_tasks.data(), sizeof(Task) * warp_tasks.size()));
         c->timing.h2d_bytes += (int64_t)(sizeof(Task) * warp_tasks.size());
         TK.valid = true; TK.cat = c->catalogue_version; TK.S = S * 16 + G; TK.R = R; TK.large_min = large_min;
     }
     const int nw = TK.nw, ncl = TK.ncl, ngrid = TK.ngrid, cluster_size = TK.cluster_size;
     CPG_TRY(c->out12.ensure(nR * 12)); CPG_TRY(c->n_iter.ensure(nR)); CPG_TRY(c->n_pts.ensure(nR));
-    CPG_CUDA(cudaMemsetAsync(c->out12.p, 0, sizeof(double) * 12 * nR, c->stream));
-    CPG_CUDA(cudaMemsetAsync(c->n_iter.p, 0xff, sizeof(int32_t) * nR, c->stream));
-    CPG_CUDA(cudaMemsetAsync(c->n_pts.p, 0xff, sizeof(int32_t) * nR, c->stream));
-    CPG_CUDA(cudaMemsetAsync(c->task_counter.p, 0, sizeof(int32_t) * 4, c->stream));
+    // (a fill kernel, not cudaMemsetAsync: the copy-engine memset of the 67 MB result array of configs[1] took ~1 ms)
+    init_results_kernel<<<grid_for((int64_t)nR * 6, 256, c->sm_count * 16), 256, 0, c->stream>>>(
+        reinterpret_cast<double2 *>(c->out12.p), c->n_iter.p, c->n_pts.p, c->task_counter.p, (int64_t)nR);
+    c->timing.kernel_launches++;
+    CPG_CUDA(cudaGetLastError());
     T.mark(1);
 
     // ---- gather (positions, masses, statistics, velocity centres)
@@ -1169,7 +1194,7 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     P.r200 = c->r200.p; P.rr = c->rr.p; P.skip = c->skip.p;
     P.n_eff = radial ? c->n_eff.p : nullptr;   // run_gather guarantees n_eff matches these radii when radial
     P.ptab = inner ? c->ptab.p : nullptr;
-    P.tasks = c->tasks.p; P.n_tasks = 0; P.task_counter = c->task_counter.p;
+    P.tasks = TK.tasks.p; P.n_tasks = 0; P.task_counter = c->task_counter.p;
     P.R = R; P.local = local ? 1 : 0; P.SAFE = SAFE;
     P.tol = IT_TOL; P.wall = IT_WALL; P.itmin = IT_MIN;
     P.out12 = c->out12.p; P.n_iter = c->n_iter.p; P.n_pts = c->n_pts.p;
