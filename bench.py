@@ -455,7 +455,8 @@ def main():
             ctx2.set_option(name, int(val))
         upload(ctx2)
         shapes(ctx2)                       # warm its buffers and scratch
-        n_pipe = 2 * max(2, min(a.steps, 4))
+        # long enough that the one compute the last upload cannot hide behind is a small share of the run
+        n_pipe = 2 * max(2, min(2 * a.steps, 10))
         errs = []
 
         copy_lock, compute_lock = threading.Lock(), threading.Lock()

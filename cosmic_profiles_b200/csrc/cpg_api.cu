@@ -692,6 +692,14 @@ CPG_API int cpg_set_particles(cpg_ctx *c, const double *xyz, const double *vxyz,
 // the device in c->idx: idx_cat == nullptr).
 static int install_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, const int32_t *obj_size, int32_t n_obj)
 {
+    // the flat catalogue is by far the largest piece: start its upload first, the host-side bookkeeping below then
+    // runs while the copy engine works (an inconsistent obj_size is found afterwards and invalidates the catalogue)
+    c->n_idx = 0; c->n_obj = 0; c->have.valid = false;
+    for (auto &tk : c->task_cache) tk.valid = false;
+    if (idx_cat) {
+        CPG_TRY(c->idx.ensure(n_idx));
+        if (n_idx) CPG_TRY(upload_chunked(c->idx.p, idx_cat, sizeof(int32_t) * n_idx, c->stream));
+    }
     std::vector<int64_t> off(n_obj + 1, 0), poff(n_obj + 1, 0);
     c->h_size.assign(obj_size, obj_size + n_obj);
     c->h_chunks.clear(); c->h_kchunks.clear();
@@ -717,7 +725,6 @@ static int install_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, 
     std::iota(c->order.begin(), c->order.end(), 0);
     std::stable_sort(c->order.begin(), c->order.end(), [&](int a, int b) { return obj_size[a] > obj_size[b]; });
 
-    if (idx_cat) CPG_TRY(c->idx.ensure(n_idx));
     CPG_TRY(c->size.ensure(n_obj));
     CPG_TRY(c->off.ensure(n_obj + 1)); CPG_TRY(c->poff.ensure(n_obj + 1));
     CPG_TRY(c->chunks.ensure(c->h_chunks.size())); CPG_TRY(c->kchunks.ensure(c->h_kchunks.size()));
@@ -726,7 +733,6 @@ static int install_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, 
     CPG_TRY(c->d_order.ensure(n_obj));
     if (n_obj)
         CPG_CUDA(cudaMemcpyAsync(c->d_order.p, c->order.data(), sizeof(int32_t) * n_obj, cudaMemcpyHostToDevice, c->stream));
-    if (n_idx && idx_cat) CPG_TRY(upload_chunked(c->idx.p, idx_cat, sizeof(int32_t) * n_idx, c->stream));
     if (n_obj) CPG_CUDA(cudaMemcpyAsync(c->size.p, obj_size, sizeof(int32_t) * n_obj, cudaMemcpyHostToDevice, c->stream));
     CPG_CUDA(cudaMemcpyAsync(c->off.p, off.data(), sizeof(int64_t) * (n_obj + 1), cudaMemcpyHostToDevice, c->stream));
     CPG_CUDA(cudaMemcpyAsync(c->poff.p, poff.data(), sizeof(int64_t) * (n_obj + 1), cudaMemcpyHostToDevice, c->stream));
