@@ -90,10 +90,10 @@ struct cpg_ctx {
     std::vector<int32_t> h_size;
     std::vector<int32_t> order;   // objects sorted by size, largest first
     // chunk lists
-    std::vector<Chunk> h_chunks, h_kchunks;
-    std::vector<int32_t> h_chunk_first, h_kchunk_first;
-    DevBuf<Chunk> chunks, kchunks;
-    DevBuf<int32_t> chunk_first, kchunk_first;
+    std::vector<Chunk> h_chunks, h_kchunks, h_schunks;   // CHUNK (statistics, binning), KDE_CHUNK, SORT_CHUNK particles
+    std::vector<int32_t> h_chunk_first, h_kchunk_first, h_schunk_first;
+    DevBuf<Chunk> chunks, kchunks, schunks;
+    DevBuf<int32_t> chunk_first, kchunk_first, schunk_first;
     // gathered SoA
     DevBuf<double> g_dx, g_dy, g_dz, g_m, g_vx, g_vy, g_vz;
     bool mass_stream_valid = false;
@@ -306,8 +306,7 @@ int run_gather(cpg_ctx *c, const double *h_centers, const double *h_r200, const 
     CPG_TRY(c->g_dx.ensure(c->n_pad)); CPG_TRY(c->g_dy.ensure(c->n_pad));
     CPG_TRY(c->g_dz.ensure(c->n_pad)); CPG_TRY(c->g_m.ensure(c->n_pad));
     c->sorted_valid = false;
-    const int nc = (int)c->h_kchunks.size();   // ordering works on 2048-particle chunks (== KDE_CHUNK)
-    static_assert(SORT_CHUNK == KDE_CHUNK, "the ordering kernels reuse the 2048-particle chunk list");
+    const int nc = (int)c->h_schunks.size();   // ordering works on SORT_CHUNK-particle chunks
     if (sort_R > 0 && n > 0 && nc > 0) {
         const int B = sort_R + 1;
         CPG_TRY(c->bucket.ensure(n)); CPG_TRY(c->tile_hist.ensure((size_t)nc * B));
@@ -315,7 +314,7 @@ int run_gather(cpg_ctx *c, const double *h_centers, const double *h_r200, const 
         CPG_TRY(c->dest.ensure(n));
         SortParams P;
         P.G = gather_view(c, L_BOX);
-        P.chunks = c->kchunks.p; P.chunk_first = c->kchunk_first.p; P.size = c->size.p;
+        P.chunks = c->schunks.p; P.chunk_first = c->schunk_first.p; P.size = c->size.p;
         P.r200 = c->r200.p; P.rr = c->rr.p; P.n_chunks = nc; P.R = sort_R;
         P.bucket = c->bucket.p; P.tile_hist = c->tile_hist.p; P.dest = c->dest.p;
         P.n_eff = c->n_eff.p;
@@ -605,7 +604,7 @@ CPG_API void cpg_destroy(cpg_ctx *c)
     DevBuf<int32_t> *i32[] = {&c->idx, &c->size, &c->chunk_first, &c->kchunk_first, &c->part_flag, &c->task_counter,
                               &c->n_iter, &c->n_pts, &c->bin_cnt, &c->counts};
     for (auto *b : i32) b->release();
-    c->off.release(); c->poff.release(); c->chunks.release(); c->kchunks.release();
+    c->off.release(); c->poff.release(); c->chunks.release(); c->kchunks.release(); c->schunks.release(); c->schunk_first.release();
     c->mass32.release(); c->skip.release(); c->bucket.release();
     for (auto &tk : c->task_cache) tk.tasks.release();
     c->grid_states.release(); c->grid_partials.release();
@@ -702,8 +701,8 @@ static int install_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, 
     }
     std::vector<int64_t> off(n_obj + 1, 0), poff(n_obj + 1, 0);
     c->h_size.assign(obj_size, obj_size + n_obj);
-    c->h_chunks.clear(); c->h_kchunks.clear();
-    c->h_chunk_first.assign(n_obj + 1, 0); c->h_kchunk_first.assign(n_obj + 1, 0);
+    c->h_chunks.clear(); c->h_kchunks.clear(); c->h_schunks.clear();
+    c->h_chunk_first.assign(n_obj + 1, 0); c->h_kchunk_first.assign(n_obj + 1, 0); c->h_schunk_first.assign(n_obj + 1, 0);
     for (int h = 0; h < n_obj; h++) {
         if (obj_size[h] < 0) {
             set_error("cpg_set_catalogue: obj_size[%d] < 0", h);
@@ -713,8 +712,10 @@ static int install_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, 
         poff[h + 1] = poff[h] + ((obj_size[h] + 1) & ~1);
         for (int s = 0; s < obj_size[h]; s += CHUNK) c->h_chunks.push_back(Chunk{h, s});
         for (int s = 0; s < obj_size[h]; s += KDE_CHUNK) c->h_kchunks.push_back(Chunk{h, s});
+        for (int s = 0; s < obj_size[h]; s += SORT_CHUNK) c->h_schunks.push_back(Chunk{h, s});
         c->h_chunk_first[h + 1] = (int32_t)c->h_chunks.size();
         c->h_kchunk_first[h + 1] = (int32_t)c->h_kchunks.size();
+        c->h_schunk_first[h + 1] = (int32_t)c->h_schunks.size();
     }
     if (off[n_obj] != n_idx) {
         set_error("cpg_set_catalogue: sum(obj_size) = %lld but idx_cat has %lld entries", (long long)off[n_obj],
@@ -728,7 +729,8 @@ static int install_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, 
     CPG_TRY(c->size.ensure(n_obj));
     CPG_TRY(c->off.ensure(n_obj + 1)); CPG_TRY(c->poff.ensure(n_obj + 1));
     CPG_TRY(c->chunks.ensure(c->h_chunks.size())); CPG_TRY(c->kchunks.ensure(c->h_kchunks.size()));
-    CPG_TRY(c->chunk_first.ensure(n_obj + 1)); CPG_TRY(c->kchunk_first.ensure(n_obj + 1));
+    CPG_TRY(c->schunks.ensure(c->h_schunks.size()));
+    CPG_TRY(c->chunk_first.ensure(n_obj + 1)); CPG_TRY(c->kchunk_first.ensure(n_obj + 1)); CPG_TRY(c->schunk_first.ensure(n_obj + 1));
     CPG_TRY(c->task_counter.ensure(4));
     CPG_TRY(c->d_order.ensure(n_obj));
     if (n_obj)
@@ -745,6 +747,11 @@ static int install_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, 
     CPG_CUDA(cudaMemcpyAsync(c->chunk_first.p, c->h_chunk_first.data(), sizeof(int32_t) * (n_obj + 1),
                              cudaMemcpyHostToDevice, c->stream));
     CPG_CUDA(cudaMemcpyAsync(c->kchunk_first.p, c->h_kchunk_first.data(), sizeof(int32_t) * (n_obj + 1),
+                             cudaMemcpyHostToDevice, c->stream));
+    if (!c->h_schunks.empty())
+        CPG_CUDA(cudaMemcpyAsync(c->schunks.p, c->h_schunks.data(), sizeof(Chunk) * c->h_schunks.size(),
+                                 cudaMemcpyHostToDevice, c->stream));
+    CPG_CUDA(cudaMemcpyAsync(c->schunk_first.p, c->h_schunk_first.data(), sizeof(int32_t) * (n_obj + 1),
                              cudaMemcpyHostToDevice, c->stream));
     // index range check on the device: an out-of-range index would be an illegal address in the gather
     if (n_idx > 0) {

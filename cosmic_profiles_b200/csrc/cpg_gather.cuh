@@ -359,7 +359,10 @@ __device__ __forceinline__ void load_relative(const GatherParams &G, int h, int6
     dz = __dsub_rn(z, G.centers[3 * h + 2]);
 }
 
-constexpr int SORT_CHUNK = 2048;   // particles per CTA of the ordering kernels (8 per thread)
+#ifndef CPG_SORT_CHUNK
+#define CPG_SORT_CHUNK 1024
+#endif
+constexpr int SORT_CHUNK = CPG_SORT_CHUNK;   // particles per CTA of the ordering kernels
 
 __global__ void __launch_bounds__(256) bucket_hist_kernel(const SortParams P)
 {
