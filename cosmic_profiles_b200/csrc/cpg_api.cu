@@ -109,6 +109,7 @@ struct cpg_ctx {
     uint64_t snapshot_version = 0, catalogue_version = 0;
     struct {
         bool valid = false, stats = false, vel = false;
+        bool parts_from_sort = false;   // the per-chunk statistics were produced by the ordering gather (sort chunks)
         int ptab = 0;   // prefix tensor table: 0 none, 1 positions, 2 velocities
         uint64_t snap = 0, cat = 0;
         float L_BOX = 0.f;
@@ -302,7 +303,7 @@ int run_gather(cpg_ctx *c, const double *h_centers, const double *h_r200, const 
         same = H.sort_R == sort_R && H.rr.size() == (size_t)sort_R && !memcmp(H.rr.data(), h_rr, sort_R * sizeof(double)) &&
                H.r200.size() == (size_t)c->n_obj && !memcmp(H.r200.data(), h_r200, c->n_obj * sizeof(double));
     if (same) return CPG_OK;
-    H.valid = false; H.stats = false; H.vel = false; H.ptab = 0;
+    H.valid = false; H.stats = false; H.vel = false; H.ptab = 0; H.parts_from_sort = false;
     CPG_TRY(c->g_dx.ensure(c->n_pad)); CPG_TRY(c->g_dy.ensure(c->n_pad));
     CPG_TRY(c->g_dz.ensure(c->n_pad)); CPG_TRY(c->g_m.ensure(c->n_pad));
     c->sorted_valid = false;
@@ -318,6 +319,9 @@ int run_gather(cpg_ctx *c, const double *h_centers, const double *h_r200, const 
         P.r200 = c->r200.p; P.rr = c->rr.p; P.n_chunks = nc; P.R = sort_R;
         P.bucket = c->bucket.p; P.tile_hist = c->tile_hist.p; P.dest = c->dest.p;
         P.n_eff = c->n_eff.p;
+        CPG_TRY(c->part_mass.ensure(nc)); CPG_TRY(c->part_flag.ensure(nc)); CPG_TRY(c->part_mm.ensure((size_t)2 * nc));
+        P.part_mass = c->part_mass.p; P.part_spread = c->part_flag.p; P.part_mminmax = c->part_mm.p;
+        H.parts_from_sort = true;
         CPG_CUDA(cudaFuncSetAttribute(gather_bucketed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)GATHER_BUCKETED_SMEM));
         bucket_hist_kernel<<<nc, 256, 0, c->stream>>>(P);
@@ -344,18 +348,21 @@ int run_gather(cpg_ctx *c, const double *h_centers, const double *h_r200, const 
 int run_stats(cpg_ctx *c)
 {
     if (c->have.valid && c->have.stats) return CPG_OK;
+    const bool fused = c->have.valid && c->have.parts_from_sort;   // chunk partials already written by the ordering gather
     const int nc = (int)c->h_chunks.size();
-    CPG_TRY(c->part_mass.ensure(nc)); CPG_TRY(c->part_flag.ensure(nc)); CPG_TRY(c->part_mm.ensure((size_t)2 * nc));
+    if (!fused) {
+        CPG_TRY(c->part_mass.ensure(nc)); CPG_TRY(c->part_flag.ensure(nc)); CPG_TRY(c->part_mm.ensure((size_t)2 * nc));
+    }
     CPG_TRY(c->obj_mass.ensure(c->n_obj)); CPG_TRY(c->skip.ensure(c->n_obj)); CPG_TRY(c->obj_eqm.ensure(c->n_obj));
-    if (nc > 0) {
+    if (nc > 0 && !fused) {
         stats_chunk_kernel<<<nc, 256, 0, c->stream>>>(soa_view(c), c->chunks.p, nc, c->part_mass.p, c->part_flag.p,
                                                      c->part_mm.p);
         c->timing.kernel_launches++;
     }
     if (c->n_obj > 0) {
         stats_final_kernel<<<grid_for(c->n_obj, 128, 1 << 30), 128, 0, c->stream>>>(
-            c->chunk_first.p, c->size.p, c->n_obj, c->part_mass.p, c->part_flag.p, c->part_mm.p, c->obj_mass.p, c->skip.p,
-            c->obj_eqm.p);
+            fused ? c->schunk_first.p : c->chunk_first.p, c->size.p, c->n_obj, c->part_mass.p, c->part_flag.p, c->part_mm.p,
+            c->obj_mass.p, c->skip.p, c->obj_eqm.p);
         c->timing.kernel_launches++;
     }
     CPG_CUDA(cudaGetLastError());

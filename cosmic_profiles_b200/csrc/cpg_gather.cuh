@@ -343,6 +343,11 @@ struct SortParams {
     int32_t *tile_hist;           // (n_chunks, R+1): counts, then exclusive offsets inside the object
     int32_t *dest;                // (n_idx) or nullptr
     int32_t *n_eff;               // (n_obj, R)
+    // per-chunk statistics, produced by the gather while the chunk sits in shared memory (what stats_chunk_kernel
+    // computes from a second read of the gathered streams): mass sum, spread flag, (min, max) mass
+    double *part_mass;            // (n_chunks)
+    int32_t *part_spread;         // (n_chunks)
+    double *part_mminmax;         // (n_chunks, 2)
 };
 
 __device__ __forceinline__ void load_relative(const GatherParams &G, int h, int64_t first, int64_t j, double &dx,
@@ -512,9 +517,30 @@ __global__ void __launch_bounds__(256) gather_bucketed_kernel(const SortParams P
     }
     __syncthreads();
     const int n = end - ck.start;
+    double msum = 0.0, mlo = 1e300, mhi = -1e300;
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
         const int64_t o = pbase + sdest[j];
-        P.G.dx[o] = sx[j]; P.G.dy[o] = sy[j]; P.G.dz[o] = sz[j]; P.G.m[o] = sm[j];
+        const double mj = sm[j];
+        P.G.dx[o] = sx[j]; P.G.dy[o] = sy[j]; P.G.dz[o] = sz[j]; P.G.m[o] = mj;
+        msum += mj;
+        mlo = fmin(mlo, mj); mhi = fmax(mhi, mj);
+    }
+    if (P.part_mass) {   // fixed reduction order: deterministic chunk totals
+        for (int o = 16; o > 0; o >>= 1) {
+            msum += __shfl_xor_sync(0xffffffffu, msum, o);
+            mlo = fmin(mlo, __shfl_xor_sync(0xffffffffu, mlo, o));
+            mhi = fmax(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
+        }
+        __syncthreads();   // sx is free now: reuse its first 24 doubles as reduction scratch
+        if (lane == 0) { sx[warp] = msum; sx[8 + warp] = mlo; sx[16 + warp] = mhi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0, lo = 1e300, hi = -1e300;
+            for (int w = 0; w < 8; w++) { t += sx[w]; lo = fmin(lo, sx[8 + w]); hi = fmax(hi, sx[16 + w]); }
+            P.part_mass[blockIdx.x] = t;
+            P.part_spread[blockIdx.x] = 1;
+            P.part_mminmax[2 * blockIdx.x] = lo; P.part_mminmax[2 * blockIdx.x + 1] = hi;
+        }
     }
     if (threadIdx.x == 0 && end == N && (N & 1)) {   // pad element of an odd-sized object
         P.G.dx[pbase + N] = 1e150; P.G.dy[pbase + N] = 1e150; P.G.dz[pbase + N] = 1e150; P.G.m[pbase + N] = 0.0;
