@@ -325,7 +325,7 @@ int run_gather(cpg_ctx *c, const double *h_centers, const double *h_r200, const 
         CPG_CUDA(cudaFuncSetAttribute(gather_bucketed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)GATHER_BUCKETED_SMEM));
         bucket_hist_kernel<<<nc, 256, 0, c->stream>>>(P);
-        bucket_scan_kernel<<<grid_for((int64_t)c->n_obj * 32, 128, 1 << 30), 128, 0, c->stream>>>(P, c->n_obj);
+        bucket_scan_kernel<<<c->n_obj, 256, 0, c->stream>>>(P, c->n_obj);
         gather_bucketed_kernel<<<nc, 256, GATHER_BUCKETED_SMEM, c->stream>>>(P);
         c->timing.kernel_launches += 3;
         c->sorted_valid = true;
@@ -360,7 +360,7 @@ int run_stats(cpg_ctx *c)
         c->timing.kernel_launches++;
     }
     if (c->n_obj > 0) {
-        stats_final_kernel<<<grid_for(c->n_obj, 128, 1 << 30), 128, 0, c->stream>>>(
+        stats_final_kernel<<<grid_for((int64_t)c->n_obj * 32, 128, 1 << 30), 128, 0, c->stream>>>(
             fused ? c->schunk_first.p : c->chunk_first.p, c->size.p, c->n_obj, c->part_mass.p, c->part_flag.p, c->part_mm.p,
             c->obj_mass.p, c->skip.p, c->obj_eqm.p);
         c->timing.kernel_launches++;
@@ -404,8 +404,7 @@ int run_ptab(cpg_ctx *c, bool use_vel)
     CPG_TRY(c->ptab.ensure(((size_t)(c->n_pad >> 7) + (size_t)c->n_obj + 1) * 6));
     if (nc > 0) {
         tile_tensor_kernel<<<nc, 256, 0, c->stream>>>(soa_view(c), c->kchunks.p, nc, use_vel ? 1 : 0, c->ptab.p);
-        tile_tensor_scan_kernel<<<grid_for((int64_t)c->n_obj * 32, 128, 1 << 30), 128, 0, c->stream>>>(soa_view(c), c->n_obj,
-                                                                                                     c->ptab.p);
+        tile_tensor_scan_kernel<<<c->n_obj, 256, 0, c->stream>>>(soa_view(c), c->n_obj, c->ptab.p);
         c->timing.kernel_launches += 2;
     }
     CPG_CUDA(cudaGetLastError());

@@ -164,15 +164,23 @@ __global__ void stats_final_kernel(const int32_t *chunk_first /* n_obj+1 */, con
                                    const double *part_mass, const int32_t *part_spread, const double *part_mminmax,
                                    double *obj_mass, uint8_t *skip, double *obj_equal_mass)
 {
-    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    // a warp per object, lanes over its chunks (fixed assignment and reduction tree: deterministic mass)
+    const int h = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (h >= n_obj) return;
+    const int lane = threadIdx.x & 31;
     double m = 0.0, mlo = 1e300, mhi = -1e300;
     int spread = 0;
-    for (int c = chunk_first[h]; c < chunk_first[h + 1]; c++) {
+    for (int c = chunk_first[h] + lane; c < chunk_first[h + 1]; c += 32) {
         m += part_mass[c];
         spread |= part_spread[c];
         mlo = fmin(mlo, part_mminmax[2 * c]); mhi = fmax(mhi, part_mminmax[2 * c + 1]);
     }
+    for (int o = 16; o > 0; o >>= 1) {
+        m += __shfl_xor_sync(0xffffffffu, m, o);
+        mlo = fmin(mlo, __shfl_xor_sync(0xffffffffu, mlo, o));
+        mhi = fmax(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
+    }
+    if (lane != 0) return;
     obj_mass[h] = m;
     obj_equal_mass[h] = (mlo == mhi && mlo > 0.0) ? mlo : 0.0;   // > 0: every member has exactly this mass
     // The reference leaves an object untouched when calcLocalSpread(xyz) == 0 (helper_class.pyx:62-80 with
@@ -406,35 +414,54 @@ __global__ void __launch_bounds__(256) bucket_hist_kernel(const SortParams P)
 
 // Exclusive offsets of every (chunk, bucket) inside its object, bucket-major then chunk order (= stable), and
 // the prefix lengths n_eff.  A warp per object, lanes over buckets.
-__global__ void __launch_bounds__(128) bucket_scan_kernel(const SortParams P, int n_obj)
+__global__ void __launch_bounds__(256) bucket_scan_kernel(const SortParams P, int n_obj)
 {
-    const int lane = threadIdx.x & 31;
-    const int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // A CTA per object: warp w owns buckets w, w + 8, ...; its lanes run over the object's chunks 32 at a time (an
+    // object of 10^6 particles has ~10^3 chunks: one warp walking them bucket group by bucket group was a 0.35 ms tail).
+    __shared__ int s_tot[SORT_MAX_B], s_start[SORT_MAX_B];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int h = blockIdx.x;
     if (h >= n_obj) return;
     const int R = P.R, B = R + 1;
     const int c0 = P.chunk_first[h], c1 = P.chunk_first[h + 1];
-    int carry = 0;
-    for (int b0 = 0; b0 < B; b0 += 32) {
-        const int b = b0 + lane;
+    for (int b = warp; b < B; b += 8) {
         int tot = 0;
-        if (b < B)
-            for (int c = c0; c < c1; c++) tot += P.tile_hist[(size_t)c * B + b];
-        int incl = tot;
+        for (int c = c0 + lane; c < c1; c += 32) tot += P.tile_hist[(size_t)c * B + b];
+        tot = __reduce_add_sync(0xffffffffu, tot);
+        if (lane == 0) s_tot[b] = tot;
+    }
+    __syncthreads();
+    if (warp == 0) {   // exclusive scan over the buckets: where each bucket starts inside the object
+        int carry = 0;
+        for (int b0 = 0; b0 < B; b0 += 32) {
+            const int b = b0 + lane;
+            const int tot = b < B ? s_tot[b] : 0;
+            int incl = tot;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        int run = carry + incl - tot;
-        if (b < B) {
-            for (int c = c0; c < c1; c++) {
-                const int t = P.tile_hist[(size_t)c * B + b];
-                P.tile_hist[(size_t)c * B + b] = run;
-                run += t;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
+            if (b < B) s_start[b] = carry + incl - tot;
             if (b < R) P.n_eff[(size_t)h * R + b] = carry + incl;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
         }
-        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncthreads();
+    for (int b = warp; b < B; b += 8) {   // per chunk: offset of its share of bucket b (chunk order = catalogue order)
+        int run = s_start[b];
+        for (int cb = c0; cb < c1; cb += 32) {
+            const int c = cb + lane;
+            const int t = c < c1 ? P.tile_hist[(size_t)c * B + b] : 0;
+            int incl = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (c < c1) P.tile_hist[(size_t)c * B + b] = run + incl - t;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
     }
 }
 
@@ -596,20 +623,25 @@ __global__ void __launch_bounds__(256) tile_tensor_kernel(const SoA soa, const C
     }
 }
 
-// In-place inclusive scan of the tile rows of every object (a warp per object, 32 tiles per step, fixed tree).
-__global__ void __launch_bounds__(128) tile_tensor_scan_kernel(const SoA soa, int n_obj, double *ptab)
+// In-place inclusive scan of the tile rows of every object: a CTA per object, warp w scans the w-th eighth of the
+// tiles (32 tiles per step, fixed tree), then every warp adds the totals of the segments before its own (fixed order).
+__global__ void __launch_bounds__(256) tile_tensor_scan_kernel(const SoA soa, int n_obj, double *ptab)
 {
-    const int h = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    __shared__ double s_seg[8][6];
+    const int h = blockIdx.x;
     if (h >= n_obj) return;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nt = soa.size[h] / PT_TILE;
+    if (nt == 0) return;
     double *rows = ptab + ptab_row0(soa.poff, h) * 6;
+    const int per = (nt + 7) / 8;
+    const int t_lo = min(nt, warp * per), t_hi = min(nt, t_lo + per);
     double carry[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int t0 = 0; t0 < nt; t0 += 32) {
+    for (int t0 = t_lo; t0 < t_hi; t0 += 32) {
         const int t = t0 + lane;
         double v[6];
 #pragma unroll
-        for (int c = 0; c < 6; c++) v[c] = t < nt ? rows[(size_t)t * 6 + c] : 0.0;
+        for (int c = 0; c < 6; c++) v[c] = t < t_hi ? rows[(size_t)t * 6 + c] : 0.0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
 #pragma unroll
@@ -621,10 +653,22 @@ __global__ void __launch_bounds__(128) tile_tensor_scan_kernel(const SoA soa, in
 #pragma unroll
         for (int c = 0; c < 6; c++) {
             v[c] += carry[c];
-            if (t < nt) rows[(size_t)t * 6 + c] = v[c];
+            if (t < t_hi) rows[(size_t)t * 6 + c] = v[c];
             carry[c] = __shfl_sync(0xffffffffu, v[c], 31);
         }
     }
+    if (lane == 0)
+#pragma unroll
+        for (int c = 0; c < 6; c++) s_seg[warp][c] = carry[c];
+    __syncthreads();
+    if (warp == 0) return;
+    double add[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int w = 0; w < warp; w++)
+#pragma unroll
+        for (int c = 0; c < 6; c++) add[c] += s_seg[w][c];
+    for (int t = t_lo + lane; t < t_hi; t += 32)
+#pragma unroll
+        for (int c = 0; c < 6; c++) rows[(size_t)t * 6 + c] += add[c];
 }
 
 }  // namespace cpg
