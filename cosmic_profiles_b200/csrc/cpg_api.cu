@@ -317,7 +317,8 @@ int run_gather(cpg_ctx *c, const double *h_centers, const double *h_r200, const 
         P.G = gather_view(c, L_BOX);
         P.chunks = c->schunks.p; P.chunk_first = c->schunk_first.p; P.size = c->size.p;
         P.r200 = c->r200.p; P.rr = c->rr.p; P.n_chunks = nc; P.R = sort_R;
-        P.bucket = c->bucket.p; P.tile_hist = c->tile_hist.p; P.dest = c->dest.p;
+        P.bucket = c->bucket.p; P.tile_hist = c->tile_hist.p;
+        P.dest = c->have_vel ? c->dest.p : nullptr;   // catalogue -> slot map: only the velocity gather needs it
         P.n_eff = c->n_eff.p;
         CPG_TRY(c->part_mass.ensure(nc)); CPG_TRY(c->part_flag.ensure(nc)); CPG_TRY(c->part_mm.ensure((size_t)2 * nc));
         P.part_mass = c->part_mass.p; P.part_spread = c->part_flag.p; P.part_mminmax = c->part_mm.p;
