@@ -212,6 +212,9 @@ CPG_API int cpg_get_timing(cpg_ctx *ctx, cpg_timing *out);
  *                      call redoes the gather even if snapshot, catalogue, centres and L_BOX are unchanged
  *   "radial_order"     1 (default): gather every object in radial-bucket order and let shell k stream only
  *                      the particles with |x-c| < d_k (they are the only possible members); 0: catalogue order
+ *   "upload_threads"   host threads (0..8, default 8) that stage PAGEABLE host arrays of >= 64 MB through page-locked bounce
+ *                      buffers in cpg_set_particles / cpg_set_catalogue; 0 leaves them to cudaMemcpyAsync.  Page-locked
+ *                      sources are always copied directly.
  *   "prefix_table"     1 (default): non-reduced ellipsoid-based shapes on radially ordered particles take the tensor
  *                      sums of the whole 128-particle tiles at |x-c| < s*d (certain members) from a per-object prefix
  *                      table built once per gather instead of streaming them every Katz iteration; 0: no inner prefix

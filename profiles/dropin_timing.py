@@ -13,6 +13,9 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 from cosmic_profiles_b200 import dens_profs_algos as D, shape_profs_algos as S  # noqa: E402
 
+from cosmic_profiles_b200 import session  # noqa: E402
+if "--upload-threads" in sys.argv:
+    session.options["upload_threads"] = int(sys.argv[sys.argv.index("--upload-threads") + 1])
 tab = bench.halo_table(10000, 20260101)
 cat = bench.generate_on_device(tab, 20260101, 0)
 xyz, m, idx = np.array(cat["xyz"]), np.array(cat["masses"]), np.array(cat["idx_cat"])     # pageable copies
@@ -37,4 +40,5 @@ timed("calcMorphGlobal_com", lambda: S.calcMorphGlobal(xyz, m, r200, idx, sz, 0.
 timed("calcDensProfsSphDirectBinning_com", lambda: D.calcDensProfsSphDirectBinning(xyz, m, r200, np.logspace(-2, 0, 50), idx, sz, 0.0, "com"))
 out["particles"] = int(sz.sum())
 out["h2d_bytes"] = int(xyz.nbytes + m.nbytes + idx.nbytes)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "dropin_timing.json"), "w"), indent=1)
+out["upload_threads"] = session.options.get("upload_threads", 8)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "dropin_timing_t%d.json" % out["upload_threads"]), "w"), indent=1)

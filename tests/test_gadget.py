@@ -185,9 +185,9 @@ def test_gpu_block_ingest_bit_exact(dt):
 
 @pytest.mark.gpu
 def test_gpu_pageable_upload_round_trip():
-    """Plain (pageable) numpy arrays, uploaded in 32 MB pieces (ragged last piece): what arrives on the device must be
-    the bytes that were sent.  (A threaded bounce-buffer upload was measured and dropped: the driver's own pageable
-    path already moves configs[1]'s 3.4 GB at ~42 GB/s on this box, profiles/r1b_dropin_timing.json.)"""
+    """Plain (pageable) numpy arrays of >= 64 MB take the threaded bounce-buffer upload (8 MB pieces, ragged last
+    piece), smaller ones and option upload_threads=0 the direct path: what arrives on the device must be the bytes
+    that were sent (profiles/r1c_dropin_timing.json: 2.5-4x on the drop-in drivers' wall time)."""
     from cosmic_profiles_b200 import _lib
     rng = np.random.default_rng(3)
     n = 3_000_017
@@ -198,7 +198,11 @@ def test_gpu_pageable_upload_round_trip():
     ctx.set_particles(xyz, v, m)
     x2, v2, m2 = ctx.get_particles(n, with_vel=True)
     assert np.array_equal(x2, xyz) and np.array_equal(v2, v) and np.array_equal(m2, m)
-    ctx.set_particles(xyz[::-1].copy(), None, m)
+    ctx.set_particles(xyz[::-1].copy(), None, m)      # second upload reuses the bounce buffers
     x3, _, _ = ctx.get_particles(n)
     assert np.array_equal(x3, xyz[::-1])
+    ctx.set_option("upload_threads", 0)
+    ctx.set_particles(xyz, None, m)
+    x4, _, _ = ctx.get_particles(n)
+    assert np.array_equal(x4, xyz)
     ctx.close()
