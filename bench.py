@@ -327,6 +327,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly one JSON line: whatever libraries write to fd 1 on the way (NCCL prints its version
+    # banner there) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     config = {"workload": "BASELINE configs[1]: %d mock Einasto halos/GPU, sizes p(N)~N^-1.9 on [1e3,1e6], "
                           "ellipsoid-based local shapes (70 shells, non-reduced, IT_TOL 1e-2) + global shape, "
                           "CENTER=com given" % a.halos,
@@ -352,7 +361,7 @@ def main():
                                  "sample": info["sample"]},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     import torch
@@ -539,7 +548,7 @@ def main():
                              "streamed_GBps": visited_all / world * BYTES_PER_PI / (kern_ms * 1e-3) / 1e9},
                 "cpu_baseline": cpu, "clocks": clk, "breakdown_ms_per_step_rank0": {k_: round(v_, 3) for k_, v_ in brk.items()},
                 "particle_iterations_per_step": pi_all, "particles_per_gpu": n_part}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
