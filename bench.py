@@ -48,10 +48,12 @@ def log(*a):
 
 # ------------------------------------------------------------------------------------------- workload
 
-def halo_table(n_halos, seed):
+def halo_table(n_halos, seed, size_seed=None):
+    """size_seed: seed of the object sizes (default seed + 1).  Under torchrun every rank draws its own shapes,
+    orientations and particles but the SAME sizes, so that the per-GPU work is fixed as N grows (weak scaling)."""
     from cosmic_profiles_b200.mock import _radius_sampler, power_law_sizes, random_rotations
     rng = np.random.default_rng(seed)
-    sizes = power_law_sizes(n_halos, 1000, 1000000, -1.9, seed=seed + 1)
+    sizes = power_law_sizes(n_halos, 1000, 1000000, -1.9, seed=(seed + 1) if size_seed is None else size_seed)
     q = rng.uniform(0.5, 0.9, size=n_halos)
     s = 0.3 + (q - 0.3) * rng.uniform(size=n_halos)
     r_vir = rng.uniform(0.5, 1.5, size=n_halos) * (sizes / 1.0e4) ** (1.0 / 3.0) * 0.3
@@ -374,7 +376,7 @@ def main():
     from cosmic_profiles_b200 import _lib
 
     t0 = time.perf_counter()
-    tab = halo_table(a.halos, rank_seed(a.seed, rank))
+    tab = halo_table(a.halos, rank_seed(a.seed, rank), size_seed=a.seed + 1)
     cat = generate_on_device(tab, rank_seed(a.seed, rank), local_rank)
     n_part = int(cat["obj_size"].sum())
     log("[rank %d] catalogue: %d objects, %d particles (%.2f GB x,y,z,m), generated in %.1f s"
