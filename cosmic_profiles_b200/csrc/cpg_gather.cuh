@@ -506,12 +506,19 @@ __global__ void __launch_bounds__(256) gather_bucketed_kernel(const SortParams P
         s_bstart[threadIdx.x] = run;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {   // exclusive scan of the bucket totals: where each bucket starts inside the chunk
-        int run = 0;
-        for (int k = 0; k < B; k++) {
-            const int t = s_bstart[k];
-            s_bstart[k] = run;
-            run += t;
+    if (warp == 0) {   // exclusive scan of the bucket totals (warp scan, 32 buckets per step): where each bucket starts inside the chunk
+        int carry = 0;
+        for (int k0 = 0; k0 < B; k0 += 32) {
+            const int k = k0 + lane;
+            const int t = k < B ? s_bstart[k] : 0;
+            int incl = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (k < B) s_bstart[k] = carry + incl - t;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
     __syncthreads();
