@@ -753,7 +753,12 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
 // same convergence decisions without any global-memory traffic.  C == 1 degenerates to a plain CTA
 // per task (no cluster barrier).  Partials are double-buffered: one barrier per iteration.
 // ------------------------------------------------------------------------------------------------
-constexpr int CLUSTER_KERNEL_WARPS = 8;
+#ifndef CPG_CLUSTER_WARPS
+#define CPG_CLUSTER_WARPS 12
+#endif
+// 12 warps x 16 KB rings + statics = 207 KB of shared memory: one CTA per SM either way, but 12 resident warps instead of 8
+// (the register file then allows 168 registers per thread)
+constexpr int CLUSTER_KERNEL_WARPS = CPG_CLUSTER_WARPS;
 
 template <int S, bool SHELL, bool REDUCED, bool VDISP>
 __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kernel(const MorphParams P)
