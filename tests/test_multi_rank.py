@@ -78,3 +78,14 @@ def test_shim_sharding_matches_unsharded(monkeypatch):
             assert np.array_equal(a, b, equal_nan=True)
         assert np.array_equal(S.last_info["n_iter"], ref_info["n_iter"])
         assert np.array_equal(S.last_info["n_pts"], ref_info["n_pts"])
+
+
+def test_weak_scaling_tables_share_sizes():
+    """Every rank draws its own shapes and orientations but the same object sizes (fixed per-GPU work)."""
+    import numpy as np
+    import bench
+    t0 = bench.halo_table(500, bench.rank_seed(11, 0), size_seed=12)
+    t3 = bench.halo_table(500, bench.rank_seed(11, 3), size_seed=12)
+    assert np.array_equal(t0["sizes"], t3["sizes"])
+    assert not np.array_equal(t0["q"], t3["q"]) and not np.array_equal(t0["centre"], t3["centre"])
+    assert np.array_equal(bench.halo_table(500, 11)["sizes"], t0["sizes"])       # rank 0 == the single-GPU catalogue
