@@ -29,7 +29,7 @@ class Timing(ctypes.Structure):
 EXPORTS = ["cpg_device_count", "cpg_last_error", "cpg_version", "cpg_create", "cpg_destroy", "cpg_set_particles",
            "cpg_set_catalogue", "cpg_shape", "cpg_dens_sph", "cpg_dens_ell", "cpg_dens_kernel", "cpg_obj_masses",
            "cpg_get_timing", "cpg_set_option", "cpg_host_alloc", "cpg_host_free", "cpg_get_prefix_lengths", "cpg_centers",
-           "cpg_obj_cat", "cpg_obj_cat_fetch", "cpg_use_obj_cat", "cpg_set_particles_gadget", "cpg_get_particles", "cpg_fit_profiles"]
+           "cpg_obj_cat", "cpg_obj_cat_fetch", "cpg_use_obj_cat", "cpg_set_particles_gadget", "cpg_get_particles", "cpg_fit_profiles", "cpg_shape_interp"]
 
 
 def load():
@@ -72,6 +72,8 @@ def load():
                                            ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                            ctypes.c_double]
     L.cpg_get_particles.argtypes = [vp, _D, _D, _D]
+    L.cpg_shape_interp.argtypes = [vp, _D, _D, _D, ctypes.c_int32, _D, _D, _D, _D, _D, _D, ctypes.c_int32, _D, _D, _D, _D, _D,
+                                   _D]
     L.cpg_fit_profiles.argtypes = [vp, _D, _D, _I, _D, _D, _D, _D, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                    ctypes.c_double, ctypes.c_double, _D, _D, _I, _I]
     for f in EXPORTS:
@@ -204,7 +206,27 @@ class Context:
                                     _dp(dens), _ip(cnt)), "cpg_dens_sph")
         return dens, cnt
 
+    def shape_interp(self, r200, r_over_r200, bin_edges, a, b, c, major, inter, minor, fetch=False):
+        """Interpolate the shape profiles onto the density bins on the device (cpg_shape_interp).  The result stays
+        resident for dens_ell(centers, None, ...); fetch=True also returns (ai, bi, ci, mj, it, mn)."""
+        n, R, Rs = self.n_obj, len(r_over_r200), a.shape[1]
+        out = [None] * 6
+        if fetch:
+            out = [np.zeros((n, R + 1)) for _ in range(3)] + [np.zeros((n, R, 3)) for _ in range(3)]
+        _check(self._L.cpg_shape_interp(self._h, _dp(f64(r200)), _dp(f64(r_over_r200)), _dp(f64(bin_edges)), R, _dp(f64(a)),
+                                        _dp(f64(b)), _dp(f64(c)), _dp(f64(major)), _dp(f64(inter)), _dp(f64(minor)), Rs,
+                                        *[_dp(o) for o in out]), "cpg_shape_interp")
+        self._interp_R = R
+        return tuple(out) if fetch else None
+
     def dens_ell(self, centers, a, b, c, major, inter, minor, L_BOX):
+        if a is None:   # profiles interpolated on the device by shape_interp()
+            n, R = self.n_obj, self._interp_R
+            dens = np.zeros((n, R))
+            cnt = np.zeros((n, R), dtype=np.int32)
+            _check(self._L.cpg_dens_ell(self._h, _dp(f64(centers)), None, None, None, None, None, None, R, float(L_BOX),
+                                        _dp(dens), _ip(cnt)), "cpg_dens_ell")
+            return dens, cnt
         n, R = self.n_obj, major.shape[1]
         dens = np.zeros((n, R))
         cnt = np.zeros((n, R), dtype=np.int32)

@@ -18,6 +18,7 @@
 #include "cpg_fit.cuh"
 #include "cpg_gadget.cuh"
 #include "cpg_gather.cuh"
+#include "cpg_interp.cuh"
 #include "cpg_morph.cuh"
 
 namespace cpg {
@@ -154,6 +155,9 @@ struct cpg_ctx {
     DevBuf<int64_t> oc_shoff, oc_start, oc_passoff, oc_idxoff, oc_cstart, oc_coff;
     DevBuf<Pair64> oc_tiles;
     DevBuf<unsigned char> raw_block;   // a snapshot block as stored on disk, before conversion to fp64
+    DevBuf<double> ip_a, ip_b, ip_c, ip_major, ip_inter, ip_minor, ip_rr, ip_edges;   // raw shape profiles for cpg_shape_interp
+    int interp_R = 0;          // > 0: d_a ... d_minor hold profiles interpolated on the device for this many bins
+    int32_t interp_n = 0;
     DevBuf<double> fit_radii, fit_lmed, fit_avg, fit_x0, fit_best, fit_fun;
     DevBuf<int32_t> fit_nvalid, fit_nfev, fit_nit;
     bool oc_valid = false;
@@ -695,6 +699,8 @@ CPG_API void cpg_destroy(cpg_ctx *c)
     c->oc_err.release(); c->oc_r200in.release(); c->oc_r200.release(); c->oc_shoff.release(); c->oc_start.release();
     c->oc_passoff.release(); c->oc_idxoff.release(); c->oc_cstart.release(); c->oc_coff.release();
     c->oc_tiles.release(); c->raw_block.release();
+    c->ip_a.release(); c->ip_b.release(); c->ip_c.release(); c->ip_major.release(); c->ip_inter.release();
+    c->ip_minor.release(); c->ip_rr.release(); c->ip_edges.release();
     c->fit_radii.release(); c->fit_lmed.release(); c->fit_avg.release(); c->fit_x0.release(); c->fit_best.release();
     c->fit_fun.release(); c->fit_nvalid.release(); c->fit_nfev.release(); c->fit_nit.release();
     for (auto &e : c->ev) if (e) cudaEventDestroy(e);
@@ -1422,9 +1428,15 @@ CPG_API int cpg_dens_ell(cpg_ctx *c, const double *centers, const double *a, con
 {
     CPG_TRY(use_device(c));
     const int n = c->n_obj;
-    if (R < 1 || R > DENS_MAX_R || (n > 0 && (!centers || !a || !b || !cc || !major || !inter || !minor || !dens))) {
+    const bool resident = !a && !b && !cc && !major && !inter && !minor;   // profiles left by cpg_shape_interp
+    if (R < 1 || R > DENS_MAX_R || (n > 0 && (!centers || !dens)) ||
+        (n > 0 && !resident && (!a || !b || !cc || !major || !inter || !minor))) {
         set_error("cpg_dens_ell: bad arguments (1 <= R <= %d)", DENS_MAX_R);
         return CPG_ERR_ARGUMENT;
+    }
+    if (resident && n > 0 && (c->interp_R != R || c->interp_n != n)) {
+        set_error("cpg_dens_ell: no interpolated profiles for %d objects x %d bins on the device (call cpg_shape_interp)", n, R);
+        return CPG_ERR_STATE;
     }
     Timer T(c);
     if (n == 0) return CPG_OK;
@@ -1433,13 +1445,16 @@ CPG_API int cpg_dens_ell(cpg_ctx *c, const double *centers, const double *a, con
     CPG_TRY(dens_common_begin(c, T, centers, nullptr, L_BOX));
     CPG_TRY(c->d_a.ensure(nR1)); CPG_TRY(c->d_b.ensure(nR1)); CPG_TRY(c->d_c.ensure(nR1));
     CPG_TRY(c->d_major.ensure(nR * 3)); CPG_TRY(c->d_inter.ensure(nR * 3)); CPG_TRY(c->d_minor.ensure(nR * 3));
-    CPG_CUDA(cudaMemcpyAsync(c->d_a.p, a, sizeof(double) * nR1, cudaMemcpyHostToDevice, c->stream));
-    CPG_CUDA(cudaMemcpyAsync(c->d_b.p, b, sizeof(double) * nR1, cudaMemcpyHostToDevice, c->stream));
-    CPG_CUDA(cudaMemcpyAsync(c->d_c.p, cc, sizeof(double) * nR1, cudaMemcpyHostToDevice, c->stream));
-    CPG_CUDA(cudaMemcpyAsync(c->d_major.p, major, sizeof(double) * nR * 3, cudaMemcpyHostToDevice, c->stream));
-    CPG_CUDA(cudaMemcpyAsync(c->d_inter.p, inter, sizeof(double) * nR * 3, cudaMemcpyHostToDevice, c->stream));
-    CPG_CUDA(cudaMemcpyAsync(c->d_minor.p, minor, sizeof(double) * nR * 3, cudaMemcpyHostToDevice, c->stream));
-    c->timing.h2d_bytes += (int64_t)(sizeof(double) * (3 * nR1 + 9 * nR));
+    if (!resident) {
+        c->interp_R = 0;
+        CPG_CUDA(cudaMemcpyAsync(c->d_a.p, a, sizeof(double) * nR1, cudaMemcpyHostToDevice, c->stream));
+        CPG_CUDA(cudaMemcpyAsync(c->d_b.p, b, sizeof(double) * nR1, cudaMemcpyHostToDevice, c->stream));
+        CPG_CUDA(cudaMemcpyAsync(c->d_c.p, cc, sizeof(double) * nR1, cudaMemcpyHostToDevice, c->stream));
+        CPG_CUDA(cudaMemcpyAsync(c->d_major.p, major, sizeof(double) * nR * 3, cudaMemcpyHostToDevice, c->stream));
+        CPG_CUDA(cudaMemcpyAsync(c->d_inter.p, inter, sizeof(double) * nR * 3, cudaMemcpyHostToDevice, c->stream));
+        CPG_CUDA(cudaMemcpyAsync(c->d_minor.p, minor, sizeof(double) * nR * 3, cudaMemcpyHostToDevice, c->stream));
+        c->timing.h2d_bytes += (int64_t)(sizeof(double) * (3 * nR1 + 9 * nR));
+    }
     CPG_TRY(c->bin_mass.ensure((size_t)nc * R)); CPG_TRY(c->bin_cnt.ensure((size_t)nc * R));
     CPG_TRY(c->dens.ensure(nR)); CPG_TRY(c->counts.ensure(nR));
     T.mark(1);
@@ -1462,6 +1477,67 @@ CPG_API int cpg_dens_ell(cpg_ctx *c, const double *centers, const double *a, con
     c->timing.kernel_launches++;
     CPG_CUDA(cudaGetLastError());
     return dens_common_end(c, T, dens, counts, nR);
+}
+
+CPG_API int cpg_shape_interp(cpg_ctx *c, const double *r200, const double *r_over_r200, const double *bin_edges, int32_t R,
+                             const double *a, const double *b, const double *cc, const double *major, const double *inter,
+                             const double *minor, int32_t Rs, double *ai, double *bi, double *ci, double *mj, double *it,
+                             double *mn)
+{
+    CPG_TRY(use_device(c));
+    const int n = c->n_obj;
+    if (R < 1 || R > DENS_MAX_R || Rs < 2 || Rs > INTERP_MAX_RS ||
+        (n > 0 && (!r200 || !r_over_r200 || !bin_edges || !a || !b || !cc || !major || !inter || !minor))) {
+        set_error("cpg_shape_interp: bad arguments (1 <= R <= %d, 2 <= Rs <= %d)", DENS_MAX_R, INTERP_MAX_RS);
+        return CPG_ERR_ARGUMENT;
+    }
+    c->interp_R = 0;
+    Timer T(c);
+    if (n == 0) return CPG_OK;
+    const size_t nRs = (size_t)n * Rs, nR = (size_t)n * R, nR1 = (size_t)n * (R + 1);
+    T.mark(0);
+    CPG_TRY(c->r200.ensure(n)); CPG_TRY(c->ip_rr.ensure(R)); CPG_TRY(c->ip_edges.ensure(R + 1));
+    CPG_TRY(c->ip_a.ensure(nRs)); CPG_TRY(c->ip_b.ensure(nRs)); CPG_TRY(c->ip_c.ensure(nRs));
+    CPG_TRY(c->ip_major.ensure(nRs * 3)); CPG_TRY(c->ip_inter.ensure(nRs * 3)); CPG_TRY(c->ip_minor.ensure(nRs * 3));
+    CPG_TRY(c->d_a.ensure(nR1)); CPG_TRY(c->d_b.ensure(nR1)); CPG_TRY(c->d_c.ensure(nR1));
+    CPG_TRY(c->d_major.ensure(nR * 3)); CPG_TRY(c->d_inter.ensure(nR * 3)); CPG_TRY(c->d_minor.ensure(nR * 3));
+    const struct { double *dst; const double *src; size_t cnt; } up[] = {
+        {c->r200.p, r200, (size_t)n}, {c->ip_rr.p, r_over_r200, (size_t)R}, {c->ip_edges.p, bin_edges, (size_t)R + 1},
+        {c->ip_a.p, a, nRs}, {c->ip_b.p, b, nRs}, {c->ip_c.p, cc, nRs},
+        {c->ip_major.p, major, nRs * 3}, {c->ip_inter.p, inter, nRs * 3}, {c->ip_minor.p, minor, nRs * 3}};
+    for (const auto &u : up) {
+        CPG_CUDA(cudaMemcpyAsync(u.dst, u.src, sizeof(double) * u.cnt, cudaMemcpyHostToDevice, c->stream));
+        c->timing.h2d_bytes += (int64_t)(sizeof(double) * u.cnt);
+    }
+    T.mark(1);
+    T.mark(2);
+    InterpParams Q;
+    Q.r200 = c->r200.p; Q.rr = c->ip_rr.p; Q.edges = c->ip_edges.p;
+    Q.a = c->ip_a.p; Q.b = c->ip_b.p; Q.c = c->ip_c.p;
+    Q.major = c->ip_major.p; Q.inter = c->ip_inter.p; Q.minor = c->ip_minor.p;
+    Q.n_obj = n; Q.R = R; Q.Rs = Rs;
+    Q.ai = c->d_a.p; Q.bi = c->d_b.p; Q.ci = c->d_c.p; Q.mj = c->d_major.p; Q.it = c->d_inter.p; Q.mn = c->d_minor.p;
+    shape_interp_kernel<<<(n + INTERP_WARPS - 1) / INTERP_WARPS, INTERP_WARPS * 32, 0, c->stream>>>(Q);
+    CPG_CUDA(cudaGetLastError());
+    c->timing.kernel_launches = 1;
+    c->timing.hot_kernel_launches = 1;
+    T.mark(3);
+    const struct { double *dst; const double *src; size_t cnt; } down[] = {
+        {ai, c->d_a.p, nR1}, {bi, c->d_b.p, nR1}, {ci, c->d_c.p, nR1},
+        {mj, c->d_major.p, nR * 3}, {it, c->d_inter.p, nR * 3}, {mn, c->d_minor.p, nR * 3}};
+    for (const auto &d : down)
+        if (d.dst) {
+            CPG_CUDA(cudaMemcpyAsync(d.dst, d.src, sizeof(double) * d.cnt, cudaMemcpyDeviceToHost, c->stream));
+            c->timing.d2h_bytes += (int64_t)(sizeof(double) * d.cnt);
+        }
+    T.mark(4);
+    CPG_CUDA(cudaStreamSynchronize(c->stream));
+    c->timing.h2d_ms = Timer::ms(c->ev[0], c->ev[1]);
+    c->timing.kernel_ms = Timer::ms(c->ev[2], c->ev[3]);
+    c->timing.d2h_ms = Timer::ms(c->ev[3], c->ev[4]);
+    c->interp_R = R;
+    c->interp_n = n;
+    return CPG_OK;
 }
 
 CPG_API int cpg_dens_kernel(cpg_ctx *c, const double *centers, const double *r200, const double *r_over_r200, int32_t R,

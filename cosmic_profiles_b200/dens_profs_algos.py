@@ -69,6 +69,10 @@ def calcDensProfsSphDirectBinning(xyz, masses, r200s, r_over_r200, idx_cat, obj_
     return dens
 
 
+device_interp = True               # interpolate the shape profiles on the device (cpg_shape_interp) ...
+MAX_DEVICE_INTERP_SHELLS = 256     # ... for profiles of up to this many shells; beyond that the NumPy twin below
+
+
 def _interp_rows(X, Y, Xnew):
     """Row-wise scipy.interpolate.interp1d(X[p], Y[p], bounds_error=False, fill_value='extrapolate')(Xnew[p]),
     vectorised over the rows p.  Operation for operation what scipy 1.x does for kind='linear' with
@@ -129,10 +133,16 @@ def calcDensProfsEllDirectBinning(xyz, masses, r200s, r_over_r200, a, b, c, majo
     a, b, c = (_lib.f64(np.asarray(v)) for v in (a, b, c))
     major, inter, minor = (_lib.f64(np.asarray(v)) for v in (major, inter, minor))
     assert a.shape[0] == b.shape[0] and b.shape[0] == c.shape[0]
-    ai, bi, ci, mj, it, mn = interpolate_shapes(r200s, r_over_r200, a, b, c, major, inter, minor)
     ctx = _context(xyz, masses, idx_cat, obj_size)
     cen = _centres(ctx, xyz, masses, idx_cat, obj_size, L_BOX, CENTER, centers)
-    dens, cnt = ctx.dens_ell(cen, ai, bi, ci, mj, it, mn, L_BOX)
+    if device_interp and 2 <= a.shape[1] <= MAX_DEVICE_INTERP_SHELLS:
+        # the interpolation of :163-195 on the device; the profiles never come back to the host
+        r = _lib.f64(np.asarray(r_over_r200))
+        ctx.shape_interp(r200s, r, ell_bin_edges(r), a, b, c, major, inter, minor)
+        dens, cnt = ctx.dens_ell(cen, None, None, None, None, None, None, L_BOX)
+    else:
+        ai, bi, ci, mj, it, mn = interpolate_shapes(r200s, r_over_r200, a, b, c, major, inter, minor)
+        dens, cnt = ctx.dens_ell(cen, ai, bi, ci, mj, it, mn, L_BOX)
     last_info.clear()
     last_info.update(counts=cnt, timing=[ctx.timing()])
     return dens

@@ -109,10 +109,23 @@ CPG_API int cpg_dens_sph(cpg_ctx *ctx, const double *centers, const double *r200
 /* Ellipsoidal-shell direct binning.  Replaces the prange part of calcDensProfsEllDirectBinning
  * (dens_profs_algos.pyx:196-218) and CythonHelpers.calcDensProfBruteForceEll (helper_class.pyx:246-306).
  * a,b,c (n_obj,R+1) and major,inter,minor (n_obj,R,3) are the scipy-interpolated profiles of :163-195
- * (computed by the shim with the same scipy).  Empty bin -> NaN. */
+ * (computed by the shim with the same scipy), or all six NULL to use the profiles cpg_shape_interp left on the
+ * device.  Empty bin -> NaN. */
 CPG_API int cpg_dens_ell(cpg_ctx *ctx, const double *centers, const double *a, const double *b, const double *c,
                          const double *major, const double *inter, const double *minor, int32_t R, float L_BOX,
                          double *dens, int32_t *counts);
+
+/* Shape-profile interpolation onto the density bins, on the device.  Replaces the
+ * per-object loop of calcDensProfsEllDirectBinning that calls scipy.interpolate.interp1d(a[p], y, bounds_error=False,
+ * fill_value='extrapolate') twelve times (dens_profs_algos.pyx:163-195): a, b, c (n_obj,Rs) and major, inter, minor
+ * (n_obj,Rs,3) are the local shape profiles (NaN where a shell did not converge), r_over_r200 (R) the bin centres and
+ * bin_edges (R+1) the edges of :155-156, both in units of r200 (n_obj).  2 <= Rs <= 256.  Bit-identical to scipy's
+ * linear interp1d.  The interpolated profiles stay on the device: a following cpg_dens_ell call with all six profile
+ * pointers NULL uses them.  ai, bi, ci (n_obj,R+1), mj, it, mn (n_obj,R,3): optional host copies (each may be NULL). */
+CPG_API int cpg_shape_interp(cpg_ctx *ctx, const double *r200, const double *r_over_r200, const double *bin_edges,
+                             int32_t R, const double *a, const double *b, const double *c, const double *major,
+                             const double *inter, const double *minor, int32_t Rs, double *ai, double *bi, double *ci,
+                             double *mj, double *it, double *mn);
 
 /* Kernel-based estimator.  Replaces calcDensProfsKernelBased (dens_profs_algos.pyx:221-280) and
  * CythonHelpers.calcKTilde (helper_class.pyx:417-428), mixed fp32/fp64 expression tree reproduced. */

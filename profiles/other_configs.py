@@ -124,8 +124,13 @@ def sec_config2():
 
 
     ms, tim = timed(ell, 2)
+    # the same interpolation on the device (cpg_shape_interp), profiles staying resident for the binning
+    ms_ip, tim_ip = timed(lambda: (ctx.shape_interp(cat["r200"], rb, D.ell_bin_edges(rb), d_, d_ * q_, d_ * s_, o[:, :, 3:6],
+                                                    o[:, :, 6:9], o[:, :, 9:12]), ctx.timing())[1], 3)
+    ms_dev, _ = timed(lambda: ctx.dens_ell(cat["centers"], None, None, None, None, None, None, 0.0), 2)
     out["config2_dens_ell_R50"] = dict(halos=nh, particles=npart, wall_ms=ms, kernel_ms=tim["kernel_ms"],
-                                       host_scipy_interp_s=interp_s,
+                                       host_numpy_interp_s=interp_s, device_interp_wall_ms=ms_ip,
+                                       device_interp_kernel_ms=tim_ip["kernel_ms"], wall_ms_resident_profiles=ms_dev,
                                        particle_bin_tests_per_s=npart * 50 / (tim["kernel_ms"] * 1e-3))
 
 

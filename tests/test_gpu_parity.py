@@ -322,3 +322,35 @@ def test_device_centres_large_objects(gpu):
                 want = O.centres(Xb, M, I, sizes, box, center, shape_path)
                 got = ctx.centers(1 if center == "mode" else 0, shape_path, box, ref)
                 assert np.abs(got - want).max() <= 1e-11 * max(np.abs(want).max(), 1.0), (box, center, shape_path)
+
+
+def test_device_shape_interpolation(gpu):
+    """cpg_shape_interp against its NumPy twin (itself pinned bit-for-bit against scipy.interpolate.interp1d in
+    tests/test_interp_rows.py): NaN abscissae from unconverged shells, unsorted abscissae, extrapolation on both
+    sides, an object without a converged shell -- bit-identical, NaN pattern included -- and the ellipsoidal
+    binning fed from the device-resident profiles equals the binning fed from the host-interpolated ones."""
+    from cosmic_profiles_b200 import _lib, dens_profs_algos as D
+    from cosmic_profiles_b200.mock import make_catalogue
+    from tests.test_interp_rows import _case
+    rb = np.logspace(-2, 0.3, 23)
+    for seed, shuffle, nanf in ((1, False, 0.15), (2, True, 0.15), (9, False, 0.0)):
+        r200, a, b, c, mj, it, mn = _case(seed, shuffle=shuffle, nan_frac=nanf)
+        n = len(r200)
+        cat = make_catalogue([300] * n, seed=seed)
+        ctx = _lib.Context(0)
+        ctx.set_particles(cat["xyz"], None, cat["masses"])
+        ctx.set_catalogue(cat["idx_cat"], cat["obj_size"])
+        with np.errstate(all="ignore"):
+            want = D.interpolate_shapes(r200, rb, a, b, c, mj, it, mn)
+        got = ctx.shape_interp(r200, rb, D.ell_bin_edges(rb), a, b, c, mj, it, mn, fetch=True)
+        for w, g, nm in zip(want, got, "a b c major inter minor".split()):
+            assert w.shape == g.shape, nm
+            assert np.array_equal(w, g, equal_nan=True), "%s differs (seed %d)" % (nm, seed)
+        cen = np.array([cat["xyz"][cat["idx_cat"][300 * h:300 * (h + 1)]].mean(0) for h in range(n)])
+        d_dev, c_dev = ctx.dens_ell(cen, None, None, None, None, None, None, 0.0)
+        d_host, c_host = ctx.dens_ell(cen, *want, 0.0)
+        # (bin masses are accumulated with shared-memory atomics: the last bit depends on the arrival order)
+        assert np.array_equal(c_dev, c_host) and np.allclose(d_dev, d_host, rtol=1e-12, atol=0.0, equal_nan=True)
+        with pytest.raises(_lib.CosmicGpuError):     # the host call above replaced the resident profiles
+            ctx.dens_ell(cen, None, None, None, None, None, None, 0.0)
+        ctx.close()
