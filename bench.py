@@ -523,7 +523,7 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None
         try:   # DRAM bytes of the two local-shape kernels from the committed ncu capture of this workload
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1d_traffic.json")))
             if int(tr.get("workload_halos", -1)) == a.halos:
                 traffic = float(tr["dram_bytes_per_local_shape_launch_set"])
         except Exception:
@@ -541,7 +541,7 @@ def main():
                 "gpu_launches": int(launches_all),
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic,
-                             "traffic_source": "profiles/r1c_traffic.json (ncu --set full, same workload)" if traffic else None,
+                             "traffic_source": "profiles/r1d_traffic.json (ncu --set full, same workload)" if traffic else None,
                              "kernel": "morph_warp_kernel/morph_cluster_kernel (local shapes)",
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                              "algorithmic_bytes_per_launch_set": pi_local_all / world * BYTES_PER_PI,
