@@ -927,7 +927,7 @@ __global__ void grid_init_kernel(const MorphParams P, const Task *tasks, GridSta
     if (lane == 0) { gs->amask = amask; gs->halo = halo; gs->shell0 = tk.shell0; gs->nshell = tk.nshell; }
 }
 
-constexpr int GRID_KERNEL_WARPS = 8;
+constexpr int GRID_KERNEL_WARPS = 12;
 
 template <int S, bool SHELL, bool REDUCED, bool VDISP>
 __global__ void __launch_bounds__(GRID_KERNEL_WARPS * 32) grid_pass_kernel(const MorphParams P, const GridState *gs,
