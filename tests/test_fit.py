@@ -112,3 +112,26 @@ def test_gpu_fits_golden(case):
     print(name, "same path %d/%d, max rel %.2e" % (same_path[fin].sum(), fin.sum(), rel.max()))
     assert same_path[fin].mean() >= 0.9, (name, rel, D.last_info["nfev"], counts[:, 0])
     assert rel.max() < 1e-2, (name, rel)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nbins", [5, 8, 33, 70])
+def test_gpu_fits_vs_restatement_bin_counts(nbins):
+    """Bin counts on both sides of NumPy's pairwise-sum regimes (n < 8 sequential; 8 accumulators; a remainder) and
+    of the 32-lane round boundary, against the CPU restatement (which is pinned to the reference)."""
+    from cosmic_profiles_b200 import dens_profs_tools as D
+    rng = np.random.default_rng(nbins)
+    rr = np.logspace(-1.6, 0, nbins)
+    n = 12
+    r200 = rng.uniform(0.3, 1.2, size=n)
+    rs = r200 / rng.uniform(4, 10, size=n)
+    r = rr[None, :] * r200[:, None]
+    dens = 1e14 / ((r / rs[:, None]) * (1 + r / rs[:, None]) ** 2) * np.exp(rng.normal(0, 0.1, size=r.shape))
+    method = {"profile": "nfw"}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want, info = F.fitDensProfHelper(dens, rr, r200, method)
+        got = D.fitDensProfHelper(dens, rr, r200, method)
+    rel = np.max(np.abs(got - want) / np.abs(want), axis=1)
+    same = (D.last_info["nfev"] == info[:, 0]) & (rel < 1e-9)
+    assert same.mean() >= 0.75 and rel.max() < 1e-2, (rel, D.last_info["nfev"], info[:, 0])
