@@ -13,28 +13,40 @@ from numpy.random import default_rng
 
 def _reference_points(n):
     rng = default_rng(seed=0)
-    return rng.choice(np.arange(n), (min(50, n),), replace=False)
+    # == rng.choice(np.arange(n), ...) of python_routines.py:512-513, without materialising arange(n)
+    return rng.choice(n, (min(50, n),), replace=False)
 
 
 _choice_cache = {}
 
 
+def _choices(n):
+    choose = _choice_cache.get(n)
+    if choose is None:
+        choose = _reference_points(n)
+        if len(_choice_cache) < 100000:
+            _choice_cache[n] = choose
+    return choose
+
+
 def reference_points(xyz, idx_cat, obj_size):
     """The reference point respectPBCNoRef / calcCoM average from <= 50 seeded random members of every object
     (python_routines.py:512-514, :540-542).  Needed by the device centre finder when L_BOX != 0, where the
-    reference point decides which particles are translated by +-L_BOX."""
-    off = np.concatenate(([0], np.cumsum(np.asarray(obj_size, dtype=np.int64))))
+    reference point decides which particles are translated by +-L_BOX.  Objects of >= 50 members are handled in
+    one vectorised gather + mean (same summation order as np.average over the 50 rows of one object)."""
+    obj_size = np.asarray(obj_size, dtype=np.int64)
+    off = np.concatenate(([0], np.cumsum(obj_size)))
     ref = np.zeros((len(obj_size), 3), dtype=np.float64)
-    for p in range(len(obj_size)):
+    big = np.flatnonzero(obj_size >= 50)
+    if len(big):
+        pick = np.empty((len(big), 50), dtype=np.int64)
+        for k, p in enumerate(big):
+            pick[k] = _choices(int(obj_size[p]))
+        members = np.asarray(idx_cat)[pick + off[big][:, None]]
+        ref[big] = np.average(xyz[members], axis=1)
+    for p in np.flatnonzero((obj_size > 0) & (obj_size < 50)):
         n = int(obj_size[p])
-        if n == 0:
-            continue
-        choose = _choice_cache.get(n)
-        if choose is None:
-            choose = _reference_points(n)
-            if len(_choice_cache) < 100000:
-                _choice_cache[n] = choose
-        ref[p] = np.average(xyz[idx_cat[off[p]:off[p + 1]][choose]], axis=0)
+        ref[p] = np.average(xyz[idx_cat[off[p]:off[p + 1]][_choices(n)]], axis=0)
     return ref
 
 
