@@ -36,6 +36,7 @@ def timed(name, fn, n=3):
 
 timed("calcMorphLocal_com", lambda: S.calcMorphLocal(xyz, m, r200, idx, sz, 0.0, bench.RR, 1e-2, 100, 10, "com", False, False))
 timed("calcMorphLocal_mode", lambda: S.calcMorphLocal(xyz, m, r200, idx, sz, 0.0, bench.RR, 1e-2, 100, 10, "mode", False, False))
+timed("calcMorphLocal_com_periodic_box_L100", lambda: S.calcMorphLocal(xyz, m, r200, idx, sz, 100.0, bench.RR, 1e-2, 100, 10, "com", False, False))
 timed("calcMorphGlobal_com", lambda: S.calcMorphGlobal(xyz, m, r200, idx, sz, 0.0, 1e-2, 100, 10, "com", 6.0, False))
 timed("calcDensProfsSphDirectBinning_com", lambda: D.calcDensProfsSphDirectBinning(xyz, m, r200, np.logspace(-2, 0, 50), idx, sz, 0.0, "com"))
 out["particles"] = int(sz.sum())
