@@ -82,6 +82,16 @@ res = dict(workload="configs[1], %d objects, %d particles; variant reduced=%s sh
            n_iter_mismatches_global=int((nit_g[pick][:, 0] != rit_g).sum()), n_pts_mismatches_global=int((npt_g[pick][:, 0] != rpt_g).sum()),
            nan_pattern_mismatches=nan_q + nan_s, max_rel_q_local=ql, max_rel_s_local=sl, max_rel_q_global=qg, max_rel_s_global=sg,
            oracle="oracle/cp_oracle.c (C restatement, pinned against the compiled reference), %d threads, %.1f s" % (cores, cpu_s))
+import zlib  # noqa: E402
+if len(pick) == a.halos and not (a.reduced or a.shell) and a.halos == 10000:
+    # the whole catalogue was compared: record checksums of the (oracle-verified) integer outputs for
+    # tests/test_gpu_full_size.py
+    clean = all(res[k] == 0 for k in res if "mismatches" in k)
+    res["verified_checksums"] = dict(
+        clean=clean, particle_iterations=int((nit_l.clip(0).sum(1).astype(np.int64) * sizes).sum() + (nit_g.clip(0)[:, 0].astype(np.int64) * sizes).sum()),
+        sum_n_pts_local=int(npt_l.clip(0).astype(np.int64).sum()), sum_n_pts_global=int(npt_g.clip(0).astype(np.int64).sum()),
+        crc_n_iter_local=zlib.crc32(np.ascontiguousarray(nit_l).tobytes()), crc_n_pts_local=zlib.crc32(np.ascontiguousarray(npt_l).tobytes()),
+        crc_n_iter_global=zlib.crc32(np.ascontiguousarray(nit_g).tobytes()), crc_n_pts_global=zlib.crc32(np.ascontiguousarray(npt_g).tobytes()))
 print(json.dumps(res, indent=1))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "parity_at_scale%s.json" % a.tag), "w"), indent=1)
