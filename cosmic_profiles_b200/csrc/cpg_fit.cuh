@@ -3,9 +3,9 @@
 // Replaces fitDensProfHelper -> fitDensProf -> toMinimize (cosmic_profiles/dens_profs/dens_profs_tools.py:325-359,
 // :232-323, :227-230) and the four models (:22-79).  The reference maps scipy.optimize.minimize(method='Powell',
 // bounds=...) over the objects in a process pool; the minimiser is scipy's (1.18.1, scipy/optimize/_optimize.py):
-// _minimize_powell with _linesearch_powell / _line_for_search / _minimize_scalar_bounded.  Here one WARP fits one
-// object: the Powell / fmin control flow is warp-uniform (every lane carries the same scalars), the n <= 128 terms of
-// the objective are spread over the lanes and summed in NumPy's pairwise order, so that every function value is the
+// _minimize_powell with _linesearch_powell / _line_for_search / _minimize_scalar_bounded.  Here one WARP (two for
+// more than 32 bins) fits one object: the Powell / fmin control flow is uniform over its lanes (every lane carries the
+// same scalars), the n <= 128 terms of the objective are spread over the lanes and summed in NumPy's pairwise order, so that every function value is the
 // reference's up to the last-bit differences between CUDA's and NumPy's log / pow / exp / tan.
 //
 // Arithmetic is written with explicit round-to-nearest intrinsics: no FMA contraction (Python floats and NumPy
@@ -16,7 +16,7 @@
 namespace cpg {
 
 constexpr int FIT_MAX_BINS = 128;   // NumPy's pairwise sum is a single block up to 128 elements
-constexpr int FIT_WARPS = 4;        // warps (objects) per CTA
+constexpr int FIT_WARPS = 4;        // warps per CTA (4 objects, or 2 objects of two warps each)
 enum { FIT_NFW = 0, FIT_HERNQUIST = 1, FIT_EINASTO = 2, FIT_ABG = 3 };
 
 struct FitParams {
@@ -40,8 +40,16 @@ __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, 
 __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double dvd(double a, double b) { return __ddiv_rn(a, b); }
 
-// dens_profs_tools.py:22-79 on scalars
-__device__ __forceinline__ double model(int profile, double r, const double *x)
+// dens_profs_tools.py:22-79 on scalars.  k0 is the per-evaluation constant of the model (the same for every bin, so
+// computing it once per evaluation is bit-identical): einasto -2/alpha, alpha_beta_gamma (beta-gamma)/alpha.
+__device__ __forceinline__ double model_const(int profile, const double *x)
+{
+    if (profile == FIT_EINASTO) return dvd(-2.0, x[1]);
+    if (profile == FIT_ABG) return dvd(sub(x[2], x[3]), x[1]);
+    return 0.0;
+}
+
+__device__ __forceinline__ double model(int profile, double r, const double *x, double k0)
 {
     if (profile == FIT_NFW) {            // rho_s/((r/r_s)*(1+r/r_s)**2)
         const double u = dvd(r, x[1]), w = add(1.0, u);
@@ -53,19 +61,29 @@ __device__ __forceinline__ double model(int profile, double r, const double *x)
     }
     if (profile == FIT_EINASTO) {        // rho_s*np.exp(-2/alpha*((r/r_s)**alpha-1))
         const double u = dvd(r, x[2]);
-        return mul(x[0], exp(mul(dvd(-2.0, x[1]), sub(pow(u, x[1]), 1.0))));
+        return mul(x[0], exp(mul(k0, sub(pow(u, x[1]), 1.0))));
     }
     // rho_s/((r/r_s)**gamma*(1+(r/r_s)**alpha)**((beta-gamma)/alpha))
     const double u = dvd(r, x[4]);
-    return dvd(x[0], mul(pow(u, x[3]), pow(add(1.0, pow(u, x[1])), dvd(sub(x[2], x[3]), x[1]))));
+    return dvd(x[0], mul(pow(u, x[3]), pow(add(1.0, pow(u, x[1])), k0)));
 }
 
-// One warp, one object.  All members are warp-uniform except `lane`.
+// One object, W warps (W = 2 when it has more than 32 bins: a second round of bins on 8 of 32 lanes would double
+// the latency of every evaluation).  All warps of an object carry identical state and take identical decisions:
+// they read the same terms from shared memory.  All members are uniform over the object's lanes except lane / tid.
 template <int N>
 struct Problem {
     const double *radii, *lmed;
-    double *terms;          // shared scratch, FIT_MAX_BINS doubles of this warp
+    double *terms;          // shared scratch, FIT_MAX_BINS doubles of this object
     int n, profile, lane;
+    int tid, nthreads, bar_id;   // thread index inside the object's W warps, 32 W, named barrier (W > 1)
+
+    __device__ __forceinline__ void obj_sync() const
+    {
+        if (nthreads == 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+    }
+
     int ncalls, maxfun;
     bool aborted;           // scipy's _MaxFuncCallError
     double lb[N], ub[N];
@@ -79,11 +97,12 @@ struct Problem {
         }
         ncalls++;
         const double dn = (double)n;
-        for (int i = lane; i < n; i += 32) {
-            const double t = sub(lmed[i], log(model(profile, radii[i], x)));
+        const double k0 = model_const(profile, x);
+        for (int i = tid; i < n; i += nthreads) {
+            const double t = sub(lmed[i], log(model(profile, radii[i], x, k0)));
             terms[i] = dvd(mul(t, t), dn);
         }
-        __syncwarp();
+        obj_sync();
         double res;
         if (n < 8) {
             res = n > 0 ? terms[0] : 0.0;
@@ -100,7 +119,7 @@ struct Problem {
             res = add(add(add(r0, r1), add(r2, r3)), add(add(r4, r5), add(r6, r7)));
             for (; i < n; i++) res = add(res, terms[i]);
         }
-        __syncwarp();
+        obj_sync();   // nobody overwrites the terms before every warp has summed them
         return res;
     }
 
@@ -338,24 +357,27 @@ __device__ void powell(Problem<N> &P, double (&x)[N], double xtol, double ftol, 
 
 }  // namespace fit
 
-template <int N>
+template <int N, int W>
 __global__ void __launch_bounds__(FIT_WARPS * 32) fit_profiles_kernel(const FitParams Q)
 {
-    __shared__ double s_terms[FIT_WARPS][FIT_MAX_BINS];
-    __shared__ double s_radii[FIT_WARPS][FIT_MAX_BINS];
-    __shared__ double s_lmed[FIT_WARPS][FIT_MAX_BINS];
+    constexpr int OBJS = FIT_WARPS / W;   // objects per CTA
+    __shared__ double s_terms[OBJS][FIT_MAX_BINS];
+    __shared__ double s_radii[OBJS][FIT_MAX_BINS];
+    __shared__ double s_lmed[OBJS][FIT_MAX_BINS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int obj = blockIdx.x * FIT_WARPS + warp;
-    if (obj >= Q.n_obj) return;   // whole warp
+    const int slot = warp / W, sub = warp % W;
+    const int obj = blockIdx.x * OBJS + slot;
+    if (obj >= Q.n_obj) return;   // all W warps of the object
     fit::Problem<N> P;
     P.n = Q.n_valid[obj];
-    for (int i = lane; i < P.n; i += 32) {
-        s_radii[warp][i] = Q.radii[(size_t)obj * Q.R + i];
-        s_lmed[warp][i] = Q.lmed[(size_t)obj * Q.R + i];
+    P.lane = lane; P.tid = sub * 32 + lane; P.nthreads = 32 * W; P.bar_id = 1 + slot;
+    for (int i = P.tid; i < P.n; i += P.nthreads) {
+        s_radii[slot][i] = Q.radii[(size_t)obj * Q.R + i];
+        s_lmed[slot][i] = Q.lmed[(size_t)obj * Q.R + i];
     }
-    __syncwarp();
-    P.radii = s_radii[warp]; P.lmed = s_lmed[warp]; P.terms = s_terms[warp];
-    P.profile = Q.profile; P.lane = lane; P.ncalls = 0; P.maxfun = N * 1000; P.aborted = false;
+    P.obj_sync();
+    P.radii = s_radii[slot]; P.lmed = s_lmed[slot]; P.terms = s_terms[slot];
+    P.profile = Q.profile; P.ncalls = 0; P.maxfun = N * 1000; P.aborted = false;
     double x[N];
 #pragma unroll
     for (int i = 0; i < N; i++) {
@@ -366,7 +388,7 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) fit_profiles_kernel(const FitP
     int nit = 0;
     bool unsupported = false;
     fit::powell<N>(P, x, Q.xtol, Q.ftol, fval, nit, unsupported);
-    if (lane == 0) {
+    if (P.tid == 0) {
         // best_fit[0] *= np.average(median)   (dens_profs_tools.py:320)
         Q.best[(size_t)obj * N] = unsupported ? nan("") : fit::mul(x[0], Q.avg[obj]);
         for (int i = 1; i < N; i++) Q.best[(size_t)obj * N + i] = unsupported ? nan("") : x[i];

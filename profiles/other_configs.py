@@ -305,7 +305,7 @@ def sec_fits():
                      evaluations_per_s_kernel=float(info["nfev"].sum()) / (info["timing"]["kernel_ms"] * 1e-3),
                      finite_rows=int(np.isfinite(best).all(1).sum()))
         if ref_ok:
-            ns = min(nh, 8 * cores)
+            ns = min(nh, int(os.environ.get("CP_FIT_SAMPLE", 8 * cores)))
             pick = np.random.default_rng(1).choice(nh, ns, replace=False)
             jobs = [(rr, method, (dens[i], cat["r200"][i], int(i))) for i in pick]
             with mp.get_context("fork").Pool(cores) as pool:
@@ -315,6 +315,27 @@ def sec_fits():
                 dt = time.perf_counter() - t0
             fin = np.isfinite(ref).all(1) & np.isfinite(best[pick]).all(1)
             rel = np.max(np.abs(best[pick][fin] - ref[fin]) / np.abs(ref[fin]), axis=1)
+            # where the two optimisers ended in different points: how do the objective values compare?
+            radii, lmed, n_valid, avg = DT.prepare(dens[pick], rr, cat["r200"][pick])
+
+            def psi2(x, j):   # toMinimize on the normalised profile (dens_profs_tools.py:227-230), x[0] un-scaled again
+                m = int(n_valid[j])
+                xx = np.array(x, dtype=np.float64)
+                xx[0] = xx[0] / avg[j]
+                r = radii[j, :m]
+                if prof == "nfw":
+                    mod = xx[0] / ((r / xx[1]) * (1 + r / xx[1]) ** 2)
+                elif prof == "hernquist":
+                    mod = xx[0] / ((r / xx[1]) * (1 + r / xx[1]) ** 3)
+                elif prof == "einasto":
+                    mod = xx[0] * np.exp(-2 / xx[1] * ((r / xx[2]) ** xx[1] - 1))
+                else:
+                    mod = xx[0] / ((r / xx[4]) ** xx[3] * (1 + (r / xx[4]) ** xx[1]) ** ((xx[2] - xx[3]) / xx[1]))
+                return float(np.sum((lmed[j, :m] - np.log(mod)) ** 2 / m))
+            far = np.flatnonzero(fin)[rel > 1e-6]
+            dpsi = [(psi2(best[pick][j], j), psi2(ref[j], j)) for j in far]
+            entry.update(sample_objects_beyond_1e6=int(len(far)),
+                         psi2_gpu_over_ref_of_those=[round(a_ / b_, 6) if b_ > 0 else None for a_, b_ in dpsi][:8])
             entry.update(reference_fits_per_s=ns / dt, reference_cores=cores, reference_sample=ns,
                          speedup=(nh / (ms * 1e-3)) / (ns / dt), sample_within_1e9=float((rel < 1e-9).mean()),
                          sample_within_1e4=float((rel < 1e-4).mean()), sample_max_rel=float(rel.max()),
