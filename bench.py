@@ -547,7 +547,12 @@ def main():
                              "algorithmic_bytes_per_launch_set": pi_local_all / world * BYTES_PER_PI,
                              "kernel_ms": kern_ms, "frac_of_8TBps_nominal": achieved / 8000.0,
                              "streamed_particle_iterations": visited_all / world,
-                             "streamed_GBps": visited_all / world * BYTES_PER_PI / (kern_ms * 1e-3) / 1e9},
+                             "streamed_GBps": visited_all / world * BYTES_PER_PI / (kern_ms * 1e-3) / 1e9,
+                             "note": "achieved = algorithmic bytes (32 B x particle-iterations, the reference's unit of work) / "
+                                     "kernel time, as the contract defines it; frac > 1 because the radial ordering and the prefix "
+                                     "tensor table let a Katz iteration skip most of an object's particles (streamed_GBps: the "
+                                     "bytes really passed over; traffic: DRAM bytes under ncu).  The kernels are FP64-issue bound "
+                                     "(45 % of the FP64 pipe, profiles/r1d_ncu_morph_kernels.txt), not HBM bound."},
                 "cpu_baseline": cpu, "clocks": clk, "breakdown_ms_per_step_rank0": {k_: round(v_, 3) for k_, v_ in brk.items()},
                 "particle_iterations_per_step": pi_all, "particles_per_gpu": n_part}
         emit(line)
