@@ -90,6 +90,7 @@ struct cpg_ctx {
     cudaEvent_t up_ev[UP_THREADS][UP_BUFS] = {};
     bool up_ready = false;
     int opt_upload_threads = UP_THREADS;   // 0: leave pageable sources to cudaMemcpyAsync
+    int opt_direct_results = 1;            // cpg_shape: kernels store results straight into page-locked caller buffers
     // snapshot
     DevBuf<double> xyz, vxyz, masses;
     int64_t n_part = 0;
@@ -350,6 +351,17 @@ __global__ void init_results_kernel(double2 *__restrict__ out12, int32_t *__rest
     for (int64_t i = i0; i < nR * 6; i += stride) out12[i] = make_double2(0.0, 0.0);
     for (int64_t i = i0; i < nR; i += stride) { n_iter[i] = -1; n_pts[i] = -1; }
     if (i0 < 4) counters[i0] = 0;
+}
+
+// Device-side alias of a page-locked host buffer (nullptr if `p` is pageable or device memory).
+void *pinned_device_alias(const void *p)
+{
+    cudaPointerAttributes at;
+    if (!p || cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 
 struct Timer {
@@ -747,6 +759,8 @@ CPG_API int cpg_set_option(cpg_ctx *c, const char *name, int64_t value)
             return CPG_ERR_ARGUMENT;
         }
         c->opt_upload_threads = (int)value;
+    } else if (!strcmp(name, "direct_results")) {
+        c->opt_direct_results = value != 0;
     } else if (!strcmp(name, "radial_order")) {
         c->opt_radial_order = value != 0;
     } else if (!strcmp(name, "prefix_table")) {
@@ -1291,10 +1305,34 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
         TK.valid = true; TK.cat = c->catalogue_version; TK.S = S * 16 + G; TK.R = R; TK.large_min = large_min;
     }
     const int nw = TK.nw, ncl = TK.ncl, ngrid = TK.ngrid, cluster_size = TK.cluster_size;
-    CPG_TRY(c->out12.ensure(nR * 12)); CPG_TRY(c->n_iter.ensure(nR)); CPG_TRY(c->n_pts.ensure(nR));
+    // Page-locked result buffers (cpg_host_alloc): the kernels store every finished halo-shell straight into them
+    // while they run, so the results cross PCIe under the kernels instead of in a 74 MB copy after them (configs[1]:
+    // 1.3 ms per step on one GPU, 4.3 ms when 8 GPUs share the host's DMA bandwidth).  The buffers are initialised
+    // on the host (zeros / -1: what the reference returns for failed shells) by a few threads while the GPU gathers.
+    double *d_out12 = c->opt_direct_results ? (double *)pinned_device_alias(out12) : nullptr;
+    int32_t *d_nit = c->opt_direct_results ? (int32_t *)pinned_device_alias(n_iter) : nullptr;
+    int32_t *d_npt = c->opt_direct_results ? (int32_t *)pinned_device_alias(n_pts) : nullptr;
+    const bool direct = d_out12 && d_nit && d_npt;
+    std::vector<std::thread> fillers;
+    if (direct) {
+        const int nt = 4;
+        for (int t = 0; t < nt; t++)
+            fillers.emplace_back([=]() {
+                const size_t a0 = nR * 12 * t / nt, a1 = nR * 12 * (t + 1) / nt, b0 = nR * t / nt, b1 = nR * (t + 1) / nt;
+                memset(out12 + a0, 0, sizeof(double) * (a1 - a0));
+                memset(n_iter + b0, 0xff, sizeof(int32_t) * (b1 - b0));
+                memset(n_pts + b0, 0xff, sizeof(int32_t) * (b1 - b0));
+            });
+    } else {
+        CPG_TRY(c->out12.ensure(nR * 12)); CPG_TRY(c->n_iter.ensure(nR)); CPG_TRY(c->n_pts.ensure(nR));
+    }
+    struct Joiner {   // every exit path waits for the fill threads
+        std::vector<std::thread> &th;
+        ~Joiner() { for (auto &x : th) if (x.joinable()) x.join(); }
+    } joiner{fillers};
     // (a fill kernel, not cudaMemsetAsync: the copy-engine memset of the 67 MB result array of configs[1] took ~1 ms)
-    init_results_kernel<<<grid_for((int64_t)nR * 6, 256, c->sm_count * 16), 256, 0, c->stream>>>(
-        reinterpret_cast<double2 *>(c->out12.p), c->n_iter.p, c->n_pts.p, c->task_counter.p, (int64_t)nR);
+    init_results_kernel<<<grid_for(std::max<int64_t>((int64_t)(direct ? 0 : nR) * 6, 4), 256, c->sm_count * 16), 256, 0, c->stream>>>(
+        reinterpret_cast<double2 *>(c->out12.p), c->n_iter.p, c->n_pts.p, c->task_counter.p, (int64_t)(direct ? 0 : nR));
     c->timing.kernel_launches++;
     CPG_CUDA(cudaGetLastError());
     T.mark(1);
@@ -1319,7 +1357,8 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     P.tasks = TK.tasks.p; P.n_tasks = 0; P.task_counter = c->task_counter.p;
     P.R = R; P.local = local ? 1 : 0; P.SAFE = SAFE;
     P.tol = IT_TOL; P.wall = IT_WALL; P.itmin = IT_MIN;
-    P.out12 = c->out12.p; P.n_iter = c->n_iter.p; P.n_pts = c->n_pts.p;
+    P.out12 = direct ? d_out12 : c->out12.p; P.n_iter = direct ? d_nit : c->n_iter.p; P.n_pts = direct ? d_npt : c->n_pts.p;
+    for (auto &x : fillers) x.join();   // the host-side initialisation ran under the gather; it must end before a kernel stores
     if (ngrid > 0) {
         int rcg;
         if (S == 4) rcg = dispatch_grid<4>(c, P, shell_based != 0, reduced != 0, use_vel != 0, nw + ncl, ngrid);
@@ -1336,9 +1375,12 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     T.mark(3);
 
     // ---- results
-    CPG_CUDA(cudaMemcpyAsync(out12, c->out12.p, sizeof(double) * 12 * nR, cudaMemcpyDeviceToHost, c->stream));
-    CPG_CUDA(cudaMemcpyAsync(n_iter, c->n_iter.p, sizeof(int32_t) * nR, cudaMemcpyDeviceToHost, c->stream));
-    CPG_CUDA(cudaMemcpyAsync(n_pts, c->n_pts.p, sizeof(int32_t) * nR, cudaMemcpyDeviceToHost, c->stream));
+    if (!direct) {
+        CPG_CUDA(cudaMemcpyAsync(out12, c->out12.p, sizeof(double) * 12 * nR, cudaMemcpyDeviceToHost, c->stream));
+        CPG_CUDA(cudaMemcpyAsync(n_iter, c->n_iter.p, sizeof(int32_t) * nR, cudaMemcpyDeviceToHost, c->stream));
+        CPG_CUDA(cudaMemcpyAsync(n_pts, c->n_pts.p, sizeof(int32_t) * nR, cudaMemcpyDeviceToHost, c->stream));
+    }
+    // (direct: the same bytes crossed PCIe as stores of the kernels)
     c->timing.d2h_bytes = (int64_t)(nR * (12 * sizeof(double) + 2 * sizeof(int32_t)));
     if (obj_mass) {
         CPG_CUDA(cudaMemcpyAsync(obj_mass, c->obj_mass.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
