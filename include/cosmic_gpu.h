@@ -200,8 +200,10 @@ CPG_API int cpg_fit_profiles(cpg_ctx *ctx, const double *radii, const double *lm
                              int32_t R, int32_t profile, double xtol, double ftol, double *best, double *fun,
                              int32_t *nfev, int32_t *nit);
 
-/* Page-locked host buffers for results (device->host copies into pageable memory run at a fraction of the
- * PCIe rate).  No counterpart in the reference, whose drivers np.zeros() their outputs
+/* Page-locked host buffers for results.  When out12, n_iter and n_pts of cpg_shape all live in such buffers, the
+ * kernels store every finished halo-shell straight into them while they run (no result copy after the kernels; option
+ * "direct_results" = 0 restores the copy); pageable result buffers are filled by an ordinary device->host copy, which
+ * runs at a fraction of the PCIe rate.  No counterpart in the reference, whose drivers np.zeros() their outputs
  * (shape_profs_algos.pyx:560-572). */
 CPG_API int cpg_host_alloc(size_t bytes, void **out);
 CPG_API void cpg_host_free(void *p);
@@ -225,6 +227,7 @@ CPG_API int cpg_get_timing(cpg_ctx *ctx, cpg_timing *out);
  *                      call redoes the gather even if snapshot, catalogue, centres and L_BOX are unchanged
  *   "radial_order"     1 (default): gather every object in radial-bucket order and let shell k stream only
  *                      the particles with |x-c| < d_k (they are the only possible members); 0: catalogue order
+ *   "direct_results"   1 (default): cpg_shape stores results directly into page-locked caller buffers (see cpg_host_alloc)
  *   "upload_threads"   host threads (0..8, default 8) that stage PAGEABLE host arrays of >= 64 MB through page-locked bounce
  *                      buffers in cpg_set_particles / cpg_set_catalogue; 0 leaves them to cudaMemcpyAsync.  Page-locked
  *                      sources are always copied directly.
