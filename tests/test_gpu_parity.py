@@ -354,3 +354,23 @@ def test_device_shape_interpolation(gpu):
         with pytest.raises(_lib.CosmicGpuError):     # the host call above replaced the resident profiles
             ctx.dens_ell(cen, None, None, None, None, None, None, 0.0)
         ctx.close()
+
+
+def test_direct_result_stores_equal_the_copied_results(gpu, big):
+    """cpg_shape with page-locked result buffers lets the kernels store results straight into them; with the option
+    off (or pageable buffers) the results are copied after the kernels.  Both must deliver the same bytes."""
+    from cosmic_profiles_b200 import _lib
+    cat, _, cen, _ = big
+    rr = np.logspace(-1.5, 0, 9)
+    ctx = _lib.Context(0)
+    ctx.set_particles(cat["xyz"], None, cat["masses"])
+    ctx.set_catalogue(cat["idx_cat"], cat["obj_size"])
+    res = {}
+    for direct in (1, 0):
+        ctx.set_option("direct_results", direct)
+        out, nit, npt, m, _ = ctx.shape(cen, cat["r200"], rr, True, 0.0, 0.0, 1e-2, 100, 10, True, True, False)
+        res[direct] = (out.copy(), nit.copy(), npt.copy(), m.copy())
+    for a, b in zip(res[1], res[0]):
+        assert np.array_equal(a, b)
+    assert (res[1][1] > 0).any() and (res[1][0] == 0).any()      # converged and failed halo-shells both present
+    ctx.close()
