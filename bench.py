@@ -4,21 +4,28 @@
 A step = one pass of the hot path over one synthetic catalogue:
     calcMorphLocal  (ellipsoid-based, non-reduced, default Katz config: 70 shells logspace(-1.5,0), IT_TOL 1e-2,
                      IT_WALL 100, IT_MIN 10; python_routines.py:698)  +  calcMorphGlobal (SAFE=6)
-on 10^4 mock Einasto halos whose sizes follow p(N) ~ N^-1.9 on [1e3, 1e6] (~9e7 particles, 2.9 GB of
-fp64 x,y,z,m: larger than the 126 MB L2, so no L2 flush is needed between steps).
+on mock Einasto halos whose sizes follow p(N) ~ N^-1.9 on [1e3, 1e6]: 10^4 of them per GPU (~9e7 particles, 2.9 GB
+of fp64 x,y,z,m per GPU: larger than the 126 MB L2, so no L2 flush is needed between steps).
 Centres are an input of the path (north_star); they are computed once outside the timed region.
 
-metric  = particle-iterations/s,  PI = sum_h N_h * sum_k (shape-tensor evaluations of halo-shell (h,k))
-value   = PI / device time of the cpg_shape calls with snapshot + catalogue already resident in HBM
-e2e     = PI / time of the full C-ABI sequence from pinned HOST buffers (cpg_set_particles +
-          cpg_set_catalogue + cpg_shape x2, results copied back) per step
-roofline= algorithmic bytes (32 B per particle-iteration) / CUDA-event time of the
-          morphology kernels of the local-shape call, against the measured HBM copy bandwidth
-cpu_baseline = the reference's own compiled calcMorphLocal+calcMorphGlobal (oracle/_ref) on a bounded,
-          stratified sample of the same catalogue, all host cores.
+Several GPUs (torchrun, one rank per GPU): ONE catalogue of N x 10^4 objects -- one draw of the size table for the whole
+catalogue -- is split over the ranks by the library's particle-count-balanced LPT partition (cpg_partition_lpt, the
+function cpg_multi shards with); every rank generates and owns only its shard.  No data-path collective; the per-object
+results are gathered to rank 0 once, outside the timed steps, and that gather is reported (multi_gpu.host_gather_ms).
+`--scaling strong --halos-total H` keeps the catalogue fixed (H objects) as N grows instead.
 
-`--impl reference` times only that reference arm (rank 0).  Under torchrun each rank owns one GPU and its
-own catalogue of the per-GPU size (weak scaling, no data-path collective).
+metric  = particle-iterations/s,  PI = sum_h N_h * sum_k (shape-tensor evaluations of halo-shell (h,k))
+value   = PI of all ranks / max over ranks of the device time of the cpg_shape calls, snapshot + catalogue resident
+e2e     = PI / time of the full C-ABI sequence from pinned HOST buffers (cpg_set_particles + cpg_set_catalogue +
+          cpg_shape x2, results copied back) per step
+roofline= the local-shape morphology kernels against the MEASURED fp64 multiply-add peak of the device (they are
+          fp64-pipe bound, not HBM bound): fp64 work from the kernels' own tile counters / CUDA-event time; the
+          contract's HBM figures (algorithmic bytes, physical DRAM traffic under ncu) are reported beside it
+cpu_baseline = the reference's own compiled calcMorphLocal+calcMorphGlobal (oracle/_ref) on a bounded,
+          seeded sample of the same catalogue, all host cores; calcMassesCenters timed separately ("centres excluded").
+
+`--impl reference` times only that reference arm (rank 0).  `--config {0,2,3,4}` measures one of the other BASELINE
+configurations on one GPU instead (its own JSON line, same keys).
 """
 import argparse
 import json
@@ -61,6 +68,28 @@ def halo_table(n_halos, seed, size_seed=None):
     centre = rng.uniform(20.0, 80.0, size=(n_halos, 3))
     u, cdf = _radius_sampler("einasto", 5.0)
     return dict(sizes=sizes, q=q, s=s, r_vir=r_vir, rot=rot, centre=centre, u=u, cdf=cdf)
+
+
+def global_halos(halos_per_gpu, world):
+    """Weak scaling: the ONE catalogue that N ranks share holds N x halos_per_gpu objects."""
+    return int(halos_per_gpu) * int(world)
+
+
+def rank_objects(sizes, rank, world):
+    """Catalogue rows owned by `rank`: the library's particle-count-balanced LPT partition (cpg_partition_lpt)."""
+    from cosmic_profiles_b200 import _lib
+    if world == 1:
+        return np.arange(len(sizes))
+    owner = _lib.partition_lpt(np.asarray(sizes, dtype=np.float64), world)
+    return np.flatnonzero(owner == rank)
+
+
+def table_rows(tab, rows):
+    """The object table restricted to `rows` (a rank's shard)."""
+    out = dict(tab)
+    for k in ("sizes", "q", "s", "r_vir", "rot", "centre"):
+        out[k] = tab[k][rows]
+    return out
 
 
 def generate_on_device(tab, seed, device):
@@ -189,12 +218,57 @@ def time_reference(cat, pick, steps, warmup):
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
+    # "centres excluded" (SURVEY.md 8(d)): both reference drivers run the serial Python centre loop once each
+    # (shape_profs_algos.pyx:586-591, :696-701); the GPU arm takes centres as given.  Timed on its own through
+    # calcMassesCenters, which runs the same loop (dens_profs_algos.pyx:39-44).
+    cen_s = None
+    if kind == "reference":
+        c0 = time.perf_counter()
+        with ref_loader.quiet_stdout():
+            ns.calcMassesCenters(xyz, m, idx, sizes, 0.0, "com")
+        cen_s = time.perf_counter() - c0
     info = dict(kind=kind, cores=cores,
                 sample="%d of %d objects (seeded random subset, objects <= budget/16, %d particles, %.3g particle-iterations), "
                        "calcMorphLocal 70 shells + calcMorphGlobal incl. the reference's own centre loop, "
                        "OMP_NUM_THREADS=%d" % (len(pick), len(cat["obj_size"]), int(sizes.sum()), pi, cores),
-                seconds_per_step=dt)
+                seconds_per_step=dt, centres_seconds=cen_s,
+                centres_excluded_value=(pi / max(dt - 2.0 * cen_s, 1e-9)) if cen_s is not None else None)
     return pi / dt, info
+
+
+def time_dropin(cat, pi_step):
+    """e2e_dropin: the call a user of the reference makes -- the public drivers calcMorphLocal + calcMorphGlobal of
+    cosmic_profiles_b200 (what install() binds into the reference's classes) with plain PAGEABLE numpy arrays and no
+    centres given ('com' centres on the device, as the reference's drivers compute them inside).  cold: first call on
+    a fresh session, snapshot upload included; warm: the same arrays again (the reference's class hands the same xyz /
+    masses to every driver, cosmic_base_class.pyx:155,232: the snapshot cache skips the upload)."""
+    from cosmic_profiles_b200 import session, shape_profs_algos as S
+    xyz = np.array(cat["xyz"], copy=True)          # pageable copies: what a numpy user holds
+    masses = np.array(cat["masses"], copy=True)
+    idx = np.array(cat["idx_cat"], copy=True)
+    size = np.array(cat["obj_size"], copy=True)
+    r200 = np.array(cat["r200"], copy=True)
+    k = (KATZ["IT_TOL"], KATZ["IT_WALL"], KATZ["IT_MIN"])
+
+    def pair():
+        t0 = time.perf_counter()
+        S.calcMorphLocal(xyz, masses, r200, idx, size, 0.0, RR, *k, "com", False, False)
+        t1 = time.perf_counter()
+        S.calcMorphGlobal(xyz, masses, r200, idx, size, 0.0, *k, "com", SAFE, False)
+        t2 = time.perf_counter()
+        return 1e3 * (t1 - t0), 1e3 * (t2 - t1)
+    session.close_all()
+    pair()                      # first use of the session: device buffers, pinned scratch (not a steady-state cost)
+    session.close_all_snapshots()
+    cold = pair()               # buffers exist, snapshot not resident: uploads included
+    warm = min((pair() for _ in range(3)), key=sum)
+    session.close_all()
+    return {"unit": UNIT, "cold_ms": {"calcMorphLocal": cold[0], "calcMorphGlobal": cold[1]},
+            "warm_ms": {"calcMorphLocal": warm[0], "calcMorphGlobal": warm[1]},
+            "cold_value": pi_step / (sum(cold) * 1e-3), "warm_value": pi_step / (sum(warm) * 1e-3),
+            "h2d_bytes_cold": int(xyz.nbytes + masses.nbytes + 12 * len(size)),
+            "note": "public drop-in drivers, pageable numpy in, reference tuple out (NaN masking, recentring included); "
+                    "centres 'com' computed on the device inside the call"}
 
 
 # ------------------------------------------------------------------------------------------ clocks
@@ -321,6 +395,12 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=8.0e6, help="particles in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="e2e: only the strictly serial measurement")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the e2e_dropin measurement (public drivers, pageable numpy)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: N x --halos objects in the one catalogue; strong: --halos-total objects whatever N")
+    ap.add_argument("--halos-total", type=int, default=100000, help="objects of the catalogue under --scaling strong")
+    ap.add_argument("--config", type=int, default=1, choices=[0, 1, 2, 3, 4],
+                    help="BASELINE.json configuration to measure (1 = the headline; the others: one GPU, own JSON line)")
     ap.add_argument("--seed", type=int, default=20260101)
     ap.add_argument("--opt", action="append", default=[], help="scheduling tunable name=value (cpg_set_option)")
     a = ap.parse_args()
@@ -375,14 +455,23 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from cosmic_profiles_b200 import _lib
 
+    # ---- ONE catalogue, partitioned over the ranks -----------------------------------------------------------
     t0 = time.perf_counter()
-    tab = halo_table(a.halos, rank_seed(a.seed, rank), size_seed=a.seed + 1)
-    cat = generate_on_device(tab, rank_seed(a.seed, rank), local_rank)
+    n_global = a.halos_total if a.scaling == "strong" else global_halos(a.halos, world)
+    tab = halo_table(n_global, a.seed)
+    tp0 = time.perf_counter()
+    mine = rank_objects(tab["sizes"], rank, world)
+    partition_ms = 1e3 * (time.perf_counter() - tp0)
+    cat = generate_on_device(table_rows(tab, mine), rank_seed(a.seed, rank), local_rank)
     n_part = int(cat["obj_size"].sum())
-    log("[rank %d] catalogue: %d objects, %d particles (%.2f GB x,y,z,m), generated in %.1f s"
-        % (rank, a.halos, n_part, n_part * 32 / 1e9, time.perf_counter() - t0))
+    n_mine = len(mine)
+    log("[rank %d] shard: %d of %d objects, %d particles (%.2f GB x,y,z,m), partition %.1f ms, generated in %.1f s"
+        % (rank, n_mine, n_global, n_part, n_part * 32 / 1e9, partition_ms, time.perf_counter() - t0))
+    config["halos_total"] = n_global
+    config["sharding"] = "one catalogue, objects split by the library's LPT partition on particle counts (cpg_partition_lpt)"
 
     ctx = _lib.Context(local_rank)
+    ctx.set_option("snapshot_cache", 0)   # every upload() of the e2e phases must really move its bytes
     for kv in a.opt:
         name, val = kv.split("=")
         ctx.set_option(name, int(val))
@@ -397,10 +486,12 @@ def main():
         # global-shape call of the same step then reuses it, as a getShapeCatLocal + getShapeCatGlobal
         # sequence on one catalogue would
         ctx.set_option("invalidate_gather", 1)
-        out_l, nit_l, _, _, _ = ctx.shape(cat["centers"], cat["r200"], RR, True, 0.0, 0.0, *k, False, False, False)
+        out_l, nit_l, _, _, _ = ctx.shape(cat["centers"], cat["r200"], RR, True, 0.0, 0.0, *k, False, False, False,
+                                          zero_copy=True)
         nit_l = nit_l.copy()   # a view into the context's page-locked result scratch
         t_l = ctx.timing()
-        out_g, nit_g, _, _, _ = ctx.shape(cat["centers"], cat["r200"], None, False, SAFE, 0.0, *k, False, False, False)
+        out_g, nit_g, _, _, _ = ctx.shape(cat["centers"], cat["r200"], None, False, SAFE, 0.0, *k, False, False, False,
+                                          zero_copy=True)
         nit_g = nit_g.copy()
         t_g = ctx.timing()
         return nit_l, nit_g, t_l, t_g
@@ -432,6 +523,7 @@ def main():
     kern_local_ms = 0.0
     launches = 0
     hot_launches_local = 0
+    fma_local = 0.0
     w0 = time.perf_counter()
     for _ in range(a.steps):
         _, _, t_l, t_g = shapes()
@@ -442,8 +534,12 @@ def main():
                 brk[nm + "_" + kk] = brk.get(nm + "_" + kk, 0.0) + t[kk] / a.steps
         kern_local_ms += t_l["kernel_ms"]
         hot_launches_local += t_l["hot_kernel_launches"]
+        # fp64 work of the local-shape kernels from their own counters: per 128-particle tile 6 products per particle,
+        # per (tile, shell) 6 tensor updates per particle (the membership test itself runs in fp32)
+        fma_local += 128.0 * 6.0 * (t_l["tile_visits"] + t_l["tile_shell_visits"])
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - w0)
+    fp64_peak = ctx.measure_fp64_peak()   # TFMA/s, outside every timed region
 
     # ---- end-to-end timing from pinned host buffers (e2e) ---------------------------------------
     # Streaming configuration of the public option "direct_results" (include/cosmic_gpu.h): the result copy of a step
@@ -467,6 +563,7 @@ def main():
     e2e_ms, e2e_mode = e2e_serial_ms, "serial"
     if not a.no_pipeline:
         ctx2 = _lib.Context(local_rank)
+        ctx2.set_option("snapshot_cache", 0)
         for kv in a.opt:
             name, val = kv.split("=")
             ctx2.set_option(name, int(val))
@@ -506,21 +603,69 @@ def main():
         if pipe_ms < e2e_serial_ms:
             e2e_ms, e2e_mode = pipe_ms, "double-buffered (2 contexts, uploads of step i+1 overlap kernels of step i)"
         ctx2.close()
+    # host->device ceiling of this box with all ranks copying at once (what bounds e2e): plain pinned copies of the
+    # same size as one step's inputs, CUDA events, no kernels
+    h2d_probe = torch.from_numpy(cat["xyz"])
+    dev_probe = torch.empty_like(h2d_probe, device="cuda")
+    barrier()
+    p0 = time.perf_counter()
+    for _ in range(2):
+        dev_probe.copy_(h2d_probe, non_blocking=True)
+    barrier()
+    h2d_gbs = 2 * cat["xyz"].nbytes / (time.perf_counter() - p0) / 1e9
+    del dev_probe
     clk = clocks.stop(t_clk0, time.perf_counter())   # the resident-input steps and both e2e measurements
-    h2d = int(cat["xyz"].nbytes + cat["masses"].nbytes + cat["idx_cat"].nbytes + cat["obj_size"].nbytes
+    cat_ranges = bool(_lib.catalogue_ranges(cat["idx_cat"], cat["obj_size"])[0])
+    # bytes that really cross PCIe per step: a contiguous-range catalogue travels as (start, size) per object
+    idx_bytes = (8 + 4) * n_mine if cat_ranges else cat["idx_cat"].nbytes + cat["obj_size"].nbytes
+    h2d = int(cat["xyz"].nbytes + cat["masses"].nbytes + idx_bytes
               + 2 * (cat["centers"].nbytes + cat["r200"].nbytes) + RR.nbytes)
     d2h = int(t_l["d2h_bytes"] + t_g["d2h_bytes"])
 
+    # ---- host gather of the per-object results to rank 0 (outside the timed steps; N > 1 only) ---------------
+    gather_ms = 0.0
+    if world > 1:
+        ctx.set_option("direct_results", 1)
+        out_l, nit_all, npt_all, _, _ = ctx.shape(cat["centers"], cat["r200"], RR, True, 0.0, 0.0, *k, False, False, False)
+        barrier()
+        g0 = time.perf_counter()
+        n_all = [None] * world
+        dist.all_gather_object(n_all, n_mine)
+        n_max = max(n_all)
+        send = torch.zeros((n_max, len(RR), 12), dtype=torch.float64, device="cuda")
+        send[:n_mine].copy_(torch.from_numpy(out_l))
+        recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+        dist.gather(send, recv, dst=0)
+        if rank == 0:
+            full = np.zeros((n_global, len(RR), 12))
+            owner = _lib.partition_lpt(np.asarray(tab["sizes"], dtype=np.float64), world)
+            for r in range(world):
+                full[np.flatnonzero(owner == r)] = recv[r][:n_all[r]].cpu().numpy()
+        barrier()
+        gather_ms = 1e3 * (time.perf_counter() - g0)
+
     # ---- reduce over ranks: time = max, work = sum -------------------------------------------------
-    (step_ms, wall_step_ms, e2e_step_ms, kern_ms, e2e_serial_step_ms), (pi_all, pi_local_all, launches_all, h2d_all, d2h_all, visited_all) = \
-        reduce_over_ranks([dev_ms / a.steps, wall_ms / a.steps, e2e_ms, kern_local_ms / a.steps, e2e_serial_ms],
-                          [pi_step, pi_local, float(launches), float(h2d), float(d2h), visited_local], world, "cuda")
+    (step_ms, wall_step_ms, e2e_step_ms, kern_ms, e2e_serial_step_ms, part_ms), \
+        (pi_all, pi_local_all, launches_all, h2d_all, d2h_all, visited_all, fma_all, kern_sum, step_sum, npart_all, h2d_gbs_all) = \
+        reduce_over_ranks([dev_ms / a.steps, wall_ms / a.steps, e2e_ms, kern_local_ms / a.steps, e2e_serial_ms, partition_ms],
+                          [pi_step, pi_local, float(launches), float(h2d), float(d2h), visited_local, fma_local / a.steps,
+                           kern_local_ms / a.steps, dev_ms / a.steps, float(n_part), h2d_gbs], world, "cuda")
+    per_rank = None
+    if world > 1:
+        mine_stats = [rank, n_mine, n_part, dev_ms / a.steps, kern_local_ms / a.steps, pi_step]
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine_stats)
 
     cpu = None
+    dropin = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         pick = stratified_sample(sizes, a.cpu_budget)
         v, info = time_reference(cat, pick, 1, 0)
-        cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]}
+        cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"],
+               "centres_excluded_value": info.get("centres_excluded_value"),
+               "centres_seconds": info.get("centres_seconds")}
+    if rank == 0 and world == 1 and not a.no_dropin:
+        dropin = time_dropin(cat, pi_step)
 
     if rank == 0:
         peaks = {}
@@ -528,41 +673,76 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None
-        try:   # DRAM bytes of the two local-shape kernels from the committed ncu capture of this workload
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1d_traffic.json")))
-            if int(tr.get("workload_halos", -1)) == a.halos:
-                traffic = float(tr["dram_bytes_per_local_shape_launch_set"])
-        except Exception:
-            pass
-        achieved = pi_local_all / world * BYTES_PER_PI / (kern_ms * 1e-3) / 1e9   # per GPU, GB/s
+        traffic_src = None
+        for fn in ("r2_traffic.json", "r1d_traffic.json"):   # DRAM bytes of the local-shape kernels under ncu, same workload
+            try:
+                tr = json.load(open(os.path.join(ROOT, "profiles", fn)))
+                if int(tr.get("workload_halos", -1)) == a.halos and world == 1:
+                    traffic = float(tr["dram_bytes_per_local_shape_launch_set"])
+                    traffic_src = "profiles/%s (ncu --set full, same workload)" % fn
+                    break
+            except Exception:
+                pass
+        kern_mean = kern_sum / world
+        algorithmic_gbs = pi_local_all / world * BYTES_PER_PI / (kern_ms * 1e-3) / 1e9   # per GPU
+        achieved_tflops = 2.0 * fma_all / world / (kern_mean * 1e-3) / 1e12               # per GPU, 2 flop per FMA
+        peak_tflops = 2.0 * fp64_peak
         line = {"metric": METRIC, "value": pi_all / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
-                "warmup": a.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
+                "warmup": a.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": a.scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "halo_shells_per_s": world * a.halos * 71 / (step_ms * 1e-3),
+                "halo_shells_per_s": n_global * 71 / (step_ms * 1e-3),
                 "wall_ms_per_step": wall_step_ms,
                 "e2e": {"value": pi_all / (e2e_step_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d_all),
                         "d2h_bytes_per_step": int(d2h_all), "ms_per_step": e2e_step_ms, "mode": e2e_mode,
                         "serial_ms_per_step": e2e_serial_step_ms, "options": E2E_OPTIONS,
-                        "serial_value": pi_all / (e2e_serial_step_ms * 1e-3)},
+                        "serial_value": pi_all / (e2e_serial_step_ms * 1e-3),
+                        "catalogue_as_ranges": cat_ranges,
+                        "h2d_ceiling_GBps_all_ranks": h2d_gbs_all,
+                        "h2d_ceiling_ms_per_step": h2d_all / (h2d_gbs_all * 1e9) * 1e3 if h2d_gbs_all else None,
+                        "note": "h2d_ceiling: plain pinned host->device copies issued by all ranks at once on this box; "
+                                "e2e cannot be faster than h2d_bytes / that rate"},
+                "e2e_dropin": dropin,
                 "gpu_launches": int(launches_all),
-                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": traffic,
-                             "traffic_source": "profiles/r1d_traffic.json (ncu --set full, same workload)" if traffic else None,
+                "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+                             "frac": achieved_tflops / peak_tflops if peak_tflops else None, "traffic": traffic,
+                             "traffic_source": traffic_src,
                              "kernel": "morph_warp_kernel/morph_cluster_kernel (local shapes)",
-                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                             "algorithmic_bytes_per_launch_set": pi_local_all / world * BYTES_PER_PI,
-                             "kernel_ms": kern_ms, "frac_of_8TBps_nominal": achieved / 8000.0,
-                             "streamed_particle_iterations": visited_all / world,
-                             "streamed_GBps": visited_all / world * BYTES_PER_PI / (kern_ms * 1e-3) / 1e9,
-                             "note": "achieved = algorithmic bytes (32 B x particle-iterations, the reference's unit of work) / "
-                                     "kernel time, as the contract defines it; frac > 1 because the radial ordering and the prefix "
-                                     "tensor table let a Katz iteration skip most of an object's particles (streamed_GBps: the "
-                                     "bytes really passed over; traffic: DRAM bytes under ncu).  The kernels are FP64-issue bound "
-                                     "(45 % of the FP64 pipe, profiles/r1d_ncu_morph_kernels.txt), not HBM bound."},
+                             "peak_source": "measured in this run: cpg_measure_fp64_peak (independent DFMA chains on every SM, "
+                                            "CUDA events), x2 flop per multiply-add (of measured)",
+                             "fp64_fma_per_launch_set": fma_all / world,
+                             "kernel_ms": kern_ms, "kernel_ms_mean_over_ranks": kern_mean,
+                             "hbm": {"peak_GBps": hbm_peak,
+                                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                                     "physical_GBps": traffic / (kern_ms * 1e-3) / 1e9 if traffic else None,
+                                     "physical_frac": traffic / (kern_ms * 1e-3) / 1e9 / hbm_peak if traffic else None,
+                                     "algorithmic_bytes_per_launch_set": pi_local_all / world * BYTES_PER_PI,
+                                     "algorithmic_GBps": algorithmic_gbs,
+                                     "algorithmic_frac": algorithmic_gbs / hbm_peak,
+                                     "streamed_particle_iterations": visited_all / world,
+                                     "streamed_GBps": visited_all / world * BYTES_PER_PI / (kern_ms * 1e-3) / 1e9},
+                             "note": "The morphology loop is bound by the fp64 pipe, not by HBM: achieved = fp64 multiply-adds the "
+                                     "kernels issue for particle products and tensor updates (their own tile counters: 128 particles "
+                                     "x 6 per tile + 128 x 6 per (tile, shell); membership tests run in fp32, eigen-solves not counted) "
+                                     "/ CUDA-event kernel time, against the fp64 FMA rate measured on this GPU in this run.  hbm.physical "
+                                     "= DRAM bytes under ncu / kernel time; hbm.algorithmic = 32 B x particle-iterations (the contract's "
+                                     "SURVEY 8(d) figure), > peak because the radial ordering and the prefix tensor table let an "
+                                     "iteration skip most of an object's particles."},
                 "cpu_baseline": cpu, "clocks": clk, "breakdown_ms_per_step_rank0": {k_: round(v_, 3) for k_, v_ in brk.items()},
-                "particle_iterations_per_step": pi_all, "particles_per_gpu": n_part}
+                "particle_iterations_per_step": pi_all, "particles_total": int(npart_all)}
+        if world > 1:
+            steps_r = [r[3] for r in per_rank]
+            kerns_r = [r[4] for r in per_rank]
+            line["multi_gpu"] = {"partition": "LPT on particle counts (cpg_partition_lpt), one catalogue of %d objects" % n_global,
+                                 "partition_ms": part_ms, "host_gather_ms": gather_ms,
+                                 "host_gather": "per-object results (n, 70, 12) of every rank gathered to rank 0 over NCCL and "
+                                                "scattered into catalogue order on the host; once, outside the timed steps",
+                                 "per_rank": [{"rank": r[0], "objects": r[1], "particles": r[2], "ms_per_step": r[3],
+                                               "local_kernel_ms": r[4], "particle_iterations": r[5]} for r in per_rank],
+                                 "imbalance_step_max_over_mean": max(steps_r) / (sum(steps_r) / world),
+                                 "imbalance_kernel_max_over_mean": max(kerns_r) / (sum(kerns_r) / world),
+                                 "imbalance_particles_max_over_mean": max(r[2] for r in per_rank) / (npart_all / world)}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

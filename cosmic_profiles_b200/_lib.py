@@ -2,6 +2,7 @@
 missing CUDA device raises, loudly."""
 import ctypes
 import os
+import threading
 
 import numpy as np
 
@@ -20,7 +21,8 @@ class CosmicGpuError(RuntimeError):
 class Timing(ctypes.Structure):
     _fields_ = [("h2d_ms", ctypes.c_double), ("gather_ms", ctypes.c_double), ("kernel_ms", ctypes.c_double),
                 ("d2h_ms", ctypes.c_double), ("kernel_launches", ctypes.c_int32),
-                ("hot_kernel_launches", ctypes.c_int32), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64)]
+                ("hot_kernel_launches", ctypes.c_int32), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64),
+                ("tile_visits", ctypes.c_int64), ("tile_shell_visits", ctypes.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -29,7 +31,13 @@ class Timing(ctypes.Structure):
 EXPORTS = ["cpg_device_count", "cpg_last_error", "cpg_version", "cpg_create", "cpg_destroy", "cpg_set_particles",
            "cpg_set_catalogue", "cpg_shape", "cpg_dens_sph", "cpg_dens_ell", "cpg_dens_kernel", "cpg_obj_masses",
            "cpg_get_timing", "cpg_set_option", "cpg_host_alloc", "cpg_host_free", "cpg_get_prefix_lengths", "cpg_centers",
-           "cpg_obj_cat", "cpg_obj_cat_fetch", "cpg_use_obj_cat", "cpg_set_particles_gadget", "cpg_get_particles", "cpg_fit_profiles", "cpg_shape_interp"]
+           "cpg_obj_cat", "cpg_obj_cat_fetch", "cpg_use_obj_cat", "cpg_set_particles_gadget", "cpg_get_particles", "cpg_fit_profiles", "cpg_shape_interp",
+           "cpg_set_particles_segments", "cpg_set_catalogue_ranges", "cpg_catalogue_ranges", "cpg_host_token",
+           "cpg_measure_fp64_peak", "cpg_partition_lpt", "cpg_multi_create", "cpg_multi_destroy", "cpg_multi_devices",
+           "cpg_multi_context", "cpg_multi_set_option", "cpg_multi_set_snapshot", "cpg_multi_shard", "cpg_multi_shape",
+           "cpg_multi_get_info", "cpg_get_stat"]
+_I64 = ctypes.POINTER(ctypes.c_int64)
+_NO_INT_RESTYPE = ("cpg_last_error", "cpg_version", "cpg_destroy", "cpg_host_free", "cpg_multi_destroy", "cpg_multi_context")
 
 
 def load():
@@ -76,8 +84,28 @@ def load():
                                    _D]
     L.cpg_fit_profiles.argtypes = [vp, _D, _D, _I, _D, _D, _D, _D, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                    ctypes.c_double, ctypes.c_double, _D, _D, _I, _I]
+    L.cpg_set_particles_segments.argtypes = [vp, _D, _D, _D, _I64, _I64, ctypes.c_int64]
+    L.cpg_set_catalogue_ranges.argtypes = [vp, _I64, _I, ctypes.c_int32]
+    L.cpg_catalogue_ranges.argtypes = [_I, ctypes.c_int64, _I, ctypes.c_int32, _I64]
+    L.cpg_host_token.argtypes = [vp, ctypes.c_size_t, ctypes.c_int32, ctypes.POINTER(ctypes.c_uint64)]
+    L.cpg_measure_fp64_peak.argtypes = [vp, _D]
+    L.cpg_partition_lpt.argtypes = [_D, ctypes.c_int32, ctypes.c_int32, _I]
+    L.cpg_multi_create.argtypes = [_I, ctypes.c_int32, ctypes.POINTER(vp)]
+    L.cpg_multi_destroy.argtypes = [vp]
+    L.cpg_multi_destroy.restype = None
+    L.cpg_multi_devices.argtypes = [vp]
+    L.cpg_multi_context.argtypes = [vp, ctypes.c_int32]
+    L.cpg_multi_context.restype = vp
+    L.cpg_multi_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_int64]
+    L.cpg_multi_set_snapshot.argtypes = [vp, _D, _D, _D, ctypes.c_int64, _I, ctypes.c_int64, _I, ctypes.c_int32]
+    L.cpg_multi_shard.argtypes = [vp, ctypes.c_int32, _I, _I64, _I]
+    L.cpg_multi_shape.argtypes = [vp, _D, ctypes.c_int32, _D, _D, _D, ctypes.c_int32, ctypes.c_int32, ctypes.c_double,
+                                  ctypes.c_float, ctypes.c_double, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                  ctypes.c_int32, ctypes.c_int32, _D, _I, _I, _D, _D, _D]
+    L.cpg_get_stat.argtypes = [vp, ctypes.c_char_p, _I64]
+    L.cpg_multi_get_info.argtypes = [vp, ctypes.c_int32, _I, _I, _I64, ctypes.POINTER(Timing), _D]
     for f in EXPORTS:
-        if f not in ("cpg_last_error", "cpg_version", "cpg_destroy", "cpg_host_free"):
+        if f not in _NO_INT_RESTYPE:
             getattr(L, f).restype = ctypes.c_int
     _lib = L
     return L
@@ -108,6 +136,33 @@ def i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
+def partition_lpt(cost, n_parts):
+    """owner[h] = part of object h (cpg_partition_lpt: greedy longest-processing-time on `cost`)."""
+    cost = f64(np.asarray(cost))
+    owner = np.zeros(cost.shape[0], dtype=np.int32)
+    _check(load().cpg_partition_lpt(_dp(cost), cost.shape[0], int(n_parts), _ip(owner)), "cpg_partition_lpt")
+    return owner
+
+
+def catalogue_ranges(idx_cat, obj_size):
+    """(contiguous?, obj_start int64 (n_obj,)): whether every object of the flat catalogue is a contiguous ascending
+    run of snapshot indices (cpg_catalogue_ranges)."""
+    idx_cat, obj_size = i32(np.asarray(idx_cat)), i32(np.asarray(obj_size))
+    start = np.zeros(obj_size.shape[0], dtype=np.int64)
+    rc = load().cpg_catalogue_ranges(_ip(idx_cat), idx_cat.shape[0], _ip(obj_size), obj_size.shape[0],
+                                     start.ctypes.data_as(_I64))
+    if rc < 0:
+        _check(rc, "cpg_catalogue_ranges")
+    return bool(rc), start
+
+
+def host_token(a, full=False):
+    a = np.ascontiguousarray(a)
+    tok = ctypes.c_uint64()
+    _check(load().cpg_host_token(ctypes.c_void_p(a.ctypes.data), a.nbytes, int(bool(full)), ctypes.byref(tok)), "cpg_host_token")
+    return int(tok.value)
+
+
 class PinnedBuffer:
     """Grow-only page-locked host scratch (cpg_host_alloc) handed out as numpy views."""
 
@@ -133,20 +188,27 @@ class PinnedBuffer:
 
 
 class Context:
-    """One CUDA device with a resident snapshot + catalogue (cpg_ctx)."""
+    """One CUDA device with a resident snapshot + catalogue (cpg_ctx).  One caller at a time: `lock` is held by the
+    drop-in drivers for a whole set-snapshot -> compute -> copy-out sequence."""
 
-    def __init__(self, device=0):
-        self._h = ctypes.c_void_p()
+    def __init__(self, device=0, _borrowed=None):
         self._L = load()
-        _check(self._L.cpg_create(int(device), ctypes.byref(self._h)), "cpg_create")
+        self._owned = _borrowed is None
+        if _borrowed is None:
+            self._h = ctypes.c_void_p()
+            _check(self._L.cpg_create(int(device), ctypes.byref(self._h)), "cpg_create")
+        else:   # a slot of a cpg_multi handle, destroyed with it
+            self._h = ctypes.c_void_p(_borrowed)
         self.device = int(device)
         self.n_obj = 0
         self.have_vel = False
+        self.lock = threading.RLock()
         self._pin = [PinnedBuffer() for _ in range(3)]
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
-            self._L.cpg_destroy(self._h)
+            if self._owned:
+                self._L.cpg_destroy(self._h)   # drains the context's streams before anything is freed
             self._h = ctypes.c_void_p()
             for b in self._pin:
                 b.release()
@@ -178,8 +240,47 @@ class Context:
                "cpg_set_catalogue")
         self.n_obj = int(obj_size.shape[0])
 
+    def set_catalogue_ranges(self, obj_start, obj_size):
+        """Objects as contiguous snapshot ranges [obj_start[h], obj_start[h] + obj_size[h]): no flat index array."""
+        obj_start = np.ascontiguousarray(obj_start, dtype=np.int64)
+        obj_size = i32(obj_size)
+        if obj_start.shape != obj_size.shape:
+            raise ValueError("obj_start and obj_size must have the same length")
+        _check(self._L.cpg_set_catalogue_ranges(self._h, obj_start.ctypes.data_as(_I64), _ip(obj_size),
+                                                obj_size.shape[0]), "cpg_set_catalogue_ranges")
+        self.n_obj = int(obj_size.shape[0])
+
+    def set_particles_segments(self, xyz, vxyz, masses, seg_start, seg_len):
+        """Snapshot := concatenation of the particle ranges [seg_start[i], seg_start[i] + seg_len[i]) of the host arrays."""
+        xyz, masses = f64(xyz), f64(masses)
+        vxyz = None if vxyz is None else f64(vxyz)
+        seg_start = np.ascontiguousarray(seg_start, dtype=np.int64)
+        seg_len = np.ascontiguousarray(seg_len, dtype=np.int64)
+        if seg_start.shape != seg_len.shape or seg_start.ndim != 1:
+            raise ValueError("seg_start and seg_len must be 1-d arrays of the same length")
+        if len(seg_start) and (int((seg_start + seg_len).max()) > xyz.shape[0] or masses.shape[0] != xyz.shape[0]):
+            raise ValueError("a segment reaches past the end of the particle arrays")
+        _check(self._L.cpg_set_particles_segments(self._h, _dp(xyz), _dp(vxyz), _dp(masses), seg_start.ctypes.data_as(_I64),
+                                                  seg_len.ctypes.data_as(_I64), seg_start.shape[0]),
+               "cpg_set_particles_segments")
+        self.have_vel = vxyz is not None
+
+    def stat(self, name):
+        v = ctypes.c_int64()
+        _check(self._L.cpg_get_stat(self._h, name.encode(), ctypes.byref(v)), "cpg_get_stat")
+        return int(v.value)
+
+    def measure_fp64_peak(self):
+        """Measured fp64 multiply-add rate of the device in 1e12 FMA/s (cpg_measure_fp64_peak)."""
+        v = ctypes.c_double()
+        _check(self._L.cpg_measure_fp64_peak(self._h, ctypes.byref(v)), "cpg_measure_fp64_peak")
+        return float(v.value)
+
     def shape(self, centers, r200, r_over_r200, local, SAFE, L_BOX, IT_TOL, IT_WALL, IT_MIN, reduced, shell_based,
-              use_vel):
+              use_vel, zero_copy=False):
+        """Returns (out12, n_iter, n_pts, obj_mass, vcenters) as fresh arrays.  zero_copy=True returns out12 / n_iter /
+        n_pts as views of the context's page-locked result scratch instead: valid only until the next shape() call
+        on this context or its close() (bench.py uses that to keep the copy out of its timed region)."""
         n = self.n_obj
         centers = f64(centers)
         r200 = f64(r200)
@@ -196,6 +297,8 @@ class Context:
                                  float(L_BOX), float(IT_TOL), int(IT_WALL), int(IT_MIN), int(bool(reduced)),
                                  int(bool(shell_based)), int(bool(use_vel)), _dp(out), _ip(nit), _ip(npt), _dp(m),
                                  _dp(vc)), "cpg_shape")
+        if not zero_copy:
+            out, nit, npt = out.copy(), nit.copy(), npt.copy()
         return out, nit, npt, m, vc
 
     def dens_sph(self, centers, r200, bin_edges, L_BOX):
@@ -333,3 +436,161 @@ class Context:
         t = Timing()
         _check(self._L.cpg_get_timing(self._h, ctypes.byref(t)), "cpg_get_timing")
         return t.as_dict()
+
+
+
+class MultiContext:
+    """Several devices behind one handle (cpg_multi): the objects of ONE catalogue are dealt to the devices by a
+    particle-count-balanced LPT partition; every device receives only its own objects' particles."""
+
+    def __init__(self, devices):
+        devices = [int(d) for d in devices]
+        self._L = load()
+        self._h = ctypes.c_void_p()
+        arr = np.asarray(devices, dtype=np.int32)
+        _check(self._L.cpg_multi_create(_ip(arr), len(devices), ctypes.byref(self._h)), "cpg_multi_create")
+        self.devices = devices
+        self.contexts = [Context(d, _borrowed=self._L.cpg_multi_context(self._h, k)) for k, d in enumerate(devices)]
+        self.shards = [np.zeros(0, dtype=np.int32) for _ in devices]
+        self.n_obj = 0
+        self.lock = threading.RLock()
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            for c in self.contexts:
+                c.close()
+            self._L.cpg_multi_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name, value):
+        _check(self._L.cpg_multi_set_option(self._h, name.encode(), int(value)), "cpg_multi_set_option")
+
+    def set_snapshot(self, xyz, vxyz, masses, idx_cat, obj_size):
+        xyz, masses = f64(xyz), f64(masses)
+        vxyz = None if vxyz is None else f64(vxyz)
+        idx_cat, obj_size = i32(idx_cat), i32(obj_size)
+        if xyz.ndim != 2 or xyz.shape[1] != 3 or masses.shape[0] != xyz.shape[0]:
+            raise ValueError("xyz must be (N,3) and masses (N,)")
+        if vxyz is not None and vxyz.shape != xyz.shape:
+            raise ValueError("vxyz must match xyz")
+        _check(self._L.cpg_multi_set_snapshot(self._h, _dp(xyz), _dp(vxyz), _dp(masses), xyz.shape[0], _ip(idx_cat),
+                                              idx_cat.shape[0], _ip(obj_size), obj_size.shape[0]), "cpg_multi_set_snapshot")
+        self.n_obj = int(obj_size.shape[0])
+        for k, c in enumerate(self.contexts):
+            nd, npart = ctypes.c_int32(), ctypes.c_int64()
+            _check(self._L.cpg_multi_shard(self._h, k, ctypes.byref(nd), ctypes.byref(npart), None), "cpg_multi_shard")
+            objs = np.zeros(nd.value, dtype=np.int32)
+            _check(self._L.cpg_multi_shard(self._h, k, None, None, _ip(objs)), "cpg_multi_shard")
+            self.shards[k] = objs
+            c.n_obj = int(nd.value)
+            c.have_vel = vxyz is not None
+
+    def shape(self, centers, center_mode, ref_points, r200, r_over_r200, local, SAFE, L_BOX, IT_TOL, IT_WALL, IT_MIN,
+              reduced, shell_based, use_vel):
+        """cpg_multi_shape.  centers given (center_mode = -1) or computed per device (0 'com', 1 'mode').
+        Returns (out12, n_iter, n_pts, obj_mass, vcenters, centers)."""
+        n = self.n_obj
+        r200 = f64(r200)
+        rr = f64(r_over_r200) if local else None
+        R = int(rr.shape[0]) if local else 1
+        cen_in = None if centers is None else f64(centers)
+        ref = None if ref_points is None else f64(ref_points)
+        out = np.zeros((n, R, 12))
+        nit = np.full((n, R), -1, dtype=np.int32)
+        npt = np.full((n, R), -1, dtype=np.int32)
+        m = np.zeros(n)
+        vc = np.zeros((n, 3))
+        cen_out = np.zeros((n, 3))
+        _check(self._L.cpg_multi_shape(self._h, _dp(cen_in), int(center_mode), _dp(ref), _dp(r200), _dp(rr), R,
+                                       int(bool(local)), float(SAFE), float(L_BOX), float(IT_TOL), int(IT_WALL),
+                                       int(IT_MIN), int(bool(reduced)), int(bool(shell_based)), int(bool(use_vel)),
+                                       _dp(out), _ip(nit), _ip(npt), _dp(m), _dp(vc), _dp(cen_out)), "cpg_multi_shape")
+        return out, nit, npt, m, vc, (cen_in if center_mode < 0 else cen_out)
+
+    def info(self):
+        """Per slot: device, objects, resident particles, timing of its last call; plus the host-side times (ms)."""
+        per, host = [], None
+        for k in range(len(self.contexts)):
+            dev, nd, npart, t = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64(), Timing()
+            hm = np.zeros(4)
+            _check(self._L.cpg_multi_get_info(self._h, k, ctypes.byref(dev), ctypes.byref(nd), ctypes.byref(npart),
+                                              ctypes.byref(t), _dp(hm)), "cpg_multi_get_info")
+            per.append(dict(device=int(dev.value), n_obj=int(nd.value), n_part=int(npart.value), timing=t.as_dict()))
+            host = dict(partition_ms=float(hm[0]), upload_ms=float(hm[1]), scatter_ms=float(hm[2]), call_ms=float(hm[3]))
+        return dict(devices=per, host=host)
+
+
+class DeviceGroup:
+    """What the drop-in drivers talk to: one device (a Context) or several (a MultiContext) behind the same few
+    operations.  rows(fn) runs fn(ctx, objs) for every shard on its own host thread (objs = catalogue rows of the
+    shard, None for the single-device case = all rows in order) and scatters the per-shard result arrays into
+    catalogue order."""
+
+    def __init__(self, devices):
+        self.devices = [int(d) for d in devices]
+        self.multi = MultiContext(self.devices) if len(self.devices) > 1 else None
+        self.single = Context(self.devices[0]) if self.multi is None else None
+        self.lock = self.multi.lock if self.multi else self.single.lock
+        self.n_obj = 0
+
+    @property
+    def contexts(self):
+        return self.multi.contexts if self.multi else [self.single]
+
+    def close(self):
+        (self.multi or self.single).close()
+
+    def set_option(self, name, value):
+        (self.multi or self.single).set_option(name, value)
+
+    def set_snapshot(self, xyz, vxyz, masses, idx_cat, obj_size):
+        if self.multi:
+            self.multi.set_snapshot(xyz, vxyz, masses, idx_cat, obj_size)
+        else:
+            self.single.set_particles(xyz, vxyz, masses)
+            self.single.set_catalogue(idx_cat, obj_size)
+        self.n_obj = int(np.asarray(obj_size).shape[0])
+
+    def shards(self):
+        if self.multi:
+            return [(c, o) for c, o in zip(self.multi.contexts, self.multi.shards) if len(o)]
+        return [(self.single, None)]
+
+    def rows(self, fn):
+        """fn(ctx, objs) -> array or tuple of arrays whose first axis runs over the shard's objects."""
+        shards = self.shards()
+        if len(shards) == 1 and shards[0][1] is None:
+            return fn(self.single, None)
+        res, errs = [None] * len(shards), []
+
+        def work(k):
+            try:
+                res[k] = fn(*shards[k])
+            except Exception as e:   # re-raised in the caller's thread
+                errs.append(e)
+        th = [threading.Thread(target=work, args=(k,)) for k in range(len(shards))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+        first = res[0]
+        many = isinstance(first, tuple)
+        outs = []
+        for j in range(len(first) if many else 1):
+            a0 = first[j] if many else first
+            full = np.zeros((self.n_obj,) + a0.shape[1:], dtype=a0.dtype)
+            for (ctx, objs), r in zip(shards, res):
+                full[objs] = r[j] if many else r
+            outs.append(full)
+        return tuple(outs) if many else outs[0]
+
+    def timings(self):
+        return [c.timing() for c, _ in self.shards()]

@@ -7,7 +7,9 @@
 #include <stdarg.h>
 
 #include <algorithm>
+#include <climits>
 #include <atomic>
+#include <chrono>
 #include <new>
 #include <numeric>
 #include <thread>
@@ -95,9 +97,34 @@ struct cpg_ctx {
     DevBuf<double> xyz, vxyz, masses;
     int64_t n_part = 0;
     bool have_vel = false;
-    // catalogue
+    // catalogue: flat int32 index array, or (cat_ranges) one contiguous snapshot range per object and no index array
     DevBuf<int32_t> idx, size;
-    DevBuf<int64_t> off, poff;
+    DevBuf<int64_t> off, poff, start;
+    bool cat_ranges = false;
+    int64_t cat_max_idx = -1;     // largest snapshot index the catalogue refers to
+    bool cat_stale = false;       // a later, smaller snapshot no longer covers the catalogue: compute calls refuse
+    // what the device currently holds, as seen from the host (cpg_set_particles / cpg_set_catalogue skip the upload
+    // when asked for the same thing again: the reference's class passes the same arrays to every driver,
+    // common/cosmic_base_class.pyx:155,232,863)
+    int opt_snapshot_cache = 1;   // 0 off, 1 pointer + length + sampled content token, 2 pointer + length + full hash
+    int opt_detect_ranges = 1;    // cpg_set_catalogue: recognise contiguous-range catalogues, keep no index array
+    struct {
+        bool valid = false;
+        const void *xyz = nullptr, *vxyz = nullptr, *masses = nullptr;
+        int64_t n = 0;
+        int mode = 0;
+        uint64_t tok[3] = {0, 0, 0};
+    } snap_key;
+    struct {
+        bool valid = false, ranges = false;
+        int64_t n_idx = 0;
+        uint64_t hash = 0;
+        std::vector<int64_t> start;
+        std::vector<int32_t> size;
+    } cat_key;
+    uint64_t uploads_skipped = 0;
+    DevBuf<unsigned long long> morph_stats;   // [0] tiles, [1] tile-shells visited by the morphology kernels of a call
+    DevBuf<double> peak_scratch;
     int64_t n_idx = 0, n_pad = 0;
     int32_t n_obj = 0;
     std::vector<int32_t> h_size;
@@ -185,27 +212,44 @@ int use_device(cpg_ctx *c)
     return CPG_OK;
 }
 
+// Entry check of every compute call: device current, catalogue still covered by the snapshot.
+int compute_ready(cpg_ctx *c)
+{
+    CPG_TRY(use_device(c));
+    if (c->cat_stale) {
+        set_error("the catalogue indexes particles up to %lld but the snapshot uploaded after it has only %lld: "
+                  "call cpg_set_catalogue again", (long long)c->cat_max_idx, (long long)c->n_part);
+        return CPG_ERR_STATE;
+    }
+    return CPG_OK;
+}
+
 // Large host->device transfers are issued in pieces: the copy engine serves streams copy by copy, so a small
 // upload of another context (centres, radii) is not stuck behind a multi-GB transfer for tens of ms.
 // Pageable source: cudaMemcpyAsync bounces every piece through the driver's staging buffer from the calling thread
 // alone (12 GB/s on the 16-core host measured here, a fifth of the PCIe rate).  Here up to UP_THREADS host threads
 // each own two page-locked bounce buffers and a stream: thread t copies pieces t, t + T, ... into its buffers and queues
 // their host->device copies, so that the host-side memcpy of one piece overlaps the PCIe transfer of others.
+int ensure_upload_buffers(cpg_ctx *c)
+{
+    if (c->up_ready) return CPG_OK;
+    for (int t = 0; t < cpg_ctx::UP_THREADS; t++) {
+        CPG_CUDA(cudaStreamCreateWithFlags(&c->up_stream[t], cudaStreamNonBlocking));
+        for (int b = 0; b < cpg_ctx::UP_BUFS; b++) {
+            CPG_CUDA(cudaHostAlloc((void **)&c->up_buf[t][b], cpg_ctx::UP_PIECE, cudaHostAllocDefault));
+            CPG_CUDA(cudaEventCreateWithFlags(&c->up_ev[t][b], cudaEventDisableTiming));
+        }
+    }
+    c->up_ready = true;
+    return CPG_OK;
+}
+
 int upload_pageable(cpg_ctx *c, void *dst, const void *src, size_t bytes)
 {
     constexpr int NB = cpg_ctx::UP_BUFS;
     const int T = std::min(c->opt_upload_threads, (int)cpg_ctx::UP_THREADS);
     const size_t piece = cpg_ctx::UP_PIECE;
-    if (!c->up_ready) {
-        for (int t = 0; t < cpg_ctx::UP_THREADS; t++) {
-            CPG_CUDA(cudaStreamCreateWithFlags(&c->up_stream[t], cudaStreamNonBlocking));
-            for (int b = 0; b < NB; b++) {
-                CPG_CUDA(cudaHostAlloc((void **)&c->up_buf[t][b], piece, cudaHostAllocDefault));
-                CPG_CUDA(cudaEventCreateWithFlags(&c->up_ev[t][b], cudaEventDisableTiming));
-            }
-        }
-        c->up_ready = true;
-    }
+    CPG_TRY(ensure_upload_buffers(c));
     const size_t n_pieces = (bytes + piece - 1) / piece;
     std::atomic<int> failed{0};
     auto work = [&](int t) {
@@ -256,6 +300,187 @@ int upload_chunked(cpg_ctx *c, void *dst, const void *src, size_t bytes, cudaStr
     for (size_t o = 0; o < bytes; o += piece) {
         const size_t nb = std::min(piece, bytes - o);
         CPG_CUDA(cudaMemcpyAsync((char *)dst + o, (const char *)src + o, nb, cudaMemcpyHostToDevice, stream));
+    }
+    return CPG_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Host-side helpers of the snapshot / catalogue cache and of the sharded uploads.
+// ---------------------------------------------------------------------------------------------------
+inline uint64_t mix64(uint64_t h, uint64_t w)
+{
+    h ^= w;
+    h *= 0x9E3779B97F4A7C15ull;
+    return h ^ (h >> 29);
+}
+
+uint64_t hash_bytes(const unsigned char *p, size_t n, uint64_t seed)
+{
+    // four independent lanes (the multiply chain is the bottleneck of one), folded at the end
+    uint64_t h0 = seed, h1 = seed ^ 0x1111111111111111ull, h2 = seed ^ 0x2222222222222222ull, h3 = seed ^ 0x3333333333333333ull;
+    size_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        uint64_t w[4];
+        memcpy(w, p + i, 32);
+        h0 = mix64(h0, w[0]); h1 = mix64(h1, w[1]); h2 = mix64(h2, w[2]); h3 = mix64(h3, w[3]);
+    }
+    uint64_t tail = 0;
+    if (i < n) {
+        unsigned char t[32] = {0};
+        memcpy(t, p + i, n - i);
+        uint64_t w[4];
+        memcpy(w, t, 32);
+        h0 = mix64(h0, w[0]); h1 = mix64(h1, w[1]); h2 = mix64(h2, w[2]); h3 = mix64(h3, w[3]);
+        tail = n - i;
+    }
+    return mix64(mix64(mix64(mix64(h0, h1), h2), h3), (uint64_t)n ^ (tail << 56));
+}
+
+int host_threads(size_t bytes)
+{
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t want = bytes / ((size_t)16 << 20) + 1;   // one thread per 16 MB
+    return (int)std::min<size_t>(std::min<size_t>(want, 8), hw);
+}
+
+// Content token of a host array.  full: hash of every byte (multi-threaded); else: the first and last 4 KB and 4096
+// evenly spaced 64-byte blocks -- enough to notice a rescaled, recentred, re-read or reordered snapshot, not a
+// deliberate edit of a few particles in place (callers that do that use snapshot_cache = 2 or 0).
+uint64_t host_token(const void *ptr, size_t bytes, bool full)
+{
+    const unsigned char *p = (const unsigned char *)ptr;
+    if (!p || bytes == 0) return 0x5eedull;
+    if (!full) {
+        uint64_t h = hash_bytes(p, std::min<size_t>(bytes, 4096), 1);
+        if (bytes > 4096) h = mix64(h, hash_bytes(p + bytes - 4096, 4096, 2));
+        if (bytes > 8192) {
+            const size_t nblk = 4096, span = bytes - 64;
+            for (size_t k = 0; k < nblk; k++) h = mix64(h, hash_bytes(p + (size_t)((double)span * (double)k / (double)nblk), 64, 3));
+        }
+        return h;
+    }
+    const int T = host_threads(bytes);
+    std::vector<uint64_t> part(T, 0);
+    auto work = [&](int t) {
+        const size_t a = bytes * (size_t)t / T, b = bytes * (size_t)(t + 1) / T;
+        part[t] = hash_bytes(p + a, b - a, 7 + t);
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    uint64_t h = 11;
+    for (int t = 0; t < T; t++) h = mix64(h, part[t]);
+    return h;
+}
+
+// One pass over a flat index catalogue: is every object a contiguous ascending run of snapshot indices (the FoF /
+// SUBFIND layout, gadget/gen_catalogues.pyx:29-35)?  Also the largest / smallest index and a hash of all entries.
+struct CatScan {
+    bool contiguous = true;
+    int64_t min_idx = INT64_MAX, max_idx = -1;
+    uint64_t hash = 0;
+    std::vector<int64_t> start;   // first snapshot index of every object (objects of size 0: 0)
+};
+
+void scan_catalogue(const int32_t *idx, const int64_t *off, int32_t n_obj, CatScan &out)
+{
+    const int64_t n_idx = off[n_obj];
+    out.start.assign((size_t)n_obj, 0);
+    const int T = host_threads((size_t)n_idx * 4);
+    std::vector<CatScan> part(T);
+    auto work = [&](int t) {
+        CatScan &r = part[t];
+        // objects [h0, h1): split by entries
+        const int64_t e0 = n_idx * t / T, e1 = n_idx * (t + 1) / T;
+        int h0 = (int)(std::upper_bound(off, off + n_obj + 1, e0) - off) - 1;
+        int h1 = (t == T - 1) ? n_obj : (int)(std::upper_bound(off, off + n_obj + 1, e1) - off) - 1;
+        if (t == 0) h0 = 0;
+        h0 = std::max(h0, 0);
+        uint64_t h = 17 + (uint64_t)t;
+        for (int o = h0; o < h1; o++) {
+            const int64_t a = off[o], b = off[o + 1];
+            if (b == a) continue;
+            const int32_t *q = idx + a;
+            const int64_t first = q[0], n = b - a;
+            out.start[o] = first;
+            bool run = true;
+            int32_t lo = q[0], hi = q[0];
+            uint64_t hh = 0;
+            for (int64_t i = 0; i < n; i++) {
+                const int32_t v = q[i];
+                run &= (v == (int32_t)(first + i));
+                lo = std::min(lo, v); hi = std::max(hi, v);
+                hh = hh * 0x100000001B3ull + (uint32_t)v;
+            }
+            if (first + n - 1 > 0x7fffffffLL) run = false;
+            r.contiguous &= run;
+            r.min_idx = std::min<int64_t>(r.min_idx, lo);
+            r.max_idx = std::max<int64_t>(r.max_idx, hi);
+            h = mix64(h, hh ^ (uint64_t)n);
+        }
+        r.hash = h;
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    uint64_t h = 23;
+    for (auto &r : part) {
+        out.contiguous &= r.contiguous;
+        out.min_idx = std::min(out.min_idx, r.min_idx);
+        out.max_idx = std::max(out.max_idx, r.max_idx);
+        h = mix64(h, r.hash);
+    }
+    out.hash = h;
+}
+
+// Upload the concatenation of the element ranges [seg_start[i], seg_start[i] + seg_len[i]) of a host array (elements of
+// `esz` bytes) to dst.  Always staged through the page-locked bounce buffers by the upload threads (the packing of
+// the segments is a host memcpy either way); prefix[i] = elements before segment i, prefix[n_seg] = total.
+int upload_segments(cpg_ctx *c, void *dst, const void *src, size_t esz, const int64_t *seg_start, const int64_t *seg_len,
+                    int64_t n_seg, const std::vector<int64_t> &prefix)
+{
+    const size_t bytes = (size_t)prefix[n_seg] * esz;
+    if (bytes == 0) return CPG_OK;
+    CPG_TRY(ensure_upload_buffers(c));
+    constexpr int NB = cpg_ctx::UP_BUFS;
+    const int T = std::max(1, std::min(c->opt_upload_threads > 0 ? c->opt_upload_threads : 4, (int)cpg_ctx::UP_THREADS));
+    const size_t piece = cpg_ctx::UP_PIECE;
+    const size_t n_pieces = (bytes + piece - 1) / piece;
+    std::atomic<int> failed{0};
+    auto work = [&](int t) {
+        if (cudaSetDevice(c->device) != cudaSuccess) { failed = 1; return; }
+        int turn = 0;
+        for (size_t i = (size_t)t; i < n_pieces && !failed; i += T, turn++) {
+            const int b = turn % NB;
+            const size_t o = i * piece, nb = std::min(piece, bytes - o);
+            if (turn >= NB && cudaEventSynchronize(c->up_ev[t][b]) != cudaSuccess) { failed = 1; return; }
+            // pack [o, o + nb) of the concatenated stream
+            size_t done = 0;
+            int64_t sg = (int64_t)(std::upper_bound(prefix.begin(), prefix.end(), (int64_t)(o / esz)) - prefix.begin()) - 1;
+            while (done < nb) {
+                const size_t so = (size_t)prefix[sg] * esz, sl = (size_t)seg_len[sg] * esz;
+                const size_t within = (o + done) - so;
+                const size_t take = std::min(nb - done, sl - within);
+                if (take) memcpy(c->up_buf[t][b] + done, (const char *)src + (size_t)seg_start[sg] * esz + within, take);
+                done += take;
+                if (within + take == sl) sg++;
+            }
+            if (cudaMemcpyAsync((char *)dst + o, c->up_buf[t][b], nb, cudaMemcpyHostToDevice, c->up_stream[t]) != cudaSuccess ||
+                cudaEventRecord(c->up_ev[t][b], c->up_stream[t]) != cudaSuccess) { failed = 1; return; }
+        }
+        if (cudaStreamSynchronize(c->up_stream[t]) != cudaSuccess) failed = 1;
+    };
+    std::vector<std::thread> th;
+    const int nt = (int)std::min<size_t>((size_t)T, n_pieces);
+    for (int t = 1; t < nt; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    if (failed) {
+        set_error("upload_segments: a CUDA call failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return CPG_ERR_CUDA;
     }
     return CPG_OK;
 }
@@ -315,7 +540,7 @@ GatherParams gather_view(cpg_ctx *c, float L_BOX)
 {
     GatherParams G;
     G.xyz = c->xyz.p; G.vxyz = c->vxyz.p; G.masses = c->masses.p;
-    G.idx = c->idx.p; G.off = c->off.p; G.poff = c->poff.p;
+    G.idx = c->cat_ranges ? nullptr : c->idx.p; G.start = c->start.p; G.off = c->off.p; G.poff = c->poff.p;
     G.centers = c->centers.p; G.vcenters = c->vcenters.p;
     G.n_obj = c->n_obj; G.n_idx = c->n_idx; G.L_BOX = L_BOX;
     G.dx = c->g_dx.p; G.dy = c->g_dy.p; G.dz = c->g_dz.p; G.m = c->g_m.p;
@@ -344,8 +569,9 @@ __global__ void idx_range_kernel(const int32_t *idx, int64_t n, int32_t *minmax)
 // Result arrays of cpg_shape: out12 zeros (what the reference returns for a failed halo-shell), counters -1
 // (= the per-object early exit), work-queue heads 0.
 __global__ void init_results_kernel(double2 *__restrict__ out12, int32_t *__restrict__ n_iter, int32_t *__restrict__ n_pts,
-                                    int32_t *__restrict__ counters, int64_t nR)
+                                    int32_t *__restrict__ counters, unsigned long long *__restrict__ stats, int64_t nR)
 {
+    if (blockIdx.x == 0 && threadIdx.x < 2) stats[threadIdx.x] = 0ull;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (int64_t i = i0; i < nR * 6; i += stride) out12[i] = make_double2(0.0, 0.0);
@@ -627,6 +853,25 @@ int dispatch_grid(cpg_ctx *c, const MorphParams &P, bool shell, bool reduced, bo
     return CPG_ERR_ARGUMENT;
 }
 
+int init_context(cpg_ctx *c)
+{
+    CPG_CUDA(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CPG_CUDA(cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major < 9) {
+        set_error("cpg_create: device %d is sm_%d%d; this build targets sm_100a (thread-block clusters required)",
+                  c->device, prop.major, prop.minor);
+        return CPG_ERR_NO_DEVICE;
+    }
+    c->sm_count = prop.multiProcessorCount;
+    CPG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CPG_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    for (auto &e : c->ev) CPG_CUDA(cudaEventCreate(&e));
+    CPG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CPG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    return CPG_OK;
+}
+
 int pow2_floor(int64_t v)
 {
     int p = 1;
@@ -669,21 +914,11 @@ CPG_API int cpg_create(int device, cpg_ctx **out)
     cpg_ctx *c = new (std::nothrow) cpg_ctx();
     if (!c) return CPG_ERR_NOMEM;
     c->device = device;
-    CPG_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CPG_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 9) {
-        set_error("cpg_create: device %d is sm_%d%d; this build targets sm_100a (thread-block clusters required)",
-                  device, prop.major, prop.minor);
-        delete c;
-        return CPG_ERR_NO_DEVICE;
+    const int rc = init_context(c);
+    if (rc != CPG_OK) {   // release whatever was created (streams, events) together with the context
+        cpg_destroy(c);
+        return rc;
     }
-    c->sm_count = prop.multiProcessorCount;
-    CPG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CPG_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-    for (auto &e : c->ev) CPG_CUDA(cudaEventCreate(&e));
-    CPG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    CPG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     *out = c;
     return CPG_OK;
 }
@@ -692,7 +927,12 @@ CPG_API void cpg_destroy(cpg_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    // kernels of a failed call may still be storing into page-locked caller memory: drain every stream first
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
+    for (auto &us : c->up_stream)
+        if (us) cudaStreamSynchronize(us);
+    (void)cudaGetLastError();
     DevBuf<double> *dbl[] = {&c->xyz, &c->vxyz, &c->masses, &c->g_dx, &c->g_dy, &c->g_dz, &c->g_m, &c->g_vx, &c->g_vy,
                              &c->g_vz, &c->centers, &c->vcenters, &c->r200, &c->rr, &c->obj_mass, &c->part_mass,
                              &c->vpart, &c->part_mm, &c->obj_eqm, &c->out12, &c->d_a, &c->d_b, &c->d_c, &c->d_major, &c->d_inter, &c->d_minor,
@@ -759,6 +999,15 @@ CPG_API int cpg_set_option(cpg_ctx *c, const char *name, int64_t value)
             return CPG_ERR_ARGUMENT;
         }
         c->opt_upload_threads = (int)value;
+    } else if (!strcmp(name, "snapshot_cache")) {
+        if (value < 0 || value > 2) {
+            set_error("snapshot_cache must be 0 (off), 1 (sampled content token) or 2 (full hash)");
+            return CPG_ERR_ARGUMENT;
+        }
+        c->opt_snapshot_cache = (int)value;
+        if (value == 0) { c->snap_key.valid = false; c->cat_key.valid = false; }
+    } else if (!strcmp(name, "detect_ranges")) {
+        c->opt_detect_ranges = value != 0;
     } else if (!strcmp(name, "direct_results")) {
         c->opt_direct_results = value != 0;
     } else if (!strcmp(name, "radial_order")) {
@@ -778,6 +1027,25 @@ CPG_API int cpg_set_option(cpg_ctx *c, const char *name, int64_t value)
     return CPG_OK;
 }
 
+// Snapshot bookkeeping shared by the three upload entry points.
+static void snapshot_begin(cpg_ctx *c)
+{
+    // a failed upload must not leave a usable but inconsistent snapshot behind
+    c->have.valid = false; c->mass_stream_valid = false;
+    c->n_part = 0;
+    c->snap_key.valid = false;
+}
+
+static void snapshot_done(cpg_ctx *c, int64_t n_part, bool have_vel)
+{
+    c->n_part = n_part;
+    c->have_vel = have_vel;
+    c->snapshot_version++;
+    // a catalogue installed for an earlier, larger snapshot must not be used against this one (the device buffers
+    // never shrink, so the gather would not fault: it would read stale particles)
+    c->cat_stale = c->n_obj > 0 && c->cat_max_idx >= n_part;
+}
+
 CPG_API int cpg_set_particles(cpg_ctx *c, const double *xyz, const double *vxyz, const double *masses, int64_t n_part)
 {
     CPG_TRY(use_device(c));
@@ -785,32 +1053,80 @@ CPG_API int cpg_set_particles(cpg_ctx *c, const double *xyz, const double *vxyz,
         set_error("cpg_set_particles: bad arguments");
         return CPG_ERR_ARGUMENT;
     }
+    // same arrays as last time?  (pointer, length and a content token; see "snapshot_cache")
+    uint64_t tok[3] = {0, 0, 0};
+    const int mode = c->opt_snapshot_cache;
+    if (mode > 0) {
+        tok[0] = host_token(xyz, sizeof(double) * 3 * (size_t)n_part, mode == 2);
+        tok[1] = host_token(masses, sizeof(double) * (size_t)n_part, mode == 2);
+        tok[2] = vxyz ? host_token(vxyz, sizeof(double) * 3 * (size_t)n_part, mode == 2) : 0;
+        auto &K = c->snap_key;
+        if (K.valid && K.mode >= mode && K.xyz == xyz && K.vxyz == vxyz && K.masses == masses && K.n == n_part &&
+            K.tok[0] == tok[0] && K.tok[1] == tok[1] && K.tok[2] == tok[2] && c->n_part == n_part) {
+            c->uploads_skipped++;
+            return CPG_OK;
+        }
+    }
+    snapshot_begin(c);
     CPG_TRY(c->xyz.ensure((size_t)n_part * 3));
     CPG_TRY(c->masses.ensure((size_t)n_part));
     CPG_TRY(upload_chunked(c, c->xyz.p, xyz, sizeof(double) * 3 * n_part, c->stream));
     CPG_TRY(upload_chunked(c, c->masses.p, masses, sizeof(double) * n_part, c->stream));
-    c->have_vel = vxyz != nullptr;
     if (vxyz) {
         CPG_TRY(c->vxyz.ensure((size_t)n_part * 3));
         CPG_TRY(upload_chunked(c, c->vxyz.p, vxyz, sizeof(double) * 3 * n_part, c->stream));
     }
     CPG_CUDA(cudaStreamSynchronize(c->stream));
-    c->n_part = n_part;
-    c->mass_stream_valid = false;
-    c->snapshot_version++;
-    c->have.valid = false;
+    snapshot_done(c, n_part, vxyz != nullptr);
+    if (mode > 0) {
+        auto &K = c->snap_key;
+        K.valid = true; K.mode = mode; K.xyz = xyz; K.vxyz = vxyz; K.masses = masses; K.n = n_part;
+        K.tok[0] = tok[0]; K.tok[1] = tok[1]; K.tok[2] = tok[2];
+    }
     return CPG_OK;
 }
 
-// Catalogue bookkeeping shared by cpg_set_catalogue (idx_cat on the host) and cpg_use_obj_cat (idx_cat already on
-// the device in c->idx: idx_cat == nullptr).
-static int install_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, const int32_t *obj_size, int32_t n_obj)
+CPG_API int cpg_set_particles_segments(cpg_ctx *c, const double *xyz, const double *vxyz, const double *masses,
+                                       const int64_t *seg_start, const int64_t *seg_len, int64_t n_seg)
+{
+    CPG_TRY(use_device(c));
+    if (n_seg < 0 || (n_seg > 0 && (!xyz || !masses || !seg_start || !seg_len))) {
+        set_error("cpg_set_particles_segments: bad arguments");
+        return CPG_ERR_ARGUMENT;
+    }
+    std::vector<int64_t> prefix((size_t)n_seg + 1, 0);
+    for (int64_t i = 0; i < n_seg; i++) {
+        if (seg_start[i] < 0 || seg_len[i] < 0) {
+            set_error("cpg_set_particles_segments: segment %lld has a negative start or length", (long long)i);
+            return CPG_ERR_ARGUMENT;
+        }
+        prefix[i + 1] = prefix[i] + seg_len[i];
+    }
+    const int64_t n_part = prefix[n_seg];
+    snapshot_begin(c);
+    CPG_TRY(c->xyz.ensure((size_t)n_part * 3));
+    CPG_TRY(c->masses.ensure((size_t)n_part));
+    if (vxyz) CPG_TRY(c->vxyz.ensure((size_t)n_part * 3));
+    CPG_CUDA(cudaStreamSynchronize(c->stream));   // earlier work may still read the old snapshot
+    CPG_TRY(upload_segments(c, c->xyz.p, xyz, 3 * sizeof(double), seg_start, seg_len, n_seg, prefix));
+    CPG_TRY(upload_segments(c, c->masses.p, masses, sizeof(double), seg_start, seg_len, n_seg, prefix));
+    if (vxyz) CPG_TRY(upload_segments(c, c->vxyz.p, vxyz, 3 * sizeof(double), seg_start, seg_len, n_seg, prefix));
+    snapshot_done(c, n_part, vxyz != nullptr);
+    return CPG_OK;
+}
+
+// Catalogue bookkeeping shared by cpg_set_catalogue (idx_cat on the host), cpg_set_catalogue_ranges (no index array)
+// and cpg_use_obj_cat (idx_cat already on the device in c->idx: idx_cat == nullptr, obj_start == nullptr).
+// scan: what scan_catalogue found out about a host idx_cat (nullptr: not scanned).
+static int install_catalogue(cpg_ctx *c, const int32_t *idx_cat, const int64_t *obj_start, int64_t n_idx,
+                             const int32_t *obj_size, int32_t n_obj, const CatScan *scan = nullptr)
 {
     // the flat catalogue is by far the largest piece: start its upload first, the host-side bookkeeping below then
     // runs while the copy engine works (an inconsistent obj_size is found afterwards and invalidates the catalogue)
-    c->n_idx = 0; c->n_obj = 0; c->have.valid = false;
+    c->n_idx = 0; c->n_obj = 0; c->have.valid = false; c->cat_key.valid = false; c->cat_stale = false;
     for (auto &tk : c->task_cache) tk.valid = false;
-    if (idx_cat) {
+    const bool ranges = obj_start != nullptr;
+    if (idx_cat && !ranges) {
         CPG_TRY(c->idx.ensure(n_idx));
         if (n_idx) CPG_TRY(upload_chunked(c, c->idx.p, idx_cat, sizeof(int32_t) * n_idx, c->stream));
     }
@@ -818,6 +1134,7 @@ static int install_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, 
     c->h_size.assign(obj_size, obj_size + n_obj);
     c->h_chunks.clear(); c->h_kchunks.clear(); c->h_schunks.clear();
     c->h_chunk_first.assign(n_obj + 1, 0); c->h_kchunk_first.assign(n_obj + 1, 0); c->h_schunk_first.assign(n_obj + 1, 0);
+    int64_t max_idx = -1, min_idx = INT64_MAX;
     for (int h = 0; h < n_obj; h++) {
         if (obj_size[h] < 0) {
             set_error("cpg_set_catalogue: obj_size[%d] < 0", h);
@@ -831,6 +1148,10 @@ static int install_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, 
         c->h_chunk_first[h + 1] = (int32_t)c->h_chunks.size();
         c->h_kchunk_first[h + 1] = (int32_t)c->h_kchunks.size();
         c->h_schunk_first[h + 1] = (int32_t)c->h_schunks.size();
+        if (ranges && obj_size[h] > 0) {
+            min_idx = std::min(min_idx, obj_start[h]);
+            max_idx = std::max(max_idx, obj_start[h] + obj_size[h] - 1);
+        }
     }
     if (off[n_obj] != n_idx) {
         set_error("cpg_set_catalogue: sum(obj_size) = %lld but idx_cat has %lld entries", (long long)off[n_obj],
@@ -848,6 +1169,11 @@ static int install_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, 
     CPG_TRY(c->chunk_first.ensure(n_obj + 1)); CPG_TRY(c->kchunk_first.ensure(n_obj + 1)); CPG_TRY(c->schunk_first.ensure(n_obj + 1));
     CPG_TRY(c->task_counter.ensure(4));
     CPG_TRY(c->d_order.ensure(n_obj));
+    if (ranges) {
+        CPG_TRY(c->start.ensure(n_obj));
+        if (n_obj)
+            CPG_CUDA(cudaMemcpyAsync(c->start.p, obj_start, sizeof(int64_t) * n_obj, cudaMemcpyHostToDevice, c->stream));
+    }
     if (n_obj)
         CPG_CUDA(cudaMemcpyAsync(c->d_order.p, c->order.data(), sizeof(int32_t) * n_obj, cudaMemcpyHostToDevice, c->stream));
     if (n_obj) CPG_CUDA(cudaMemcpyAsync(c->size.p, obj_size, sizeof(int32_t) * n_obj, cudaMemcpyHostToDevice, c->stream));
@@ -868,8 +1194,10 @@ static int install_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, 
                                  cudaMemcpyHostToDevice, c->stream));
     CPG_CUDA(cudaMemcpyAsync(c->schunk_first.p, c->h_schunk_first.data(), sizeof(int32_t) * (n_obj + 1),
                              cudaMemcpyHostToDevice, c->stream));
-    // index range check on the device: an out-of-range index would be an illegal address in the gather
-    if (n_idx > 0) {
+    // index range check: an out-of-range index would be an illegal address in the gather
+    if (scan) {
+        min_idx = scan->min_idx; max_idx = scan->max_idx;
+    } else if (!ranges && n_idx > 0) {   // on the device (the flat array is already there)
         const int32_t init[2] = {0x7fffffff, -0x7fffffff - 1};
         int32_t got[2];
         CPG_CUDA(cudaMemcpyAsync(c->task_counter.p, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
@@ -877,22 +1205,29 @@ static int install_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, 
         CPG_CUDA(cudaGetLastError());
         CPG_CUDA(cudaMemcpyAsync(got, c->task_counter.p, sizeof got, cudaMemcpyDeviceToHost, c->stream));
         CPG_CUDA(cudaStreamSynchronize(c->stream));
-        if (got[0] < 0 || (int64_t)got[1] >= c->n_part) {
-            set_error("cpg_set_catalogue: idx_cat range [%d, %d] outside the %lld uploaded particles", got[0], got[1],
-                      (long long)c->n_part);
-            c->n_idx = 0; c->n_obj = 0;
-            return CPG_ERR_ARGUMENT;
-        }
+        min_idx = got[0]; max_idx = got[1];
     }
     CPG_CUDA(cudaStreamSynchronize(c->stream));
+    if (n_idx > 0 && (min_idx < 0 || max_idx >= c->n_part)) {
+        set_error("cpg_set_catalogue: idx_cat range [%lld, %lld] outside the %lld uploaded particles", (long long)min_idx,
+                  (long long)max_idx, (long long)c->n_part);
+        return CPG_ERR_ARGUMENT;
+    }
     c->n_idx = n_idx;
     c->n_pad = poff[n_obj];
     c->n_obj = n_obj;
+    c->cat_ranges = ranges;
+    c->cat_max_idx = n_idx > 0 ? max_idx : -1;
     c->mass_stream_valid = false;
     c->catalogue_version++;
     c->have.valid = false;
     for (auto &tk : c->task_cache) tk.valid = false;
     return CPG_OK;
+}
+
+static bool same_sizes(const std::vector<int32_t> &a, const int32_t *b, int32_t n)
+{
+    return a.size() == (size_t)n && (n == 0 || !memcmp(a.data(), b, sizeof(int32_t) * (size_t)n));
 }
 
 CPG_API int cpg_set_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, const int32_t *obj_size, int32_t n_obj)
@@ -902,7 +1237,86 @@ CPG_API int cpg_set_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx,
         set_error("cpg_set_catalogue: bad arguments");
         return CPG_ERR_ARGUMENT;
     }
-    return install_catalogue(c, idx_cat, n_idx, obj_size, n_obj);
+    if (!c->opt_detect_ranges && !c->opt_snapshot_cache) return install_catalogue(c, idx_cat, nullptr, n_idx, obj_size, n_obj);
+    // one multi-threaded pass over the flat array: contiguous-range detection, index range, content hash
+    std::vector<int64_t> off((size_t)n_obj + 1, 0);
+    for (int h = 0; h < n_obj; h++) {
+        if (obj_size[h] < 0) {
+            set_error("cpg_set_catalogue: obj_size[%d] < 0", h);
+            return CPG_ERR_ARGUMENT;
+        }
+        off[h + 1] = off[h] + obj_size[h];
+    }
+    if (off[n_obj] != n_idx) {
+        set_error("cpg_set_catalogue: sum(obj_size) = %lld but idx_cat has %lld entries", (long long)off[n_obj], (long long)n_idx);
+        return CPG_ERR_ARGUMENT;
+    }
+    CatScan sc;
+    scan_catalogue(idx_cat, off.data(), n_obj, sc);
+    const bool ranges = c->opt_detect_ranges && sc.contiguous;
+    auto &K = c->cat_key;
+    if (c->opt_snapshot_cache && K.valid && !c->cat_stale && K.ranges == ranges && K.n_idx == n_idx && K.hash == sc.hash &&
+        same_sizes(K.size, obj_size, n_obj) && c->n_obj == n_obj && c->cat_max_idx < c->n_part) {
+        c->uploads_skipped++;
+        return CPG_OK;
+    }
+    const int rc = install_catalogue(c, idx_cat, ranges ? sc.start.data() : nullptr, n_idx, obj_size, n_obj, &sc);
+    if (rc == CPG_OK && c->opt_snapshot_cache) {
+        K.valid = true; K.ranges = ranges; K.n_idx = n_idx; K.hash = sc.hash;
+        K.size.assign(obj_size, obj_size + n_obj);
+    }
+    return rc;
+}
+
+CPG_API int cpg_set_catalogue_ranges(cpg_ctx *c, const int64_t *obj_start, const int32_t *obj_size, int32_t n_obj)
+{
+    CPG_TRY(use_device(c));
+    if (n_obj < 0 || (n_obj > 0 && (!obj_start || !obj_size))) {
+        set_error("cpg_set_catalogue_ranges: bad arguments");
+        return CPG_ERR_ARGUMENT;
+    }
+    int64_t n_idx = 0;
+    for (int h = 0; h < n_obj; h++) {
+        if (obj_size[h] < 0 || (obj_size[h] > 0 && obj_start[h] < 0)) {
+            set_error("cpg_set_catalogue_ranges: object %d has a negative start or size", h);
+            return CPG_ERR_ARGUMENT;
+        }
+        n_idx += obj_size[h];
+    }
+    static const int64_t none = 0;
+    return install_catalogue(c, nullptr, n_obj ? obj_start : &none, n_idx, obj_size, n_obj);
+}
+
+CPG_API int cpg_catalogue_ranges(const int32_t *idx_cat, int64_t n_idx, const int32_t *obj_size, int32_t n_obj,
+                                 int64_t *obj_start_out)
+{
+    if (n_idx < 0 || n_obj < 0 || (n_idx > 0 && !idx_cat) || (n_obj > 0 && (!obj_size || !obj_start_out))) {
+        set_error("cpg_catalogue_ranges: bad arguments");
+        return CPG_ERR_ARGUMENT;
+    }
+    std::vector<int64_t> off((size_t)n_obj + 1, 0);
+    for (int h = 0; h < n_obj; h++) {
+        if (obj_size[h] < 0) {
+            set_error("cpg_catalogue_ranges: obj_size[%d] < 0", h);
+            return CPG_ERR_ARGUMENT;
+        }
+        off[h + 1] = off[h] + obj_size[h];
+    }
+    if (off[n_obj] != n_idx) {
+        set_error("cpg_catalogue_ranges: sum(obj_size) = %lld but idx_cat has %lld entries", (long long)off[n_obj], (long long)n_idx);
+        return CPG_ERR_ARGUMENT;
+    }
+    CatScan sc;
+    scan_catalogue(idx_cat, off.data(), n_obj, sc);
+    for (int h = 0; h < n_obj; h++) obj_start_out[h] = sc.start[h];
+    return sc.contiguous ? 1 : 0;
+}
+
+CPG_API int cpg_host_token(const void *p, size_t bytes, int32_t full, uint64_t *token_out)
+{
+    if (!token_out || (bytes > 0 && !p)) return CPG_ERR_ARGUMENT;
+    *token_out = host_token(p, bytes, full != 0);
+    return CPG_OK;
 }
 
 // ---- Gadget / FoF ingest ----------------------------------------------------------
@@ -1037,7 +1451,7 @@ CPG_API int cpg_use_obj_cat(cpg_ctx *c)
     CPG_TRY(c->idx.ensure((size_t)c->oc_n_idx));
     if (c->oc_n_idx)
         CPG_CUDA(cudaMemcpyAsync(c->idx.p, c->oc_idx.p, sizeof(int32_t) * (size_t)c->oc_n_idx, cudaMemcpyDeviceToDevice, c->stream));
-    return install_catalogue(c, nullptr, c->oc_n_idx, sizes.data(), (int32_t)c->oc_n_pass);
+    return install_catalogue(c, nullptr, nullptr, c->oc_n_idx, sizes.data(), (int32_t)c->oc_n_pass);
 }
 
 }  // extern "C"
@@ -1085,6 +1499,7 @@ CPG_API int cpg_set_particles_gadget(cpg_ctx *c, const void *pos, int32_t pos_is
     }
     Timer T(c);
     T.mark(0);
+    snapshot_begin(c);
     CPG_TRY(c->xyz.ensure((size_t)n_part * 3));
     CPG_TRY(c->masses.ensure((size_t)n_part));
     CPG_TRY(ingest_block(c, pos, pos_is_f32, c->xyz.p, n_part * 3, length_unit_fac, 0, 1.0));
@@ -1098,7 +1513,6 @@ CPG_API int cpg_set_particles_gadget(cpg_ctx *c, const void *pos, int32_t pos_is
                                                                                          (1.0 * mass_table) / mass_unit_fac);
         c->timing.kernel_launches++;
     }
-    c->have_vel = vel != nullptr;
     if (vel) {
         CPG_TRY(c->vxyz.ensure((size_t)n_part * 3));
         // array *= np.sqrt(head.time)  (readgadget.py:116)
@@ -1109,10 +1523,7 @@ CPG_API int cpg_set_particles_gadget(cpg_ctx *c, const void *pos, int32_t pos_is
     CPG_CUDA(cudaGetLastError());
     CPG_CUDA(cudaStreamSynchronize(c->stream));
     c->timing.h2d_ms = Timer::ms(c->ev[0], c->ev[1]);
-    c->n_part = n_part;
-    c->mass_stream_valid = false;
-    c->snapshot_version++;
-    c->have.valid = false;
+    snapshot_done(c, n_part, vel != nullptr);
     return CPG_OK;
 }
 
@@ -1209,7 +1620,7 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
                       int32_t reduced, int32_t shell_based, int32_t use_vel, double *out12, int32_t *n_iter,
                       int32_t *n_pts, double *obj_mass, double *vcenters)
 {
-    CPG_TRY(use_device(c));
+    CPG_TRY(compute_ready(c));
     const int n = c->n_obj;
     if (!local) R = 1;
     if (R < 1 || R > 32767 || (n > 0 && (!centers || !r200 || !out12 || !n_iter || !n_pts)) || (local && !r_over_r200)) {
@@ -1224,7 +1635,21 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     Timer T(c);
     if (n == 0) return CPG_OK;
     const size_t nR = (size_t)n * R;
+    // Any error exit below must not leave kernels behind that still store into the caller's page-locked result
+    // buffers (direct_results): drain both streams before returning a failure.
+    struct DrainOnError {
+        cpg_ctx *c;
+        bool ok = false;
+        ~DrainOnError()
+        {
+            if (ok) return;
+            cudaStreamSynchronize(c->stream);
+            cudaStreamSynchronize(c->stream2);
+            (void)cudaGetLastError();
+        }
+    } drain{c};
     T.mark(0);
+    CPG_TRY(c->morph_stats.ensure(2));
     CPG_TRY(c->centers.ensure((size_t)n * 3)); CPG_TRY(c->r200.ensure(n)); CPG_TRY(c->rr.ensure(R));
     c->stage_used = 0;
     CPG_TRY(small_upload(c, c->centers.p, centers, sizeof(double) * 3 * n));
@@ -1332,7 +1757,8 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     } joiner{fillers};
     // (a fill kernel, not cudaMemsetAsync: the copy-engine memset of the 67 MB result array of configs[1] took ~1 ms)
     init_results_kernel<<<grid_for(std::max<int64_t>((int64_t)(direct ? 0 : nR) * 6, 4), 256, c->sm_count * 16), 256, 0, c->stream>>>(
-        reinterpret_cast<double2 *>(c->out12.p), c->n_iter.p, c->n_pts.p, c->task_counter.p, (int64_t)(direct ? 0 : nR));
+        reinterpret_cast<double2 *>(c->out12.p), c->n_iter.p, c->n_pts.p, c->task_counter.p, c->morph_stats.p,
+        (int64_t)(direct ? 0 : nR));
     c->timing.kernel_launches++;
     CPG_CUDA(cudaGetLastError());
     T.mark(1);
@@ -1358,6 +1784,7 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     P.R = R; P.local = local ? 1 : 0; P.SAFE = SAFE;
     P.tol = IT_TOL; P.wall = IT_WALL; P.itmin = IT_MIN;
     P.out12 = direct ? d_out12 : c->out12.p; P.n_iter = direct ? d_nit : c->n_iter.p; P.n_pts = direct ? d_npt : c->n_pts.p;
+    P.stats = c->morph_stats.p;
     for (auto &x : fillers) x.join();   // the host-side initialisation ran under the gather; it must end before a kernel stores
     if (ngrid > 0) {
         int rcg;
@@ -1390,12 +1817,17 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
         CPG_CUDA(cudaMemcpyAsync(vcenters, c->vcenters.p, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
         c->timing.d2h_bytes += (int64_t)sizeof(double) * 3 * n;
     }
+    unsigned long long h_stats[2] = {0, 0};
+    CPG_CUDA(cudaMemcpyAsync(h_stats, c->morph_stats.p, sizeof h_stats, cudaMemcpyDeviceToHost, c->stream));
     T.mark(4);
     CPG_CUDA(cudaStreamSynchronize(c->stream));
+    drain.ok = true;
     c->timing.h2d_ms = Timer::ms(c->ev[0], c->ev[1]);
     c->timing.gather_ms = Timer::ms(c->ev[1], c->ev[2]);
     c->timing.kernel_ms = Timer::ms(c->ev[2], c->ev[3]);
     c->timing.d2h_ms = Timer::ms(c->ev[3], c->ev[4]);
+    c->timing.tile_visits = (int64_t)h_stats[0];
+    c->timing.tile_shell_visits = (int64_t)h_stats[1];
     return CPG_OK;
 }
 
@@ -1437,7 +1869,7 @@ static int dens_common_end(cpg_ctx *c, Timer &T, double *dens, int32_t *counts, 
 CPG_API int cpg_dens_sph(cpg_ctx *c, const double *centers, const double *r200, const double *bin_edges, int32_t R,
                          float L_BOX, double *dens, int32_t *counts)
 {
-    CPG_TRY(use_device(c));
+    CPG_TRY(compute_ready(c));
     const int n = c->n_obj;
     if (R < 1 || R > DENS_MAX_R || (n > 0 && (!centers || !r200 || !bin_edges || !dens))) {
         set_error("cpg_dens_sph: bad arguments (1 <= R <= %d)", DENS_MAX_R);
@@ -1476,7 +1908,7 @@ CPG_API int cpg_dens_ell(cpg_ctx *c, const double *centers, const double *a, con
                          const double *major, const double *inter, const double *minor, int32_t R, float L_BOX,
                          double *dens, int32_t *counts)
 {
-    CPG_TRY(use_device(c));
+    CPG_TRY(compute_ready(c));
     const int n = c->n_obj;
     const bool resident = !a && !b && !cc && !major && !inter && !minor;   // profiles left by cpg_shape_interp
     if (R < 1 || R > DENS_MAX_R || (n > 0 && (!centers || !dens)) ||
@@ -1593,7 +2025,7 @@ CPG_API int cpg_shape_interp(cpg_ctx *c, const double *r200, const double *r_ove
 CPG_API int cpg_dens_kernel(cpg_ctx *c, const double *centers, const double *r200, const double *r_over_r200, int32_t R,
                             float L_BOX, double *dens)
 {
-    CPG_TRY(use_device(c));
+    CPG_TRY(compute_ready(c));
     const int n = c->n_obj;
     if (R < 1 || R > DENS_MAX_R || (n > 0 && (!centers || !r200 || !r_over_r200 || !dens))) {
         set_error("cpg_dens_kernel: bad arguments (1 <= R <= %d)", DENS_MAX_R);
@@ -1628,7 +2060,7 @@ CPG_API int cpg_dens_kernel(cpg_ctx *c, const double *centers, const double *r20
 
 CPG_API int cpg_obj_masses(cpg_ctx *c, double *obj_mass)
 {
-    CPG_TRY(use_device(c));
+    CPG_TRY(compute_ready(c));
     const int n = c->n_obj;
     if (n > 0 && !obj_mass) return CPG_ERR_ARGUMENT;
     Timer T(c);
@@ -1648,7 +2080,7 @@ CPG_API int cpg_obj_masses(cpg_ctx *c, double *obj_mass)
 CPG_API int cpg_centers(cpg_ctx *c, int32_t mode, int32_t shape_path, double L_BOX, const double *ref_points,
                         double *centers_out)
 {
-    CPG_TRY(use_device(c));
+    CPG_TRY(compute_ready(c));
     const int n = c->n_obj;
     if ((n > 0 && !centers_out) || (mode != 0 && mode != 1) || (L_BOX != 0.0 && !ref_points)) {
         set_error("cpg_centers: bad arguments (L_BOX != 0 needs the reference points of respectPBCNoRef)");
@@ -1738,6 +2170,22 @@ CPG_API int cpg_get_prefix_lengths(cpg_ctx *c, int32_t *n_eff, int32_t R)
     return CPG_OK;
 }
 
+CPG_API int cpg_get_stat(cpg_ctx *c, const char *name, int64_t *out)
+{
+    if (!c || !name || !out) return CPG_ERR_ARGUMENT;
+    if (!strcmp(name, "uploads_skipped")) *out = (int64_t)c->uploads_skipped;
+    else if (!strcmp(name, "catalogue_as_ranges")) *out = c->cat_ranges ? 1 : 0;
+    else if (!strcmp(name, "n_part")) *out = c->n_part;
+    else if (!strcmp(name, "n_obj")) *out = c->n_obj;
+    else if (!strcmp(name, "snapshot_version")) *out = (int64_t)c->snapshot_version;
+    else if (!strcmp(name, "catalogue_version")) *out = (int64_t)c->catalogue_version;
+    else {
+        set_error("cpg_get_stat: unknown name %s", name);
+        return CPG_ERR_ARGUMENT;
+    }
+    return CPG_OK;
+}
+
 CPG_API int cpg_get_timing(cpg_ctx *c, cpg_timing *out)
 {
     if (!c || !out) return CPG_ERR_ARGUMENT;
@@ -1746,3 +2194,5 @@ CPG_API int cpg_get_timing(cpg_ctx *c, cpg_timing *out)
 }
 
 }  // extern "C"
+
+#include "cpg_multi.inl"

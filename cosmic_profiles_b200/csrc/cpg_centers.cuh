@@ -27,10 +27,10 @@ struct CenterParams {
     double *centers;           // (n_obj,3) out
 };
 
-__device__ __forceinline__ void unwrapped(const CenterParams &P, int64_t first, int i, const double *ref, double &x, double &y,
+__device__ __forceinline__ void unwrapped(const CenterParams &P, int h, int64_t first, int i, const double *ref, double &x, double &y,
                                           double &z, double &m)
 {
-    const int64_t g = P.G.idx[first + i];
+    const int64_t g = cat_index(P.G, h, first, first + i);
     x = P.G.xyz[3 * g]; y = P.G.xyz[3 * g + 1]; z = P.G.xyz[3 * g + 2];
     m = P.G.masses[g];
     if (P.L_BOX != 0.0) {   // python_routines.py:514-525
@@ -85,13 +85,13 @@ __global__ void __launch_bounds__(256) centers_kernel(const CenterParams P)
         double o[3] = {ref[0], ref[1], ref[2]};
         if (!P.ref) {
             double x, y, z, m;
-            unwrapped(P, first, 0, ref, x, y, z, m);
+            unwrapped(P, h, first, 0, ref, x, y, z, m);
             o[0] = x; o[1] = y; o[2] = z;
         }
         double v[4] = {0.0, 0.0, 0.0, 0.0};
         for (int i = tid; i < N; i += blockDim.x) {
             double x, y, z, m;
-            unwrapped(P, first, i, ref, x, y, z, m);
+            unwrapped(P, h, first, i, ref, x, y, z, m);
             v[0] = fma(m, x - o[0], v[0]); v[1] = fma(m, y - o[1], v[1]); v[2] = fma(m, z - o[2], v[2]);
             v[3] += m;
         }
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) centers_kernel(const CenterParams P)
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
         for (int i = tid; i < N; i += blockDim.x) {
             double x, y, z, m;
-            unwrapped(P, first, i, ref, x, y, z, m);
+            unwrapped(P, h, first, i, ref, x, y, z, m);
             lo[0] = fmin(lo[0], x); hi[0] = fmax(hi[0], x);
             lo[1] = fmin(lo[1], y); hi[1] = fmax(hi[1], y);
             lo[2] = fmin(lo[2], z); hi[2] = fmax(hi[2], z);
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) centers_kernel(const CenterParams P)
         double v[4] = {0.0, 0.0, 0.0, 0.0};
         for (int j = tid; j < n_alive; j += blockDim.x) {
             double x, y, z, m;
-            unwrapped(P, first, A[j], ref, x, y, z, m);
+            unwrapped(P, h, first, A[j], ref, x, y, z, m);
             v[0] = fma(x, m, v[0]); v[1] = fma(y, m, v[1]); v[2] = fma(z, m, v[2]);
             v[3] += m;
         }
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) centers_kernel(const CenterParams P)
             if (j < n_alive) {
                 p = A[j];
                 double x, y, z, m;
-                unwrapped(P, first, p, ref, x, y, z, m);
+                unwrapped(P, h, first, p, ref, x, y, z, m);
                 const double ax = x - cx, ay = y - cy, az = z - cz;
                 keep = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az))) < rad;
             }
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(256) centers_mode_cluster_kernel(const CenterP
         double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
         for (int i = lo + tid; i < hi; i += blockDim.x) {
             double x, y, z, m;
-            unwrapped(P, first, i, ref, x, y, z, m);
+            unwrapped(P, h, first, i, ref, x, y, z, m);
             mn[0] = fmin(mn[0], x); mx[0] = fmax(mx[0], x);
             mn[1] = fmin(mn[1], y); mx[1] = fmax(mx[1], y);
             mn[2] = fmin(mn[2], z); mx[2] = fmax(mx[2], z);
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) centers_mode_cluster_kernel(const CenterP
         double v[4] = {0.0, 0.0, 0.0, 0.0};
         for (int j = tid; j < n_alive; j += blockDim.x) {
             double x, y, z, m;
-            unwrapped(P, first, A[j], ref, x, y, z, m);
+            unwrapped(P, h, first, A[j], ref, x, y, z, m);
             v[0] = fma(x, m, v[0]); v[1] = fma(y, m, v[1]); v[2] = fma(z, m, v[2]);
             v[3] += m;
         }
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) centers_mode_cluster_kernel(const CenterP
             if (j < n_alive) {
                 p = A[j];
                 double x, y, z, m;
-                unwrapped(P, first, p, ref, x, y, z, m);
+                unwrapped(P, h, first, p, ref, x, y, z, m);
                 const double ax = x - cx, ay = y - cy, az = z - cz;
                 keep = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay)), __dmul_rn(az, az))) < rad;
             }

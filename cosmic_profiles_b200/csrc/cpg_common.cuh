@@ -59,6 +59,7 @@ struct MorphParams {
     double *out12;             // (n_obj, R, 12), pre-zeroed
     int32_t *n_iter;           // (n_obj, R), pre-set to -1
     int32_t *n_pts;            // (n_obj, R), pre-set to -1
+    unsigned long long *stats; // [0] tiles passed over, [1] (tile, shell) pairs among them; or nullptr
 };
 
 __device__ __forceinline__ double warp_sum(double v)

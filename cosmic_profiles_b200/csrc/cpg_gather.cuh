@@ -22,7 +22,9 @@ struct GatherParams {
     const double *xyz;       // (n_part,3)
     const double *vxyz;      // (n_part,3) or nullptr
     const double *masses;    // (n_part)
-    const int32_t *idx;      // (n_idx)
+    const int32_t *idx;      // (n_idx), or nullptr: every object is a contiguous range of the snapshot (FoF order,
+                             // gadget/gen_catalogues.pyx:29-35) and entry j of object h is particle start[h] + (j - off[h])
+    const int64_t *start;    // (n_obj) first particle of every object (ranges catalogue only)
     const int64_t *off;      // (n_obj+1) catalogue offsets
     const int64_t *poff;     // (n_obj+1) padded SoA offsets (even)
     const double *centers;   // (n_obj,3)
@@ -33,6 +35,12 @@ struct GatherParams {
     double *dx, *dy, *dz, *m, *vx, *vy, *vz;
     const int32_t *dest;     // (n_idx) slot of catalogue entry j inside its object (radial ordering) or nullptr
 };
+
+// Snapshot index of catalogue entry j, which belongs to object h whose entries start at `first`.
+__device__ __forceinline__ int64_t cat_index(const GatherParams &G, int h, int64_t first, int64_t j)
+{
+    return G.idx ? (int64_t)G.idx[j] : G.start[h] + (j - first);
+}
 
 __device__ __forceinline__ int find_object(const int64_t *off, int n_obj, int64_t j)
 {
@@ -62,10 +70,10 @@ __global__ void __launch_bounds__(256) gather_pos_kernel(const GatherParams G)
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < G.n_idx; j += stride) {
         const int h = find_object(G.off, G.n_obj, j);
         const int64_t first = G.off[h], last = G.off[h + 1];
-        const int64_t g = G.idx[j];
+        const int64_t g = cat_index(G, h, first, j);
         double x = G.xyz[3 * g], y = G.xyz[3 * g + 1], z = G.xyz[3 * g + 2];
         if (G.L_BOX != 0.0f) {
-            const int64_t g0 = G.idx[first];
+            const int64_t g0 = cat_index(G, h, first, first);
             pbc_reflect(x, y, z, G.xyz[3 * g0], G.xyz[3 * g0 + 1], G.L_BOX);
         }
         const int64_t o = G.poff[h] + (G.dest ? (int64_t)G.dest[j] : (j - first));
@@ -87,7 +95,7 @@ __global__ void __launch_bounds__(256) gather_vel_kernel(const GatherParams G)
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < G.n_idx; j += stride) {
         const int h = find_object(G.off, G.n_obj, j);
         const int64_t first = G.off[h], last = G.off[h + 1];
-        const int64_t g = G.idx[j];
+        const int64_t g = cat_index(G, h, first, j);
         const int64_t o = G.poff[h] + (G.dest ? (int64_t)G.dest[j] : (j - first));
         G.vx[o] = __dsub_rn(G.vxyz[3 * g], G.vcenters[3 * h]);
         G.vy[o] = __dsub_rn(G.vxyz[3 * g + 1], G.vcenters[3 * h + 1]);
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__(128) mass32_kernel(const GatherParams G, int n
 #pragma unroll
                 for (int b = 0; b < PF; b++) {
                     const int i = s0 + 32 * b + lane;
-                    pre[b] = (i < N) ? G.masses[G.idx[first + i]] : 0.0;
+                    pre[b] = (i < N) ? G.masses[cat_index(G, h, first, first + i)] : 0.0;
                 }
 #pragma unroll
                 for (int b = 0; b < PF; b++) {
@@ -303,7 +311,7 @@ __global__ void __launch_bounds__(256) vsum_chunk_kernel(const GatherParams G, c
     const int end = min(N, ck.start + CHUNK);
     double v[3] = {0.0, 0.0, 0.0};
     for (int i = ck.start + threadIdx.x; i < end; i += blockDim.x) {
-        const int64_t g = G.idx[first + i];
+        const int64_t g = cat_index(G, ck.halo, first, first + i);
         const double m = G.masses[g];
         v[0] = fma(m, G.vxyz[3 * g], v[0]);
         v[1] = fma(m, G.vxyz[3 * g + 1], v[1]);
@@ -361,10 +369,10 @@ struct SortParams {
 __device__ __forceinline__ void load_relative(const GatherParams &G, int h, int64_t first, int64_t j, double &dx,
                                               double &dy, double &dz, int64_t &g)
 {
-    g = G.idx[j];
+    g = cat_index(G, h, first, j);
     double x = G.xyz[3 * g], y = G.xyz[3 * g + 1], z = G.xyz[3 * g + 2];
     if (G.L_BOX != 0.0f) {
-        const int64_t g0 = G.idx[first];
+        const int64_t g0 = cat_index(G, h, first, first);
         pbc_reflect(x, y, z, G.xyz[3 * g0], G.xyz[3 * g0 + 1], G.L_BOX);
     }
     dx = __dsub_rn(x, G.centers[3 * h]);

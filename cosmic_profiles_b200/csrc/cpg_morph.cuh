@@ -32,18 +32,29 @@ enum {
     F_D2,                                           // d^2
     F_THR,                                          // inner-ellipsoid threshold: 1 (shell), -1 (first shell: disabled)
     F_BXX, F_BYY, F_BZZ, F_BXY, F_BXZ, F_BYZ,       // B = R^T diag(1/(d-delta)^2, 1/(q d-delta)^2, 1/(s d-delta)^2) R
-    F_PAD0,
-    F_PAD1,
+    F_QQ,                                           // q*q, s*s: the divisors of the reference's own expression
+    F_SS,                                           //   p0^2 + p1^2/q^2 + p2^2/s^2 (exact_member)
     F_V,                                            // 9 slots: eigenvector basis of the previous iteration
-    F_SLOTS = 26                                    // (even: rows stay 16-byte aligned for the double2 loads)
+    F_BA2 = F_V + 9, F_BB2, F_BC2,                  // (d-delta)^2, (q d-delta)^2, (s d-delta)^2 (shell variant, exact_member)
+    F_F32,                                          // 8 slots = 16 floats: the fp32 pre-classification frame (FrameF32)
+    F_SLOTS = F_F32 + 8                             // (even: rows stay 16-byte aligned for the double2 / float4 loads)
 };
-static_assert(F_V == 16 && F_SLOTS % 2 == 0, "frame layout");
+// fp32 pre-classification frame, 16 floats at F_F32: A (as F_AXX.., rounded to fp32), lo, hi, B, loB, hiB.
+// See classify_f32 for what lo/hi mean.
+enum { G_A = 0, G_LO = 6, G_HI = 7, G_B = 8, G_LOB = 14, G_HIB = 15 };
+static_assert(F_V == 16 && F_F32 % 2 == 0 && F_SLOTS % 2 == 0, "frame layout");
+
+constexpr int TILE_PAIRS = 64;   // particle pairs per tile of a stream (1 KB)
 
 struct Particle {              // one particle as seen by the accumulators
     double xx, yy, zz, xy, xz, yz;   // products of the centre-relative position
     double m;
     double t[6];               // products the tensor is built from (velocities; VDISP only)
 };
+
+#ifndef CPG_F32_TEST
+#define CPG_F32_TEST 1   // 1: fp32 pre-classification of the membership tests (non-reduced variants); 0: all-fp64 tests
+#endif
 
 template <bool REDUCED, bool VDISP>
 __device__ __forceinline__ void accumulate(double (&acc)[7], int &cnt, bool sel, double v, const Particle &p)
@@ -90,12 +101,74 @@ __device__ __forceinline__ void accumulate(double (&acc)[7], int &cnt, bool sel,
     }
 }
 
-// Pass 0 (spherical start, shape_profs_algos.pyx:206-212 / :81-87) runs through the same code with A = B = I
-// and thr = (d-delta)^2: the fma chain below then evaluates ((xx + yy) + zz) + 0 + 0 + 0 with xx, yy, zz
-// the exactly rounded squares, i.e. bit for bit the reference's r2 -- no separate code path (the kernels
-// are instruction-cache bound enough as it is).
-// Pass k>=1: membership in the ellipsoid (shell) of the previous eigen-decomposition
-// (shape_profs_algos.pyx:247-260 / :122-143) fused with the next tensor accumulation.
+// Pass 0 (spherical start, shape_profs_algos.pyx:206-212 / :81-87) runs through the same code with the identity
+// frame (q = s = 1) and thr = (d-delta)^2 -- no separate code path.
+//
+// Membership of a particle in the ellipsoid (shell) of the previous eigen-decomposition
+// (shape_profs_algos.pyx:247-260 / :122-143), fused with the next tensor accumulation.
+//
+// fp32 pre-classification (non-reduced variants).  The fp64 pipe is the kernels' bottleneck and the membership
+// test was 6 of the ~14 fp64 instructions per particle-shell.  Here the quadratic form v = x^T A x is evaluated
+// in fp32 (x, A rounded to fp32, 6 FFMA) and compared with TWO thresholds:
+//      v32 < lo  -> member,      v32 > hi -> not a member,      otherwise -> undecided,
+//   lo = d^2 (1 - K) rounded down, hi = d^2 (1 + K) rounded up,  K = 3 * 2^-20 / s^2.
+// Error bound: x32 = x(1+e), |e| <= u = 2^-24; each product carries <= 3u, A32 <= u, the FFMA chain <= 6u, so
+// |v32 - x^T A x| <= 10.1 u * sum_ij |A_ij||x_i||x_j| <= 10.1 u * sqrt(3) * lambda_max(A) * |x|^2, with
+// lambda_max(A) = 1/s^2 (s <= q <= 1).  Every particle the pass tests lies in the shell's radial prefix,
+// |x|^2 < d^2 (1 + 1e-12), or beyond it in the prefix's last tile, where |x|^2 >= d^2 and v >= |x|^2 (A >= I): in both
+// cases a "member" / "not a member" verdict of the fp32 test is the verdict of ANY fp64 evaluation of the
+// reference's expression (their differences are ~1e-15 |x|^2 / s^2, seven orders below the band), so the fp32 path
+// never decides a case that rounding could decide differently.  The undecided particles (a fraction ~K of them) are
+// re-tested by exact_member() with the reference's own expression and operand order.  Non-finite fp32 values
+// (the 1e150 pad sentinel, NaN input) fail both comparisons of the "undecided" test and the "member" test: not a
+// member, as in fp64.  K >= 1/4 (s < 3.4e-3) or d^2 outside [1e-30, 1e30] switches the fp32 test off for the shell
+// (lo = -inf: everything is undecided).  The inner ellipsoid of the shell variant is handled the same way with
+// B, thr and an absolute band 3 * 2^-20 * lambda_max(B) * d^2.
+template <bool SHELL>
+__device__ __noinline__ bool exact_member(const double *F, double x, double y, double z)
+{
+    // shape_profs_algos.pyx:247-256 (and :139 for the shell): rotate into the eigenframe, then
+    // p0^2 + p1^2/q^2 + p2^2/s^2 < d^2, left to right, true divisions, no contraction.  With the identity frame of
+    // pass 0 this is bit for bit (x^2 + y^2) + z^2 of :206 / :82.
+    const double *V = F + F_V;
+    const double p0 = __dadd_rn(__dadd_rn(__dmul_rn(V[6], x), __dmul_rn(V[7], y)), __dmul_rn(V[8], z));
+    const double p1 = __dadd_rn(__dadd_rn(__dmul_rn(V[3], x), __dmul_rn(V[4], y)), __dmul_rn(V[5], z));
+    const double p2 = __dadd_rn(__dadd_rn(__dmul_rn(V[0], x), __dmul_rn(V[1], y)), __dmul_rn(V[2], z));
+    const double s0 = __dmul_rn(p0, p0), s1 = __dmul_rn(p1, p1), s2 = __dmul_rn(p2, p2);
+    const double v = __dadd_rn(__dadd_rn(s0, __ddiv_rn(s1, F[F_QQ])), __ddiv_rn(s2, F[F_SS]));
+    bool sel = v < F[F_D2];
+    if (SHELL && sel && F[F_THR] >= 0.0) {   // thr < 0: first shell, no inner ellipsoid (:130)
+        const double u = __dadd_rn(__dadd_rn(__ddiv_rn(s0, F[F_BA2]), __ddiv_rn(s1, F[F_BB2])), __ddiv_rn(s2, F[F_BC2]));
+        sel = u >= F[F_THR];
+    }
+    return sel;
+}
+
+constexpr double F32_GAMMA3 = 3.0 / 1048576.0;   // 3 * 2^-20 (see above: 10.1 u sqrt(3) = 1.05e-6 < 2.86e-6)
+
+// The fp32 frame of a shell from its fp64 frame.  amax = lambda_max(A) = 1/s^2, bmax = lambda_max(B).
+__device__ __forceinline__ void write_f32_frame(double *F, double amax, double bmax, bool shell)
+{
+    float *G = reinterpret_cast<float *>(F + F_F32);
+    const double d2 = F[F_D2];
+    const double K = F32_GAMMA3 * amax;
+    const bool ok = (K < 0.25) && (d2 > 1e-30) && (d2 < 1e30);
+#pragma unroll
+    for (int r = 0; r < 6; r++) G[G_A + r] = (float)F[F_AXX + r];
+    G[G_LO] = ok ? __double2float_rd(d2 * (1.0 - K)) : -INFINITY;
+    G[G_HI] = ok ? __double2float_ru(d2 * (1.0 + K)) : INFINITY;
+    if (shell) {
+        const double thr = F[F_THR];
+        const double KB = F32_GAMMA3 * bmax * d2 * 1.000001;   // absolute: |x|^2 < d^2 (1 + 1e-12) for every member of the outer ellipsoid
+        const bool okb = ok && (KB < 1e30) && (fabs(thr) < 1e30);
+#pragma unroll
+        for (int r = 0; r < 6; r++) G[G_B + r] = (float)F[F_BXX + r];
+        G[G_LOB] = okb ? __double2float_rd(thr - KB) : -INFINITY;
+        G[G_HIB] = okb ? __double2float_ru(thr + KB) : INFINITY;
+    }
+}
+
+// All-fp64 membership + accumulation (the reduced variants, whose weight m / r_ell^2 needs the fp64 value anyway).
 template <int S, bool SHELL, bool REDUCED, bool VDISP, int NP>
 __device__ __forceinline__ void passk_particles(const Particle (&p)[NP], const double *frames, unsigned smask,
                                                 double (&acc)[S][7], int (&cnt)[S])
@@ -129,6 +202,106 @@ __device__ __forceinline__ void passk_particles(const Particle (&p)[NP], const d
             for (int j = 0; j < NP; j++) accumulate<REDUCED, VDISP>(acc[s], cnt[s], sel[j], v[j], p[j]);
         }
     }
+}
+
+// One tile (this lane's pairs `lane` and `lane + 32`: 4 particles) of the non-reduced variants, in two phases so
+// that the fp64 products never live at the same time as the fp32 ones:
+//   1. classify the 4 particles against every shell of `smask` in fp32 (classification comment above), undecided
+//      ones through exact_member(); the verdicts are 4 bits per shell in one register;
+//   2. per particle: the six fp64 products (positions, or velocities for the dispersion tensor) once, then the
+//      predicated tensor updates of the shells it is a member of.
+template <int S, bool SHELL, bool VDISP>
+__device__ __forceinline__ void tile_f32(const unsigned char *tile, int lane, const double *frames, unsigned smask,
+                                         double (&acc)[S][7], int (&cnt)[S])
+{
+    const double2 *T = reinterpret_cast<const double2 *>(tile);   // stream st, pair pi: T[st * TILE_PAIRS + pi]
+    unsigned bits = 0;   // bit 4 s + j: particle j is a member of shell s
+    {
+        float f[4][6];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int pi = lane + 32 * h;
+            const double2 x = T[pi], y = T[TILE_PAIRS + pi], z = T[2 * TILE_PAIRS + pi];
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                // round to nearest (the error bound assumes it); 1e150 (pad sentinel) becomes inf
+                const float fx = (float)(e ? x.y : x.x), fy = (float)(e ? y.y : y.x), fz = (float)(e ? z.y : z.x);
+                float *g = f[2 * h + e];
+                g[0] = fx * fx; g[1] = fy * fy; g[2] = fz * fz; g[3] = fx * fy; g[4] = fx * fz; g[5] = fy * fz;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            if (smask & (1u << s)) {   // warp-uniform
+                const float4 *G4 = reinterpret_cast<const float4 *>(frames + s * F_SLOTS + F_F32);
+                const float4 g0 = G4[0], g1 = G4[1];   // (Axx,Ayy,Azz,Axy) (Axz,Ayz,lo,hi)
+                float4 g2, g3;
+                if (SHELL) { g2 = G4[2]; g3 = G4[3]; }   // (Bxx,Byy,Bzz,Bxy) (Bxz,Byz,loB,hiB)
+                const bool off = !(g1.z > -INFINITY);
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    v[j] = fmaf(g1.y, f[j][5], fmaf(g1.x, f[j][4], fmaf(g0.w, f[j][3],
+                           fmaf(g0.z, f[j][2], fmaf(g0.y, f[j][1], g0.x * f[j][0])))));
+                unsigned sel = 0, und = off ? 0xfu : 0u;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    bool in = v[j] < g1.z;
+                    bool un = (v[j] >= g1.z) && (v[j] <= g1.w);
+                    if (SHELL) {
+                        const float u = fmaf(g3.y, f[j][5], fmaf(g3.x, f[j][4], fmaf(g2.w, f[j][3],
+                                        fmaf(g2.z, f[j][2], fmaf(g2.y, f[j][1], g2.x * f[j][0])))));
+                        un = un || (in && (((u >= g3.z) && (u <= g3.w)) || !(g3.z > -INFINITY)));
+                        in = in && (u > g3.w);
+                    }
+                    sel |= (in ? 1u : 0u) << j;
+                    und |= (un ? 1u : 0u) << j;
+                }
+                if (__any_sync(0xffffffffu, und != 0)) {   // rare: the reference's own fp64 expression decides
+#pragma unroll 1
+                    for (int j = 0; j < 4; j++) {
+                        if (und & (1u << j)) {
+                            const int pi = lane + 32 * (j >> 1);
+                            const double2 x = T[pi], y = T[TILE_PAIRS + pi], z = T[2 * TILE_PAIRS + pi];
+                            const bool m = exact_member<SHELL>(frames + s * F_SLOTS, (j & 1) ? x.y : x.x,
+                                                               (j & 1) ? y.y : y.x, (j & 1) ? z.y : z.x);
+                            sel = (sel & ~(1u << j)) | ((m ? 1u : 0u) << j);
+                        }
+                    }
+                }
+                bits |= sel << (4 * s);
+            }
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int pi = lane + 32 * h;
+        const double2 m2 = T[3 * TILE_PAIRS + pi];
+        const double2 a2 = T[(VDISP ? 4 : 0) * TILE_PAIRS + pi], b2 = T[(VDISP ? 5 : 1) * TILE_PAIRS + pi],
+                      c2 = T[(VDISP ? 6 : 2) * TILE_PAIRS + pi];
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int j = 2 * h + e;
+            const double a = e ? a2.y : a2.x, b = e ? b2.y : b2.x, c = e ? c2.y : c2.x, m = e ? m2.y : m2.x;
+            // component order of the accumulators: xx, xy, xz, yy, yz, zz
+            const double pxx = a * a, pxy = a * b, pxz = a * c, pyy = b * b, pyz = b * c, pzz = c * c;
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                if (smask & (1u << s)) {   // warp-uniform
+                    if (bits & (1u << (4 * s + j))) {   // predicated updates (no mass sum: only ratios of the tensor are used)
+                        acc[s][0] = fma(m, pxx, acc[s][0]);
+                        acc[s][1] = fma(m, pxy, acc[s][1]);
+                        acc[s][2] = fma(m, pxz, acc[s][2]);
+                        acc[s][3] = fma(m, pyy, acc[s][3]);
+                        acc[s][4] = fma(m, pyz, acc[s][4]);
+                        acc[s][5] = fma(m, pzz, acc[s][5]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < S; s++) cnt[s] += __popc((bits >> (4 * s)) & 0xfu);
 }
 
 // A = w2 * e2 e2^T + w1 * e1 e1^T + w0 * e0 e0^T as (xx, yy, zz, 2xy, 2xz, 2yz); v = eigenvectors of eigh3.
@@ -229,19 +402,28 @@ __device__ __forceinline__ void katz_step(KatzState &st, const double (&tot)[7],
 #pragma unroll
         for (int r = 0; r < 9; r++) frame[F_V + r] = v[r];
         // v[6..8] major (e2), v[3..5] intermediate (e1), v[0..2] minor (e0)
-        const double iq2 = 1.0 / (st.q * st.q), is2 = 1.0 / (st.s * st.s);
+        const double qq = __dmul_rn(st.q, st.q), ss = __dmul_rn(st.s, st.s);   // q_new**2, s_new**2 (:251)
+        const double iq2 = 1.0 / qq, is2 = 1.0 / ss;
         quad_form(frame + F_AXX, v, 1.0, iq2, is2);
+        frame[F_QQ] = qq; frame[F_SS] = ss;
+        double bmax = 0.0;
         if (SHELL) {
             const bool first = (st.d == st.delta);   // shape_profs_algos.pyx:130: first shell -> ellipsoid test only
-            const double a = st.d - st.delta, b = st.q * st.d - st.delta, c = st.s * st.d - st.delta;
+            // (d-delta_d)**2, (q_new*d-delta_d)**2, (s_new*d-delta_d)**2 of :139
+            const double a = __dsub_rn(st.d, st.delta), b = __dsub_rn(__dmul_rn(st.q, st.d), st.delta),
+                         c = __dsub_rn(__dmul_rn(st.s, st.d), st.delta);
+            const double a2 = __dmul_rn(a, a), b2 = __dmul_rn(b, b), c2 = __dmul_rn(c, c);
             if (first) {
 #pragma unroll
                 for (int r = 0; r < 6; r++) frame[F_BXX + r] = 0.0;
             } else {
-                quad_form(frame + F_BXX, v, 1.0 / (a * a), 1.0 / (b * b), 1.0 / (c * c));
+                quad_form(frame + F_BXX, v, 1.0 / a2, 1.0 / b2, 1.0 / c2);
+                bmax = fmax(1.0 / a2, fmax(1.0 / b2, 1.0 / c2));
             }
+            frame[F_BA2] = a2; frame[F_BB2] = b2; frame[F_BC2] = c2;
             frame[F_THR] = first ? -1.0 : 1.0;
         }
+        if (CPG_F32_TEST) write_f32_frame(frame, is2, bmax, SHELL);
         *nin_slot = ip.pairs_inside(k, st.s);
     }
     st.iteration += 1;
@@ -281,7 +463,6 @@ __device__ __forceinline__ void make_tensor_products(double u, double v, double 
 // with registers tied up, and an object whose radial prefix fits in the ring (<= 512 particles per warp)
 // is loaded once and stays resident in shared memory for all Katz iterations of the task.
 // ------------------------------------------------------------------------------------------------
-constexpr int TILE_PAIRS = 64;
 constexpr int MAX_SORT_R = 256;   // == SORT_MAX_B of cpg_gather.cuh: radial ordering exists for R <= 255
 constexpr int RING_MAX_STAGES = 4;
 
@@ -334,13 +515,23 @@ struct WarpRing {
     uint32_t seq;         // tiles issued so far by this warp (stage = seq % STAGES, parity = (seq / STAGES) & 1)
     uint32_t res_seq;     // first sequence number of the resident tiles of the current task
     bool res_loaded;      // resident tiles are in place
+    uint32_t st_tiles, st_tshells;   // statistics: tiles this warp passed over, (tile, shell) pairs among them
 };
+
+__device__ __forceinline__ void ring_flush_stats(WarpRing &r, unsigned long long *stats, int lane)
+{
+    if (stats && lane == 0 && r.st_tiles) {
+        atomicAdd(stats, (unsigned long long)r.st_tiles);
+        atomicAdd(stats + 1, (unsigned long long)r.st_tshells);
+    }
+    r.st_tiles = 0; r.st_tshells = 0;
+}
 
 // arrivals: 1 for the TMA ring (the elected lane's arrive.expect_tx), 32 for the per-lane cp.async ring (every lane's
 // cp.async.mbarrier.arrive.noinc)
 __device__ __forceinline__ void ring_init(WarpRing &r, unsigned char *buf, uint64_t *bar, int lane, uint32_t arrivals = 1)
 {
-    r.buf = buf; r.bar = bar; r.seq = 0; r.res_seq = 0; r.res_loaded = false;
+    r.buf = buf; r.bar = bar; r.seq = 0; r.res_seq = 0; r.res_loaded = false; r.st_tiles = 0; r.st_tshells = 0;
     r.buf_s = smem_u32(buf); r.bar_s = smem_u32(bar);
     if (lane == 0) {
         for (int s = 0; s < RING_MAX_STAGES; s++) mbar_init(bar + s, arrivals);
@@ -399,6 +590,12 @@ __device__ __forceinline__ void ring_issue_lanes(const WarpRing &r, uint32_t seq
         }
     }
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <bool VDISP>
+__device__ __forceinline__ const unsigned char *ring_tile(const WarpRing &r, uint32_t seq)
+{
+    return r.buf + (seq % RingCfg<VDISP>::STAGES) * RingCfg<VDISP>::STAGE_BYTES;
 }
 
 // The two particles of pair `pi` of the tile in ring slot `seq` (this lane consumes pairs lane and lane+32).
@@ -497,8 +694,11 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
         for (int s = 0; s < S; s++)
             if (t * TILE_PAIRS < npr[s] && t >= tin[s]) smask |= 1u << s;
         smask &= amask;
+        if (smask != 0) { ring.st_tiles += 1; ring.st_tshells += __popc(smask); }
         if (smask == 0) {
             // (resident tasks only)
+        } else if (CPG_F32_TEST && !REDUCED) {
+            tile_f32<S, SHELL, VDISP>(ring_tile<VDISP>(ring, seq), lane, frames, smask, acc, cnt);
         } else if (VDISP) {
             // two particles at a time: the dispersion variant carries 13 doubles per particle
 #pragma unroll
@@ -600,8 +800,12 @@ __device__ __forceinline__ void init_frames(double *frames, int *np, int *nin, c
         F[F_THR] = __dmul_rn(in, in);   // pass 0: r2 >= (d-delta)^2 (shell variant; 0 for the first shell)
 #pragma unroll
         for (int r = 0; r < 6; r++) F[F_AXX + r] = F[F_BXX + r] = (r < 3) ? 1.0 : 0.0;   // A = B = I
+        // starting basis: major = x, intermediate = y, minor = z (v[6..8], v[3..5], v[0..2]), so that exact_member's
+        // p0^2 + p1^2/1 + p2^2/1 is the reference's (x^2 + y^2) + z^2 of pass 0, same order
 #pragma unroll
-        for (int r = 0; r < 9; r++) F[F_V + r] = (r == 0 || r == 4 || r == 8) ? 1.0 : 0.0;
+        for (int r = 0; r < 9; r++) F[F_V + r] = (r == 2 || r == 4 || r == 6) ? 1.0 : 0.0;
+        F[F_QQ] = 1.0; F[F_SS] = 1.0; F[F_BA2] = 1.0; F[F_BB2] = 1.0; F[F_BC2] = 1.0;
+        if (CPG_F32_TEST) write_f32_frame(F, 1.0, 1.0, true);
         np[L.ls] = (ne + 1) >> 1;
     }
 }
@@ -742,7 +946,9 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
             if (amask == 0)
                 break;
         }
+        if (ring.st_tiles > (1u << 20)) ring_flush_stats(ring, P.stats, lane);
     }
+    ring_flush_stats(ring, P.stats, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -878,6 +1084,7 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
         run_pass<S, SHELL, REDUCED, VDISP>(P.soa, base, active_npairs<S>(npr, amask), tile0, tstride, lane, ring,
                                            resident, npairs_task, frames, npr, nin, amask, acc, cnt);
     }
+    ring_flush_stats(ring, P.stats, lane);
     if (C > 1)
         cluster.sync();   // nobody leaves while a peer may still read its shared memory
 }
@@ -955,6 +1162,7 @@ __global__ void __launch_bounds__(GRID_KERNEL_WARPS * 32) grid_pass_kernel(const
     int cnt[S];
     run_pass<S, SHELL, REDUCED, VDISP>(P.soa, P.soa.poff[halo], active_npairs<S>(npr, amask), blockIdx.x * NW + warp,
                                        gridDim.x * NW, lane, ring, false, 0, s_frames, npr, s_nin, amask, acc, cnt);
+    ring_flush_stats(ring, P.stats, lane);
     double val[NV];
     pack_values<S>(acc, cnt, val);
     const double mine = warp_sum_transpose<NV>(val, lane);

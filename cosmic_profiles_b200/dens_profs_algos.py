@@ -18,20 +18,19 @@ def _prep(xyz, masses, idx_cat, obj_size):
             _lib.i32(np.asarray(obj_size)))
 
 
-def _context(xyz, masses, idx_cat, obj_size):
-    ctx = _session.get_context((_session.devices or [0])[0])
-    ctx.set_particles(xyz, None, masses)
-    ctx.set_catalogue(idx_cat, obj_size)
-    return ctx
+def _rows(a, objs):
+    """Rows of a per-object array that belong to a shard (objs None: the single-device case, all rows)."""
+    return a if objs is None else np.ascontiguousarray(a[objs])
 
 
-def _centres(ctx, xyz, masses, idx_cat, obj_size, L_BOX, CENTER, centers):
+def _centres(grp, xyz, masses, idx_cat, obj_size, L_BOX, CENTER, centers):
     """Density paths: calcMode starts from rad = 1000 (dens_profs_algos.pyx:42)."""
     if centers is not None:
         return _lib.f64(centers)
     if _session.gpu_centers:
         ref = _centers.reference_points(xyz, idx_cat, obj_size) if L_BOX != 0.0 else None
-        return ctx.centers(1 if CENTER == 'mode' else 0, False, L_BOX, ref)
+        mode = 1 if CENTER == 'mode' else 0
+        return grp.rows(lambda ctx, objs: ctx.centers(mode, False, L_BOX, None if ref is None else _rows(ref, objs)))
     return _centers.compute_centers(xyz, masses, idx_cat, obj_size, L_BOX, CENTER, False)
 
 
@@ -39,9 +38,10 @@ def calcMassesCenters(xyz, masses, idx_cat, obj_size, L_BOX, CENTER):
     xyz, masses, idx_cat, obj_size = _prep(xyz, masses, idx_cat, obj_size)
     if len(obj_size) == 0:
         return np.zeros((0, 3)), np.zeros(0)
-    ctx = _context(xyz, masses, idx_cat, obj_size)
-    cen = _centres(ctx, xyz, masses, idx_cat, obj_size, L_BOX, CENTER, None)
-    m = ctx.obj_masses()
+    with _session.locked_group() as grp:
+        grp.set_snapshot(xyz, None, masses, idx_cat, obj_size)
+        cen = _centres(grp, xyz, masses, idx_cat, obj_size, L_BOX, CENTER, None)
+        m = grp.rows(lambda ctx, objs: ctx.obj_masses())
     return _centers.recentre(cen, L_BOX), m
 
 
@@ -61,11 +61,15 @@ def calcDensProfsSphDirectBinning(xyz, masses, r200s, r_over_r200, idx_cat, obj_
     R = len(r_over_r200)
     if len(obj_size) == 0:
         return np.zeros((0, R), dtype=np.float64)
-    ctx = _context(xyz, masses, idx_cat, obj_size)
-    cen = _centres(ctx, xyz, masses, idx_cat, obj_size, L_BOX, CENTER, centers)
-    dens, cnt = ctx.dens_sph(cen, r200s, sph_bin_edges(r_over_r200), L_BOX)
+    r200s = _lib.f64(np.asarray(r200s))
+    edges = sph_bin_edges(r_over_r200)
+    with _session.locked_group() as grp:
+        grp.set_snapshot(xyz, None, masses, idx_cat, obj_size)
+        cen = _centres(grp, xyz, masses, idx_cat, obj_size, L_BOX, CENTER, centers)
+        dens, cnt = grp.rows(lambda ctx, objs: ctx.dens_sph(_rows(cen, objs), _rows(r200s, objs), edges, L_BOX))
+        timing = grp.timings()
     last_info.clear()
-    last_info.update(counts=cnt, timing=[ctx.timing()])
+    last_info.update(counts=cnt, timing=timing)
     return dens
 
 
@@ -133,18 +137,25 @@ def calcDensProfsEllDirectBinning(xyz, masses, r200s, r_over_r200, a, b, c, majo
     a, b, c = (_lib.f64(np.asarray(v)) for v in (a, b, c))
     major, inter, minor = (_lib.f64(np.asarray(v)) for v in (major, inter, minor))
     assert a.shape[0] == b.shape[0] and b.shape[0] == c.shape[0]
-    ctx = _context(xyz, masses, idx_cat, obj_size)
-    cen = _centres(ctx, xyz, masses, idx_cat, obj_size, L_BOX, CENTER, centers)
-    if device_interp and 2 <= a.shape[1] <= MAX_DEVICE_INTERP_SHELLS:
-        # the interpolation of :163-195 on the device; the profiles never come back to the host
-        r = _lib.f64(np.asarray(r_over_r200))
-        ctx.shape_interp(r200s, r, ell_bin_edges(r), a, b, c, major, inter, minor)
-        dens, cnt = ctx.dens_ell(cen, None, None, None, None, None, None, L_BOX)
-    else:
-        ai, bi, ci, mj, it, mn = interpolate_shapes(r200s, r_over_r200, a, b, c, major, inter, minor)
-        dens, cnt = ctx.dens_ell(cen, ai, bi, ci, mj, it, mn, L_BOX)
+    r = _lib.f64(np.asarray(r_over_r200))
+    on_device = device_interp and 2 <= a.shape[1] <= MAX_DEVICE_INTERP_SHELLS
+    if not on_device:
+        prof = interpolate_shapes(r200s, r_over_r200, a, b, c, major, inter, minor)
+
+    def shard(ctx, objs):
+        if on_device:
+            # the interpolation of :163-195 on the device; the profiles never come back to the host
+            ctx.shape_interp(_rows(r200s, objs), r, ell_bin_edges(r), *[_rows(v, objs) for v in (a, b, c, major, inter, minor)])
+            return ctx.dens_ell(_rows(cen, objs), None, None, None, None, None, None, L_BOX)
+        return ctx.dens_ell(_rows(cen, objs), *[_rows(v, objs) for v in prof], L_BOX)
+
+    with _session.locked_group() as grp:
+        grp.set_snapshot(xyz, None, masses, idx_cat, obj_size)
+        cen = _centres(grp, xyz, masses, idx_cat, obj_size, L_BOX, CENTER, centers)
+        dens, cnt = grp.rows(shard)
+        timing = grp.timings()
     last_info.clear()
-    last_info.update(counts=cnt, timing=[ctx.timing()])
+    last_info.update(counts=cnt, timing=timing)
     return dens
 
 
@@ -153,9 +164,12 @@ def calcDensProfsKernelBased(xyz, masses, r200s, r_over_r200, idx_cat, obj_size,
     R = len(r_over_r200)
     if len(obj_size) == 0:
         return np.zeros((0, R), dtype=np.float64)
-    ctx = _context(xyz, masses, idx_cat, obj_size)
-    cen = _centres(ctx, xyz, masses, idx_cat, obj_size, L_BOX, CENTER, centers)
-    dens = ctx.dens_kernel(cen, r200s, r_over_r200, L_BOX)
+    r200s = _lib.f64(np.asarray(r200s))
+    with _session.locked_group() as grp:
+        grp.set_snapshot(xyz, None, masses, idx_cat, obj_size)
+        cen = _centres(grp, xyz, masses, idx_cat, obj_size, L_BOX, CENTER, centers)
+        dens = grp.rows(lambda ctx, objs: ctx.dens_kernel(_rows(cen, objs), _rows(r200s, objs), r_over_r200, L_BOX))
+        timing = grp.timings()
     last_info.clear()
-    last_info.update(timing=[ctx.timing()])
+    last_info.update(timing=timing)
     return dens

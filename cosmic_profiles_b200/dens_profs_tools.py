@@ -85,8 +85,36 @@ def fitDensProfHelper(dens_profs, ROverR200, r200s, method):
     lb = np.array([b[0] for b in bnds], dtype=np.float64)
     ub = np.array([b[1] for b in bnds], dtype=np.float64)
     x0 = _initial_guess(prof, r200s)
-    ctx = session.get_context((session.devices or [0])[0])
-    best, fun, nfev, nit = ctx.fit_profiles(radii, lmed, n_valid, avg, x0, lb, ub, PROFILE_ID[prof])
+    # objects are independent (the reference maps them over a process pool, :347-348): equal slices per device
+    with session.locked_group() as grp:
+        ctxs = grp.contexts
+        n = dens.shape[0]
+        cuts = [n * k // len(ctxs) for k in range(len(ctxs) + 1)] if n >= 2 * len(ctxs) else [0] + [n] * len(ctxs)
+        parts, errs = [None] * len(ctxs), []
+
+        def work(k):
+            a, b = cuts[k], cuts[k + 1]
+            if b > a:
+                try:
+                    parts[k] = ctxs[k].fit_profiles(radii[a:b], lmed[a:b], n_valid[a:b], avg[a:b], x0[a:b], lb, ub,
+                                                    PROFILE_ID[prof]) + (ctxs[k].timing(),)
+                except Exception as e:   # re-raised below, in the caller's thread
+                    errs.append(e)
+        import threading
+        th = [threading.Thread(target=work, args=(k,)) for k in range(1, len(ctxs))]
+        for t in th:
+            t.start()
+        work(0)
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+    parts = [p for p in parts if p is not None]
+    if parts:
+        best, fun, nfev, nit = (np.concatenate([p[j] for p in parts]) for j in range(4))
+    else:
+        best, fun = np.zeros((0, NPARS[prof])), np.zeros(0)
+        nfev = nit = np.zeros(0, dtype=np.int32)
     last_info.clear()
-    last_info.update(fun=fun, nfev=nfev, nit=nit, timing=ctx.timing())
+    last_info.update(fun=fun, nfev=nfev, nit=nit, timing=parts[0][4] if parts else None, timings=[p[4] for p in parts])
     return best

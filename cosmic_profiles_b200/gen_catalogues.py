@@ -21,8 +21,9 @@ def calcObjCat(nb_shs, sh_len, fof_sizes, group_r200, MIN_NUMBER_PTCS):
     if nb_shs.shape[0] == 0:
         # the reference reaches np.max of an empty array (:76)
         raise ValueError("zero-size array to reduction operation maximum which has no identity")
-    ctx = session.get_context((session.devices or [0])[0])
-    idx, r200, size = ctx.obj_cat(nb_shs, sh_len, fof_sizes, group_r200, int(MIN_NUMBER_PTCS))
+    # one device: the scans are a millisecond of work; the catalogue is sharded later, with its particles
+    with session.locked_group() as grp:
+        idx, r200, size = grp.contexts[0].obj_cat(nb_shs, sh_len, fof_sizes, group_r200, int(MIN_NUMBER_PTCS))
     return idx, r200, size
 
 

@@ -26,8 +26,9 @@ def install(target=None):
         target = importlib.import_module("cosmic_profiles.common.cosmic_base_class")
     impl = _implementations()
     for n in DRIVER_NAMES:
-        if n not in _saved:
-            _saved[n] = (target, getattr(target, n, None))
+        key = (n, id(target))   # per target module: a second install(target=other) records that module's originals too
+        if key not in _saved:
+            _saved[key] = (target, getattr(target, n, None))
         setattr(target, n, impl[n])
     return target
 
@@ -65,7 +66,7 @@ def install_gadget(targets=None):
 
 
 def uninstall():
-    for n, (target, fn) in list(_saved.items()):
+    for key, (target, fn) in list(_saved.items()):
         if fn is not None:
-            setattr(target, n[0] if isinstance(n, tuple) else n, fn)
-        del _saved[n]
+            setattr(target, key[0], fn)
+        del _saved[key]

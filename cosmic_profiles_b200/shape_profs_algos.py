@@ -6,11 +6,9 @@ Everything numeric runs in libcosmicgpu.so (sm_100a); this module only does what
 Python around its prange: centres (:586-591), zero -> NaN masking (:616-624), recentring (:627) and the
 (d, q, s, minor, inter, major, centers, m) packing (:628).  No CPU fallback.
 """
-import threading
-
 import numpy as np
 
-from . import _lib, centers as _centers, partition as _partition, session as _session
+from . import _lib, centers as _centers, session as _session
 
 last_info = {}   # n_iter / n_pts / timing of the most recent call (the reference keeps these as locals)
 
@@ -19,21 +17,6 @@ def _nan0(a):
     a = np.array(a, dtype=np.float64, copy=True)
     a[a == 0.0] = np.nan
     return a
-
-
-def _run_one(device, xyz, vxyz, masses, idx_cat, obj_size, cen, r200, rr, local, SAFE, L_BOX, IT_TOL, IT_WALL,
-             IT_MIN, reduced, shell_based, CENTER="com"):
-    """Returns (out, nit, npt, m, vc, centres, timing)."""
-    ctx = _session.get_context(device)
-    ctx.set_particles(xyz, vxyz, masses)
-    ctx.set_catalogue(idx_cat, obj_size)
-    if cen is None:   # centres on the device (shape path: calcMode starts from the bounding-box extent)
-        ref = _centers.reference_points(xyz, idx_cat, obj_size) if L_BOX != 0.0 else None
-        cen = ctx.centers(1 if CENTER == 'mode' else 0, True, L_BOX, ref)
-    # out/nit/npt are views into the context's page-locked scratch, valid until its next shape() call;
-    # every caller below copies out of them before touching the context again
-    return ctx.shape(cen, r200, rr, local, SAFE, L_BOX, IT_TOL, IT_WALL, IT_MIN, reduced, shell_based,
-                     vxyz is not None) + (cen, ctx.timing())
 
 
 def _morph(xyz, vxyz, masses, r200, idx_cat, obj_size, L_BOX, r_over_r200, IT_TOL, IT_WALL, IT_MIN, CENTER, SAFE,
@@ -46,54 +29,33 @@ def _morph(xyz, vxyz, masses, r200, idx_cat, obj_size, L_BOX, r_over_r200, IT_TO
     obj_size = _lib.i32(np.asarray(obj_size))
     rr = _lib.f64(np.asarray(r_over_r200)) if local else None
     n = int(obj_size.shape[0])
-    R = int(rr.shape[0]) if local else 1
     if centers is not None:
         cen = _lib.f64(centers)
     elif _session.gpu_centers:
-        cen = None          # computed on the device by every shard (cpg_centers)
+        cen = None          # computed on the device(s) that hold the objects (cpg_centers)
     else:
         cen = _centers.compute_centers(xyz, masses, idx_cat, obj_size, L_BOX, CENTER, shape_path=True)
-    devs = _session.devices or [0]
-    args = (rr, local, SAFE, L_BOX, IT_TOL, IT_WALL, IT_MIN, reduced, shell_based, CENTER)
-    if len(devs) == 1 or n < 2 * len(devs):
-        out, nit, npt, m, vc, cen, tim = _run_one(devs[0], xyz, vxyz, masses, idx_cat, obj_size, cen, r200, *args)
-        nit, npt = nit.copy(), npt.copy()
-        timings = [tim]
-    else:
-        # objects are independent: shard them, one host thread per device, disjoint output slices
-        parts = _partition.lpt_partition(obj_size.astype(np.float64) * R, len(devs))
-        out = np.zeros((n, R, 12))
-        nit = np.full((n, R), -1, dtype=np.int32)
-        npt = np.full((n, R), -1, dtype=np.int32)
-        m = np.zeros(n)
-        vc = np.zeros((n, 3))
-        cen_all = np.zeros((n, 3))
-        timings = [None] * len(devs)
-        errors = []
-
-        def work(k):
-            try:
-                objs = parts[k]
-                if len(objs) == 0:
-                    return
-                sub_idx, sub_size = _partition.sub_catalogue(idx_cat, obj_size, objs)
-                # ship only this shard's particles; the shard catalogue becomes 0..n_sub-1
-                local_idx = np.arange(len(sub_idx), dtype=np.int32)
-                res = _run_one(devs[k], xyz[sub_idx], None if vxyz is None else vxyz[sub_idx], masses[sub_idx],
-                               local_idx, sub_size, None if cen is None else cen[objs], r200[objs], *args)
-                out[objs], nit[objs], npt[objs], m[objs], vc[objs], cen_all[objs] = res[:6]
-                timings[k] = res[6]
-            except Exception as e:   # surfaced below, in the caller's thread
-                errors.append(e)
-
-        threads = [threading.Thread(target=work, args=(k,)) for k in range(len(devs))]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        if errors:
-            raise errors[0]
-        cen = cen_all
+    mode = -1 if cen is not None else (1 if CENTER == 'mode' else 0)
+    # the reference point of python_routines.respectPBCNoRef decides which particles move in a periodic box
+    ref = _centers.reference_points(xyz, idx_cat, obj_size) if (cen is None and L_BOX != 0.0) else None
+    args = (rr, local, SAFE, L_BOX, IT_TOL, IT_WALL, IT_MIN, reduced, shell_based, vxyz is not None)
+    # objects are independent (shape_profs_algos.pyx:592: prange over objects): with several devices in
+    # session.devices the library deals them out by particle count (cpg_multi); one lock for the whole sequence
+    with _session.locked_group() as grp:
+        if grp.multi is not None and n >= 2 * len(grp.devices):
+            grp.set_snapshot(xyz, vxyz, masses, idx_cat, obj_size)
+            out, nit, npt, m, vc, cen = grp.multi.shape(cen, mode, ref, r200, *args)
+            timings = grp.timings()
+            extra = grp.multi.info()
+        else:   # one device (or too few objects to shard: everything on the first one)
+            ctx = grp.contexts[0]
+            ctx.set_particles(xyz, vxyz, masses)
+            ctx.set_catalogue(idx_cat, obj_size)
+            if cen is None:   # shape path: calcMode starts from the bounding-box extent
+                cen = ctx.centers(mode, True, L_BOX, ref)
+            out, nit, npt, m, vc = ctx.shape(cen, r200, *args)
+            timings = [ctx.timing()]
+            extra = None
     d = _nan0(out[:, :, 0])
     q = _nan0(out[:, :, 1])
     s = _nan0(out[:, :, 2])
@@ -106,7 +68,7 @@ def _morph(xyz, vxyz, masses, r200, idx_cat, obj_size, L_BOX, r_over_r200, IT_TO
         major, inter, minor = major[:, 0], inter[:, 0], minor[:, 0]
         nit, npt = nit[:, 0], npt[:, 0]
     last_info.clear()
-    last_info.update(n_iter=nit, n_pts=npt, vcenters=vc, timing=timings)
+    last_info.update(n_iter=nit, n_pts=npt, vcenters=vc, timing=timings, multi=extra)
     return d, q, s, minor, inter, major, cen_out, m
 
 

@@ -53,6 +53,10 @@ typedef struct cpg_timing {
     int32_t hot_kernel_launches;    /* of which hot kernels (the ones kernel_ms covers) */
     int64_t h2d_bytes;
     int64_t d2h_bytes;
+    /* cpg_shape only: 128-particle tiles the morphology kernels passed over, and (tile, shell) pairs among them --
+     * the fp64 work of a call is 128 * (6 * tile_visits + 6 * tile_shell_visits) multiply-adds (bench.py's fp64 roofline) */
+    int64_t tile_visits;
+    int64_t tile_shell_visits;
 } cpg_timing;
 
 CPG_API int cpg_device_count(void);
@@ -74,6 +78,27 @@ CPG_API int cpg_set_particles(cpg_ctx *ctx, const double *xyz, const double *vxy
  * them (shape_profs_algos.pyx:557); offsets are 64-bit here. */
 CPG_API int cpg_set_catalogue(cpg_ctx *ctx, const int32_t *idx_cat, int64_t n_idx, const int32_t *obj_size,
                               int32_t n_obj);
+
+/* Snapshot as the concatenation of element ranges of the host arrays: particles [seg_start[i], seg_start[i] +
+ * seg_len[i]) of xyz / vxyz / masses, i = 0..n_seg-1, become the device snapshot (host threads pack the ranges
+ * straight into page-locked bounce buffers).  Used to ship one shard of a halo-partitioned catalogue to its GPU
+ * (replaces the fancy-indexed copy xyz[sub_idx] a host-side sharding would need); cpg_multi_set_snapshot builds on it. */
+CPG_API int cpg_set_particles_segments(cpg_ctx *ctx, const double *xyz, const double *vxyz, const double *masses,
+                                       const int64_t *seg_start, const int64_t *seg_len, int64_t n_seg);
+
+/* Index catalogue whose objects are contiguous snapshot ranges (FoF / SUBFIND order, what calcCSHIdxs produces,
+ * gadget/gen_catalogues.pyx:29-35): object h = particles [obj_start[h], obj_start[h] + obj_size[h]).  No flat index
+ * array exists on either side (4 bytes per particle less over PCIe and in HBM) and the gather reads the snapshot
+ * coalesced.  cpg_set_catalogue recognises such catalogues by itself (option "detect_ranges").
+ * cpg_catalogue_ranges is the host-side test it uses: returns 1 and fills obj_start_out (n_obj) when every object of
+ * the flat catalogue is a contiguous ascending run, 0 when not, < 0 on bad arguments.  No device needed. */
+CPG_API int cpg_set_catalogue_ranges(cpg_ctx *ctx, const int64_t *obj_start, const int32_t *obj_size, int32_t n_obj);
+CPG_API int cpg_catalogue_ranges(const int32_t *idx_cat, int64_t n_idx, const int32_t *obj_size, int32_t n_obj,
+                                 int64_t *obj_start_out);
+
+/* Content token of a host array as the snapshot cache computes it (option "snapshot_cache"): full == 0: first and
+ * last 4 KB plus 4096 evenly spaced 64-byte blocks; full != 0: every byte.  No device needed. */
+CPG_API int cpg_host_token(const void *p, size_t bytes, int32_t full, uint64_t *token_out);
 
 /*
  * Katz-Dubinski iterative morphology for every object of the catalogue.
@@ -212,8 +237,50 @@ CPG_API void cpg_host_free(void *p);
  * particles shell k actually streams per Katz iteration; see cpg_gather.cuh "Radial ordering"). */
 CPG_API int cpg_get_prefix_lengths(cpg_ctx *ctx, int32_t *n_eff, int32_t R);
 
+/* Counters of a context (diagnostics, tests): "uploads_skipped" (calls the snapshot cache answered), "catalogue_as_ranges"
+ * (1: the resident catalogue is kept as contiguous ranges), "n_part", "n_obj", "snapshot_version", "catalogue_version". */
+CPG_API int cpg_get_stat(cpg_ctx *ctx, const char *name, int64_t *out);
+
 /* Timing breakdown of the most recent compute call on this context. */
 CPG_API int cpg_get_timing(cpg_ctx *ctx, cpg_timing *out);
+
+/* Measured fp64 multiply-add peak of the context's device in 1e12 FMA/s (independent FMA chains on every SM, CUDA
+ * events, best of a few repetitions): the denominator of bench.py's fp64 roofline. */
+CPG_API int cpg_measure_fp64_peak(cpg_ctx *ctx, double *tfma_per_s);
+
+/*
+ * Several GPUs of one box.  The reference spreads the objects of ONE catalogue over the
+ * host's cores (prange, shape_profs_algos.pyx:592, dens_profs_algos.pyx:102); cpg_multi spreads them over devices:
+ * a particle-count-balanced LPT partition of the objects (cpg_partition_lpt: descending cost, each object to the least
+ * loaded part; owner_out[h] = part of object h), every device receives only its own objects' particles and runs the
+ * single-device path on its own host thread, results land in the rows of the caller's arrays.  No collective.
+ *   cpg_multi_set_snapshot  = cpg_set_particles + cpg_set_catalogue for the whole catalogue (contiguous-range
+ *                             catalogues ship each shard's ranges only; others ship the snapshot to every device)
+ *   cpg_multi_shape         = cpg_shape; center_mode < 0: centers (n_obj,3) given; 0 / 1: 'com' / 'mode' centres
+ *                             computed per device (cpg_centers, shape path; ref_points as there) -> centers_out
+ *   cpg_multi_context       = the single-device context of a slot (owned by the handle) for the other entry points,
+ *   cpg_multi_shard           with cpg_multi_shard giving the catalogue rows (ascending) that slot holds
+ *   cpg_multi_get_info      = per slot: device ordinal, objects, resident particles, timing of its last call;
+ *                             host_ms[4] = partition, sharded upload, result scatter (mean per device), last call (wall)
+ */
+typedef struct cpg_multi cpg_multi;
+CPG_API int cpg_partition_lpt(const double *cost, int32_t n, int32_t n_parts, int32_t *owner_out);
+CPG_API int cpg_multi_create(const int32_t *devices, int32_t n_dev, cpg_multi **out);
+CPG_API void cpg_multi_destroy(cpg_multi *m);
+CPG_API int cpg_multi_devices(cpg_multi *m);
+CPG_API cpg_ctx *cpg_multi_context(cpg_multi *m, int32_t slot);
+CPG_API int cpg_multi_set_option(cpg_multi *m, const char *name, int64_t value);
+CPG_API int cpg_multi_set_snapshot(cpg_multi *m, const double *xyz, const double *vxyz, const double *masses,
+                                   int64_t n_part, const int32_t *idx_cat, int64_t n_idx, const int32_t *obj_size,
+                                   int32_t n_obj);
+CPG_API int cpg_multi_shard(cpg_multi *m, int32_t slot, int32_t *n_obj_out, int64_t *n_part_out, int32_t *objs_out);
+CPG_API int cpg_multi_shape(cpg_multi *m, const double *centers, int32_t center_mode, const double *ref_points,
+                            const double *r200, const double *r_over_r200, int32_t R, int32_t local, double SAFE,
+                            float L_BOX, double IT_TOL, int32_t IT_WALL, int32_t IT_MIN, int32_t reduced,
+                            int32_t shell_based, int32_t use_vel, double *out12, int32_t *n_iter, int32_t *n_pts,
+                            double *obj_mass, double *vcenters, double *centers_out);
+CPG_API int cpg_multi_get_info(cpg_multi *m, int32_t slot, int32_t *device, int32_t *n_obj, int64_t *n_part,
+                               cpg_timing *timing, double *host_ms);
 
 /* Tunables (scheduling only; results do not depend on them beyond fp64 summation order):
  *   "shells_per_pass"  1,2,4 or 0=auto   how many shells of one object share one read of its particles
@@ -231,6 +298,12 @@ CPG_API int cpg_get_timing(cpg_ctx *ctx, cpg_timing *out);
  *   "upload_threads"   host threads (0..8, default 8) that stage PAGEABLE host arrays of >= 64 MB through page-locked bounce
  *                      buffers in cpg_set_particles / cpg_set_catalogue; 0 leaves them to cudaMemcpyAsync.  Page-locked
  *                      sources are always copied directly.
+ *   "snapshot_cache"   1 (default): cpg_set_particles / cpg_set_catalogue return at once when called with the arrays the
+ *                      device already holds -- same pointers, same lengths, same content token (the reference's class
+ *                      hands the same xyz / masses / idx_cat to every driver, common/cosmic_base_class.pyx:155,232,863);
+ *                      the token samples the arrays (cpg_host_token), the flat catalogue is hashed in full.  2: full
+ *                      hash of the particle arrays too; 0: always upload
+ *   "detect_ranges"    1 (default): cpg_set_catalogue keeps a contiguous-range catalogue as ranges (no index array)
  *   "prefix_table"     1 (default): non-reduced ellipsoid-based shapes on radially ordered particles take the tensor
  *                      sums of the whole 128-particle tiles at |x-c| < s*d (certain members) from a per-object prefix
  *                      table built once per gather instead of streaming them every Katz iteration; 0: no inner prefix
