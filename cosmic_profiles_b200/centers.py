@@ -4,8 +4,10 @@ The reference computes object centres in a serial Python loop ahead of every dri
 (cosmic_profiles/shape_profs/shape_profs_algos.pyx:586-591, dens_profs/dens_profs_algos.pyx:39-44,96-101)
 with the helpers of cosmic_profiles/common/python_routines.py (calcMode :287-306, respectPBCNoRef :499-528,
 calcCoM :530-547, recentreObject :549-565).  Centres are an INPUT of the GPU path (BASELINE.json
-north_star); they are produced here with the same numpy operations so that they are bit-identical to the
-reference's.  A device-side centre finder is SURVEY.md section 8(f) "next" row 1.
+north_star).  By default the drop-in drivers compute them on the device (cpg_centers, csrc/cpg_centers.cuh; agreement
+with the reference's centres <= 1e-12, tests/test_gpu_scale_parity.py); this module is the host alternative
+(`session.gpu_centers = False`): the same numpy operations as the reference, bit-identical centres.  It also supplies
+the seeded reference points the device centre finder needs in a periodic box, and recentreObject.
 """
 import numpy as np
 from numpy.random import default_rng

@@ -1658,7 +1658,7 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     c->timing.h2d_bytes = (int64_t)sizeof(double) * (4 * (int64_t)n + (local ? R : 0));
 
     // ---- task list: objects largest first; S shells of one object per task
-    const int warp_slots = c->sm_count * 12;   // resident warps of the warp kernel (3 CTAs x 4 warps per SM)
+    const int warp_slots = c->sm_count * 4 * CPG_WARP_MINB;   // resident warps of the warp kernel (CPG_WARP_MINB CTAs x 4 warps per SM)
     const int64_t n_units = (int64_t)n * R;
     int S = c->opt_shells_per_pass;
     if (S == 0) {
@@ -1671,7 +1671,8 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
         if (R >= 4 && (n_units / 4 >= 4 * (int64_t)warp_slots || mean_size >= 200000)) S = 4;
     }
     if (S > R) S = pow2_floor(R);
-    int64_t large_min = c->opt_large_halo_min > 0 ? c->opt_large_halo_min : (int64_t)131072;
+    // (the warp kernel keeps prefix lengths as 16-bit pair counts: its objects must stay below 131072 particles)
+    int64_t large_min = c->opt_large_halo_min > 0 ? std::min<int64_t>(c->opt_large_halo_min, 131072) : (int64_t)131072;
     // few tasks: a warp per task would leave the GPU to a handful of long-running warps (non-converging shells
     // iterate up to IT_WALL times); give every task of a non-tiny object a CTA / cluster instead
     if (c->opt_large_halo_min == 0 && (n_units + S - 1) / S < 8 * (int64_t)warp_slots) large_min = 4096;

@@ -52,6 +52,9 @@ struct Particle {              // one particle as seen by the accumulators
     double t[6];               // products the tensor is built from (velocities; VDISP only)
 };
 
+#ifndef CPG_FP64_PAIRS
+#define CPG_FP64_PAIRS 0   // 1: the all-fp64 path works on one particle pair at a time (rolled loop)
+#endif
 #ifndef CPG_F32_TEST
 #define CPG_F32_TEST 1   // 1: fp32 pre-classification of the membership tests (non-reduced variants); 0: all-fp64 tests
 #endif
@@ -204,104 +207,128 @@ __device__ __forceinline__ void passk_particles(const Particle (&p)[NP], const d
     }
 }
 
-// One tile (this lane's pairs `lane` and `lane + 32`: 4 particles) of the non-reduced variants, in two phases so
-// that the fp64 products never live at the same time as the fp32 ones:
-//   1. classify the 4 particles against every shell of `smask` in fp32 (classification comment above), undecided
-//      ones through exact_member(); the verdicts are 4 bits per shell in one register;
-//   2. per particle: the six fp64 products (positions, or velocities for the dispersion tensor) once, then the
-//      predicated tensor updates of the shells it is a member of.
+// The undecided particles of the fp32 pre-classification, re-tested in fp64: with the quadratic form (what
+// passk_particles evaluates; exact squares, so that pass 0 is the reference's ((xx+yy)+zz)), or -- for needle-like
+// shells, K >= F32_NEEDLE_K, where the quadratic form itself loses digits to cancellation, and for shells whose fp32
+// test is switched off -- with the reference's own rotate-then-sum expression (exact_member).  Out of line: it runs
+// for a fraction ~K of the particles.  v0, v1 (u0, u1): the fp32 forms of the pair's two particles; m2: their fp32
+// verdicts (bit e = particle e is a member); returns the corrected verdicts.
+constexpr float F32_NEEDLE_K = 1e-3f;   // K = 3 * 2^-20 / s^2 >= 1e-3  <=>  s <= 0.053
+
+struct PairForms { float v0, v1, u0, u1; };
+
+// Returns the forms with every UNDECIDED particle's pair (v, u) replaced by a verdict the caller's own comparisons
+// read back: (v, u) = (-1, +inf) for a member (v < lo_eff and u > hiB_eff always hold: lo_eff >= 0, hiB_eff <= FLT_MAX),
+// (+inf, u) for a non-member.  Decided particles keep their values.
+template <bool SHELL>
+__device__ __noinline__ PairForms redecide_pair(const double *F, const unsigned char *tile, int pi, PairForms w)
+{
+    const float4 *G4 = reinterpret_cast<const float4 *>(F + F_F32);
+    const float lo = G4[1].z, hi = G4[1].w;
+    const bool off = !(lo > -INFINITY);
+    float loB = 0.f, hiB = 0.f;
+    bool offB = false;
+    if (SHELL) { loB = G4[3].z; hiB = G4[3].w; offB = !(loB > -INFINITY); }
+    const bool needle = off || (hi - lo > 2.0f * F32_NEEDLE_K * hi);   // hi - lo = 2 K d^2
+    const double2 *T = reinterpret_cast<const double2 *>(tile);
+    const double2 x = T[pi], y = T[TILE_PAIRS + pi], z = T[2 * TILE_PAIRS + pi];
+#pragma unroll 1
+    for (int e = 0; e < 2; e++) {
+        const float vj = e ? w.v1 : w.v0;
+        bool un = off || ((vj >= lo) && (vj <= hi));
+        if (SHELL) {
+            const float uj = e ? w.u1 : w.u0;
+            un = un || ((vj < lo) && (((uj >= loB) && (uj <= hiB)) || offB));
+        }
+        if (un) {
+            const double px = e ? x.y : x.x, py = e ? y.y : y.x, pz = e ? z.y : z.x;
+            bool mem;
+            if (needle) {
+                mem = exact_member<SHELL>(F, px, py, pz);
+            } else {
+                const double xx = __dmul_rn(px, px), yy = __dmul_rn(py, py), zz = __dmul_rn(pz, pz);
+                const double xy = px * py, xz = px * pz, yz = py * pz;
+                const double v = fma(F[F_AYZ], yz, fma(F[F_AXZ], xz, fma(F[F_AXY], xy, fma(F[F_AZZ], zz, fma(F[F_AYY], yy, F[F_AXX] * xx)))));
+                mem = v < F[F_D2];
+                if (SHELL) {
+                    const double u = fma(F[F_BYZ], yz, fma(F[F_BXZ], xz, fma(F[F_BXY], xy, fma(F[F_BZZ], zz, fma(F[F_BYY], yy, F[F_BXX] * xx)))));
+                    mem = mem && (u >= F[F_THR]);
+                }
+            }
+            const float nv = mem ? -1.0f : INFINITY;
+            if (e) { w.v1 = nv; w.u1 = INFINITY; } else { w.v0 = nv; w.u0 = INFINITY; }
+        }
+    }
+    return w;
+}
+
+// One particle pair (pair `pi` of the tile: 2 particles per lane) of the non-reduced variants: per shell the
+// membership of the two particles is decided in fp32 (classification comment above) and the tensor updates are
+// predicated fp64 FMAs on the six products formed once per particle.  Undecided particles (rare; warp vote) go through
+// redecide_pair.  Called for pairs lane and lane + 32 from a loop that is NOT unrolled: half the registers and half
+// the code of a 4-particle body (the kernels are bound by issue slots and the instruction cache, not by ILP: the
+// other resident warps fill the latency of the two fp32 chains).  Branch-free by construction (bitwise bool
+// operators: no short-circuit evaluation, which the compiler would turn into divergent branches).
 template <int S, bool SHELL, bool VDISP>
-__device__ __forceinline__ void tile_f32(const unsigned char *tile, int lane, const double *frames, unsigned smask,
+__device__ __forceinline__ void pair_f32(const unsigned char *tile, int pi, const double *frames, unsigned smask,
                                          double (&acc)[S][7], int (&cnt)[S])
 {
     const double2 *T = reinterpret_cast<const double2 *>(tile);   // stream st, pair pi: T[st * TILE_PAIRS + pi]
-    unsigned bits = 0;   // bit 4 s + j: particle j is a member of shell s
+    float f[2][6];     // fp32 products of the position: xx, yy, zz, xy, xz, yz
+    double t[2][6];    // fp64 products the tensor is built from (positions, or velocities): xx, xy, xz, yy, yz, zz
+    double pm[2];
     {
-        float f[4][6];
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int pi = lane + 32 * h;
-            const double2 x = T[pi], y = T[TILE_PAIRS + pi], z = T[2 * TILE_PAIRS + pi];
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                // round to nearest (the error bound assumes it); 1e150 (pad sentinel) becomes inf
-                const float fx = (float)(e ? x.y : x.x), fy = (float)(e ? y.y : y.x), fz = (float)(e ? z.y : z.x);
-                float *g = f[2 * h + e];
-                g[0] = fx * fx; g[1] = fy * fy; g[2] = fz * fz; g[3] = fx * fy; g[4] = fx * fz; g[5] = fy * fz;
-            }
-        }
-#pragma unroll
-        for (int s = 0; s < S; s++) {
-            if (smask & (1u << s)) {   // warp-uniform
-                const float4 *G4 = reinterpret_cast<const float4 *>(frames + s * F_SLOTS + F_F32);
-                const float4 g0 = G4[0], g1 = G4[1];   // (Axx,Ayy,Azz,Axy) (Axz,Ayz,lo,hi)
-                float4 g2, g3;
-                if (SHELL) { g2 = G4[2]; g3 = G4[3]; }   // (Bxx,Byy,Bzz,Bxy) (Bxz,Byz,loB,hiB)
-                const bool off = !(g1.z > -INFINITY);
-                float v[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    v[j] = fmaf(g1.y, f[j][5], fmaf(g1.x, f[j][4], fmaf(g0.w, f[j][3],
-                           fmaf(g0.z, f[j][2], fmaf(g0.y, f[j][1], g0.x * f[j][0])))));
-                unsigned sel = 0, und = off ? 0xfu : 0u;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    bool in = v[j] < g1.z;
-                    bool un = (v[j] >= g1.z) && (v[j] <= g1.w);
-                    if (SHELL) {
-                        const float u = fmaf(g3.y, f[j][5], fmaf(g3.x, f[j][4], fmaf(g2.w, f[j][3],
-                                        fmaf(g2.z, f[j][2], fmaf(g2.y, f[j][1], g2.x * f[j][0])))));
-                        un = un || (in && (((u >= g3.z) && (u <= g3.w)) || !(g3.z > -INFINITY)));
-                        in = in && (u > g3.w);
-                    }
-                    sel |= (in ? 1u : 0u) << j;
-                    und |= (un ? 1u : 0u) << j;
-                }
-                if (__any_sync(0xffffffffu, und != 0)) {   // rare: the reference's own fp64 expression decides
-#pragma unroll 1
-                    for (int j = 0; j < 4; j++) {
-                        if (und & (1u << j)) {
-                            const int pi = lane + 32 * (j >> 1);
-                            const double2 x = T[pi], y = T[TILE_PAIRS + pi], z = T[2 * TILE_PAIRS + pi];
-                            const bool m = exact_member<SHELL>(frames + s * F_SLOTS, (j & 1) ? x.y : x.x,
-                                                               (j & 1) ? y.y : y.x, (j & 1) ? z.y : z.x);
-                            sel = (sel & ~(1u << j)) | ((m ? 1u : 0u) << j);
-                        }
-                    }
-                }
-                bits |= sel << (4 * s);
-            }
-        }
-    }
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int pi = lane + 32 * h;
-        const double2 m2 = T[3 * TILE_PAIRS + pi];
-        const double2 a2 = T[(VDISP ? 4 : 0) * TILE_PAIRS + pi], b2 = T[(VDISP ? 5 : 1) * TILE_PAIRS + pi],
-                      c2 = T[(VDISP ? 6 : 2) * TILE_PAIRS + pi];
+        const double2 x = T[pi], y = T[TILE_PAIRS + pi], z = T[2 * TILE_PAIRS + pi], m = T[3 * TILE_PAIRS + pi];
+        double2 a = x, b = y, c = z;
+        if (VDISP) { a = T[4 * TILE_PAIRS + pi]; b = T[5 * TILE_PAIRS + pi]; c = T[6 * TILE_PAIRS + pi]; }
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-            const int j = 2 * h + e;
-            const double a = e ? a2.y : a2.x, b = e ? b2.y : b2.x, c = e ? c2.y : c2.x, m = e ? m2.y : m2.x;
-            // component order of the accumulators: xx, xy, xz, yy, yz, zz
-            const double pxx = a * a, pxy = a * b, pxz = a * c, pyy = b * b, pyz = b * c, pzz = c * c;
-#pragma unroll
-            for (int s = 0; s < S; s++) {
-                if (smask & (1u << s)) {   // warp-uniform
-                    if (bits & (1u << (4 * s + j))) {   // predicated updates (no mass sum: only ratios of the tensor are used)
-                        acc[s][0] = fma(m, pxx, acc[s][0]);
-                        acc[s][1] = fma(m, pxy, acc[s][1]);
-                        acc[s][2] = fma(m, pxz, acc[s][2]);
-                        acc[s][3] = fma(m, pyy, acc[s][3]);
-                        acc[s][4] = fma(m, pyz, acc[s][4]);
-                        acc[s][5] = fma(m, pzz, acc[s][5]);
-                    }
-                }
-            }
+            // round to nearest (the error bound assumes it); 1e150 (pad sentinel) becomes inf
+            const float fx = (float)(e ? x.y : x.x), fy = (float)(e ? y.y : y.x), fz = (float)(e ? z.y : z.x);
+            f[e][0] = fx * fx; f[e][1] = fy * fy; f[e][2] = fz * fz; f[e][3] = fx * fy; f[e][4] = fx * fz; f[e][5] = fy * fz;
+            const double ta = e ? a.y : a.x, tb = e ? b.y : b.x, tc = e ? c.y : c.x;
+            t[e][0] = ta * ta; t[e][1] = ta * tb; t[e][2] = ta * tc; t[e][3] = tb * tb; t[e][4] = tb * tc; t[e][5] = tc * tc;
+            pm[e] = e ? m.y : m.x;
         }
     }
 #pragma unroll
-    for (int s = 0; s < S; s++) cnt[s] += __popc((bits >> (4 * s)) & 0xfu);
+    for (int s = 0; s < S; s++) {
+        if (smask & (1u << s)) {   // warp-uniform
+            const float4 *G4 = reinterpret_cast<const float4 *>(frames + s * F_SLOTS + F_F32);
+            const float4 g0 = G4[0], g1 = G4[1];   // (Axx,Ayy,Azz,Axy) (Axz,Ayz,lo,hi)
+            PairForms w;
+            w.v0 = fmaf(g1.y, f[0][5], fmaf(g1.x, f[0][4], fmaf(g0.w, f[0][3], fmaf(g0.z, f[0][2], fmaf(g0.y, f[0][1], g0.x * f[0][0])))));
+            w.v1 = fmaf(g1.y, f[1][5], fmaf(g1.x, f[1][4], fmaf(g0.w, f[1][3], fmaf(g0.z, f[1][2], fmaf(g0.y, f[1][1], g0.x * f[1][0])))));
+            w.u0 = 0.f; w.u1 = 0.f;
+            const bool off = !(g1.z > -INFINITY);    // fp32 test switched off for this shell: everything undecided
+            const float lo_eff = off ? 0.0f : g1.z;
+            bool und = off | ((w.v0 >= g1.z) & (w.v0 <= g1.w)) | ((w.v1 >= g1.z) & (w.v1 <= g1.w));
+            float hiB_eff = 0.f;
+            if (SHELL) {
+                const float4 g2 = G4[2], g3 = G4[3];   // (Bxx,Byy,Bzz,Bxy) (Bxz,Byz,loB,hiB)
+                w.u0 = fmaf(g3.y, f[0][5], fmaf(g3.x, f[0][4], fmaf(g2.w, f[0][3], fmaf(g2.z, f[0][2], fmaf(g2.y, f[0][1], g2.x * f[0][0])))));
+                w.u1 = fmaf(g3.y, f[1][5], fmaf(g3.x, f[1][4], fmaf(g2.w, f[1][3], fmaf(g2.z, f[1][2], fmaf(g2.y, f[1][1], g2.x * f[1][0])))));
+                const bool offB = !(g3.z > -INFINITY);
+                hiB_eff = offB ? 3.0e38f : g3.w;
+                und = und | ((w.v0 < g1.z) & (offB | ((w.u0 >= g3.z) & (w.u0 <= g3.w))))
+                          | ((w.v1 < g1.z) & (offB | ((w.u1 >= g3.z) & (w.u1 <= g3.w))));
+            }
+            if (__any_sync(0xffffffffu, und))   // rare: fp64 decides the undecided ones
+                w = redecide_pair<SHELL>(frames + s * F_SLOTS, tile, pi, w);
+            bool in0 = w.v0 < lo_eff, in1 = w.v1 < lo_eff;
+            if (SHELL) { in0 = in0 & (w.u0 > hiB_eff); in1 = in1 & (w.u1 > hiB_eff); }
+            if (in0) {   // predicated updates (no mass sum: only ratios of the tensor are used)
+#pragma unroll
+                for (int c = 0; c < 6; c++) acc[s][c] = fma(pm[0], t[0][c], acc[s][c]);
+                cnt[s] += 1;
+            }
+            if (in1) {
+#pragma unroll
+                for (int c = 0; c < 6; c++) acc[s][c] = fma(pm[1], t[1][c], acc[s][c]);
+                cnt[s] += 1;
+            }
+        }
+    }
 }
 
 // A = w2 * e2 e2^T + w1 * e1 e1^T + w0 * e0 e0^T as (xx, yy, zz, 2xy, 2xz, 2yz); v = eigenvectors of eigh3.
@@ -324,8 +351,21 @@ __device__ __forceinline__ void quad_form(double *A, const double (&v)[9], doubl
 struct InnerPrefix {
     const double *rr;
     const int *neff;
+    // compact copies for the warp kernel's shared memory: radii rounded UP to fp32 (a bucket that passes the test with
+    // the rounded-up radius passes it with the true one) and prefix lengths in pairs (objects < 131072 particles)
+    const float *rr_up = nullptr;
+    const uint16_t *npairs16 = nullptr;
     __device__ __forceinline__ int pairs_inside(int k, double s) const
     {
+        if (rr_up) {
+            const double lim = s * (double)rr_up[k] * (1.0 - 1e-7);   // rr_up[k] <= rr[k] (1 + 6e-8): still below s * rr[k] (1 - 1e-9)
+            int lo = -1, hi = k;   // rr_up[lo] <= lim < rr_up[hi]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if ((double)rr_up[mid] <= lim) lo = mid; else hi = mid;
+            }
+            return lo >= 0 ? (int)npairs16[lo] : 0;
+        }
         if (!rr) return 0;
         const double lim = s * rr[k] * (1.0 - 1e-9);
         int lo = -1, hi = k;   // rr[lo] <= lim < rr[hi]   (rr ascending, rr[k] > lim)
@@ -464,12 +504,15 @@ __device__ __forceinline__ void make_tensor_products(double u, double v, double 
 // is loaded once and stays resident in shared memory for all Katz iterations of the task.
 // ------------------------------------------------------------------------------------------------
 constexpr int MAX_SORT_R = 256;   // == SORT_MAX_B of cpg_gather.cuh: radial ordering exists for R <= 255
+#ifndef CPG_RING_STAGES
+#define CPG_RING_STAGES 4   // tiles of 4 KB per warp ring (positions); 3 leaves room for a fourth CTA of the warp kernel per SM
+#endif
 constexpr int RING_MAX_STAGES = 4;
 
 template <bool VDISP>
 struct RingCfg {
     static constexpr int NSTREAM = VDISP ? 7 : 4;
-    static constexpr int STAGES = VDISP ? 2 : 4;   // 16 KB (positions) / 14 KB (with velocities) per warp
+    static constexpr int STAGES = VDISP ? 2 : CPG_RING_STAGES;   // 16 KB (positions) / 14 KB (with velocities) per warp
     static constexpr int STREAM_BYTES = TILE_PAIRS * 16;
     static constexpr int STAGE_BYTES = NSTREAM * STREAM_BYTES;
     static constexpr int WARP_BYTES = STAGES * STAGE_BYTES;
@@ -698,10 +741,20 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
         if (smask == 0) {
             // (resident tasks only)
         } else if (CPG_F32_TEST && !REDUCED) {
-            tile_f32<S, SHELL, VDISP>(ring_tile<VDISP>(ring, seq), lane, frames, smask, acc, cnt);
+            const unsigned char *tile = ring_tile<VDISP>(ring, seq);
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) pair_f32<S, SHELL, VDISP>(tile, lane + 32 * h, frames, smask, acc, cnt);
         } else if (VDISP) {
             // two particles at a time: the dispersion variant carries 13 doubles per particle
 #pragma unroll
+            for (int h = 0; h < 2; h++) {
+                Particle p[2];
+                ring_read_pair<VDISP>(ring, seq, lane + 32 * h, p[0], p[1]);
+                passk_particles<S, SHELL, REDUCED, VDISP, 2>(p, frames, smask, acc, cnt);
+            }
+        } else if (CPG_FP64_PAIRS) {
+            // (fewer registers and half the code; two fp64 chains per shell instead of four)
+#pragma unroll 1
             for (int h = 0; h < 2; h++) {
                 Particle p[2];
                 ring_read_pair<VDISP>(ring, seq, lane + 32 * h, p[0], p[1]);
@@ -840,8 +893,8 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
     __shared__ __align__(16) double s_frames[WARP_KERNEL_WARPS][NS * F_SLOTS];
     __shared__ __align__(8) uint64_t s_bar[WARP_KERNEL_WARPS][RING_MAX_STAGES];
     __shared__ int s_np[WARP_KERNEL_WARPS][NS], s_nin[WARP_KERNEL_WARPS][NS];
-    __shared__ double s_rr[MAX_SORT_R];                       // shell radii (inner-prefix lookup)
-    __shared__ int s_neff[WARP_KERNEL_WARPS][MAX_SORT_R];      // prefix lengths of the warp's current object
+    __shared__ float s_rr[MAX_SORT_R];                              // shell radii rounded up (inner-prefix lookup)
+    __shared__ uint16_t s_neff[WARP_KERNEL_WARPS][MAX_SORT_R];      // prefix lengths (pairs) of the warp's current object
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *frames = s_frames[warp];
     int *np = s_np[warp], *nin = s_nin[warp];
@@ -851,12 +904,13 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
     ring_init(ring, s_ring_w + warp * RingCfg<VDISP>::WARP_BYTES, s_bar[warp], lane, WARP_RING_LANES ? 32u : 1u);
     const bool use_inner = !SHELL && !REDUCED && P.n_eff != nullptr && P.ptab != nullptr;
     if (use_inner) {
-        for (int j = threadIdx.x; j < P.R; j += blockDim.x) s_rr[j] = P.rr[j];
+        for (int j = threadIdx.x; j < P.R; j += blockDim.x) s_rr[j] = __double2float_ru(P.rr[j]);
         __syncthreads();
     }
     InnerPrefix ip;
-    ip.rr = use_inner ? s_rr : nullptr;
-    ip.neff = s_neff[warp];
+    ip.rr = nullptr; ip.neff = nullptr;
+    ip.rr_up = use_inner ? s_rr : nullptr;
+    ip.npairs16 = s_neff[warp];
     const double *ptab = use_inner ? P.ptab : nullptr;
 
     for (;;) {
@@ -881,7 +935,8 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
         const size_t out_idx = (size_t)halo * P.R + k;
         __syncwarp();
         if (use_inner) {   // the object's prefix lengths up to the task's last shell
-            for (int j = lane; j < tk.shell0 + tk.nshell; j += 32) s_neff[warp][j] = P.n_eff[(size_t)halo * P.R + j];
+            for (int j = lane; j < tk.shell0 + tk.nshell; j += 32)
+                s_neff[warp][j] = (uint16_t)(P.n_eff[(size_t)halo * P.R + j] >> 1);   // objects of the warp kernel: < 131072 particles
             __syncwarp();
         }
         init_frames(frames, np, nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);

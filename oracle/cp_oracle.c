@@ -10,7 +10,7 @@
  * shapes only, cosmic_profiles/tests/test_shapes.py:94-124), so this restatement
  * is pinned against the reference itself, compiled from /root/reference by
  * oracle/build_ref.py into oracle/_ref, on seeded inputs
- * (tests/test_oracle_vs_ref.py, tests/golden npz fixtures + tests/golden/make_golden.py).
+ * (tests/test_oracle_golden.py against the tests/golden npz fixtures written by tests/golden/make_golden.py).
  *
  * Everything that decides an integer (particle membership, iteration count) is
  * written with the reference's exact operand order; build with

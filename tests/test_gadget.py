@@ -206,3 +206,50 @@ def test_gpu_pageable_upload_round_trip():
     x4, _, _ = ctx.get_particles(n)
     assert np.array_equal(x4, xyz)
     ctx.close()
+
+
+# ---- the reference's own reader as the oracle of the block arithmetic (tests/golden/make_gadget_io_golden.py) --------
+
+def _io_cases():
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gadget_io_golden.npz"))
+    return z, [str(c) for c in z["cases"]]
+
+
+def test_oracle_read_field_arith_matches_the_reference_reader():
+    """readgadget.read_block ran unmodified (h5py served by oracle/stubs/h5py) on float32 / float64 snapshots with and
+    without a Masses dataset, a != 1, two unit systems, one- and two-file snapshots: the restatement reproduces its
+    float64 outputs bit for bit -- this pins the oracle of the ingest row."""
+    z, cases = _io_cases()
+    assert len(cases) == 4
+    for c in cases:
+        # Python floats, as the reference's config module holds them: under NumPy >= 2 promotion a Python-float divisor
+        # keeps the dataset's precision (a float32 block is divided in float32), an np.float64 one would not
+        lf, mf, vf = (float(v) for v in z[c + "/unit_fac"])
+        t = float(z[c + "/time"])
+        n = z[c + "/pos"].shape[0]
+        assert z[c + "/ref_pos"].dtype == np.float64
+        assert np.array_equal(O.read_field_arith("POS ", z[c + "/pos"], lf), z[c + "/ref_pos"]), c
+        assert np.array_equal(O.read_field_arith("VEL ", z[c + "/vel"], vf, time=t), z[c + "/ref_vel"]), c
+        mass = z[c + "/mass"] if (c + "/mass") in z.files else None
+        got = O.read_field_arith("MASS", mass, mf, mass_table=float(z[c + "/mass_table"]), n_part=n)
+        assert np.array_equal(got, z[c + "/ref_mass"]), c
+
+
+@pytest.mark.gpu
+def test_gpu_block_ingest_matches_the_reference_reader():
+    """cpg_set_particles_gadget on the raw datasets against what the reference's reader returned for the same files."""
+    from cosmic_profiles_b200 import _lib, readgadget as RG
+    z, cases = _io_cases()
+    ctx = _lib.Context(0)
+    try:
+        for c in cases:
+            lf, mf, vf = (float(v) for v in z[c + "/unit_fac"])
+            mass = z[c + "/mass"] if (c + "/mass") in z.files else None
+            n = z[c + "/pos"].shape[0]
+            RG.upload_snapshot(ctx, z[c + "/pos"], z[c + "/vel"], mass, float(z[c + "/mass_table"]), lf, mf, vf, float(z[c + "/time"]))
+            x, v, m = ctx.get_particles(n, with_vel=True)
+            assert np.array_equal(x, z[c + "/ref_pos"]), c
+            assert np.array_equal(v, z[c + "/ref_vel"]), c
+            assert np.array_equal(m, z[c + "/ref_mass"]), c
+    finally:
+        ctx.close()
