@@ -524,6 +524,7 @@ def main():
     launches = 0
     hot_launches_local = 0
     fma_local = 0.0
+    per_ts = 1.0 if ctx.stat("f32_test") else 2.0
     w0 = time.perf_counter()
     for _ in range(a.steps):
         _, _, t_l, t_g = shapes()
@@ -534,9 +535,9 @@ def main():
                 brk[nm + "_" + kk] = brk.get(nm + "_" + kk, 0.0) + t[kk] / a.steps
         kern_local_ms += t_l["kernel_ms"]
         hot_launches_local += t_l["hot_kernel_launches"]
-        # fp64 work of the local-shape kernels from their own counters: per 128-particle tile 6 products per particle,
-        # per (tile, shell) 6 tensor updates per particle (the membership test itself runs in fp32)
-        fma_local += 128.0 * 6.0 * (t_l["tile_visits"] + t_l["tile_shell_visits"])
+        # fp64 work of the local-shape kernels' streaming loop from their own counters: per 128-particle tile 6 products
+        # per particle; per (tile, shell) 6 multiply-adds of the membership form + 6 tensor updates per particle
+        fma_local += 128.0 * 6.0 * (t_l["tile_visits"] + per_ts * t_l["tile_shell_visits"])
     barrier()
     wall_ms = 1e3 * (time.perf_counter() - w0)
     fp64_peak = ctx.measure_fp64_peak()   # TFMA/s, outside every timed region
@@ -685,6 +686,13 @@ def main():
                     break
             except Exception:
                 pass
+        pipe_occ = None
+        try:   # ncu: sm__inst_executed_pipe_fp64 of the two local-shape kernels / the microbenchmark's ceiling in the same units
+            po = json.load(open(os.path.join(ROOT, "profiles", "r2_fp64_pipe.json")))
+            pipe_occ = {"warp_kernel": po["warp_kernel_pct"] / po["dfma_ceiling_pct"],
+                        "cluster_kernel": po["cluster_kernel_pct"] / po["dfma_ceiling_pct"], "source": "profiles/r2_fp64_pipe.json"}
+        except Exception:
+            pass
         kern_mean = kern_sum / world
         algorithmic_gbs = pi_local_all / world * BYTES_PER_PI / (kern_ms * 1e-3) / 1e9   # per GPU
         achieved_tflops = 2.0 * fma_all / world / (kern_mean * 1e-3) / 1e12               # per GPU, 2 flop per FMA
@@ -722,10 +730,13 @@ def main():
                                      "algorithmic_frac": algorithmic_gbs / hbm_peak,
                                      "streamed_particle_iterations": visited_all / world,
                                      "streamed_GBps": visited_all / world * BYTES_PER_PI / (kern_ms * 1e-3) / 1e9},
-                             "note": "The morphology loop is bound by the fp64 pipe, not by HBM: achieved = fp64 multiply-adds the "
-                                     "kernels issue for particle products and tensor updates (their own tile counters: 128 particles "
-                                     "x 6 per tile + 128 x 6 per (tile, shell); membership tests run in fp32, eigen-solves not counted) "
-                                     "/ CUDA-event kernel time, against the fp64 FMA rate measured on this GPU in this run.  hbm.physical "
+                             "fp64_pipe_occupancy_ncu": pipe_occ,
+                             "note": "The morphology loop is bound by the fp64 pipe, not by HBM: achieved = fp64 multiply-adds of the "
+                                     "streaming loop (the kernels' own tile counters: 128 particles x 6 products per tile + 128 x 12 per "
+                                     "(tile, shell): membership form + tensor update) / CUDA-event kernel time, against the fp64 FMA rate "
+                                     "measured on this GPU in this run.  The per-iteration eigen-solves (4 useful lanes per warp "
+                                     "instruction) are not counted as useful work but occupy the same pipe: fp64_pipe_occupancy_ncu "
+                                     "is the pipe's busy fraction under ncu relative to what the DFMA microbenchmark sustains.  hbm.physical "
                                      "= DRAM bytes under ncu / kernel time; hbm.algorithmic = 32 B x particle-iterations (the contract's "
                                      "SURVEY 8(d) figure), > peak because the radial ordering and the prefix tensor table let an "
                                      "iteration skip most of an object's particles."},

@@ -2176,6 +2176,7 @@ CPG_API int cpg_get_stat(cpg_ctx *c, const char *name, int64_t *out)
     if (!c || !name || !out) return CPG_ERR_ARGUMENT;
     if (!strcmp(name, "uploads_skipped")) *out = (int64_t)c->uploads_skipped;
     else if (!strcmp(name, "catalogue_as_ranges")) *out = c->cat_ranges ? 1 : 0;
+    else if (!strcmp(name, "f32_test")) *out = CPG_F32_TEST;
     else if (!strcmp(name, "n_part")) *out = c->n_part;
     else if (!strcmp(name, "n_obj")) *out = c->n_obj;
     else if (!strcmp(name, "snapshot_version")) *out = (int64_t)c->snapshot_version;

@@ -56,7 +56,13 @@ struct Particle {              // one particle as seen by the accumulators
 #define CPG_FP64_PAIRS 0   // 1: the all-fp64 path works on one particle pair at a time (rolled loop)
 #endif
 #ifndef CPG_F32_TEST
-#define CPG_F32_TEST 1   // 1: fp32 pre-classification of the membership tests (non-reduced variants); 0: all-fp64 tests
+// 0 (default): all-fp64 membership tests.  1: fp32 pre-classification of the membership tests of the non-reduced
+// variants with an exact fp64 re-test of the undecided particles (pair_f32 below).  Measured on configs[1], B200
+// (profiles/README.md, round 2): the all-fp64 kernels saturate the fp64 pipe (0.45 of the 0.455 warp-DFMA/clk/SMSP the
+// pipe sustains, profiles/micro/fp64_lanes.cu); the fp32 variant halves the fp64 instructions of the streaming loop but
+// its compare / select / convert instructions make it issue-bound: 24.3 ms against 19.4 ms for the local-shape kernels.
+// Kept as a build option (make EXTRA=-DCPG_F32_TEST=1); the GPU suite passes with either setting.
+#define CPG_F32_TEST 0
 #endif
 
 template <bool REDUCED, bool VDISP>

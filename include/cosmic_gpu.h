@@ -54,7 +54,9 @@ typedef struct cpg_timing {
     int64_t h2d_bytes;
     int64_t d2h_bytes;
     /* cpg_shape only: 128-particle tiles the morphology kernels passed over, and (tile, shell) pairs among them --
-     * the fp64 work of a call is 128 * (6 * tile_visits + 6 * tile_shell_visits) multiply-adds (bench.py's fp64 roofline) */
+     * the fp64 work of the streaming loop is 128 * (6 * tile_visits + 12 * tile_shell_visits) multiply-adds: 6 products
+     * per particle, 6 for the membership form and 6 tensor updates per particle and shell (bench.py's fp64 roofline;
+     * 6 instead of 12 when the library is built with the fp32 pre-classification) */
     int64_t tile_visits;
     int64_t tile_shell_visits;
 } cpg_timing;
@@ -238,7 +240,8 @@ CPG_API void cpg_host_free(void *p);
 CPG_API int cpg_get_prefix_lengths(cpg_ctx *ctx, int32_t *n_eff, int32_t R);
 
 /* Counters of a context (diagnostics, tests): "uploads_skipped" (calls the snapshot cache answered), "catalogue_as_ranges"
- * (1: the resident catalogue is kept as contiguous ranges), "n_part", "n_obj", "snapshot_version", "catalogue_version". */
+ * (1: the resident catalogue is kept as contiguous ranges), "n_part", "n_obj", "snapshot_version", "catalogue_version",
+ * "f32_test" (build option CPG_F32_TEST: 1 = membership tests pre-classified in fp32). */
 CPG_API int cpg_get_stat(cpg_ctx *ctx, const char *name, int64_t *out);
 
 /* Timing breakdown of the most recent compute call on this context. */
