@@ -428,7 +428,7 @@ def main():
             return
         use_all_host_cores()
         import torch
-        tab = halo_table(a.halos, a.seed)
+        tab = halo_table(a.halos, a.seed)   # the per-GPU catalogue size: the sample is drawn from 10^4 objects at every N
         if torch.cuda.is_available():
             cat = generate_on_device(tab, a.seed, 0)
         else:   # CPU-only container: same generator family on the host, small sizes only
@@ -440,7 +440,8 @@ def main():
                 "warmup": a.warmup, "ms_per_step": 1e3 * info["seconds_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
-                                 "sample": info["sample"]},
+                                 "sample": info["sample"], "centres_excluded_value": info.get("centres_excluded_value"),
+                                 "centres_seconds": info.get("centres_seconds")},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         emit(line)
@@ -451,6 +452,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    if a.config != 1:
+        # the other BASELINE configurations: one GPU, one JSON line each (bench_configs.py)
+        if rank != 0:
+            return
+        import bench_configs
+        emit(bench_configs.RUN[a.config](sys.modules[__name__], a, ClockSampler(local_rank)))
+        return
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from cosmic_profiles_b200 import _lib
@@ -478,8 +486,8 @@ def main():
     k = (KATZ["IT_TOL"], KATZ["IT_WALL"], KATZ["IT_MIN"])
 
     def upload(ctx=ctx):
-        ctx.set_particles(cat["xyz"], None, cat["masses"])
-        ctx.set_catalogue(cat["idx_cat"], cat["obj_size"])
+        # cpg_set_snapshot = cpg_set_particles + cpg_set_catalogue (the host-side pass over idx_cat overlaps the DMA)
+        ctx.set_snapshot(cat["xyz"], None, cat["masses"], cat["idx_cat"], cat["obj_size"])
 
     def shapes(ctx=ctx):
         # a step always redoes the catalogue gather ("includes the on-device gather"); the

@@ -35,7 +35,7 @@ EXPORTS = ["cpg_device_count", "cpg_last_error", "cpg_version", "cpg_create", "c
            "cpg_set_particles_segments", "cpg_set_catalogue_ranges", "cpg_catalogue_ranges", "cpg_host_token",
            "cpg_measure_fp64_peak", "cpg_partition_lpt", "cpg_multi_create", "cpg_multi_destroy", "cpg_multi_devices",
            "cpg_multi_context", "cpg_multi_set_option", "cpg_multi_set_snapshot", "cpg_multi_shard", "cpg_multi_shape",
-           "cpg_multi_get_info", "cpg_get_stat"]
+           "cpg_multi_get_info", "cpg_get_stat", "cpg_set_snapshot", "cpg_unpack_shape"]
 _I64 = ctypes.POINTER(ctypes.c_int64)
 _NO_INT_RESTYPE = ("cpg_last_error", "cpg_version", "cpg_destroy", "cpg_host_free", "cpg_multi_destroy", "cpg_multi_context")
 
@@ -103,6 +103,8 @@ def load():
                                   ctypes.c_float, ctypes.c_double, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                   ctypes.c_int32, ctypes.c_int32, _D, _I, _I, _D, _D, _D]
     L.cpg_get_stat.argtypes = [vp, ctypes.c_char_p, _I64]
+    L.cpg_set_snapshot.argtypes = [vp, _D, _D, _D, ctypes.c_int64, _I, ctypes.c_int64, _I, ctypes.c_int32]
+    L.cpg_unpack_shape.argtypes = [_D, ctypes.c_int64, _D, _D, _D, _D, _D, _D]
     L.cpg_multi_get_info.argtypes = [vp, ctypes.c_int32, _I, _I, _I64, ctypes.POINTER(Timing), _D]
     for f in EXPORTS:
         if f not in _NO_INT_RESTYPE:
@@ -161,6 +163,16 @@ def host_token(a, full=False):
     tok = ctypes.c_uint64()
     _check(load().cpg_host_token(ctypes.c_void_p(a.ctypes.data), a.nbytes, int(bool(full)), ctypes.byref(tok)), "cpg_host_token")
     return int(tok.value)
+
+
+def unpack_shape(out12):
+    """(n, R, 12) rows of cpg_shape -> d, q, s (n, R) and major, inter, minor (n, R, 3), zeros -> NaN (cpg_unpack_shape)."""
+    out12 = np.ascontiguousarray(out12, dtype=np.float64)
+    n, R = out12.shape[:2]
+    d, q, s = (np.empty((n, R)) for _ in range(3))
+    major, inter, minor = (np.empty((n, R, 3)) for _ in range(3))
+    _check(load().cpg_unpack_shape(_dp(out12), n * R, _dp(d), _dp(q), _dp(s), _dp(major), _dp(inter), _dp(minor)), "cpg_unpack_shape")
+    return d, q, s, major, inter, minor
 
 
 class PinnedBuffer:
@@ -238,6 +250,21 @@ class Context:
         obj_size = i32(obj_size)
         _check(self._L.cpg_set_catalogue(self._h, _ip(idx_cat), idx_cat.shape[0], _ip(obj_size), obj_size.shape[0]),
                "cpg_set_catalogue")
+        self.n_obj = int(obj_size.shape[0])
+
+    def set_snapshot(self, xyz, vxyz, masses, idx_cat, obj_size):
+        """set_particles + set_catalogue in one call (cpg_set_snapshot): the host-side pass over the flat catalogue
+        overlaps the transfer of the particle arrays."""
+        xyz, masses = f64(xyz), f64(masses)
+        vxyz = None if vxyz is None else f64(vxyz)
+        idx_cat, obj_size = i32(idx_cat), i32(obj_size)
+        if xyz.ndim != 2 or xyz.shape[1] != 3 or masses.shape[0] != xyz.shape[0]:
+            raise ValueError("xyz must be (N,3) and masses (N,)")
+        if vxyz is not None and vxyz.shape != xyz.shape:
+            raise ValueError("vxyz must match xyz")
+        _check(self._L.cpg_set_snapshot(self._h, _dp(xyz), _dp(vxyz), _dp(masses), xyz.shape[0], _ip(idx_cat), idx_cat.shape[0],
+                                        _ip(obj_size), obj_size.shape[0]), "cpg_set_snapshot")
+        self.have_vel = vxyz is not None
         self.n_obj = int(obj_size.shape[0])
 
     def set_catalogue_ranges(self, obj_start, obj_size):
@@ -553,8 +580,7 @@ class DeviceGroup:
         if self.multi:
             self.multi.set_snapshot(xyz, vxyz, masses, idx_cat, obj_size)
         else:
-            self.single.set_particles(xyz, vxyz, masses)
-            self.single.set_catalogue(idx_cat, obj_size)
+            self.single.set_snapshot(xyz, vxyz, masses, idx_cat, obj_size)
         self.n_obj = int(np.asarray(obj_size).shape[0])
 
     def shards(self):

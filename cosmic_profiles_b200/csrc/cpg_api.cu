@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <climits>
+#include <limits>
 #include <atomic>
 #include <chrono>
 #include <new>
@@ -1230,29 +1231,28 @@ static bool same_sizes(const std::vector<int32_t> &a, const int32_t *b, int32_t 
     return a.size() == (size_t)n && (n == 0 || !memcmp(a.data(), b, sizeof(int32_t) * (size_t)n));
 }
 
-CPG_API int cpg_set_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, const int32_t *obj_size, int32_t n_obj)
+// Offsets of a flat catalogue (validated); false + error message on inconsistent sizes.
+static bool catalogue_offsets(const char *who, const int32_t *obj_size, int32_t n_obj, int64_t n_idx, std::vector<int64_t> &off)
 {
-    CPG_TRY(use_device(c));
-    if (n_idx < 0 || n_obj < 0 || (n_idx > 0 && !idx_cat) || (n_obj > 0 && !obj_size)) {
-        set_error("cpg_set_catalogue: bad arguments");
-        return CPG_ERR_ARGUMENT;
-    }
-    if (!c->opt_detect_ranges && !c->opt_snapshot_cache) return install_catalogue(c, idx_cat, nullptr, n_idx, obj_size, n_obj);
-    // one multi-threaded pass over the flat array: contiguous-range detection, index range, content hash
-    std::vector<int64_t> off((size_t)n_obj + 1, 0);
+    off.assign((size_t)n_obj + 1, 0);
     for (int h = 0; h < n_obj; h++) {
         if (obj_size[h] < 0) {
-            set_error("cpg_set_catalogue: obj_size[%d] < 0", h);
-            return CPG_ERR_ARGUMENT;
+            set_error("%s: obj_size[%d] < 0", who, h);
+            return false;
         }
         off[h + 1] = off[h] + obj_size[h];
     }
     if (off[n_obj] != n_idx) {
-        set_error("cpg_set_catalogue: sum(obj_size) = %lld but idx_cat has %lld entries", (long long)off[n_obj], (long long)n_idx);
-        return CPG_ERR_ARGUMENT;
+        set_error("%s: sum(obj_size) = %lld but idx_cat has %lld entries", who, (long long)off[n_obj], (long long)n_idx);
+        return false;
     }
-    CatScan sc;
-    scan_catalogue(idx_cat, off.data(), n_obj, sc);
+    return true;
+}
+
+// cpg_set_catalogue proper; `sc` = the result of scan_catalogue on idx_cat (contiguity, index range, content hash).
+static int set_catalogue_scanned(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, const int32_t *obj_size, int32_t n_obj,
+                                 const CatScan &sc)
+{
     const bool ranges = c->opt_detect_ranges && sc.contiguous;
     auto &K = c->cat_key;
     if (c->opt_snapshot_cache && K.valid && !c->cat_stale && K.ranges == ranges && K.n_idx == n_idx && K.hash == sc.hash &&
@@ -1266,6 +1266,47 @@ CPG_API int cpg_set_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx,
         K.size.assign(obj_size, obj_size + n_obj);
     }
     return rc;
+}
+
+CPG_API int cpg_set_catalogue(cpg_ctx *c, const int32_t *idx_cat, int64_t n_idx, const int32_t *obj_size, int32_t n_obj)
+{
+    CPG_TRY(use_device(c));
+    if (n_idx < 0 || n_obj < 0 || (n_idx > 0 && !idx_cat) || (n_obj > 0 && !obj_size)) {
+        set_error("cpg_set_catalogue: bad arguments");
+        return CPG_ERR_ARGUMENT;
+    }
+    if (!c->opt_detect_ranges && !c->opt_snapshot_cache) return install_catalogue(c, idx_cat, nullptr, n_idx, obj_size, n_obj);
+    // one multi-threaded pass over the flat array: contiguous-range detection, index range, content hash
+    std::vector<int64_t> off;
+    if (!catalogue_offsets("cpg_set_catalogue", obj_size, n_obj, n_idx, off)) return CPG_ERR_ARGUMENT;
+    CatScan sc;
+    scan_catalogue(idx_cat, off.data(), n_obj, sc);
+    return set_catalogue_scanned(c, idx_cat, n_idx, obj_size, n_obj, sc);
+}
+
+// cpg_set_particles + cpg_set_catalogue in one call: the host-side pass over the flat catalogue runs on its own threads
+// WHILE the particle arrays cross PCIe (a page-locked source is pure DMA: the scan is free).
+CPG_API int cpg_set_snapshot(cpg_ctx *c, const double *xyz, const double *vxyz, const double *masses, int64_t n_part,
+                             const int32_t *idx_cat, int64_t n_idx, const int32_t *obj_size, int32_t n_obj)
+{
+    CPG_TRY(use_device(c));
+    if (n_idx < 0 || n_obj < 0 || (n_idx > 0 && !idx_cat) || (n_obj > 0 && !obj_size)) {
+        set_error("cpg_set_snapshot: bad arguments");
+        return CPG_ERR_ARGUMENT;
+    }
+    const bool scan = c->opt_detect_ranges || c->opt_snapshot_cache;
+    std::vector<int64_t> off;
+    CatScan sc;
+    std::thread worker;
+    if (scan) {
+        if (!catalogue_offsets("cpg_set_snapshot", obj_size, n_obj, n_idx, off)) return CPG_ERR_ARGUMENT;
+        worker = std::thread([&]() { scan_catalogue(idx_cat, off.data(), n_obj, sc); });
+    }
+    const int rc = cpg_set_particles(c, xyz, vxyz, masses, n_part);
+    if (worker.joinable()) worker.join();
+    CPG_TRY(rc);
+    if (!scan) return install_catalogue(c, idx_cat, nullptr, n_idx, obj_size, n_obj);
+    return set_catalogue_scanned(c, idx_cat, n_idx, obj_size, n_obj, sc);
 }
 
 CPG_API int cpg_set_catalogue_ranges(cpg_ctx *c, const int64_t *obj_start, const int32_t *obj_size, int32_t n_obj)
@@ -1948,7 +1989,7 @@ CPG_API int cpg_dens_ell(cpg_ctx *c, const double *centers, const double *a, con
     D.a = c->d_a.p; D.b = c->d_b.p; D.c = c->d_c.p;
     D.major = c->d_major.p; D.inter = c->d_inter.p; D.minor = c->d_minor.p;
     D.part_mass = c->bin_mass.p; D.part_cnt = c->bin_cnt.p;
-    const size_t smem = (size_t)R * (EB_SLOTS * sizeof(double) + sizeof(double) + sizeof(int));
+    const size_t smem = (size_t)R * (EB_SLOTS * sizeof(double) + 2 * sizeof(unsigned long long) + sizeof(int));
     if (smem > 48 * 1024)
         CPG_CUDA(cudaFuncSetAttribute(dens_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (nc > 0) {
@@ -2134,6 +2175,38 @@ CPG_API int cpg_centers(cpg_ctx *c, int32_t mode, int32_t shape_path, double L_B
     c->timing.h2d_ms = Timer::ms(c->ev[0], c->ev[1]);
     c->timing.kernel_ms = Timer::ms(c->ev[2], c->ev[3]);
     c->timing.d2h_ms = Timer::ms(c->ev[3], c->ev[4]);
+    return CPG_OK;
+}
+
+// (n_rows, 12) results of cpg_shape -> the six arrays the reference's drivers return, zeros -> NaN
+// (shape_profs_algos.pyx:616-624), on a few host threads.
+CPG_API int cpg_unpack_shape(const double *out12, int64_t n_rows, double *d, double *q, double *s, double *major, double *inter,
+                             double *minor)
+{
+    if (n_rows < 0 || (n_rows > 0 && (!out12 || !d || !q || !s || !major || !inter || !minor))) {
+        set_error("cpg_unpack_shape: bad arguments");
+        return CPG_ERR_ARGUMENT;
+    }
+    const double nan = std::numeric_limits<double>::quiet_NaN();
+    const int T = host_threads((size_t)n_rows * 96 * 2);
+    auto work = [&](int t) {
+        const int64_t a = n_rows * t / T, b = n_rows * (t + 1) / T;
+        for (int64_t i = a; i < b; i++) {
+            const double *o = out12 + 12 * i;
+            d[i] = o[0] == 0.0 ? nan : o[0];
+            q[i] = o[1] == 0.0 ? nan : o[1];
+            s[i] = o[2] == 0.0 ? nan : o[2];
+            for (int r = 0; r < 3; r++) {
+                major[3 * i + r] = o[3 + r] == 0.0 ? nan : o[3 + r];
+                inter[3 * i + r] = o[6 + r] == 0.0 ? nan : o[6 + r];
+                minor[3 * i + r] = o[9 + r] == 0.0 ? nan : o[9 + r];
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
     return CPG_OK;
 }
 

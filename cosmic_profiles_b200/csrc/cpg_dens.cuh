@@ -36,12 +36,62 @@ __device__ __forceinline__ double r2_exact(double x, double y, double z)
     return __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
 }
 
+
+// ---- order-independent bin masses -----------------------------------------------------------------------
+// A bin's mass is a sum over whatever threads find members: floating-point atomics would make its last bit depend on
+// the arrival order.  Integer atomics are associative, so the masses are accumulated on a two-level fixed-point grid
+// anchored at the chunk's largest mass: hi = rint(m / q1), lo = rint((m - hi q1) / q2), q1 = 2^(e+1-38), q2 = q1 2^-44,
+// with 2^e <= max mass of the chunk < 2^(e+1).  |hi| <= 2^38 and |lo| <= 2^43, so a chunk of 16384 particles cannot
+// overflow 63 bits; the rounding error per particle is <= 2^-83 of the chunk's largest mass (masses 25 orders of
+// magnitude below it still keep 1e-10 relative).  The bin counts were integers all along.
+struct MassGrid {
+    double q1, inv_q1, q2, inv_q2;
+};
+
+__device__ __forceinline__ MassGrid mass_grid(double mmax)
+{
+    MassGrid g;
+    const int e = (mmax > 0.0 && mmax < 1e300) ? ilogb(mmax) : 0;
+    g.q1 = ldexp(1.0, e + 1 - 38); g.inv_q1 = ldexp(1.0, 38 - e - 1);
+    g.q2 = ldexp(g.q1, -44); g.inv_q2 = ldexp(g.inv_q1, 44);
+    return g;
+}
+
+__device__ __forceinline__ void grid_add(unsigned long long *hi, unsigned long long *lo, const MassGrid &g, double m)
+{
+    const long long h = __double2ll_rn(m * g.inv_q1);
+    const double r = fma(-(double)h, g.q1, m);           // exact: |h| < 2^53 and the product is a multiple of q1
+    const long long l = __double2ll_rn(r * g.inv_q2);
+    atomicAdd(hi, (unsigned long long)h);
+    atomicAdd(lo, (unsigned long long)l);
+}
+
+__device__ __forceinline__ double grid_value(unsigned long long hi, unsigned long long lo, const MassGrid &g)
+{
+    return (double)(long long)hi * g.q1 + (double)(long long)lo * g.q2;
+}
+
+// Largest |mass| of particles [start, end) of an object, identical in every thread of the CTA.
+__device__ __forceinline__ double chunk_max_mass(const double *m, int64_t base, int start, int end, double *s_red /* [8] */)
+{
+    double mx = 0.0;
+    for (int i = start + threadIdx.x; i < end; i += blockDim.x) mx = fmax(mx, fabs(m[base + i]));
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) mx = fmax(mx, s_red[w]);
+    return mx;
+}
+
 // ---- spherical shells (helper_class.pyx:229-240) ---------------------------------------------------
 __global__ void __launch_bounds__(256) dens_sph_kernel(const DensParams D)
 {
     __shared__ double s_e2[DENS_MAX_R + 1];
-    __shared__ double s_mass[DENS_MAX_R];
+    __shared__ unsigned long long s_hi[DENS_MAX_R], s_lo[DENS_MAX_R];
     __shared__ int s_cnt[DENS_MAX_R];
+    __shared__ double s_red[8];
     const Chunk ck = D.chunks[blockIdx.x];
     const int N = D.soa.size[ck.halo];
     const int64_t base = D.soa.poff[ck.halo];
@@ -52,7 +102,8 @@ __global__ void __launch_bounds__(256) dens_sph_kernel(const DensParams D)
         const double e = __dmul_rn(D.edges[k], rf);
         s_e2[k] = __dmul_rn(e, e);
     }
-    for (int k = threadIdx.x; k < R; k += blockDim.x) { s_mass[k] = 0.0; s_cnt[k] = 0; }
+    for (int k = threadIdx.x; k < R; k += blockDim.x) { s_hi[k] = 0ull; s_lo[k] = 0ull; s_cnt[k] = 0; }
+    const MassGrid G = mass_grid(chunk_max_mass(D.soa.m, base, ck.start, end, s_red));
     __syncthreads();
     for (int i = ck.start + threadIdx.x; i < end; i += blockDim.x) {
         const double r2 = r2_exact(D.soa.dx[base + i], D.soa.dy[base + i], D.soa.dz[base + i]);
@@ -64,20 +115,20 @@ __global__ void __launch_bounds__(256) dens_sph_kernel(const DensParams D)
                     const int mid = (lo + hi) >> 1;
                     if (s_e2[mid] <= r2) lo = mid; else hi = mid;
                 }
-                atomicAdd(&s_mass[lo], m);
+                grid_add(&s_hi[lo], &s_lo[lo], G, m);
                 atomicAdd(&s_cnt[lo], 1);
             }
         } else {
             for (int k = 0; k < R; k++)
                 if (r2 < s_e2[k + 1] && r2 >= s_e2[k]) {
-                    atomicAdd(&s_mass[k], m);
+                    grid_add(&s_hi[k], &s_lo[k], G, m);
                     atomicAdd(&s_cnt[k], 1);
                 }
         }
     }
     __syncthreads();
     for (int k = threadIdx.x; k < R; k += blockDim.x) {
-        D.part_mass[(size_t)blockIdx.x * R + k] = s_mass[k];
+        D.part_mass[(size_t)blockIdx.x * R + k] = grid_value(s_hi[k], s_lo[k], G);
         D.part_cnt[(size_t)blockIdx.x * R + k] = s_cnt[k];
     }
 }
@@ -88,11 +139,13 @@ enum { EB_E2 = 0, EB_E1 = 3, EB_E0 = 6, EB_A1 = 9, EB_B1, EB_C1, EB_A0, EB_B0, E
 
 __global__ void __launch_bounds__(256) dens_ell_kernel(const DensParams D)
 {
-    extern __shared__ double s_dyn[];   // [R][EB_SLOTS] frames, [R] mass, then [R] int counts
+    extern __shared__ double s_dyn[];   // [R][EB_SLOTS] frames, [R] + [R] fixed-point masses, then [R] int counts
+    __shared__ double s_red[8];
     const int R = D.R;
     double *s_bin = s_dyn;
-    double *s_mass = s_dyn + (size_t)R * EB_SLOTS;
-    int *s_cnt = reinterpret_cast<int *>(s_mass + R);
+    unsigned long long *s_hi = reinterpret_cast<unsigned long long *>(s_dyn + (size_t)R * EB_SLOTS);
+    unsigned long long *s_lo = s_hi + R;
+    int *s_cnt = reinterpret_cast<int *>(s_lo + R);
     const Chunk ck = D.chunks[blockIdx.x];
     const int h = ck.halo;
     const int N = D.soa.size[h];
@@ -114,9 +167,10 @@ __global__ void __launch_bounds__(256) dens_ell_kernel(const DensParams D)
         const double *A = D.a + (size_t)h * (R + 1), *Bx = D.b + (size_t)h * (R + 1), *C = D.c + (size_t)h * (R + 1);
         B[EB_A1] = A[k + 1]; B[EB_B1] = Bx[k + 1]; B[EB_C1] = C[k + 1];
         B[EB_A0] = A[k]; B[EB_B0] = Bx[k]; B[EB_C0] = C[k];
-        s_mass[k] = 0.0;
+        s_hi[k] = 0ull; s_lo[k] = 0ull;
         s_cnt[k] = 0;
     }
+    const MassGrid G = mass_grid(chunk_max_mass(D.soa.m, base, ck.start, end, s_red));
     __syncthreads();
     for (int i = ck.start + threadIdx.x; i < end; i += blockDim.x) {
         const double dx = D.soa.dx[base + i], dy = D.soa.dy[base + i], dz = D.soa.dz[base + i];
@@ -130,7 +184,7 @@ __global__ void __launch_bounds__(256) dens_ell_kernel(const DensParams D)
             if (r2_exact(u0, u1, u2) < 1.0) {
                 const double w0 = __ddiv_rn(p0, B[EB_A0]), w1 = __ddiv_rn(p1, B[EB_B0]), w2 = __ddiv_rn(p2, B[EB_C0]);
                 if (r2_exact(w0, w1, w2) >= 1.0) {
-                    atomicAdd(&s_mass[k], m);
+                    grid_add(&s_hi[k], &s_lo[k], G, m);
                     atomicAdd(&s_cnt[k], 1);
                 }
             }
@@ -138,7 +192,7 @@ __global__ void __launch_bounds__(256) dens_ell_kernel(const DensParams D)
     }
     __syncthreads();
     for (int k = threadIdx.x; k < R; k += blockDim.x) {
-        D.part_mass[(size_t)blockIdx.x * R + k] = s_mass[k];
+        D.part_mass[(size_t)blockIdx.x * R + k] = grid_value(s_hi[k], s_lo[k], G);
         D.part_cnt[(size_t)blockIdx.x * R + k] = s_cnt[k];
     }
 }

@@ -13,12 +13,6 @@ from . import _lib, centers as _centers, session as _session
 last_info = {}   # n_iter / n_pts / timing of the most recent call (the reference keeps these as locals)
 
 
-def _nan0(a):
-    a = np.array(a, dtype=np.float64, copy=True)
-    a[a == 0.0] = np.nan
-    return a
-
-
 def _morph(xyz, vxyz, masses, r200, idx_cat, obj_size, L_BOX, r_over_r200, IT_TOL, IT_WALL, IT_MIN, CENTER, SAFE,
            reduced, shell_based, local, centers=None):
     xyz = _lib.f64(np.asarray(xyz))
@@ -49,19 +43,16 @@ def _morph(xyz, vxyz, masses, r200, idx_cat, obj_size, L_BOX, r_over_r200, IT_TO
             extra = grp.multi.info()
         else:   # one device (or too few objects to shard: everything on the first one)
             ctx = grp.contexts[0]
-            ctx.set_particles(xyz, vxyz, masses)
-            ctx.set_catalogue(idx_cat, obj_size)
+            ctx.set_snapshot(xyz, vxyz, masses, idx_cat, obj_size)
             if cen is None:   # shape path: calcMode starts from the bounding-box extent
                 cen = ctx.centers(mode, True, L_BOX, ref)
-            out, nit, npt, m, vc = ctx.shape(cen, r200, *args)
+            # out / nit / npt: views of the context's page-locked scratch, consumed below while the lock is held
+            out, nit, npt, m, vc = ctx.shape(cen, r200, *args, zero_copy=True)
+            nit, npt = nit.copy(), npt.copy()
             timings = [ctx.timing()]
             extra = None
-    d = _nan0(out[:, :, 0])
-    q = _nan0(out[:, :, 1])
-    s = _nan0(out[:, :, 2])
-    major = _nan0(out[:, :, 3:6])
-    inter = _nan0(out[:, :, 6:9])
-    minor = _nan0(out[:, :, 9:12])
+        # zeros -> NaN (:616-624) and the split into the six returned arrays, on a few host threads
+        d, q, s, major, inter, minor = _lib.unpack_shape(out)
     cen_out = _centers.recentre(cen, L_BOX)
     if not local:
         d, q, s = d[:, 0], q[:, 0], s[:, 0]

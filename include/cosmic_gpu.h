@@ -81,6 +81,11 @@ CPG_API int cpg_set_particles(cpg_ctx *ctx, const double *xyz, const double *vxy
 CPG_API int cpg_set_catalogue(cpg_ctx *ctx, const int32_t *idx_cat, int64_t n_idx, const int32_t *obj_size,
                               int32_t n_obj);
 
+/* cpg_set_particles + cpg_set_catalogue in one call, the host-side pass over the flat catalogue (contiguity test,
+ * index range, content hash) overlapped with the host->device transfer of the particle arrays. */
+CPG_API int cpg_set_snapshot(cpg_ctx *ctx, const double *xyz, const double *vxyz, const double *masses, int64_t n_part,
+                             const int32_t *idx_cat, int64_t n_idx, const int32_t *obj_size, int32_t n_obj);
+
 /* Snapshot as the concatenation of element ranges of the host arrays: particles [seg_start[i], seg_start[i] +
  * seg_len[i]) of xyz / vxyz / masses, i = 0..n_seg-1, become the device snapshot (host threads pack the ranges
  * straight into page-locked bounce buffers).  Used to ship one shard of a halo-partitioned catalogue to its GPU
@@ -226,6 +231,12 @@ CPG_API int cpg_fit_profiles(cpg_ctx *ctx, const double *radii, const double *lm
                              const double *avg, const double *x0, const double *lb, const double *ub, int32_t n_obj,
                              int32_t R, int32_t profile, double xtol, double ftol, double *best, double *fun,
                              int32_t *nfev, int32_t *nit);
+
+/* Host-side helper (no device): the (n_rows,12) out12 rows of cpg_shape split into the six arrays the reference's drivers
+ * return -- d, q, s (n_rows) and major, inter, minor (n_rows,3) -- with the reference's zeros -> NaN masking
+ * (shape_profs_algos.pyx:616-624: d, q, s and every eigenvector component that is exactly 0.0). */
+CPG_API int cpg_unpack_shape(const double *out12, int64_t n_rows, double *d, double *q, double *s, double *major,
+                             double *inter, double *minor);
 
 /* Page-locked host buffers for results.  When out12, n_iter and n_pts of cpg_shape all live in such buffers, the
  * kernels store every finished halo-shell straight into them while they run (no result copy after the kernels; option
