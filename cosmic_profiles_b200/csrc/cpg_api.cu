@@ -149,7 +149,7 @@ struct cpg_ctx {
     // what the gathered SoA currently holds (skip the gather when a call asks for the same thing again)
     uint64_t snapshot_version = 0, catalogue_version = 0;
     struct {
-        bool valid = false, stats = false, vel = false;
+        bool valid = false, stats = false, vel = false, mmax = false;
         bool parts_from_sort = false;   // the per-chunk statistics were produced by the ordering gather (sort chunks)
         int ptab = 0;   // prefix tensor table: 0 none, 1 positions, 2 velocities
         uint64_t snap = 0, cat = 0;
@@ -176,7 +176,7 @@ struct cpg_ctx {
     DevBuf<double> out12;
     DevBuf<int32_t> n_iter, n_pts;
     // densities
-    DevBuf<double> d_a, d_b, d_c, d_major, d_inter, d_minor, d_edges, dens, bin_mass;
+    DevBuf<double> d_a, d_b, d_c, d_major, d_inter, d_minor, d_edges, dens, bin_mass, chunk_mmax;
     DevBuf<int32_t> bin_cnt, counts;
     // Gadget / FoF ingest (cpg_gadget.cuh): group tables, scans, the compacted central-subhalo catalogue
     DevBuf<int32_t> oc_nb, oc_shlen, oc_fof, oc_size, oc_idx, oc_err;
@@ -342,7 +342,7 @@ int host_threads(size_t bytes)
 {
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     const size_t want = bytes / ((size_t)16 << 20) + 1;   // one thread per 16 MB
-    return (int)std::min<size_t>(std::min<size_t>(want, 8), hw);
+    return (int)std::min<size_t>(std::min<size_t>(want, 12), std::max(1u, hw - 2));
 }
 
 // Content token of a host array.  full: hash of every byte (multi-threaded); else: the first and last 4 KB and 4096
@@ -408,13 +408,25 @@ void scan_catalogue(const int32_t *idx, const int64_t *off, int32_t n_obj, CatSc
             out.start[o] = first;
             bool run = true;
             int32_t lo = q[0], hi = q[0];
-            uint64_t hh = 0;
-            for (int64_t i = 0; i < n; i++) {
+            // four independent multiply-add chains (one would bound the pass at ~1 element per multiply latency)
+            uint64_t h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+            int64_t i = 0;
+            for (; i + 4 <= n; i += 4) {
+                const int32_t v0 = q[i], v1 = q[i + 1], v2 = q[i + 2], v3 = q[i + 3];
+                const int32_t e = (int32_t)(first + i);
+                run &= (v0 == e) & (v1 == e + 1) & (v2 == e + 2) & (v3 == e + 3);
+                lo = std::min(std::min(lo, v0), std::min(std::min(v1, v2), v3));
+                hi = std::max(std::max(hi, v0), std::max(std::max(v1, v2), v3));
+                h0 = h0 * 0x100000001B3ull + (uint32_t)v0; h1 = h1 * 0x100000001B3ull + (uint32_t)v1;
+                h2 = h2 * 0x100000001B3ull + (uint32_t)v2; h3 = h3 * 0x100000001B3ull + (uint32_t)v3;
+            }
+            for (; i < n; i++) {
                 const int32_t v = q[i];
                 run &= (v == (int32_t)(first + i));
                 lo = std::min(lo, v); hi = std::max(hi, v);
-                hh = hh * 0x100000001B3ull + (uint32_t)v;
+                h0 = h0 * 0x100000001B3ull + (uint32_t)v;
             }
+            const uint64_t hh = mix64(mix64(mix64(h0, h1), h2), h3);
             if (first + n - 1 > 0x7fffffffLL) run = false;
             r.contiguous &= run;
             r.min_idx = std::min<int64_t>(r.min_idx, lo);
@@ -620,7 +632,7 @@ int run_gather(cpg_ctx *c, const double *h_centers, const double *h_r200, const 
         same = H.sort_R == sort_R && H.rr.size() == (size_t)sort_R && !memcmp(H.rr.data(), h_rr, sort_R * sizeof(double)) &&
                H.r200.size() == (size_t)c->n_obj && !memcmp(H.r200.data(), h_r200, c->n_obj * sizeof(double));
     if (same) return CPG_OK;
-    H.valid = false; H.stats = false; H.vel = false; H.ptab = 0; H.parts_from_sort = false;
+    H.valid = false; H.stats = false; H.vel = false; H.mmax = false; H.ptab = 0; H.parts_from_sort = false;
     CPG_TRY(c->g_dx.ensure(c->n_pad)); CPG_TRY(c->g_dy.ensure(c->n_pad));
     CPG_TRY(c->g_dz.ensure(c->n_pad)); CPG_TRY(c->g_m.ensure(c->n_pad));
     c->sorted_valid = false;
@@ -937,7 +949,7 @@ CPG_API void cpg_destroy(cpg_ctx *c)
     DevBuf<double> *dbl[] = {&c->xyz, &c->vxyz, &c->masses, &c->g_dx, &c->g_dy, &c->g_dz, &c->g_m, &c->g_vx, &c->g_vy,
                              &c->g_vz, &c->centers, &c->vcenters, &c->r200, &c->rr, &c->obj_mass, &c->part_mass,
                              &c->vpart, &c->part_mm, &c->obj_eqm, &c->out12, &c->d_a, &c->d_b, &c->d_c, &c->d_major, &c->d_inter, &c->d_minor,
-                             &c->d_edges, &c->dens, &c->bin_mass};
+                             &c->d_edges, &c->dens, &c->bin_mass, &c->chunk_mmax};
     for (auto *b : dbl) b->release();
     DevBuf<int32_t> *i32[] = {&c->idx, &c->size, &c->chunk_first, &c->kchunk_first, &c->part_flag, &c->task_counter,
                               &c->n_iter, &c->n_pts, &c->bin_cnt, &c->counts};
@@ -1875,7 +1887,19 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
 
 static int dens_gather(cpg_ctx *c, const double *centers, float L_BOX)
 {
-    return run_gather(c, centers, nullptr, nullptr, L_BOX, 0);
+    CPG_TRY(run_gather(c, centers, nullptr, nullptr, L_BOX, 0));
+    // per-chunk largest mass: anchors the fixed-point grid of the bin masses (cpg_dens.cuh); once per gather
+    if (!c->have.mmax) {
+        const int nc = (int)c->h_chunks.size();
+        CPG_TRY(c->chunk_mmax.ensure((size_t)std::max(nc, 1)));
+        if (nc > 0) {
+            chunk_mmax_kernel<<<nc, 256, 0, c->stream>>>(soa_view(c), c->chunks.p, nc, c->chunk_mmax.p);
+            c->timing.kernel_launches++;
+            CPG_CUDA(cudaGetLastError());
+        }
+        c->have.mmax = c->have.valid;
+    }
+    return CPG_OK;
 }
 
 static int dens_common_begin(cpg_ctx *c, Timer &T, const double *centers, const double *r200, float L_BOX)
@@ -1931,7 +1955,7 @@ CPG_API int cpg_dens_sph(cpg_ctx *c, const double *centers, const double *r200, 
     T.mark(2);
     DensParams D = {};
     D.soa = soa_view(c); D.chunks = c->chunks.p; D.n_chunks = nc; D.R = R; D.r200 = c->r200.p; D.edges = c->d_edges.p;
-    D.part_mass = c->bin_mass.p; D.part_cnt = c->bin_cnt.p;
+    D.part_mass = c->bin_mass.p; D.part_cnt = c->bin_cnt.p; D.chunk_mmax = c->chunk_mmax.p;
     D.monotone = 1;
     for (int k = 0; k < R; k++)
         if (!(bin_edges[k + 1] > bin_edges[k]) || !(bin_edges[k] >= 0.0)) D.monotone = 0;
@@ -1988,7 +2012,7 @@ CPG_API int cpg_dens_ell(cpg_ctx *c, const double *centers, const double *a, con
     D.soa = soa_view(c); D.chunks = c->chunks.p; D.n_chunks = nc; D.R = R;
     D.a = c->d_a.p; D.b = c->d_b.p; D.c = c->d_c.p;
     D.major = c->d_major.p; D.inter = c->d_inter.p; D.minor = c->d_minor.p;
-    D.part_mass = c->bin_mass.p; D.part_cnt = c->bin_cnt.p;
+    D.part_mass = c->bin_mass.p; D.part_cnt = c->bin_cnt.p; D.chunk_mmax = c->chunk_mmax.p;
     const size_t smem = (size_t)R * (EB_SLOTS * sizeof(double) + 2 * sizeof(unsigned long long) + sizeof(int));
     if (smem > 48 * 1024)
         CPG_CUDA(cudaFuncSetAttribute(dens_ell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

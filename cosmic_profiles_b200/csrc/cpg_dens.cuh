@@ -27,6 +27,7 @@ struct DensParams {
     const double *major, *inter, *minor;   // ell: (n_obj, R, 3)
     int32_t monotone;          // sph: edges strictly increasing -> binary search is exact
     double ktilde_c0;          // 1/(2*(2*pi)^1.5) evaluated by the host libm like the reference
+    const double *chunk_mmax;  // (n_chunks) largest |mass| of every chunk (chunk_mmax_kernel; anchors the fixed-point grid)
     double *part_mass;         // (n_chunks, R)
     int32_t *part_cnt;         // (n_chunks, R)
 };
@@ -85,13 +86,24 @@ __device__ __forceinline__ double chunk_max_mass(const double *m, int64_t base, 
     return mx;
 }
 
+// Largest |mass| per chunk of the gathered SoA: one pass over the masses, once per gather (the density kernels of every
+// later call on the same gather reuse it).
+__global__ void __launch_bounds__(256) chunk_mmax_kernel(const SoA soa, const Chunk *chunks, int n_chunks, double *chunk_mmax)
+{
+    __shared__ double s_red[8];
+    if ((int)blockIdx.x >= n_chunks) return;
+    const Chunk ck = chunks[blockIdx.x];
+    const int end = min(soa.size[ck.halo], ck.start + CHUNK);
+    const double mx = chunk_max_mass(soa.m, soa.poff[ck.halo], ck.start, end, s_red);
+    if (threadIdx.x == 0) chunk_mmax[blockIdx.x] = mx;
+}
+
 // ---- spherical shells (helper_class.pyx:229-240) ---------------------------------------------------
 __global__ void __launch_bounds__(256) dens_sph_kernel(const DensParams D)
 {
     __shared__ double s_e2[DENS_MAX_R + 1];
     __shared__ unsigned long long s_hi[DENS_MAX_R], s_lo[DENS_MAX_R];
     __shared__ int s_cnt[DENS_MAX_R];
-    __shared__ double s_red[8];
     const Chunk ck = D.chunks[blockIdx.x];
     const int N = D.soa.size[ck.halo];
     const int64_t base = D.soa.poff[ck.halo];
@@ -103,7 +115,7 @@ __global__ void __launch_bounds__(256) dens_sph_kernel(const DensParams D)
         s_e2[k] = __dmul_rn(e, e);
     }
     for (int k = threadIdx.x; k < R; k += blockDim.x) { s_hi[k] = 0ull; s_lo[k] = 0ull; s_cnt[k] = 0; }
-    const MassGrid G = mass_grid(chunk_max_mass(D.soa.m, base, ck.start, end, s_red));
+    const MassGrid G = mass_grid(D.chunk_mmax[blockIdx.x]);
     __syncthreads();
     for (int i = ck.start + threadIdx.x; i < end; i += blockDim.x) {
         const double r2 = r2_exact(D.soa.dx[base + i], D.soa.dy[base + i], D.soa.dz[base + i]);
@@ -140,7 +152,6 @@ enum { EB_E2 = 0, EB_E1 = 3, EB_E0 = 6, EB_A1 = 9, EB_B1, EB_C1, EB_A0, EB_B0, E
 __global__ void __launch_bounds__(256) dens_ell_kernel(const DensParams D)
 {
     extern __shared__ double s_dyn[];   // [R][EB_SLOTS] frames, [R] + [R] fixed-point masses, then [R] int counts
-    __shared__ double s_red[8];
     const int R = D.R;
     double *s_bin = s_dyn;
     unsigned long long *s_hi = reinterpret_cast<unsigned long long *>(s_dyn + (size_t)R * EB_SLOTS);
@@ -170,7 +181,7 @@ __global__ void __launch_bounds__(256) dens_ell_kernel(const DensParams D)
         s_hi[k] = 0ull; s_lo[k] = 0ull;
         s_cnt[k] = 0;
     }
-    const MassGrid G = mass_grid(chunk_max_mass(D.soa.m, base, ck.start, end, s_red));
+    const MassGrid G = mass_grid(D.chunk_mmax[blockIdx.x]);
     __syncthreads();
     for (int i = ck.start + threadIdx.x; i < end; i += blockDim.x) {
         const double dx = D.soa.dx[base + i], dy = D.soa.dy[base + i], dz = D.soa.dz[base + i];
