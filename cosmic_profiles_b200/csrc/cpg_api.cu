@@ -198,6 +198,7 @@ struct cpg_ctx {
     int opt_radial_order = 1;
     int opt_prefix_table = 1;
     int opt_groups = 0;   // 0 auto, 1 one group of S shells per warp task, 2 two groups
+    int opt_batched_step = 0;   // warp kernel: one warp per CTA runs the per-iteration step of all the CTA's warps (cpg_morph.cuh, kernel 1b)
     cpg_timing timing = {};
 };
 
@@ -778,7 +779,21 @@ int launch_morph(cpg_ctx *c, MorphParams P, int n_warp_tasks, int n_cluster_task
         c->timing.kernel_launches++;
         c->timing.hot_kernel_launches++;
     }
-    if (n_warp_tasks > 0) {
+    if (n_warp_tasks > 0 && G == 1 && c->opt_batched_step) {
+        auto kern = morph_wbatch_kernel<S, SHELL, REDUCED, VDISP>;
+        const int smem = WB_WARPS * RingCfg<VDISP>::WARP_BYTES;
+        CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int per_sm = 0;
+        CPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WB_WARPS * 32, smem));
+        if (per_sm < 1) per_sm = 1;
+        const int grid = std::min((n_warp_tasks + WB_WARPS - 1) / WB_WARPS, c->sm_count * per_sm);
+        MorphParams Pw = P;
+        Pw.n_tasks = n_warp_tasks;
+        kern<<<grid, WB_WARPS * 32, smem, c->stream>>>(Pw);
+        c->timing.kernel_launches++;
+        c->timing.hot_kernel_launches++;
+        CPG_CUDA(cudaGetLastError());
+    } else if (n_warp_tasks > 0) {
         auto kern = morph_warp_kernel<S, G, SHELL, REDUCED, VDISP>;
         const int smem = WARP_KERNEL_WARPS * RingCfg<VDISP>::WARP_BYTES;
         CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1021,6 +1036,8 @@ CPG_API int cpg_set_option(cpg_ctx *c, const char *name, int64_t value)
         if (value == 0) { c->snap_key.valid = false; c->cat_key.valid = false; }
     } else if (!strcmp(name, "detect_ranges")) {
         c->opt_detect_ranges = value != 0;
+    } else if (!strcmp(name, "batched_step")) {
+        c->opt_batched_step = value != 0;
     } else if (!strcmp(name, "direct_results")) {
         c->opt_direct_results = value != 0;
     } else if (!strcmp(name, "radial_order")) {
@@ -1739,7 +1756,7 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
     const int64_t grid_min = c->opt_grid_halo_min > 0 ? c->opt_grid_halo_min : ((int64_t)1 << 22);
     cpg_ctx::TaskKey *hit = nullptr, *victim = nullptr;
     for (auto &tk : c->task_cache)
-        if (tk.valid && tk.cat == c->catalogue_version && tk.S == S * 16 + G && tk.R == R && tk.large_min == large_min &&
+        if (tk.valid && tk.cat == c->catalogue_version && tk.S == S * 16 + G + 256 * c->opt_batched_step && tk.R == R && tk.large_min == large_min &&
             tk.grid_min == grid_min && (c->opt_cluster_size == 0 || c->opt_cluster_size == tk.cluster_size))
             hit = &tk;
     for (auto &tk : c->task_cache)   // victim: a free slot, else the least recently used one
@@ -1764,6 +1781,17 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
             for (int k0 = 0; k0 < R; k0 += step)
                 dst.push_back(Task{h, (int16_t)k0, (int16_t)std::min(step, R - k0)});
         }
+        if (c->opt_batched_step && G == 1 && local && R > 1) {
+            // batched step: the warps of a CTA meet once per Katz iteration, so neighbours in the queue should stream
+            // prefixes of similar length.  Estimated pass length of (object, shells k0..k0+n-1): N (r_last / r_max)^1.5
+            // (between the r^2 of an inner cusp and the r^1 of an isothermal envelope); longest first.
+            const double rmax = r_over_r200[R - 1] > 0.0 ? r_over_r200[R - 1] : 1.0;
+            auto cost = [&](const Task &t) {
+                const double x = std::min(1.0, std::max(1e-6, r_over_r200[t.shell0 + t.nshell - 1] / rmax));
+                return (double)c->h_size[t.halo] * x * sqrt(x);
+            };
+            std::stable_sort(warp_tasks.begin(), warp_tasks.end(), [&](const Task &a, const Task &b) { return cost(a) > cost(b); });
+        }
         int cluster_size = c->opt_cluster_size;
         if (cluster_size == 0) {
             cluster_size = 1;
@@ -1781,7 +1809,7 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
         CPG_TRY(TK.tasks.ensure(warp_tasks.size()));
         CPG_TRY(small_upload(c, TK.tasks.p, warp_tasks.data(), sizeof(Task) * warp_tasks.size()));
         c->timing.h2d_bytes += (int64_t)(sizeof(Task) * warp_tasks.size());
-        TK.valid = true; TK.cat = c->catalogue_version; TK.S = S * 16 + G; TK.R = R; TK.large_min = large_min;
+        TK.valid = true; TK.cat = c->catalogue_version; TK.S = S * 16 + G + 256 * c->opt_batched_step; TK.R = R; TK.large_min = large_min;
     }
     const int nw = TK.nw, ncl = TK.ncl, ngrid = TK.ngrid, cluster_size = TK.cluster_size;
     // Page-locked result buffers (cpg_host_alloc): the kernels store every finished halo-shell straight into them

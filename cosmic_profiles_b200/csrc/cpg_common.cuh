@@ -105,6 +105,10 @@ __device__ __forceinline__ double fast_rsqrt(double x)
     return fma(y, e, y);
 }
 
+#ifndef CPG_JACOBI_TOL2
+#define CPG_JACOBI_TOL2 1e-33   // (off-diagonal norm / diagonal norm)^2 at which the sweeps stop: 3e-17 relative
+#endif
+
 __device__ __forceinline__ void jacobi_rotate(double &app, double &aqq, double &apq, double &arp, double &arq,
                                               double *vp, double *vq)
 {
@@ -160,8 +164,8 @@ __device__ __forceinline__ void eigh3(double a00, double a01, double a02, double
     for (int sweep = 0; sweep < 40; sweep++) {
         const double off = a01 * a01 + a02 * a02 + a12 * a12;
         const double dia = a00 * a00 + a11 * a11 + a22 * a22;
-        if (!(off > 1e-33 * dia))
-            break;   // off-diagonal below 3e-17 of the diagonal (eigenvectors exact to rounding), or NaN input
+        if (!(off > CPG_JACOBI_TOL2 * dia))
+            break;   // off-diagonal below sqrt(CPG_JACOBI_TOL2) of the diagonal (eigenvectors exact to rounding), or NaN input
         jacobi_rotate(a00, a11, a01, a02, a12, v0, v1);
         jacobi_rotate(a00, a22, a02, a01, a12, v0, v2);
         jacobi_rotate(a11, a22, a12, a01, a02, v1, v2);

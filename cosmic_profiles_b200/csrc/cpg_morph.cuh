@@ -22,6 +22,19 @@
 namespace cpg {
 namespace cg = cooperative_groups;
 
+#ifndef CPG_FP64_PAIRS
+#define CPG_FP64_PAIRS 0   // 1: the all-fp64 path works on one particle pair at a time (rolled loop)
+#endif
+#ifndef CPG_F32_TEST
+// 0 (default): all-fp64 membership tests.  1: fp32 pre-classification of the membership tests of the non-reduced
+// variants with an exact fp64 re-test of the undecided particles (pair_f32 below).  Measured on configs[1], B200
+// (profiles/README.md, round 2): the all-fp64 kernels saturate the fp64 pipe (0.45 of the 0.455 warp-DFMA/clk/SMSP the
+// pipe sustains, profiles/micro/fp64_lanes.cu); the fp32 variant halves the fp64 instructions of the streaming loop but
+// its compare / select / convert instructions make it issue-bound: 24.3 ms against 19.4 ms for the local-shape kernels.
+// Kept as a build option (make EXTRA=-DCPG_F32_TEST=1); the GPU suite passes with either setting.
+#define CPG_F32_TEST 0
+#endif
+
 // Frame slots (doubles) per shell in shared memory.  The ellipsoidal radius of the reference,
 //   v = p0^2 + p1^2/q^2 + p2^2/s^2  with  p = R (x - c)            (shape_profs_algos.pyx:247-256)
 // is the quadratic form v = (x-c)^T A (x-c), A = R^T diag(1, 1/q^2, 1/s^2) R.  The six products
@@ -37,12 +50,13 @@ enum {
     F_V,                                            // 9 slots: eigenvector basis of the previous iteration
     F_BA2 = F_V + 9, F_BB2, F_BC2,                  // (d-delta)^2, (q d-delta)^2, (s d-delta)^2 (shell variant, exact_member)
     F_F32,                                          // 8 slots = 16 floats: the fp32 pre-classification frame (FrameF32)
-    F_SLOTS = F_F32 + 8                             // (even: rows stay 16-byte aligned for the double2 / float4 loads)
+    // (even: rows stay 16-byte aligned for the double2 / float4 loads; the all-fp64 build stops after the basis)
+    F_SLOTS = CPG_F32_TEST ? F_F32 + 8 : F_V + 10
 };
 // fp32 pre-classification frame, 16 floats at F_F32: A (as F_AXX.., rounded to fp32), lo, hi, B, loB, hiB.
 // See classify_f32 for what lo/hi mean.
 enum { G_A = 0, G_LO = 6, G_HI = 7, G_B = 8, G_LOB = 14, G_HIB = 15 };
-static_assert(F_V == 16 && F_F32 % 2 == 0 && F_SLOTS % 2 == 0, "frame layout");
+static_assert(F_V == 16 && F_F32 % 2 == 0 && F_SLOTS % 2 == 0 && F_SLOTS >= F_V + 9, "frame layout");
 
 constexpr int TILE_PAIRS = 64;   // particle pairs per tile of a stream (1 KB)
 
@@ -52,18 +66,7 @@ struct Particle {              // one particle as seen by the accumulators
     double t[6];               // products the tensor is built from (velocities; VDISP only)
 };
 
-#ifndef CPG_FP64_PAIRS
-#define CPG_FP64_PAIRS 0   // 1: the all-fp64 path works on one particle pair at a time (rolled loop)
-#endif
-#ifndef CPG_F32_TEST
-// 0 (default): all-fp64 membership tests.  1: fp32 pre-classification of the membership tests of the non-reduced
-// variants with an exact fp64 re-test of the undecided particles (pair_f32 below).  Measured on configs[1], B200
-// (profiles/README.md, round 2): the all-fp64 kernels saturate the fp64 pipe (0.45 of the 0.455 warp-DFMA/clk/SMSP the
-// pipe sustains, profiles/micro/fp64_lanes.cu); the fp32 variant halves the fp64 instructions of the streaming loop but
-// its compare / select / convert instructions make it issue-bound: 24.3 ms against 19.4 ms for the local-shape kernels.
-// Kept as a build option (make EXTRA=-DCPG_F32_TEST=1); the GPU suite passes with either setting.
-#define CPG_F32_TEST 0
-#endif
+
 
 template <bool REDUCED, bool VDISP>
 __device__ __forceinline__ void accumulate(double (&acc)[7], int &cnt, bool sel, double v, const Particle &p)
@@ -415,6 +418,16 @@ __device__ __forceinline__ void katz_step(KatzState &st, const double (&tot)[7],
 #pragma unroll
     for (int r = 0; r < 9; r++) v[r] = vprev[r];   // warm start: basis of the previous iteration
     eigh3(tot[0] * im, tot[1] * im, tot[2] * im, tot[3] * im, tot[4] * im, tot[5] * im, w, v);
+#ifdef CPG_STEP_TWICE
+    {   // measurement only: the eigen-solve a second time on (opaquely) the same input; results unchanged
+        double w2[3], v2[9];
+#pragma unroll
+        for (int r = 0; r < 9; r++) v2[r] = vprev[r];
+        const double one = 1.0 + 0.0 * P.tol;
+        eigh3(tot[0] * im * one, tot[1] * im, tot[2] * im, tot[3] * im, tot[4] * im, tot[5] * im, w2, v2);
+        w[0] = fma(0.0, w2[0] + v2[0] + v2[4] + v2[8], w[0]);
+    }
+#endif
     if (!(w[2] > 0.0)) {
         // all-zero or NaN tensor (coincident points, a particle exactly at the centre in reduced mode): the
         // reference divides by zero here and raises; report the shell as failed instead
@@ -451,7 +464,7 @@ __device__ __forceinline__ void katz_step(KatzState &st, const double (&tot)[7],
         const double qq = __dmul_rn(st.q, st.q), ss = __dmul_rn(st.s, st.s);   // q_new**2, s_new**2 (:251)
         const double iq2 = 1.0 / qq, is2 = 1.0 / ss;
         quad_form(frame + F_AXX, v, 1.0, iq2, is2);
-        frame[F_QQ] = qq; frame[F_SS] = ss;
+        frame[F_QQ] = qq; frame[F_SS] = ss;   // (inside the frame in every build: slots 14, 15)
         double bmax = 0.0;
         if (SHELL) {
             const bool first = (st.d == st.delta);   // shape_profs_algos.pyx:130: first shell -> ellipsoid test only
@@ -466,7 +479,7 @@ __device__ __forceinline__ void katz_step(KatzState &st, const double (&tot)[7],
                 quad_form(frame + F_BXX, v, 1.0 / a2, 1.0 / b2, 1.0 / c2);
                 bmax = fmax(1.0 / a2, fmax(1.0 / b2, 1.0 / c2));
             }
-            frame[F_BA2] = a2; frame[F_BB2] = b2; frame[F_BC2] = c2;
+            if (CPG_F32_TEST) { frame[F_BA2] = a2; frame[F_BB2] = b2; frame[F_BC2] = c2; }
             frame[F_THR] = first ? -1.0 : 1.0;
         }
         if (CPG_F32_TEST) write_f32_frame(frame, is2, bmax, SHELL);
@@ -863,8 +876,11 @@ __device__ __forceinline__ void init_frames(double *frames, int *np, int *nin, c
         // p0^2 + p1^2/1 + p2^2/1 is the reference's (x^2 + y^2) + z^2 of pass 0, same order
 #pragma unroll
         for (int r = 0; r < 9; r++) F[F_V + r] = (r == 2 || r == 4 || r == 6) ? 1.0 : 0.0;
-        F[F_QQ] = 1.0; F[F_SS] = 1.0; F[F_BA2] = 1.0; F[F_BB2] = 1.0; F[F_BC2] = 1.0;
-        if (CPG_F32_TEST) write_f32_frame(F, 1.0, 1.0, true);
+        F[F_QQ] = 1.0; F[F_SS] = 1.0;
+        if (CPG_F32_TEST) {
+            F[F_BA2] = 1.0; F[F_BB2] = 1.0; F[F_BC2] = 1.0;
+            write_f32_frame(F, 1.0, 1.0, true);
+        }
         np[L.ls] = (ne + 1) >> 1;
     }
 }
@@ -1013,6 +1029,168 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
 }
 
 // ------------------------------------------------------------------------------------------------
+// Kernel 1b: the warp kernel with a BATCHED step.  The per-iteration step (eigen-solve, convergence test, next frame)
+// costs the same fp64-pipe time for 4 useful lanes as for 32 (profiles/micro/fp64_lanes.cu), and the pipe is what
+// bounds these kernels; in kernel 1 every warp spends a third of its fp64 instructions on the step of its own 4 shells.
+// Here the WB_WARPS warps of a CTA stream their own tasks as before but meet at a block barrier once per Katz iteration:
+// every warp leaves its 8 S reduced sums in shared memory, ONE warp (they take turns) runs the step for all
+// WB_WARPS x S shells at once -- lane l serves shell l % S of warp l / S -- and publishes frames, inner-prefix lengths
+// and active masks for everybody.  Per-shell arithmetic is unchanged (same katz_step, same operands), so the results
+// are those of kernel 1 bit for bit.  The shell state (q, s, iteration ...) lives in shared memory, where the stepping
+// warp finds it.  A warp whose task has finished takes the next one from the queue and re-joins at the next barrier.
+// The host orders the tasks by estimated pass length, so that the warps of a CTA wait for one another as little as possible.
+// ------------------------------------------------------------------------------------------------
+#ifndef CPG_WB_WARPS
+#define CPG_WB_WARPS 4
+#endif
+constexpr int WB_WARPS = CPG_WB_WARPS;
+
+struct ShellSlot {
+    double q, s, d, delta;
+    unsigned long long out_idx;
+    int iteration, active, k, pad;
+};
+
+template <int S, bool SHELL, bool REDUCED, bool VDISP>
+__global__ void __launch_bounds__(WB_WARPS * 32, CPG_WARP_MINB) morph_wbatch_kernel(const MorphParams P)
+{
+    static_assert(WB_WARPS * S <= 32, "one lane per shell in the batched step");
+    constexpr int NV = 8 * S;
+    extern __shared__ __align__(128) unsigned char s_ring_b[];   // WB_WARPS rings
+    __shared__ __align__(16) double s_frames[WB_WARPS][S * F_SLOTS];
+    __shared__ __align__(8) uint64_t s_bar[WB_WARPS][RING_MAX_STAGES];
+    __shared__ int s_np[WB_WARPS][S], s_nin[WB_WARPS][S];
+    __shared__ float s_rr[MAX_SORT_R];
+    __shared__ uint16_t s_neff[WB_WARPS][MAX_SORT_R];
+    __shared__ double s_red[WB_WARPS][NV];
+    __shared__ ShellSlot s_slot[WB_WARPS][S];
+    __shared__ long long s_row0[WB_WARPS];
+    __shared__ unsigned s_amask[WB_WARPS];
+    __shared__ int s_have[WB_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *frames = s_frames[warp];
+    int *np = s_np[warp], *nin = s_nin[warp];
+    const LaneMap<S> L(lane);
+    WarpRing ring;
+    ring_init(ring, s_ring_b + warp * RingCfg<VDISP>::WARP_BYTES, s_bar[warp], lane, WARP_RING_LANES ? 32u : 1u);
+    const bool use_inner = !SHELL && !REDUCED && P.n_eff != nullptr && P.ptab != nullptr;
+    if (use_inner)
+        for (int j = threadIdx.x; j < P.R; j += blockDim.x) s_rr[j] = __double2float_ru(P.rr[j]);
+    __syncthreads();
+    const double *ptab = use_inner ? P.ptab : nullptr;
+
+    bool have = false;
+    unsigned amask = 0;
+    int npr[S];
+    int npairs_task = 0;
+    bool resident = false;
+    int64_t base = 0, row0 = 0;
+#pragma unroll
+    for (int s = 0; s < S; s++) npr[s] = 0;
+
+    for (int iter = 0;; iter++) {
+        if (!have) {
+            // next live task of the queue (dead ones -- empty object, r200 == 0 -- are skipped: outputs stay zero / -1)
+            for (;;) {
+                int t = 0;
+                if (lane == 0) t = atomicAdd(P.task_counter, 1);
+                t = __shfl_sync(0xffffffffu, t, 0);
+                if (t >= P.n_tasks) break;
+                const Task tk = P.tasks[t];
+                const int halo = tk.halo;
+                if (P.skip[halo] || (P.local && P.r200[halo] == 0.0)) continue;
+                const int N = P.soa.size[halo];
+                base = P.soa.poff[halo];
+                row0 = (base >> 7) + halo;
+                KatzState st;
+                st.q = 1.0; st.s = 1.0; st.iteration = 1;
+                st.active = L.ls < tk.nshell;
+                const int k = tk.shell0 + (st.active ? L.ls : 0);
+                shell_geometry(P, halo, k, st.d, st.delta);
+                const size_t out_idx = (size_t)halo * P.R + k;
+                if (use_inner) {
+                    for (int j = lane; j < tk.shell0 + tk.nshell; j += 32)
+                        s_neff[warp][j] = (uint16_t)(P.n_eff[(size_t)halo * P.R + j] >> 1);
+                    __syncwarp();
+                }
+                InnerPrefix ip;
+                ip.rr = nullptr; ip.neff = nullptr;
+                ip.rr_up = use_inner ? s_rr : nullptr;
+                ip.npairs16 = s_neff[warp];
+                init_frames(frames, np, nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
+                if (L.writer) {
+                    ShellSlot &sl = s_slot[warp][L.ls];
+                    sl.q = 1.0; sl.s = 1.0; sl.d = st.d; sl.delta = st.delta; sl.out_idx = (unsigned long long)out_idx;
+                    sl.iteration = 1; sl.active = st.active ? 1 : 0; sl.k = k;
+                }
+                __syncwarp();
+                amask = LaneMap<S>::active_mask(st.active && L.writer);
+                npairs_task = 0;
+#pragma unroll
+                for (int s = 0; s < S; s++) npr[s] = np[s];
+                npairs_task = active_npairs<S>(npr, amask);
+                resident = (npairs_task + TILE_PAIRS - 1) / TILE_PAIRS <= RingCfg<VDISP>::STAGES;
+                ring.res_loaded = false;
+                if (lane == 0) s_row0[warp] = row0;
+                have = true;
+                break;
+            }
+        }
+        if (lane == 0) s_have[warp] = have ? 1 : 0;
+        if (!__syncthreads_or(have ? 1 : 0)) break;   // queue empty and every task of the CTA finished
+        if (have) {
+            const double tadd = table_term(ptab, row0, nin[(lane & (NV - 1)) >> 3], lane & 7);
+            double acc[S][7];
+            int cnt[S];
+            run_pass<S, SHELL, REDUCED, VDISP, WARP_RING_LANES>(P.soa, base, active_npairs<S>(npr, amask), 0, 1, lane, ring, resident,
+                                                                npairs_task, frames, npr, nin, amask, acc, cnt);
+            double val[NV];
+            pack_values<S>(acc, cnt, val);
+            const double mine = warp_sum_transpose<NV>(val, lane) + tadd;
+            if (lane < NV) s_red[warp][lane] = mine;
+        }
+        __syncthreads();   // all sums in place
+        if (warp == (iter % WB_WARPS)) {
+            const int w = lane / S, sh = lane % S;
+            const bool valid = lane < WB_WARPS * S && s_have[w] != 0;
+            KatzState st;
+            st.q = 1.0; st.s = 1.0; st.d = 1.0; st.delta = 1.0; st.iteration = 1; st.active = false;
+            double tot[7] = {0, 0, 0, 0, 0, 0, 0}, vprev[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+            int pts = 0, k = 0;
+            size_t out_idx = 0;
+            const int ws = valid ? w : 0;   // (keeps every lane's addresses in range)
+            if (valid) {
+                const ShellSlot &sl = s_slot[w][sh];
+                st.q = sl.q; st.s = sl.s; st.d = sl.d; st.delta = sl.delta; st.iteration = sl.iteration; st.active = sl.active != 0;
+                k = sl.k; out_idx = (size_t)sl.out_idx;
+#pragma unroll
+                for (int c = 0; c < 7; c++) tot[c] = s_red[w][8 * sh + c];
+                pts = (int)s_red[w][8 * sh + 7];
+#pragma unroll
+                for (int r = 0; r < 9; r++) vprev[r] = s_frames[w][sh * F_SLOTS + F_V + r];
+            }
+            InnerPrefix ip;
+            ip.rr = nullptr; ip.neff = nullptr;
+            ip.rr_up = use_inner ? s_rr : nullptr;
+            ip.npairs16 = s_neff[ws];
+            katz_step<SHELL>(st, tot, pts, P, vprev, s_frames[ws] + sh * F_SLOTS, valid, out_idx, valid, ip, k, &s_nin[ws][sh]);
+            if (valid) {
+                ShellSlot &sl = s_slot[w][sh];
+                sl.q = st.q; sl.s = st.s; sl.iteration = st.iteration; sl.active = st.active ? 1 : 0;
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, valid && st.active);
+            if (lane < WB_WARPS) s_amask[lane] = (b >> (lane * S)) & ((1u << S) - 1u);
+        }
+        __syncthreads();   // next frames, inner-prefix lengths, active masks published
+        if (have) {
+            amask = s_amask[warp];
+            if (amask == 0) have = false;
+        }
+    }
+    ring_flush_stats(ring, P.stats, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Kernel 2: a thread-block CLUSTER per task, for objects too large for one warp.  The C CTAs of a
 // cluster interleave over the object's particle pairs; per iteration every CTA publishes its S x 8
 // partial sums in its own shared memory, one cluster barrier later every CTA reads all C partials
@@ -1032,19 +1210,23 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
 {
     constexpr int NW = CLUSTER_KERNEL_WARPS, NV = 8 * S;
     extern __shared__ __align__(128) unsigned char s_ring_c[];     // NW rings
-    __shared__ __align__(16) double s_frames[NW][S * F_SLOTS];   // warp-private frames (no CTA barrier to publish)
+    // ONE set of frames per CTA, written by warp 0 and published with a block barrier: the per-iteration step
+    // (reduction, eigen-solve, next frame) costs the same fp64-pipe time whether 1 or 32 lanes are active, and the pipe
+    // is what bounds these kernels -- every warp of the CTA repeating it for private frames (round 1) was 12x the work.
+    __shared__ __align__(16) double s_frames[S * F_SLOTS];
     __shared__ __align__(8) uint64_t s_bar[NW][RING_MAX_STAGES];
     __shared__ double s_part[2][NW][NV];                        // per-warp partial sums
     __shared__ double s_cta[2][NV];                             // per-CTA partial sums, read by the cluster
-    __shared__ int s_np[NW][S], s_nin[NW][S];
+    __shared__ int s_np[S], s_nin[S];
+    __shared__ unsigned s_amask;
     __shared__ double s_rr[MAX_SORT_R];
     __shared__ int s_neff[MAX_SORT_R];
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *frames = s_frames[warp];
-    int *np = s_np[warp], *nin = s_nin[warp];
+    double *frames = s_frames;
+    int *np = s_np, *nin = s_nin;
     const LaneMap<S> L(lane);
     const int ls = L.ls;
 
@@ -1059,7 +1241,7 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     WarpRing ring;
     ring_init(ring, s_ring_c + warp * RingCfg<VDISP>::WARP_BYTES, s_bar[warp], lane);
 
-    KatzState st;
+    KatzState st;   // (kept by warp 0; the other warps only follow the published active mask)
     st.q = 1.0; st.s = 1.0; st.iteration = 1;
     st.active = ls < tk.nshell;
     const int k = tk.shell0 + (st.active ? ls : 0);
@@ -1077,10 +1259,14 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     InnerPrefix ip;
     ip.rr = use_inner ? s_rr : nullptr;
     ip.neff = s_neff;
-    init_frames(frames, np, nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
-    __syncwarp();
-    unsigned amask = LaneMap<S>::active_mask(st.active && L.writer);
-    const bool out_writer = (rank == 0 && warp == 0 && L.writer);
+    if (warp == 0) {
+        init_frames(frames, np, nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
+        const unsigned am0 = LaneMap<S>::active_mask(st.active && L.writer);
+        if (lane == 0) s_amask = am0;
+    }
+    __syncthreads();
+    unsigned amask = s_amask;
+    const bool out_writer = (rank == 0 && L.writer);   // (of warp 0)
     int npr[S];
 #pragma unroll
     for (int s = 0; s < S; s++) npr[s] = np[s];
@@ -1102,43 +1288,51 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
             const double mine = warp_sum_transpose<NV>(val, lane);
             if (lane < NV) s_part[buf][warp][lane] = mine;
         }
-        __syncthreads();
-        double tot[7] = {0, 0, 0, 0, 0, 0, 0}, vprev[9];
-        double ptsd = 0.0;
-        if (C == 1) {
-#pragma unroll
-            for (int w = 0; w < NW; w++) {
-#pragma unroll
-                for (int c = 0; c < 7; c++) tot[c] += s_part[buf][w][8 * ls + c];
-                ptsd += s_part[buf][w][8 * ls + 7];
-            }
-        } else {
+        __syncthreads();   // every warp's partial sums are in place (and every warp is done reading the frames)
+        if (C > 1) {
             if (threadIdx.x < NV) {
                 double v = 0.0;
                 for (int w = 0; w < NW; w++) v += s_part[buf][w][threadIdx.x];
                 s_cta[buf][threadIdx.x] = v;
             }
             cluster.sync();
-            for (int r = 0; r < C; r++) {
-                const double *remote = cluster.map_shared_rank(&s_cta[buf][8 * ls], r);
+        }
+        if (warp == 0) {
+            double tot[7] = {0, 0, 0, 0, 0, 0, 0}, vprev[9];
+            double ptsd = 0.0;
+            if (C == 1) {
 #pragma unroll
-                for (int c = 0; c < 7; c++) tot[c] += remote[c];
-                ptsd += remote[7];
+                for (int w = 0; w < NW; w++) {
+#pragma unroll
+                    for (int c = 0; c < 7; c++) tot[c] += s_part[buf][w][8 * ls + c];
+                    ptsd += s_part[buf][w][8 * ls + 7];
+                }
+            } else {
+                // all CTAs read the C partials in rank order: bit-identical totals, identical decisions in every CTA
+                for (int r = 0; r < C; r++) {
+                    const double *remote = cluster.map_shared_rank(&s_cta[buf][8 * ls], r);
+#pragma unroll
+                    for (int c = 0; c < 7; c++) tot[c] += remote[c];
+                    ptsd += remote[7];
+                }
             }
-        }
-        if (use_inner) {   // the inner prefix of the pass just finished comes from the table
-            const int pin = nin[ls];
+            if (use_inner) {   // the inner prefix of the pass just finished comes from the table
+                const int pin = nin[ls];
 #pragma unroll
-            for (int c = 0; c < 6; c++) tot[c] += table_term(P.ptab, row0, pin, c);
-            ptsd += table_term(P.ptab, row0, pin, 7);
-        }
+                for (int c = 0; c < 6; c++) tot[c] += table_term(P.ptab, row0, pin, c);
+                ptsd += table_term(P.ptab, row0, pin, 7);
+            }
 #pragma unroll
-        for (int r = 0; r < 9; r++) vprev[r] = frames[ls * F_SLOTS + F_V + r];
-        __syncwarp();
-        katz_step<SHELL>(st, tot, (int)ptsd, P, vprev, frames + ls * F_SLOTS, L.writer, out_idx, out_writer, ip, k,
-                         nin + ls);
-        __syncwarp();
-        amask = LaneMap<S>::active_mask(st.active && L.writer);
+            for (int r = 0; r < 9; r++) vprev[r] = frames[ls * F_SLOTS + F_V + r];
+            __syncwarp();
+            katz_step<SHELL>(st, tot, (int)ptsd, P, vprev, frames + ls * F_SLOTS, L.writer, out_idx, out_writer, ip, k,
+                             nin + ls);
+            __syncwarp();
+            const unsigned am = LaneMap<S>::active_mask(st.active && L.writer);
+            if (lane == 0) s_amask = am;
+        }
+        __syncthreads();   // next frames, inner-prefix lengths and the active mask are published
+        amask = s_amask;
         buf ^= 1;
         if (amask == 0)
             break;

@@ -300,6 +300,10 @@ CPG_API int cpg_multi_get_info(cpg_multi *m, int32_t slot, int32_t *device, int3
  *   "shells_per_pass"  1,2,4 or 0=auto   how many shells of one object share one read of its particles
  *   "shell_groups"     1 (default, also 0) or 2 groups of 4 shells per warp task: the groups are passed over one after
  *                      the other and share one reduction / eigen-solve step per Katz iteration (slower on configs[1])
+ *   "batched_step"     1: the warps of a CTA of the warp kernel meet once per Katz iteration and ONE of them runs the
+ *                      eigen-solve / convergence step for all their shells (16 useful lanes per fp64 instruction instead
+ *                      of 4).  Same results; measured slower (22.2 against 19.2 ms on configs[1]: the warps wait for one
+ *                      another more than the saved fp64 work is worth).  0 (default): every warp steps its own 4 shells
  *   "large_halo_min"   particles from which a thread-block cluster works on one object
  *   "grid_halo_min"    particles from which every Katz iteration of an object is one launch over the whole grid
  *                      (default 2^22)
