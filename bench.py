@@ -663,9 +663,14 @@ def main():
                            kern_local_ms / a.steps, dev_ms / a.steps, float(n_part), h2d_gbs], world, "cuda")
     per_rank = None
     if world > 1:
-        mine_stats = [rank, n_mine, n_part, dev_ms / a.steps, kern_local_ms / a.steps, pi_step]
+        mine_stats = [rank, n_mine, n_part, dev_ms / a.steps, kern_local_ms / a.steps, pi_step, clk]
         per_rank = [None] * world
         dist.all_gather_object(per_rank, mine_stats)
+        # the clocks line covers every GPU of the run: lowest median SM clock, union of the throttle reasons
+        meds = [r[6].get("sm_mhz") for r in per_rank if r[6].get("sm_mhz")]
+        clk = dict(clk, sm_mhz=min(meds) if meds else clk.get("sm_mhz"),
+                   reasons=sorted({x for r in per_rank for x in (r[6].get("reasons") or [])}),
+                   sm_mhz_per_rank=[r[6].get("sm_mhz") for r in per_rank], window="timed regions, all ranks")
 
     cpu = None
     dropin = None
