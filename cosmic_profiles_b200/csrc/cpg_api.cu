@@ -198,6 +198,7 @@ struct cpg_ctx {
     int opt_radial_order = 1;
     int opt_prefix_table = 1;
     int opt_groups = 0;   // 0 auto, 1 one group of S shells per warp task, 2 two groups
+    int opt_warp_ctas_per_sm = 0;   // diagnostics: resident CTAs per SM of the warp kernel (0 = as many as fit)
     int opt_batched_step = 0;   // warp kernel: one warp per CTA runs the per-iteration step of all the CTA's warps (cpg_morph.cuh, kernel 1b)
     cpg_timing timing = {};
 };
@@ -800,6 +801,7 @@ int launch_morph(cpg_ctx *c, MorphParams P, int n_warp_tasks, int n_cluster_task
         int per_sm = 0;
         CPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WARP_KERNEL_WARPS * 32, smem));
         if (per_sm < 1) per_sm = 1;
+        if (c->opt_warp_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_warp_ctas_per_sm);
         const int grid = std::min((n_warp_tasks + WARP_KERNEL_WARPS - 1) / WARP_KERNEL_WARPS, c->sm_count * per_sm);
         MorphParams Pw = P;
         Pw.n_tasks = n_warp_tasks;
@@ -1038,6 +1040,8 @@ CPG_API int cpg_set_option(cpg_ctx *c, const char *name, int64_t value)
         c->opt_detect_ranges = value != 0;
     } else if (!strcmp(name, "batched_step")) {
         c->opt_batched_step = value != 0;
+    } else if (!strcmp(name, "warp_ctas_per_sm")) {
+        c->opt_warp_ctas_per_sm = (int)value;
     } else if (!strcmp(name, "direct_results")) {
         c->opt_direct_results = value != 0;
     } else if (!strcmp(name, "radial_order")) {
@@ -1719,7 +1723,12 @@ CPG_API int cpg_shape(cpg_ctx *c, const double *centers, const double *r200, con
         }
     } drain{c};
     T.mark(0);
+#ifdef CPG_TASK_TRACE
+    CPG_TRY(c->morph_stats.ensure(2 + 4 * ((size_t)1 << 20)));
+    CPG_CUDA(cudaMemsetAsync(c->morph_stats.p, 0, sizeof(unsigned long long) * (2 + 4 * ((size_t)1 << 20)), c->stream));
+#else
     CPG_TRY(c->morph_stats.ensure(2));
+#endif
     CPG_TRY(c->centers.ensure((size_t)n * 3)); CPG_TRY(c->r200.ensure(n)); CPG_TRY(c->rr.ensure(R));
     c->stage_used = 0;
     CPG_TRY(small_upload(c, c->centers.p, centers, sizeof(double) * 3 * n));
@@ -2323,3 +2332,16 @@ CPG_API int cpg_get_timing(cpg_ctx *c, cpg_timing *out)
 }  // extern "C"
 
 #include "cpg_multi.inl"
+
+#ifdef CPG_TASK_TRACE
+// Diagnostics build only (make EXTRA=-DCPG_TASK_TRACE): per-task (start ns, end ns, smid << 32 | tiles, steps << 32 | N)
+// of the last cpg_shape call; warp-kernel task t at word 2 + 4 t, cluster-kernel task t at 2 + 4 (2^19 + t).
+extern "C" CPG_API int cpg_debug_trace(cpg_ctx *c, unsigned long long *out, int64_t n_words)
+{
+    using namespace cpg;
+    if (!c || !out) return CPG_ERR_ARGUMENT;
+    CPG_CUDA(cudaSetDevice(c->device));
+    CPG_CUDA(cudaMemcpy(out, c->morph_stats.p, sizeof(unsigned long long) * (size_t)n_words, cudaMemcpyDeviceToHost));
+    return CPG_OK;
+}
+#endif

@@ -180,6 +180,35 @@ __device__ __forceinline__ void write_f32_frame(double *F, double amax, double b
     }
 }
 
+// The quadratic form x^T A x of NP particles from their six products, A = (axx, ayy, azz, axy, axz, ayz; off-diagonals
+// doubled): one 6-term multiply-add chain per particle (default), or -- build option CPG_SPLIT_FORM=1 -- two 3-term chains
+// (squares, then mixed products) joined by one addition, written stage by stage across the particles.  The split form
+// halves the depth of the dependency chain; with the identity frame of pass 0 its first chain is the reference's
+// (x^2 + y^2) + z^2 bit for bit and the second is exactly 0.
+#ifndef CPG_SPLIT_FORM
+#define CPG_SPLIT_FORM 0   // measured (profiles/README.md, round 2 second part): no gain in the kernels, 16 more fp64 instructions per tile
+#endif
+template <int NP>
+__device__ __forceinline__ void quad_forms(double axx, double ayy, double azz, double axy, double axz, double ayz,
+                                           const Particle (&p)[NP], double (&v)[NP])
+{
+#if CPG_SPLIT_FORM
+    double a[NP], b[NP];
+#pragma unroll
+    for (int j = 0; j < NP; j++) { a[j] = axx * p[j].xx; b[j] = axy * p[j].xy; }
+#pragma unroll
+    for (int j = 0; j < NP; j++) { a[j] = fma(ayy, p[j].yy, a[j]); b[j] = fma(axz, p[j].xz, b[j]); }
+#pragma unroll
+    for (int j = 0; j < NP; j++) { a[j] = fma(azz, p[j].zz, a[j]); b[j] = fma(ayz, p[j].yz, b[j]); }
+#pragma unroll
+    for (int j = 0; j < NP; j++) v[j] = a[j] + b[j];
+#else
+#pragma unroll
+    for (int j = 0; j < NP; j++)
+        v[j] = fma(ayz, p[j].yz, fma(axz, p[j].xz, fma(axy, p[j].xy, fma(azz, p[j].zz, fma(ayy, p[j].yy, axx * p[j].xx)))));
+#endif
+}
+
 // All-fp64 membership + accumulation (the reduced variants, whose weight m / r_ell^2 needs the fp64 value anyway).
 template <int S, bool SHELL, bool REDUCED, bool VDISP, int NP>
 __device__ __forceinline__ void passk_particles(const Particle (&p)[NP], const double *frames, unsigned smask,
@@ -197,21 +226,56 @@ __device__ __forceinline__ void passk_particles(const Particle (&p)[NP], const d
             if (SHELL) { f4 = F2[4]; f5 = F2[5]; f6 = F2[6]; }   // (Bxx,Byy) (Bzz,Bxy) (Bxz,Byz)
             double v[NP];
             bool sel[NP];
+            quad_forms<NP>(f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, p, v);
+            if (SHELL) {
+                double u[NP];
+                quad_forms<NP>(f4.x, f4.y, f5.x, f5.y, f6.x, f6.y, p, u);
 #pragma unroll
-            for (int j = 0; j < NP; j++)   // NP independent chains: keep the fp64 pipe busy
-                v[j] = fma(f2.y, p[j].yz, fma(f2.x, p[j].xz, fma(f1.y, p[j].xy,
-                       fma(f1.x, p[j].zz, fma(f0.y, p[j].yy, f0.x * p[j].xx)))));
+                for (int j = 0; j < NP; j++) sel[j] = (v[j] < f3.x) && (u[j] >= f3.y);
+            } else {
 #pragma unroll
-            for (int j = 0; j < NP; j++) {
-                sel[j] = v[j] < f3.x;
-                if (SHELL) {
-                    const double u = fma(f6.y, p[j].yz, fma(f6.x, p[j].xz, fma(f5.y, p[j].xy,
-                                     fma(f5.x, p[j].zz, fma(f4.y, p[j].yy, f4.x * p[j].xx)))));
-                    sel[j] = sel[j] && (u >= f3.y);
-                }
+                for (int j = 0; j < NP; j++) sel[j] = v[j] < f3.x;
             }
 #pragma unroll
             for (int j = 0; j < NP; j++) accumulate<REDUCED, VDISP>(acc[s], cnt[s], sel[j], v[j], p[j]);
+        }
+    }
+}
+
+// The same for the non-reduced ellipsoid variant, two shells at a time.  The per-warp dependency chain, not the fp64
+// pipe, bounds the kernels (a lone warp needs ~1700 cycles for a tile whose 172 fp64 instructions occupy the pipe for
+// 344, profiles/r2k_*): per shell the chain was [frame LDS -> forms -> DSETP -> 14 cycles -> predicated updates ->
+// BSYNC / BSSY / branch].  Here the frames of two shells are fetched together, their 2 NP forms run as independent
+// chains, the 2 NP compares issue back to back and their latency hides behind each other, and there is one uniform
+// branch per pair.  A shell of the pair that is not active on this tile takes no particle (predicate in the compare).
+#ifndef CPG_SHELL_PAIRS
+#define CPG_SHELL_PAIRS 1
+#endif
+template <int S, int NP>
+__device__ __forceinline__ void passk_shell_pairs(const Particle (&p)[NP], const double *frames, unsigned smask,
+                                                  double (&acc)[S][7], int (&cnt)[S])
+{
+    static_assert(S % 2 == 0, "shell pairs");
+#pragma unroll
+    for (int h = 0; h < S; h += 2) {
+        const unsigned two = (smask >> h) & 3u;
+        if (two) {   // warp-uniform
+            const double2 *Fa = reinterpret_cast<const double2 *>(frames + h * F_SLOTS);
+            const double2 *Fb = reinterpret_cast<const double2 *>(frames + (h + 1) * F_SLOTS);
+            const double2 a0 = Fa[0], a1 = Fa[1], a2 = Fa[2], b0 = Fb[0], b1 = Fb[1], b2 = Fb[2];
+            const double da = Fa[3].x, db = Fb[3].x;
+            const bool ona = (two & 1u) != 0, onb = (two & 2u) != 0;
+            double va[NP], vb[NP];
+            quad_forms<NP>(a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, p, va);
+            quad_forms<NP>(b0.x, b0.y, b1.x, b1.y, b2.x, b2.y, p, vb);
+            bool sa[NP], sb[NP];
+#pragma unroll
+            for (int j = 0; j < NP; j++) { sa[j] = (va[j] < da) && ona; sb[j] = (vb[j] < db) && onb; }
+#pragma unroll
+            for (int j = 0; j < NP; j++) {
+                accumulate<false, false>(acc[h], cnt[h], sa[j], va[j], p[j]);
+                accumulate<false, false>(acc[h + 1], cnt[h + 1], sb[j], vb[j], p[j]);
+            }
         }
     }
 }
@@ -756,6 +820,7 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
         for (int s = 0; s < S; s++)
             if (t * TILE_PAIRS < npr[s] && t >= tin[s]) smask |= 1u << s;
         smask &= amask;
+        asm volatile("" : "+r"(smask));   // keep the mask in its register: ptxas otherwise re-derives it before every shell block
         if (smask != 0) { ring.st_tiles += 1; ring.st_tshells += __popc(smask); }
         if (smask == 0) {
             // (resident tasks only)
@@ -783,7 +848,10 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
             Particle p[4];
             ring_read_pair<VDISP>(ring, seq, lane, p[0], p[1]);
             ring_read_pair<VDISP>(ring, seq, lane + 32, p[2], p[3]);
-            passk_particles<S, SHELL, REDUCED, VDISP, 4>(p, frames, smask, acc, cnt);
+            if (CPG_SHELL_PAIRS && !SHELL && !REDUCED && S % 2 == 0)
+                passk_shell_pairs<(S % 2 == 0 ? S : 2), 4>(p, frames, smask, reinterpret_cast<double (&)[(S % 2 == 0 ? S : 2)][7]>(acc), reinterpret_cast<int (&)[(S % 2 == 0 ? S : 2)]>(cnt));
+            else
+                passk_particles<S, SHELL, REDUCED, VDISP, 4>(p, frames, smask, acc, cnt);
         }
         if (!resident && j + RING_STAGES < nmine) {
             __syncwarp();   // every lane has taken its data out of this slot
@@ -810,6 +878,37 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
     }
 }
 
+// run_pass out of line.  Inlined into the task loop of a kernel, the pass competes for registers with everything the
+// task keeps alive (Katz state, shell geometry, queue and table indices ...): at the 168-register cap ptxas then serialises
+// the membership chains, re-derives masks and addresses inside the tile loop and a lone warp needs ~1700 cycles per tile,
+// against ~650 for the same source compiled on its own (profiles/micro/loop_lab.cu).  As a function of its own the pass
+// gets the whole register budget; the caller's live values are saved around the call once per pass, and the 8 S sums
+// come back through local memory (28 words per lane and pass).
+#ifndef CPG_OUTLINE_PASS
+#define CPG_OUTLINE_PASS 0   // measured slower (call + local-memory round trip of the sums: 7.4 us per step instead of 3.7)
+#endif
+template <int S, bool SHELL, bool REDUCED, bool VDISP, bool LANES>
+__device__ __noinline__ void run_pass_outlined(SoA soa, int64_t base, int npairs, int tile0, int tstride, int lane,
+                                               WarpRing *ringp, bool resident, int npairs_task, const double *frames,
+                                               const int *nprp, const int *nin, unsigned amask, double *acc_out, int *cnt_out)
+{
+    WarpRing ring = *ringp;
+    int npr[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) npr[s] = nprp[s];
+    double acc[S][7];
+    int cnt[S];
+    run_pass<S, SHELL, REDUCED, VDISP, LANES>(soa, base, npairs, tile0, tstride, lane, ring, resident, npairs_task, frames, npr,
+                                              nin, amask, acc, cnt);
+    *ringp = ring;
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+#pragma unroll
+        for (int c = 0; c < 7; c++) acc_out[s * 7 + c] = acc[s][c];
+        cnt_out[s] = cnt[s];
+    }
+}
+
 template <int S>
 __device__ __forceinline__ int active_npairs(const int (&npr)[S], unsigned amask)
 {
@@ -825,7 +924,10 @@ __device__ __forceinline__ int active_npairs(const int (&npr)[S], unsigned amask
 // warp-shuffle reductions, eigen-solves spread over lanes (lane l serves shell l % S), persistent
 // warps pulling tasks (sorted largest first) from an atomic queue.
 // ------------------------------------------------------------------------------------------------
-constexpr int WARP_KERNEL_WARPS = 4;
+#ifndef CPG_WARP_KERNEL_WARPS
+#define CPG_WARP_KERNEL_WARPS 4
+#endif
+constexpr int WARP_KERNEL_WARPS = CPG_WARP_KERNEL_WARPS;   // warps per CTA of the warp kernel
 #ifndef CPG_WARP_RING_LANES
 #define CPG_WARP_RING_LANES 1   // 1: per-lane cp.async tile loads in the warp kernel; 0: elected-lane TMA bulk copies
 #endif
@@ -946,6 +1048,11 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
         const int halo = tk.halo;
         if (P.skip[halo] || (P.local && P.r200[halo] == 0.0))
             continue;   // shape_profs_algos.pyx:1024-1029: outputs stay zero, counters stay -1
+#ifdef CPG_TASK_TRACE
+        unsigned long long trace_t0, trace_steps = 0;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(trace_t0));
+        const uint32_t trace_tiles0 = ring.st_tiles;
+#endif
         const int N = P.soa.size[halo];
         const int64_t base = P.soa.poff[halo];
 
@@ -989,6 +1096,11 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
                     const double tadd = table_term(ptab, row0, nin[g * S + ((lane & (8 * S - 1)) >> 3)], lane & 7);
                     double acc[S][7];
                     int cnt[S];
+                    if (CPG_OUTLINE_PASS)
+                        run_pass_outlined<S, SHELL, REDUCED, VDISP, WARP_RING_LANES>(P.soa, base, active_npairs<S>(npr[g], am), 0, 1, lane,
+                                                                                    &ring, resident, npairs_task, frames + g * S * F_SLOTS,
+                                                                                    np + g * S, nin + g * S, am, &acc[0][0], cnt);
+                    else
                     run_pass<S, SHELL, REDUCED, VDISP, WARP_RING_LANES>(P.soa, base, active_npairs<S>(npr[g], am), 0, 1, lane, ring, resident,
                                                        npairs_task, frames + g * S * F_SLOTS, npr[g], nin + g * S, am, acc,
                                                        cnt);
@@ -1020,10 +1132,24 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
             katz_step<SHELL>(st, tot, pts, P, vprev, frames + ls * F_SLOTS, L.writer, out_idx, L.writer, ip, k, nin + ls);
             __syncwarp();
             amask = LM::active_mask(st.active && L.writer);
+#ifdef CPG_TASK_TRACE
+            trace_steps++;
+#endif
             if (amask == 0)
                 break;
         }
+#ifdef CPG_TASK_TRACE
+        if (lane == 0 && P.stats && t < (1 << 19)) {
+            unsigned long long t1; unsigned smid;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+            asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+            P.stats[2 + 4 * (size_t)t + 0] = trace_t0; P.stats[2 + 4 * (size_t)t + 1] = t1;
+            P.stats[2 + 4 * (size_t)t + 2] = ((unsigned long long)smid << 32) | (unsigned)(ring.st_tiles - trace_tiles0);
+            P.stats[2 + 4 * (size_t)t + 3] = (trace_steps << 32) | (unsigned)N;
+        }
+#else
         if (ring.st_tiles > (1u << 20)) ring_flush_stats(ring, P.stats, lane);
+#endif
     }
     ring_flush_stats(ring, P.stats, lane);
 }
@@ -1204,6 +1330,10 @@ __global__ void __launch_bounds__(WB_WARPS * 32, CPG_WARP_MINB) morph_wbatch_ker
 // 12 warps x 16 KB rings + statics = 207 KB of shared memory: one CTA per SM either way, but 12 resident warps instead of 8
 // (the register file then allows 168 registers per thread)
 constexpr int CLUSTER_KERNEL_WARPS = CPG_CLUSTER_WARPS;
+#ifndef CPG_CLUSTER_RING_LANES
+#define CPG_CLUSTER_RING_LANES 0   // 1: per-lane cp.async tile loads in the cluster kernel too; 0: elected-lane TMA bulk copies
+#endif
+constexpr bool CLUSTER_RING_LANES = CPG_CLUSTER_RING_LANES != 0;
 
 template <int S, bool SHELL, bool REDUCED, bool VDISP>
 __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kernel(const MorphParams P)
@@ -1237,9 +1367,13 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
         return;   // uniform over the cluster
     const int N = P.soa.size[halo];
     const int64_t base = P.soa.poff[halo];
+#ifdef CPG_TASK_TRACE
+    unsigned long long trace_t0, trace_steps = 0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(trace_t0));
+#endif
     const int tile0 = rank * NW + warp, tstride = C * NW;   // 64-pair tiles dealt round-robin to the cluster's warps
     WarpRing ring;
-    ring_init(ring, s_ring_c + warp * RingCfg<VDISP>::WARP_BYTES, s_bar[warp], lane);
+    ring_init(ring, s_ring_c + warp * RingCfg<VDISP>::WARP_BYTES, s_bar[warp], lane, CLUSTER_RING_LANES ? 32u : 1u);
 
     KatzState st;   // (kept by warp 0; the other warps only follow the published active mask)
     st.q = 1.0; st.s = 1.0; st.iteration = 1;
@@ -1279,7 +1413,7 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     double acc[S][7];
     int cnt[S];
     int buf = 0;
-    run_pass<S, SHELL, REDUCED, VDISP>(P.soa, base, npairs_task, tile0, tstride, lane, ring, resident, npairs_task,
+    run_pass<S, SHELL, REDUCED, VDISP, CLUSTER_RING_LANES>(P.soa, base, npairs_task, tile0, tstride, lane, ring, resident, npairs_task,
                                        frames, npr, nin, amask, acc, cnt);
     while (true) {
         {
@@ -1334,11 +1468,25 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
         __syncthreads();   // next frames, inner-prefix lengths and the active mask are published
         amask = s_amask;
         buf ^= 1;
+#ifdef CPG_TASK_TRACE
+        trace_steps++;
+#endif
         if (amask == 0)
             break;
-        run_pass<S, SHELL, REDUCED, VDISP>(P.soa, base, active_npairs<S>(npr, amask), tile0, tstride, lane, ring,
+        run_pass<S, SHELL, REDUCED, VDISP, CLUSTER_RING_LANES>(P.soa, base, active_npairs<S>(npr, amask), tile0, tstride, lane, ring,
                                            resident, npairs_task, frames, npr, nin, amask, acc, cnt);
     }
+#ifdef CPG_TASK_TRACE
+    if (threadIdx.x == 0 && rank == 0 && P.stats && t < (1 << 19)) {
+        unsigned long long t1; unsigned smid;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+        const size_t o = 2 + 4 * ((size_t)(1 << 19) + t);
+        P.stats[o] = trace_t0; P.stats[o + 1] = t1;
+        P.stats[o + 2] = ((unsigned long long)smid << 32) | (unsigned)ring.st_tiles;
+        P.stats[o + 3] = (trace_steps << 32) | (unsigned)N;
+    }
+#endif
     ring_flush_stats(ring, P.stats, lane);
     if (C > 1)
         cluster.sync();   // nobody leaves while a peer may still read its shared memory
