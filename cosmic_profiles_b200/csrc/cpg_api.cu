@@ -842,7 +842,7 @@ int launch_grid(cpg_ctx *c, MorphParams P, int first_task, int n_tasks)
     CPG_TRY(c->grid_states.ensure(n_tasks));
     CPG_TRY(c->grid_partials.ensure((size_t)n_cta * 8 * S));
     const Task *tasks = P.tasks + first_task;
-    grid_init_kernel<S><<<n_tasks, 32, 0, c->stream>>>(P, tasks, c->grid_states.p, n_tasks);
+    grid_init_kernel<S, SHELL><<<n_tasks, 32, 0, c->stream>>>(P, tasks, c->grid_states.p, n_tasks);
     c->timing.kernel_launches++;
     unsigned *h_amask = nullptr;
     CPG_CUDA(cudaHostAlloc((void **)&h_amask, sizeof(unsigned), cudaHostAllocDefault));

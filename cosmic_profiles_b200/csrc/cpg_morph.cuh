@@ -448,6 +448,28 @@ struct InnerPrefix {
         }
         return lo >= 0 ? neff[lo] >> 1 : 0;   // whole pairs only
     }
+    // Shell variant (shape_profs_algos.pyx:130-143): a particle belongs to the homoeoid between the ellipsoid of radius d
+    // and the inner one with semi-axes (d - delta, q d - delta, s d - delta).  With s <= q <= 1 and c = s d - delta > 0
+    // the inner ellipsoid contains the ball of radius c: the reference's p0^2/a^2 + p1^2/b^2 + p2^2/c^2 is then at most
+    // |x|^2 / c^2 < 1, so a particle at |x - centre| < c (1 - 1e-6) is NOT a member whatever the orientation, and no
+    // evaluation of the expression can say otherwise.  The radially ordered buckets j with rr[j] (1 + 1e-6) <= c / r200
+    // hold only such particles: their tiles are skipped (nothing to add: they carry no weight), exactly like the tiles
+    // past the outer prefix.  c / r200 = (s - delta / d) rr[k].  Returns the pairs in those buckets (0: no skipping).
+    __device__ __forceinline__ int pairs_below_shell(int k, double s, double d, double delta) const
+    {
+        if ((!rr_up && !rr) || k <= 0 || !(d > delta)) return 0;   // first shell (d == delta): no inner ellipsoid
+        const double frac = s - delta / d;                         // c / d
+        if (!(frac > 1e-3)) return 0;                              // c <= 0 (or tiny): the inner ball is no bound
+        // rr_up[k] (1 - 2e-7) <= rr[k]: the radius of shell k from below
+        const double lim = frac * (rr_up ? (double)rr_up[k] * (1.0 - 2e-7) : rr[k]) * (1.0 - 1e-6);
+        int lo = -1, hi = k;   // radius[lo] <= lim < radius[hi]   (ascending; radius[k] > lim because frac < 1)
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if ((rr_up ? (double)rr_up[mid] : rr[mid]) <= lim) lo = mid; else hi = mid;
+        }
+        if (lo < 0) return 0;
+        return rr_up ? (int)npairs16[lo] : neff[lo] >> 1;
+    }
 };
 
 // Per halo-shell iteration state, replicated in every lane that serves the shell.
@@ -547,7 +569,7 @@ __device__ __forceinline__ void katz_step(KatzState &st, const double (&tot)[7],
             frame[F_THR] = first ? -1.0 : 1.0;
         }
         if (CPG_F32_TEST) write_f32_frame(frame, is2, bmax, SHELL);
-        *nin_slot = ip.pairs_inside(k, st.s);
+        *nin_slot = SHELL ? ip.pairs_below_shell(k, st.s, st.d, st.delta) : ip.pairs_inside(k, st.s);
     }
     st.iteration += 1;
 }
@@ -962,12 +984,14 @@ struct LaneMap {
     }
 };
 
-template <class LM>
+template <bool SHELL, class LM>
 __device__ __forceinline__ void init_frames(double *frames, int *np, int *nin, const LM &L, const KatzState &st,
                                             int ne, const InnerPrefix &ip, int k)
 {
     if (L.writer) {
-        nin[L.ls] = st.active ? ip.pairs_inside(k, 1.0) : 0;   // pass 0: the sphere of radius d
+        // pass 0: the sphere of radius d (its inner prefix comes from the table) / the spherical shell [d - delta, d)
+        // (the particles below d - delta are skipped)
+        nin[L.ls] = !st.active ? 0 : SHELL ? ip.pairs_below_shell(k, 1.0, st.d, st.delta) : ip.pairs_inside(k, 1.0);
         double *F = frames + L.ls * F_SLOTS;
         F[F_D2] = __dmul_rn(st.d, st.d);
         const double in = __dsub_rn(st.d, st.delta);
@@ -1026,7 +1050,8 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
     const int ls = L.ls;
     WarpRing ring;
     ring_init(ring, s_ring_w + warp * RingCfg<VDISP>::WARP_BYTES, s_bar[warp], lane, WARP_RING_LANES ? 32u : 1u);
-    const bool use_inner = !SHELL && !REDUCED && P.n_eff != nullptr && P.ptab != nullptr;
+    const bool use_table = !SHELL && !REDUCED && P.n_eff != nullptr && P.ptab != nullptr;   // inner prefix from the prefix tensor table
+    const bool use_inner = use_table || (SHELL && P.n_eff != nullptr);                        // ... or skipped (shell variant)
     if (use_inner) {
         for (int j = threadIdx.x; j < P.R; j += blockDim.x) s_rr[j] = __double2float_ru(P.rr[j]);
         __syncthreads();
@@ -1035,7 +1060,7 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
     ip.rr = nullptr; ip.neff = nullptr;
     ip.rr_up = use_inner ? s_rr : nullptr;
     ip.npairs16 = s_neff[warp];
-    const double *ptab = use_inner ? P.ptab : nullptr;
+    const double *ptab = use_table ? P.ptab : nullptr;
 
     for (;;) {
         int t = 0;
@@ -1068,7 +1093,7 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
                 s_neff[warp][j] = (uint16_t)(P.n_eff[(size_t)halo * P.R + j] >> 1);   // objects of the warp kernel: < 131072 particles
             __syncwarp();
         }
-        init_frames(frames, np, nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
+        init_frames<SHELL>(frames, np, nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
         __syncwarp();
         unsigned amask = LM::active_mask(st.active && L.writer);
         int npr[G][S];
@@ -1199,11 +1224,12 @@ __global__ void __launch_bounds__(WB_WARPS * 32, CPG_WARP_MINB) morph_wbatch_ker
     const LaneMap<S> L(lane);
     WarpRing ring;
     ring_init(ring, s_ring_b + warp * RingCfg<VDISP>::WARP_BYTES, s_bar[warp], lane, WARP_RING_LANES ? 32u : 1u);
-    const bool use_inner = !SHELL && !REDUCED && P.n_eff != nullptr && P.ptab != nullptr;
+    const bool use_table = !SHELL && !REDUCED && P.n_eff != nullptr && P.ptab != nullptr;   // inner prefix from the prefix tensor table
+    const bool use_inner = use_table || (SHELL && P.n_eff != nullptr);                        // ... or skipped (shell variant)
     if (use_inner)
         for (int j = threadIdx.x; j < P.R; j += blockDim.x) s_rr[j] = __double2float_ru(P.rr[j]);
     __syncthreads();
-    const double *ptab = use_inner ? P.ptab : nullptr;
+    const double *ptab = use_table ? P.ptab : nullptr;
 
     bool have = false;
     unsigned amask = 0;
@@ -1243,7 +1269,7 @@ __global__ void __launch_bounds__(WB_WARPS * 32, CPG_WARP_MINB) morph_wbatch_ker
                 ip.rr = nullptr; ip.neff = nullptr;
                 ip.rr_up = use_inner ? s_rr : nullptr;
                 ip.npairs16 = s_neff[warp];
-                init_frames(frames, np, nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
+                init_frames<SHELL>(frames, np, nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
                 if (L.writer) {
                     ShellSlot &sl = s_slot[warp][L.ls];
                     sl.q = 1.0; sl.s = 1.0; sl.d = st.d; sl.delta = st.delta; sl.out_idx = (unsigned long long)out_idx;
@@ -1381,7 +1407,8 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     const int k = tk.shell0 + (st.active ? ls : 0);
     shell_geometry(P, halo, k, st.d, st.delta);
     const size_t out_idx = (size_t)halo * P.R + k;
-    const bool use_inner = !SHELL && !REDUCED && P.n_eff != nullptr && P.ptab != nullptr;
+    const bool use_table = !SHELL && !REDUCED && P.n_eff != nullptr && P.ptab != nullptr;   // inner prefix from the prefix tensor table
+    const bool use_inner = use_table || (SHELL && P.n_eff != nullptr);                        // ... or skipped (shell variant)
     const int64_t row0 = (base >> 7) + halo;
     if (use_inner) {
         for (int j = threadIdx.x; j < P.R; j += blockDim.x) {
@@ -1394,7 +1421,7 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     ip.rr = use_inner ? s_rr : nullptr;
     ip.neff = s_neff;
     if (warp == 0) {
-        init_frames(frames, np, nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
+        init_frames<SHELL>(frames, np, nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
         const unsigned am0 = LaneMap<S>::active_mask(st.active && L.writer);
         if (lane == 0) s_amask = am0;
     }
@@ -1450,7 +1477,7 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
                     ptsd += remote[7];
                 }
             }
-            if (use_inner) {   // the inner prefix of the pass just finished comes from the table
+            if (use_table) {   // the inner prefix of the pass just finished comes from the table
                 const int pin = nin[ls];
 #pragma unroll
                 for (int c = 0; c < 6; c++) tot[c] += table_term(P.ptab, row0, pin, c);
@@ -1508,7 +1535,7 @@ struct GridState {
     int halo, shell0, nshell;
 };
 
-template <int S>
+template <int S, bool SHELL>
 __global__ void grid_init_kernel(const MorphParams P, const Task *tasks, GridState *states, int n_tasks)
 {
     const int t = blockIdx.x;
@@ -1526,9 +1553,9 @@ __global__ void grid_init_kernel(const MorphParams P, const Task *tasks, GridSta
     shell_geometry(P, halo, k, st.d, st.delta);
     const size_t out_idx = (size_t)halo * P.R + k;
     InnerPrefix ip;   // (the host passes ptab only for the non-reduced ellipsoid variant on radially ordered particles)
-    ip.rr = (P.n_eff && P.ptab) ? P.rr : nullptr;
+    ip.rr = (P.n_eff && (P.ptab || SHELL)) ? P.rr : nullptr;
     ip.neff = P.n_eff ? P.n_eff + (size_t)halo * P.R : nullptr;
-    init_frames(gs->frames, gs->np, gs->nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : P.soa.size[halo], ip, k);
+    init_frames<SHELL>(gs->frames, gs->np, gs->nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : P.soa.size[halo], ip, k);
     if (L.writer) {
         gs->q[ls] = 1.0; gs->s[ls] = 1.0; gs->d[ls] = st.d; gs->delta[ls] = st.delta;
         gs->iteration[ls] = 1; gs->active[ls] = st.active ? 1 : 0;
@@ -1553,7 +1580,7 @@ __global__ void __launch_bounds__(GRID_KERNEL_WARPS * 32) grid_pass_kernel(const
     if (amask == 0) return;   // converged (uniform over the grid)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < S * F_SLOTS; i += blockDim.x) s_frames[i] = gs->frames[i];
-    if (threadIdx.x < S) s_nin[threadIdx.x] = (!SHELL && !REDUCED && P.ptab) ? gs->nin[threadIdx.x] : 0;
+    if (threadIdx.x < S) s_nin[threadIdx.x] = ((!SHELL && !REDUCED && P.ptab) || (SHELL && P.n_eff)) ? gs->nin[threadIdx.x] : 0;
     WarpRing ring;
     ring_init(ring, s_ring_g + warp * RingCfg<VDISP>::WARP_BYTES, s_bar[warp], lane);
     __syncthreads();
@@ -1602,7 +1629,7 @@ __global__ void grid_step_kernel(const MorphParams P, GridState *gs, const doubl
 #pragma unroll
     for (int r = 0; r < 9; r++) vprev[r] = gs->frames[ls * F_SLOTS + F_V + r];
     InnerPrefix ip;
-    ip.rr = (P.n_eff && P.ptab) ? P.rr : nullptr;
+    ip.rr = (P.n_eff && (P.ptab || SHELL)) ? P.rr : nullptr;
     ip.neff = P.n_eff ? P.n_eff + (size_t)gs->halo * P.R : nullptr;
     __syncwarp();
     katz_step<SHELL>(st, tot, pts, P, vprev, gs->frames + ls * F_SLOTS, L.writer, out_idx, L.writer, ip, k, gs->nin + ls);
