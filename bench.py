@@ -18,9 +18,11 @@ metric  = particle-iterations/s,  PI = sum_h N_h * sum_k (shape-tensor evaluatio
 value   = PI of all ranks / max over ranks of the device time of the cpg_shape calls, snapshot + catalogue resident
 e2e     = PI / time of the full C-ABI sequence from pinned HOST buffers (cpg_set_particles + cpg_set_catalogue +
           cpg_shape x2, results copied back) per step
-roofline= the local-shape morphology kernels against the MEASURED fp64 multiply-add peak of the device (they are
-          fp64-pipe bound, not HBM bound): fp64 work from the kernels' own tile counters / CUDA-event time; the
-          contract's HBM figures (algorithmic bytes, physical DRAM traffic under ncu) are reported beside it
+roofline= the local-shape morphology kernels against the MEASURED fp64 multiply-add peak of the device (fp64 is the
+          resource they use most -- 48 % of what the pipe sustains; HBM is at 0.2 of its peak; what bounds them is the
+          per-warp dependency chain at 12 resident warps per SM): fp64 work from the kernels'
+          own tile counters / CUDA-event time; the contract's HBM figures (algorithmic bytes, physical DRAM traffic
+          under ncu) are reported beside it
 cpu_baseline = the reference's own compiled calcMorphLocal+calcMorphGlobal (oracle/_ref) on a bounded,
           seeded sample of the same catalogue, all host cores; calcMassesCenters timed separately ("centres excluded").
 
@@ -746,15 +748,16 @@ def main():
                                      "streamed_particle_iterations": visited_all / world,
                                      "streamed_GBps": visited_all / world * BYTES_PER_PI / (kern_ms * 1e-3) / 1e9},
                              "fp64_pipe_occupancy_ncu": pipe_occ,
-                             "note": "The morphology loop is bound by the fp64 pipe, not by HBM: achieved = fp64 multiply-adds of the "
-                                     "streaming loop (the kernels' own tile counters: 128 particles x 6 products per tile + 128 x 12 per "
-                                     "(tile, shell): membership form + tensor update) / CUDA-event kernel time, against the fp64 FMA rate "
-                                     "measured on this GPU in this run.  The per-iteration eigen-solves (4 useful lanes per warp "
-                                     "instruction) are not counted as useful work but occupy the same pipe: fp64_pipe_occupancy_ncu "
-                                     "is the pipe's busy fraction under ncu relative to what the DFMA microbenchmark sustains.  hbm.physical "
-                                     "= DRAM bytes under ncu / kernel time; hbm.algorithmic = 32 B x particle-iterations (the contract's "
-                                     "SURVEY 8(d) figure), > peak because the radial ordering and the prefix tensor table let an "
-                                     "iteration skip most of an object's particles."},
+                             "note": "fp64 is the resource the morphology loop uses most (HBM: hbm.physical_frac of its peak): achieved = fp64 "
+                                     "multiply-adds of the streaming loop (the kernels' own tile counters: 128 particles x 6 products per "
+                                     "tile + 128 x 12 per (tile, shell): membership form + tensor update) / CUDA-event kernel time, against "
+                                     "the fp64 FMA rate measured on this GPU in this run.  fp64_pipe_occupancy_ncu = the pipe counter of the "
+                                     "two kernels under ncu / what a pure DFMA stream reads on the same counter (92 %): about half; the "
+                                     "per-iteration eigen-solves and the compares share that half with the streaming loop.  The kernels are "
+                                     "bound by the dependency chain of each warp (12 resident warps per SM at 168 registers, stall reason "
+                                     "'wait' 63 %), not by the pipe: profiles/README.md.  hbm.physical = DRAM bytes under ncu / kernel time; "
+                                     "hbm.algorithmic = 32 B x particle-iterations (the contract's SURVEY 8(d) figure), > peak because the "
+                                     "radial ordering and the prefix tensor table let an iteration skip most of an object's particles."},
                 "cpu_baseline": cpu, "clocks": clk, "breakdown_ms_per_step_rank0": {k_: round(v_, 3) for k_, v_ in brk.items()},
                 "particle_iterations_per_step": pi_all, "particles_total": int(npart_all)}
         if world > 1:

@@ -388,7 +388,7 @@ def config4(bench, a, clocks):
     roof["hbm_streamed_GBps"] = streamed / (tim["kernel_ms"] * 1e-3) / 1e9
     roof["note"] = ("hbm_streamed: 32 B x particles of the radial prefixes x iterations / kernel time: above the HBM rate because the 4 "
                     "shells of a pass share one read and the 3.2 GB of the object mostly stay in the 126 MB L2 between consecutive passes "
-                    "only in part; the pass kernel is bound by the fp64 pipe")
+                    "only in part; the pass kernel uses the fp64 pipe most (about half of what it sustains)")
     cpu = None
     if not a.no_cpu_baseline:
         # the reference on one thread (its scratch is threads x N x 68 B) on a 2e6-particle object of the same profile, same

@@ -133,6 +133,8 @@ struct cpg_ctx {
     // chunk lists
     std::vector<Chunk> h_chunks, h_kchunks, h_schunks;   // CHUNK (statistics, binning), KDE_CHUNK, SORT_CHUNK particles
     std::vector<int32_t> h_chunk_first, h_kchunk_first, h_schunk_first;
+    std::vector<int32_t> h_big_sort, h_big_stat;   // objects of more than BIG_OBJECT_CHUNKS sort / statistics chunks
+    DevBuf<int32_t> big_stat, seg_tot;
     DevBuf<Chunk> chunks, kchunks, schunks;
     DevBuf<int32_t> chunk_first, kchunk_first, schunk_first;
     // gathered SoA
@@ -658,6 +660,15 @@ int run_gather(cpg_ctx *c, const double *h_centers, const double *h_r200, const 
                                       (int)GATHER_BUCKETED_SMEM));
         bucket_hist_kernel<<<nc, 256, 0, c->stream>>>(P);
         bucket_scan_kernel<<<c->n_obj, 256, 0, c->stream>>>(P, c->n_obj);
+        for (int32_t hb : c->h_big_sort) {   // (a handful at most: objects of > 2e6 particles)
+            const int nchunk = c->h_schunk_first[hb + 1] - c->h_schunk_first[hb];
+            const int nseg = (nchunk + SCAN_SEG - 1) / SCAN_SEG;
+            CPG_TRY(c->seg_tot.ensure((size_t)nseg * B));
+            bucket_segsum_kernel<<<nseg, 256, 0, c->stream>>>(P, hb, c->seg_tot.p);
+            bucket_segscan_kernel<<<1, 256, 0, c->stream>>>(P, hb, nseg, c->seg_tot.p);
+            bucket_segapply_kernel<<<nseg, 256, 0, c->stream>>>(P, hb, c->seg_tot.p);
+            c->timing.kernel_launches += 3;
+        }
         gather_bucketed_kernel<<<nc, 256, GATHER_BUCKETED_SMEM, c->stream>>>(P);
         c->timing.kernel_launches += 3;
         c->sorted_valid = true;
@@ -696,6 +707,15 @@ int run_stats(cpg_ctx *c)
             fused ? c->schunk_first.p : c->chunk_first.p, c->size.p, c->n_obj, c->part_mass.p, c->part_flag.p, c->part_mm.p,
             c->obj_mass.p, c->skip.p, c->obj_eqm.p);
         c->timing.kernel_launches++;
+        const std::vector<int32_t> &big = fused ? c->h_big_sort : c->h_big_stat;
+        if (!big.empty()) {
+            CPG_TRY(c->big_stat.ensure(big.size()));
+            CPG_CUDA(cudaMemcpyAsync(c->big_stat.p, big.data(), sizeof(int32_t) * big.size(), cudaMemcpyHostToDevice, c->stream));
+            stats_final_big_kernel<<<(int)big.size(), 256, 0, c->stream>>>(
+                fused ? c->schunk_first.p : c->chunk_first.p, c->size.p, c->big_stat.p, c->part_mass.p, c->part_flag.p,
+                c->part_mm.p, c->obj_mass.p, c->skip.p, c->obj_eqm.p);
+            c->timing.kernel_launches++;
+        }
     }
     CPG_CUDA(cudaGetLastError());
     c->have.stats = c->have.valid;
@@ -1166,7 +1186,7 @@ static int install_catalogue(cpg_ctx *c, const int32_t *idx_cat, const int64_t *
     }
     std::vector<int64_t> off(n_obj + 1, 0), poff(n_obj + 1, 0);
     c->h_size.assign(obj_size, obj_size + n_obj);
-    c->h_chunks.clear(); c->h_kchunks.clear(); c->h_schunks.clear();
+    c->h_chunks.clear(); c->h_kchunks.clear(); c->h_schunks.clear(); c->h_big_sort.clear(); c->h_big_stat.clear();
     c->h_chunk_first.assign(n_obj + 1, 0); c->h_kchunk_first.assign(n_obj + 1, 0); c->h_schunk_first.assign(n_obj + 1, 0);
     int64_t max_idx = -1, min_idx = INT64_MAX;
     for (int h = 0; h < n_obj; h++) {
@@ -1179,6 +1199,8 @@ static int install_catalogue(cpg_ctx *c, const int32_t *idx_cat, const int64_t *
         for (int s = 0; s < obj_size[h]; s += CHUNK) c->h_chunks.push_back(Chunk{h, s});
         for (int s = 0; s < obj_size[h]; s += KDE_CHUNK) c->h_kchunks.push_back(Chunk{h, s});
         for (int s = 0; s < obj_size[h]; s += SORT_CHUNK) c->h_schunks.push_back(Chunk{h, s});
+        if ((int)c->h_chunks.size() - c->h_chunk_first[h] > BIG_OBJECT_CHUNKS) c->h_big_stat.push_back(h);
+        if ((int)c->h_schunks.size() - c->h_schunk_first[h] > BIG_OBJECT_CHUNKS) c->h_big_sort.push_back(h);
         c->h_chunk_first[h + 1] = (int32_t)c->h_chunks.size();
         c->h_kchunk_first[h + 1] = (int32_t)c->h_kchunks.size();
         c->h_schunk_first[h + 1] = (int32_t)c->h_schunks.size();

@@ -167,6 +167,11 @@ __global__ void __launch_bounds__(256) stats_chunk_kernel(const SoA soa, const C
     }
 }
 
+// Objects of more than BIG_OBJECT_CHUNKS chunks (millions of particles; BASELINE configs[4] is ONE object of 1e8) get
+// kernels of their own wherever the regular ones give an object to one warp or one CTA: a 1e8-particle object has
+// ~1e5 chunks, and one CTA walking them cost 12.4 ms in bucket_scan_kernel and 1.1 ms in stats_final_kernel.
+constexpr int BIG_OBJECT_CHUNKS = 2048;
+
 // Combine the chunk partials of every object in chunk order.
 __global__ void stats_final_kernel(const int32_t *chunk_first /* n_obj+1 */, const int32_t *size, int n_obj,
                                    const double *part_mass, const int32_t *part_spread, const double *part_mminmax,
@@ -175,6 +180,7 @@ __global__ void stats_final_kernel(const int32_t *chunk_first /* n_obj+1 */, con
     // a warp per object, lanes over its chunks (fixed assignment and reduction tree: deterministic mass)
     const int h = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (h >= n_obj) return;
+    if (chunk_first[h + 1] - chunk_first[h] > BIG_OBJECT_CHUNKS) return;   // stats_final_big_kernel's
     const int lane = threadIdx.x & 31;
     double m = 0.0, mlo = 1e300, mhi = -1e300;
     int spread = 0;
@@ -195,6 +201,36 @@ __global__ void stats_final_kernel(const int32_t *chunk_first /* n_obj+1 */, con
     // fp32 accumulators): in practice only an empty object gets there -- for coincident points the fp32
     // rounding of the mean already makes the spread non-zero.  `spread` is kept for diagnostics.
     (void)spread;
+    skip[h] = (size[h] == 0) ? 1 : 0;
+}
+
+// The same for one big object: a CTA of 256 threads over its chunks, fixed assignment and reduction order.
+__global__ void __launch_bounds__(256) stats_final_big_kernel(const int32_t *chunk_first, const int32_t *size, const int32_t *big,
+                                                              const double *part_mass, const int32_t *part_spread,
+                                                              const double *part_mminmax, double *obj_mass, uint8_t *skip,
+                                                              double *obj_equal_mass)
+{
+    __shared__ double s_m[8], s_lo[8], s_hi[8];
+    const int h = big[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double m = 0.0, mlo = 1e300, mhi = -1e300;
+    for (int c = chunk_first[h] + (int)threadIdx.x; c < chunk_first[h + 1]; c += 256) {
+        m += part_mass[c];
+        mlo = fmin(mlo, part_mminmax[2 * c]); mhi = fmax(mhi, part_mminmax[2 * c + 1]);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        m += __shfl_xor_sync(0xffffffffu, m, o);
+        mlo = fmin(mlo, __shfl_xor_sync(0xffffffffu, mlo, o));
+        mhi = fmax(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
+    }
+    if (lane == 0) { s_m[warp] = m; s_lo[warp] = mlo; s_hi[warp] = mhi; }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    m = 0.0; mlo = 1e300; mhi = -1e300;
+    for (int w = 0; w < 8; w++) { m += s_m[w]; mlo = fmin(mlo, s_lo[w]); mhi = fmax(mhi, s_hi[w]); }
+    obj_mass[h] = m;
+    obj_equal_mass[h] = (mlo == mhi && mlo > 0.0) ? mlo : 0.0;
+    (void)part_spread;
     skip[h] = (size[h] == 0) ? 1 : 0;
 }
 
@@ -432,6 +468,7 @@ __global__ void __launch_bounds__(256) bucket_scan_kernel(const SortParams P, in
     if (h >= n_obj) return;
     const int R = P.R, B = R + 1;
     const int c0 = P.chunk_first[h], c1 = P.chunk_first[h + 1];
+    if (c1 - c0 > BIG_OBJECT_CHUNKS) return;   // the three segment kernels below
     for (int b = warp; b < B; b += 8) {
         int tot = 0;
         for (int c = c0 + lane; c < c1; c += 32) tot += P.tile_hist[(size_t)c * B + b];
@@ -469,6 +506,76 @@ __global__ void __launch_bounds__(256) bucket_scan_kernel(const SortParams P, in
             }
             if (c < c1) P.tile_hist[(size_t)c * B + b] = run + incl - t;
             run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+}
+
+// bucket_scan_kernel for ONE big object, spread over the GPU: its chunks in segments of SCAN_SEG.
+//   (1) per segment and bucket, the sum over the segment's chunks (thread = bucket: coalesced rows of tile_hist);
+//   (2) one CTA: bucket totals, bucket starts, n_eff, and the offset of every (segment, bucket) inside the object;
+//   (3) per segment and bucket, the running offsets of its chunks (in place, chunk order = catalogue order).
+// Same offsets as bucket_scan_kernel produces (integers: no ordering issue).
+constexpr int SCAN_SEG = 256;
+
+__global__ void __launch_bounds__(256) bucket_segsum_kernel(const SortParams P, int h, int32_t *seg_tot)
+{
+    const int B = P.R + 1;
+    const int c0 = P.chunk_first[h] + blockIdx.x * SCAN_SEG, c1 = min(P.chunk_first[h + 1], c0 + SCAN_SEG);
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        int tot = 0;
+        for (int c = c0; c < c1; c++) tot += P.tile_hist[(size_t)c * B + b];
+        seg_tot[(size_t)blockIdx.x * B + b] = tot;
+    }
+}
+
+__global__ void __launch_bounds__(256) bucket_segscan_kernel(const SortParams P, int h, int nseg, int32_t *seg_tot)
+{
+    __shared__ int s_tot[SORT_MAX_B], s_start[SORT_MAX_B];
+    const int R = P.R, B = R + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        int tot = 0;
+        for (int sg = 0; sg < nseg; sg++) tot += seg_tot[(size_t)sg * B + b];
+        s_tot[b] = tot;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int carry = 0;
+        for (int b0 = 0; b0 < B; b0 += 32) {
+            const int b = b0 + lane;
+            const int tot = b < B ? s_tot[b] : 0;
+            int incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (b < B) s_start[b] = carry + incl - tot;
+            if (b < R) P.n_eff[(size_t)h * R + b] = carry + incl;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        int run = s_start[b];
+        for (int sg = 0; sg < nseg; sg++) {
+            const int t = seg_tot[(size_t)sg * B + b];
+            seg_tot[(size_t)sg * B + b] = run;
+            run += t;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bucket_segapply_kernel(const SortParams P, int h, const int32_t *seg_tot)
+{
+    const int B = P.R + 1;
+    const int c0 = P.chunk_first[h] + blockIdx.x * SCAN_SEG, c1 = min(P.chunk_first[h + 1], c0 + SCAN_SEG);
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        int run = seg_tot[(size_t)blockIdx.x * B + b];
+        for (int c = c0; c < c1; c++) {
+            const int t = P.tile_hist[(size_t)c * B + b];
+            P.tile_hist[(size_t)c * B + b] = run;
+            run += t;
         }
     }
 }

@@ -28,9 +28,9 @@ namespace cg = cooperative_groups;
 #ifndef CPG_F32_TEST
 // 0 (default): all-fp64 membership tests.  1: fp32 pre-classification of the membership tests of the non-reduced
 // variants with an exact fp64 re-test of the undecided particles (pair_f32 below).  Measured on configs[1], B200
-// (profiles/README.md, round 2): the all-fp64 kernels saturate the fp64 pipe (0.45 of the 0.455 warp-DFMA/clk/SMSP the
-// pipe sustains, profiles/micro/fp64_lanes.cu); the fp32 variant halves the fp64 instructions of the streaming loop but
-// its compare / select / convert instructions make it issue-bound: 24.3 ms against 19.4 ms for the local-shape kernels.
+// (profiles/README.md, round 2): the kernels are bound by the dependency chain of each of the 12 resident warps per SM,
+// not by the fp64 pipe (48 % of what it sustains); the fp32 variant halves the fp64 instructions of the streaming loop
+// but lengthens that chain with compare / select / convert instructions: 24.3 ms against 19.4 ms for the local-shape kernels.
 // Kept as a build option (make EXTRA=-DCPG_F32_TEST=1); the GPU suite passes with either setting.
 #define CPG_F32_TEST 0
 #endif
@@ -74,7 +74,7 @@ __device__ __forceinline__ void accumulate(double (&acc)[7], int &cnt, bool sel,
     // weight: m (non-reduced) or m / r_ell^2 (reduced, helper_class.pyx:54); the common 1/mass_tot factor
     // is applied once per iteration after the reduction (it only rescales the tensor).  Written as a guarded
     // block so that ptxas predicates the seven fp64 updates instead of selecting a zero weight: a particle
-    // outside the ellipsoid costs issue slots but no fp64 pipe time.
+    // outside the ellipsoid costs an issue slot and (measured, profiles/r2_loop_lab_v0.txt) most of its fp64 pipe time.
 #ifdef CPG_ACC_SELECT
     {
         double w = REDUCED ? p.m / v : p.m;
@@ -119,7 +119,7 @@ __device__ __forceinline__ void accumulate(double (&acc)[7], int &cnt, bool sel,
 // Membership of a particle in the ellipsoid (shell) of the previous eigen-decomposition
 // (shape_profs_algos.pyx:247-260 / :122-143), fused with the next tensor accumulation.
 //
-// fp32 pre-classification (non-reduced variants).  The fp64 pipe is the kernels' bottleneck and the membership
+// fp32 pre-classification (non-reduced variants).  fp64 instructions are the bulk of the streaming loop and the membership
 // test was 6 of the ~14 fp64 instructions per particle-shell.  Here the quadratic form v = x^T A x is evaluated
 // in fp32 (x, A rounded to fp32, 6 FFMA) and compared with TWO thresholds:
 //      v32 < lo  -> member,      v32 > hi -> not a member,      otherwise -> undecided,
@@ -1181,8 +1181,7 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
 
 // ------------------------------------------------------------------------------------------------
 // Kernel 1b: the warp kernel with a BATCHED step.  The per-iteration step (eigen-solve, convergence test, next frame)
-// costs the same fp64-pipe time for 4 useful lanes as for 32 (profiles/micro/fp64_lanes.cu), and the pipe is what
-// bounds these kernels; in kernel 1 every warp spends a third of its fp64 instructions on the step of its own 4 shells.
+// costs the same fp64-pipe time for 4 useful lanes as for 32 (profiles/micro/fp64_lanes.cu); in kernel 1 every warp spends a third of its fp64 instructions on the step of its own 4 shells.
 // Here the WB_WARPS warps of a CTA stream their own tasks as before but meet at a block barrier once per Katz iteration:
 // every warp leaves its 8 S reduced sums in shared memory, ONE warp (they take turns) runs the step for all
 // WB_WARPS x S shells at once -- lane l serves shell l % S of warp l / S -- and publishes frames, inner-prefix lengths
@@ -1367,8 +1366,7 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     constexpr int NW = CLUSTER_KERNEL_WARPS, NV = 8 * S;
     extern __shared__ __align__(128) unsigned char s_ring_c[];     // NW rings
     // ONE set of frames per CTA, written by warp 0 and published with a block barrier: the per-iteration step
-    // (reduction, eigen-solve, next frame) costs the same fp64-pipe time whether 1 or 32 lanes are active, and the pipe
-    // is what bounds these kernels -- every warp of the CTA repeating it for private frames (round 1) was 12x the work.
+    // (reduction, eigen-solve, next frame) costs the same time whether 1 or 32 lanes are active -- every warp of the CTA repeating it for private frames (round 1) was 12x the work.
     __shared__ __align__(16) double s_frames[S * F_SLOTS];
     __shared__ __align__(8) uint64_t s_bar[NW][RING_MAX_STAGES];
     __shared__ double s_part[2][NW][NV];                        // per-warp partial sums

@@ -82,6 +82,35 @@ __global__ void __launch_bounds__(384, 1) lab(double *out, long long *cyc, int t
         }
     }
 #endif
+#if LAB_VARIANT == 4
+    {
+        __shared__ int s_nin[12][S];
+        __shared__ double s_tot[12][32][2];
+        if (lane < S) s_nin[warp][lane] = 0;
+        s_tot[warp][lane][0] = 0.0; s_tot[warp][lane][1] = 0.0;
+        __syncwarp();
+        ring.seq = 0; ring.res_seq = 0; ring.res_loaded = true; ring.st_tiles = 0; ring.st_tshells = 0;
+        ring.buf_s = smem_u32(ring.buf); ring.bar = nullptr; ring.bar_s = 0;
+        int npr[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) npr[s] = 4 * TILE_PAIRS;
+        SoA soa = {};
+#pragma unroll 1
+        for (int it = 0; it < tiles / 4; it++) {
+            unsigned m = smask;
+            asm volatile("" : "+r"(m));
+            run_pass<S, false, false, false, true>(soa, 0, 4 * TILE_PAIRS, 0, 1, lane, ring, true, 4 * TILE_PAIRS, frames, npr, s_nin[warp], m, acc, cnt);
+            double v = 0.0;
+#pragma unroll
+            for (int s = 0; s < S; s++) { v += cnt[s];
+#pragma unroll
+                for (int c = 0; c < 7; c++) v += acc[s][c]; }
+            s_tot[warp][lane][0] += v;
+            __syncwarp();
+        }
+        acc[0][0] = s_tot[warp][lane][0];
+    }
+#endif
 #if LAB_VARIANT == 2
     // the real pass over a task that is resident in the ring (4 tiles): run_pass's own tile loop, no loads, no barriers
     {
