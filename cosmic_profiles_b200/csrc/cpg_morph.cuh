@@ -242,14 +242,14 @@ __device__ __forceinline__ void passk_particles(const Particle (&p)[NP], const d
     }
 }
 
-// The same for the non-reduced ellipsoid variant, two shells at a time.  The per-warp dependency chain, not the fp64
-// pipe, bounds the kernels (a lone warp needs ~1700 cycles for a tile whose 172 fp64 instructions occupy the pipe for
-// 344, profiles/r2k_*): per shell the chain was [frame LDS -> forms -> DSETP -> 14 cycles -> predicated updates ->
-// BSYNC / BSSY / branch].  Here the frames of two shells are fetched together, their 2 NP forms run as independent
-// chains, the 2 NP compares issue back to back and their latency hides behind each other, and there is one uniform
-// branch per pair.  A shell of the pair that is not active on this tile takes no particle (predicate in the compare).
+// The same for the non-reduced ellipsoid variant, two shells at a time (build option CPG_SHELL_PAIRS=1): the frames of
+// two shells are fetched together, their 2 NP forms run as independent chains, the 2 NP compares issue back to back and
+// there is one uniform branch per pair; a shell of the pair that is not active on this tile takes no particle
+// (predicate in the compare).  Shortens the static dependency chain of a 4-shell tile from 1322 to 821 cycles, but a
+// pair with one active shell costs as much as two: measured (profiles/README.md) 1.13 instead of 1.19 us per tile in the
+// warp kernel, 1.32 instead of 1.24 in the cluster kernel, whose tiles mostly carry all four shells -- not the default.
 #ifndef CPG_SHELL_PAIRS
-#define CPG_SHELL_PAIRS 1
+#define CPG_SHELL_PAIRS 0
 #endif
 template <int S, int NP>
 __device__ __forceinline__ void passk_shell_pairs(const Particle (&p)[NP], const double *frames, unsigned smask,
@@ -1032,6 +1032,21 @@ __device__ __forceinline__ void pack_values(const double (&acc)[S][7], const int
     }
 }
 
+// Per halo-shell iteration state parked in shared memory while the particle pass runs (see CPG_PARK_STATE).
+struct ShellSlot {
+    double q, s, d, delta;
+    unsigned long long out_idx;
+    int iteration, active, k, pad;
+};
+// 1 (default): the warp kernel keeps the Katz state of its shells (q, s, d, delta, iteration, output index) in shared
+// memory between the per-iteration steps instead of in registers.  The particle pass compiled on its own uses 156-164 of the
+// 168 registers (profiles/micro/loop_lab.cu); every value the task loop keeps alive across it pushes ptxas into
+// serialising the membership chains, re-deriving masks and addresses inside the tile loop and spilling -- a lone warp then
+// needs ~1700 cycles per tile instead of ~1200 (streamed) / ~900 (ring-resident).
+#ifndef CPG_PARK_STATE
+#define CPG_PARK_STATE 1
+#endif
+
 template <int S, int G, bool SHELL, bool REDUCED, bool VDISP>
 __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_warp_kernel(const MorphParams P)
 {
@@ -1043,6 +1058,7 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
     __shared__ int s_np[WARP_KERNEL_WARPS][NS], s_nin[WARP_KERNEL_WARPS][NS];
     __shared__ float s_rr[MAX_SORT_R];                              // shell radii rounded up (inner-prefix lookup)
     __shared__ uint16_t s_neff[WARP_KERNEL_WARPS][MAX_SORT_R];      // prefix lengths (pairs) of the warp's current object
+    __shared__ ShellSlot s_slot[CPG_PARK_STATE ? WARP_KERNEL_WARPS : 1][NS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *frames = s_frames[warp];
     int *np = s_np[warp], *nin = s_nin[warp];
@@ -1094,6 +1110,11 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
             __syncwarp();
         }
         init_frames<SHELL>(frames, np, nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
+        if (CPG_PARK_STATE && L.writer) {
+            ShellSlot &sl = s_slot[warp][ls];
+            sl.q = 1.0; sl.s = 1.0; sl.d = st.d; sl.delta = st.delta; sl.out_idx = (unsigned long long)out_idx;
+            sl.iteration = 1; sl.active = st.active ? 1 : 0; sl.k = k;
+        }
         __syncwarp();
         unsigned amask = LM::active_mask(st.active && L.writer);
         int npr[G][S];
@@ -1154,9 +1175,23 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
 #pragma unroll
             for (int r = 0; r < 9; r++) vprev[r] = frames[ls * F_SLOTS + F_V + r];
             __syncwarp();
+            if (CPG_PARK_STATE) {
+                // the state of this lane's shell comes back from shared memory, goes through the step and is parked again
+                ShellSlot &sl = s_slot[warp][ls];
+                KatzState sv;
+                sv.q = sl.q; sv.s = sl.s; sv.d = sl.d; sv.delta = sl.delta; sv.iteration = sl.iteration; sv.active = sl.active != 0;
+                const int kk = sl.k;
+                const size_t oidx = (size_t)sl.out_idx;
+                __syncwarp();
+                katz_step<SHELL>(sv, tot, pts, P, vprev, frames + ls * F_SLOTS, L.writer, oidx, L.writer, ip, kk, nin + ls);
+                if (L.writer) { sl.q = sv.q; sl.s = sv.s; sl.iteration = sv.iteration; sl.active = sv.active ? 1 : 0; }
+                __syncwarp();
+                amask = LM::active_mask(sv.active && L.writer);
+            } else {
             katz_step<SHELL>(st, tot, pts, P, vprev, frames + ls * F_SLOTS, L.writer, out_idx, L.writer, ip, k, nin + ls);
             __syncwarp();
             amask = LM::active_mask(st.active && L.writer);
+            }
 #ifdef CPG_TASK_TRACE
             trace_steps++;
 #endif
@@ -1194,12 +1229,6 @@ __global__ void __launch_bounds__(WARP_KERNEL_WARPS * 32, CPG_WARP_MINB) morph_w
 #define CPG_WB_WARPS 4
 #endif
 constexpr int WB_WARPS = CPG_WB_WARPS;
-
-struct ShellSlot {
-    double q, s, d, delta;
-    unsigned long long out_idx;
-    int iteration, active, k, pad;
-};
 
 template <int S, bool SHELL, bool REDUCED, bool VDISP>
 __global__ void __launch_bounds__(WB_WARPS * 32, CPG_WARP_MINB) morph_wbatch_kernel(const MorphParams P)

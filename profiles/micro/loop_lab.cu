@@ -82,6 +82,36 @@ __global__ void __launch_bounds__(384, 1) lab(double *out, long long *cyc, int t
         }
     }
 #endif
+#if LAB_VARIANT == 5
+    // streaming mode from global memory, sums to shared memory (no extra live registers across run_pass)
+    {
+        __shared__ int s_nin[12][S];
+        __shared__ double s_tot[12][32];
+        __shared__ __align__(8) uint64_t s_bar[12][RING_MAX_STAGES];
+        if (lane < S) s_nin[warp][lane] = 0;
+        s_tot[warp][lane] = 0.0;
+        __syncwarp();
+        ring_init(ring, ring.buf, s_bar[warp], lane, 32u);
+        const int NT = 64;
+        int npr[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) npr[s] = NT * TILE_PAIRS;
+#pragma unroll 1
+        for (int it = 0; it < tiles / NT; it++) {
+            unsigned m = smask;
+            asm volatile("" : "+r"(m));
+            run_pass<S, false, false, false, true>(gsoa, (int64_t)(blockIdx.x % 8) * NT * 128, NT * TILE_PAIRS, 0, 1, lane, ring, false, NT * TILE_PAIRS, frames, npr, s_nin[warp], m, acc, cnt);
+            double v = 0.0;
+#pragma unroll
+            for (int s = 0; s < S; s++) { v += cnt[s];
+#pragma unroll
+                for (int c = 0; c < 7; c++) v += acc[s][c]; }
+            s_tot[warp][lane] += v;
+            __syncwarp();
+        }
+        acc[0][0] = s_tot[warp][lane];
+    }
+#endif
 #if LAB_VARIANT == 4
     {
         __shared__ int s_nin[12][S];
