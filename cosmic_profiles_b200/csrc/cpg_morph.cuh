@@ -843,7 +843,9 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
             if (t * TILE_PAIRS < npr[s] && t >= tin[s]) smask |= 1u << s;
         smask &= amask;
         asm volatile("" : "+r"(smask));   // keep the mask in its register: ptxas otherwise re-derives it before every shell block
+#ifndef CPG_NO_TILE_STATS
         if (smask != 0) { ring.st_tiles += 1; ring.st_tshells += __popc(smask); }
+#endif
         if (smask == 0) {
             // (resident tasks only)
         } else if (CPG_F32_TEST && !REDUCED) {
@@ -1404,6 +1406,7 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     __shared__ unsigned s_amask;
     __shared__ double s_rr[MAX_SORT_R];
     __shared__ int s_neff[MAX_SORT_R];
+    __shared__ ShellSlot s_slot[S];   // the Katz state of the task's shells between steps (CPG_PARK_STATE: not in registers)
     cg::cluster_group cluster = cg::this_cluster();
     const int C = (int)cluster.num_blocks();
     const int rank = (int)cluster.block_rank();
@@ -1449,6 +1452,11 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
     ip.neff = s_neff;
     if (warp == 0) {
         init_frames<SHELL>(frames, np, nin, L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
+        if (CPG_PARK_STATE && L.writer) {
+            ShellSlot &sl = s_slot[ls];
+            sl.q = 1.0; sl.s = 1.0; sl.d = st.d; sl.delta = st.delta; sl.out_idx = (unsigned long long)out_idx;
+            sl.iteration = 1; sl.active = st.active ? 1 : 0; sl.k = k;
+        }
         const unsigned am0 = LaneMap<S>::active_mask(st.active && L.writer);
         if (lane == 0) s_amask = am0;
     }
@@ -1513,10 +1521,24 @@ __global__ void __launch_bounds__(CLUSTER_KERNEL_WARPS * 32) morph_cluster_kerne
 #pragma unroll
             for (int r = 0; r < 9; r++) vprev[r] = frames[ls * F_SLOTS + F_V + r];
             __syncwarp();
-            katz_step<SHELL>(st, tot, (int)ptsd, P, vprev, frames + ls * F_SLOTS, L.writer, out_idx, out_writer, ip, k,
-                             nin + ls);
-            __syncwarp();
-            const unsigned am = LaneMap<S>::active_mask(st.active && L.writer);
+            unsigned am;
+            if (CPG_PARK_STATE) {
+                ShellSlot &sl = s_slot[ls];
+                KatzState sv;
+                sv.q = sl.q; sv.s = sl.s; sv.d = sl.d; sv.delta = sl.delta; sv.iteration = sl.iteration; sv.active = sl.active != 0;
+                const int kk = sl.k;
+                const size_t oidx = (size_t)sl.out_idx;
+                __syncwarp();
+                katz_step<SHELL>(sv, tot, (int)ptsd, P, vprev, frames + ls * F_SLOTS, L.writer, oidx, out_writer, ip, kk, nin + ls);
+                if (L.writer) { sl.q = sv.q; sl.s = sv.s; sl.iteration = sv.iteration; sl.active = sv.active ? 1 : 0; }
+                __syncwarp();
+                am = LaneMap<S>::active_mask(sv.active && L.writer);
+            } else {
+                katz_step<SHELL>(st, tot, (int)ptsd, P, vprev, frames + ls * F_SLOTS, L.writer, out_idx, out_writer, ip, k,
+                                 nin + ls);
+                __syncwarp();
+                am = LaneMap<S>::active_mask(st.active && L.writer);
+            }
             if (lane == 0) s_amask = am;
         }
         __syncthreads();   // next frames, inner-prefix lengths and the active mask are published
