@@ -302,8 +302,8 @@ CPG_API int cpg_multi_get_info(cpg_multi *m, int32_t slot, int32_t *device, int3
  *                      the other and share one reduction / eigen-solve step per Katz iteration (slower on configs[1])
  *   "batched_step"     1: the warps of a CTA of the warp kernel meet once per Katz iteration and ONE of them runs the
  *                      eigen-solve / convergence step for all their shells (16 useful lanes per fp64 instruction instead
- *                      of 4).  Same results; measured slower (22.2 against 19.2 ms on configs[1]: the warps wait for one
- *                      another more than the saved fp64 work is worth).  0 (default): every warp steps its own 4 shells
+ *                      of 4).  Same results; measured slower (22.2 against 19.2 ms on configs[1]: the wait for one another
+ *                      lengthens the per-warp dependency chain that bounds the kernel).  0 (default): every warp steps its own 4 shells
  *   "large_halo_min"   particles from which a thread-block cluster works on one object
  *   "grid_halo_min"    particles from which every Katz iteration of an object is one launch over the whole grid
  *                      (default 2^22)
@@ -311,7 +311,10 @@ CPG_API int cpg_multi_get_info(cpg_multi *m, int32_t slot, int32_t *device, int3
  *   "invalidate_gather" (any value) one-shot: forget the resident gathered catalogue, so that the next compute
  *                      call redoes the gather even if snapshot, catalogue, centres and L_BOX are unchanged
  *   "radial_order"     1 (default): gather every object in radial-bucket order and let shell k stream only
- *                      the particles with |x-c| < d_k (they are the only possible members); 0: catalogue order
+ *                      the particles with |x-c| < d_k (they are the only possible members); the shell-based variant
+ *                      also skips the particles with |x-c| < s*d - delta (inside the inner ellipsoid whatever its
+ *                      orientation).  0: catalogue order, every particle tested
+ *   "warp_ctas_per_sm" diagnostics: resident CTAs (4 warps each) per SM of the warp kernel, 0 (default) = as many as fit
  *   "direct_results"   1 (default): cpg_shape stores results directly into page-locked caller buffers (see cpg_host_alloc)
  *   "upload_threads"   host threads (0..8, default 8) that stage PAGEABLE host arrays of >= 64 MB through page-locked bounce
  *                      buffers in cpg_set_particles / cpg_set_catalogue; 0 leaves them to cudaMemcpyAsync.  Page-locked
