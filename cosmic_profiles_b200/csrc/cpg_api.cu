@@ -24,6 +24,10 @@
 #include "cpg_interp.cuh"
 #include "cpg_morph.cuh"
 
+#ifndef CPG_ASYNC_DEFAULT
+#define CPG_ASYNC_DEFAULT 2   // default of the "async_step" option: 0 kernel 1, 1 kernel 1c (step warp), 2 kernel 1d (two task slots per warp)
+#endif
+
 namespace cpg {
 
 static thread_local char g_err[1024] = "";
@@ -201,6 +205,7 @@ struct cpg_ctx {
     int opt_prefix_table = 1;
     int opt_groups = 0;   // 0 auto, 1 one group of S shells per warp task, 2 two groups
     int opt_warp_ctas_per_sm = 0;   // diagnostics: resident CTAs per SM of the warp kernel (0 = as many as fit)
+    int opt_async_step = CPG_ASYNC_DEFAULT;     // warp kernel 1c: pass warps + one asynchronous step warp per CTA (cpg_morph.cuh)
     int opt_batched_step = 0;   // warp kernel: one warp per CTA runs the per-iteration step of all the CTA's warps (cpg_morph.cuh, kernel 1b)
     cpg_timing timing = {};
 };
@@ -800,7 +805,41 @@ int launch_morph(cpg_ctx *c, MorphParams P, int n_warp_tasks, int n_cluster_task
         c->timing.kernel_launches++;
         c->timing.hot_kernel_launches++;
     }
-    if (n_warp_tasks > 0 && G == 1 && c->opt_batched_step) {
+    // kernel 1d keeps two tasks per warp: only worth it when the queue is long enough to keep every slot of the GPU busy
+    const bool duo = n_warp_tasks >= 8 * c->sm_count * 12 || c->opt_async_step == 3;
+    if (n_warp_tasks > 0 && G == 1 && !VDISP && (c->opt_async_step == 2 || c->opt_async_step == 3) && duo) {
+        auto kern = morph_wduo_kernel<S, SHELL, REDUCED, false>;
+        const int smem = WD_WARPS * RingCfg<false, RING_MAX_STAGES>::WARP_BYTES;
+        CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int per_sm = 0;
+        CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WD_WARPS * 32, smem));
+        if (getenv("CPG_DEBUG")) fprintf(stderr, "[cpg] morph_wduo_kernel: %d CTAs per SM (smem %d dynamic)\n", per_sm, smem);
+        if (per_sm < 1) per_sm = 1;
+        if (c->opt_warp_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_warp_ctas_per_sm);
+        const int grid = std::min((n_warp_tasks + WD_NSLOT - 1) / WD_NSLOT, c->sm_count * per_sm);
+        MorphParams Pw = P;
+        Pw.n_tasks = n_warp_tasks;
+        kern<<<grid, WD_WARPS * 32, smem, c->stream>>>(Pw);
+        c->timing.kernel_launches++;
+        c->timing.hot_kernel_launches++;
+        CPG_CUDA(cudaGetLastError());
+    } else if (n_warp_tasks > 0 && G == 1 && !VDISP && c->opt_async_step == 1) {
+        auto kern = morph_wasync_kernel<S, SHELL, REDUCED, false>;
+        const int smem = WA_NSLOT * RingCfg<false, WA_STAGES>::WARP_BYTES;
+        CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int per_sm = 0;
+        CPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WA_THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
+        if (c->opt_warp_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_warp_ctas_per_sm);
+        const int grid = std::min((n_warp_tasks + WA_NSLOT - 1) / WA_NSLOT, c->sm_count * per_sm);
+        MorphParams Pw = P;
+        Pw.n_tasks = n_warp_tasks;
+        kern<<<grid, WA_THREADS, smem, c->stream>>>(Pw);
+        c->timing.kernel_launches++;
+        c->timing.hot_kernel_launches++;
+        CPG_CUDA(cudaGetLastError());
+    } else if (n_warp_tasks > 0 && G == 1 && c->opt_batched_step) {
         auto kern = morph_wbatch_kernel<S, SHELL, REDUCED, VDISP>;
         const int smem = WB_WARPS * RingCfg<VDISP>::WARP_BYTES;
         CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -842,8 +881,11 @@ int dispatch_morph(cpg_ctx *c, const MorphParams &P, bool shell, bool reduced, b
 {
 #define CPG_CASE(SH, RE, VD) \
     if (shell == SH && reduced == RE && vdisp == VD) return launch_morph<S, G, SH, RE, VD>(c, P, nw, ncl, cs);
-    CPG_CASE(false, false, false) CPG_CASE(false, true, false) CPG_CASE(true, false, false) CPG_CASE(true, true, false)
+    CPG_CASE(false, false, false)
+#ifndef CPG_DEV_MIN   // (development builds: only the E1 non-reduced position variant, a tenth of the compile time)
+    CPG_CASE(false, true, false) CPG_CASE(true, false, false) CPG_CASE(true, true, false)
     CPG_CASE(false, false, true) CPG_CASE(false, true, true) CPG_CASE(true, false, true) CPG_CASE(true, true, true)
+#endif
 #undef CPG_CASE
     return CPG_ERR_ARGUMENT;
 }
@@ -897,8 +939,11 @@ int dispatch_grid(cpg_ctx *c, const MorphParams &P, bool shell, bool reduced, bo
 {
 #define CPG_CASE(SH, RE, VD) \
     if (shell == SH && reduced == RE && vdisp == VD) return launch_grid<S, SH, RE, VD>(c, P, first_task, n_tasks);
-    CPG_CASE(false, false, false) CPG_CASE(false, true, false) CPG_CASE(true, false, false) CPG_CASE(true, true, false)
+    CPG_CASE(false, false, false)
+#ifndef CPG_DEV_MIN   // (development builds: only the E1 non-reduced position variant, a tenth of the compile time)
+    CPG_CASE(false, true, false) CPG_CASE(true, false, false) CPG_CASE(true, true, false)
     CPG_CASE(false, false, true) CPG_CASE(false, true, true) CPG_CASE(true, false, true) CPG_CASE(true, true, true)
+#endif
 #undef CPG_CASE
     return CPG_ERR_ARGUMENT;
 }
@@ -1058,6 +1103,8 @@ CPG_API int cpg_set_option(cpg_ctx *c, const char *name, int64_t value)
         if (value == 0) { c->snap_key.valid = false; c->cat_key.valid = false; }
     } else if (!strcmp(name, "detect_ranges")) {
         c->opt_detect_ranges = value != 0;
+    } else if (!strcmp(name, "async_step")) {
+        c->opt_async_step = (int)value;   // 0: kernel 1, 1: kernel 1c (step warp), 2: kernel 1d for long queues, 3: kernel 1d always
     } else if (!strcmp(name, "batched_step")) {
         c->opt_batched_step = value != 0;
     } else if (!strcmp(name, "warp_ctas_per_sm")) {

@@ -428,16 +428,21 @@ struct InnerPrefix {
     // the rounded-up radius passes it with the true one) and prefix lengths in pairs (objects < 131072 particles)
     const float *rr_up = nullptr;
     const uint16_t *npairs16 = nullptr;
+    // ... or, with rr_up set and npairs16 null, the object's row of the n_eff table in global memory (kernel 1c: one
+    // read per step instead of a shared-memory copy per task slot)
+    const int32_t *neff_g = nullptr;
     __device__ __forceinline__ int pairs_inside(int k, double s) const
     {
         if (rr_up) {
-            const double lim = s * (double)rr_up[k] * (1.0 - 1e-7);   // rr_up[k] <= rr[k] (1 + 6e-8): still below s * rr[k] (1 - 1e-9)
+            // rr_up[k] <= rr[k] (1 + 6e-8): still below s * rr[k] (1 - 1e-9); rounded DOWN to fp32 so that the search
+            // compares floats (a bucket that passes with the rounded-down limit passes with the true one)
+            const float lim = __double2float_rd(s * (double)rr_up[k] * (1.0 - 1e-7));
             int lo = -1, hi = k;   // rr_up[lo] <= lim < rr_up[hi]
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
-                if ((double)rr_up[mid] <= lim) lo = mid; else hi = mid;
+                if (rr_up[mid] <= lim) lo = mid; else hi = mid;
             }
-            return lo >= 0 ? (int)npairs16[lo] : 0;
+            return lo >= 0 ? (npairs16 ? (int)npairs16[lo] : (int)(neff_g[lo] >> 1)) : 0;
         }
         if (!rr) return 0;
         const double lim = s * rr[k] * (1.0 - 1e-9);
@@ -462,13 +467,14 @@ struct InnerPrefix {
         if (!(frac > 1e-3)) return 0;                              // c <= 0 (or tiny): the inner ball is no bound
         // rr_up[k] (1 - 2e-7) <= rr[k]: the radius of shell k from below
         const double lim = frac * (rr_up ? (double)rr_up[k] * (1.0 - 2e-7) : rr[k]) * (1.0 - 1e-6);
+        const float limf = __double2float_rd(lim);   // (fp32 search over rr_up: conservative, see pairs_inside)
         int lo = -1, hi = k;   // radius[lo] <= lim < radius[hi]   (ascending; radius[k] > lim because frac < 1)
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
-            if ((rr_up ? (double)rr_up[mid] : rr[mid]) <= lim) lo = mid; else hi = mid;
+            if (rr_up ? (rr_up[mid] <= limf) : (rr[mid] <= lim)) lo = mid; else hi = mid;
         }
         if (lo < 0) return 0;
-        return rr_up ? (int)npairs16[lo] : neff[lo] >> 1;
+        return rr_up ? (npairs16 ? (int)npairs16[lo] : (int)(neff_g[lo] >> 1)) : neff[lo] >> 1;
     }
 };
 
@@ -614,10 +620,10 @@ constexpr int MAX_SORT_R = 256;   // == SORT_MAX_B of cpg_gather.cuh: radial ord
 #endif
 constexpr int RING_MAX_STAGES = 4;
 
-template <bool VDISP>
+template <bool VDISP, int STG = (VDISP ? 2 : CPG_RING_STAGES)>
 struct RingCfg {
     static constexpr int NSTREAM = VDISP ? 7 : 4;
-    static constexpr int STAGES = VDISP ? 2 : CPG_RING_STAGES;   // 16 KB (positions) / 14 KB (with velocities) per warp
+    static constexpr int STAGES = STG;   // default: 16 KB (positions) / 14 KB (with velocities) per warp
     static constexpr int STREAM_BYTES = TILE_PAIRS * 16;
     static constexpr int STAGE_BYTES = NSTREAM * STREAM_BYTES;
     static constexpr int WARP_BYTES = STAGES * STAGE_BYTES;
@@ -690,10 +696,10 @@ __device__ __forceinline__ void ring_init(WarpRing &r, unsigned char *buf, uint6
 }
 
 // Issue the bulk copies of tile `t` (pairs [64 t, 64 t + n)) of every stream into ring slot `seq`.
-template <bool VDISP>
+template <bool VDISP, int STG = RingCfg<VDISP>::STAGES>
 __device__ __forceinline__ void ring_issue(const WarpRing &r, uint32_t seq, const SoA &soa, int64_t base, int t, int npairs)
 {
-    using C = RingCfg<VDISP>;
+    using C = RingCfg<VDISP, STG>;
     const uint32_t stage = seq % C::STAGES;
     const uint32_t bytes = (uint32_t)min(TILE_PAIRS, npairs - t * TILE_PAIRS) * 16u;
     const uint32_t dst = r.buf_s + stage * C::STAGE_BYTES;
@@ -715,11 +721,11 @@ __device__ __forceinline__ void ring_issue(const WarpRing &r, uint32_t seq, cons
 // stream, then arrives on the stage's mbarrier once its copies have landed.  8 warp instructions per tile instead of
 // the ~100 the elected-lane TMA issue costs (4 UBLKCP, each behind a uniform-register broadcast loop): used by the
 // warp kernel, whose tasks average fewer than 8 tiles per pass (profiles/README.md, source-page breakdown).
-template <bool VDISP>
+template <bool VDISP, int STG = RingCfg<VDISP>::STAGES>
 __device__ __forceinline__ void ring_issue_lanes(const WarpRing &r, uint32_t seq, const SoA &soa, int64_t base, int t, int npairs,
                                                  int lane)
 {
-    using C = RingCfg<VDISP>;
+    using C = RingCfg<VDISP, STG>;
     const uint32_t stage = seq % C::STAGES;
     const int n = min(TILE_PAIRS, npairs - t * TILE_PAIRS);
     const uint32_t dst = r.buf_s + stage * C::STAGE_BYTES;
@@ -740,17 +746,17 @@ __device__ __forceinline__ void ring_issue_lanes(const WarpRing &r, uint32_t seq
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-template <bool VDISP>
+template <bool VDISP, int STG = RingCfg<VDISP>::STAGES>
 __device__ __forceinline__ const unsigned char *ring_tile(const WarpRing &r, uint32_t seq)
 {
-    return r.buf + (seq % RingCfg<VDISP>::STAGES) * RingCfg<VDISP>::STAGE_BYTES;
+    return r.buf + (seq % STG) * RingCfg<VDISP, STG>::STAGE_BYTES;
 }
 
 // The two particles of pair `pi` of the tile in ring slot `seq` (this lane consumes pairs lane and lane+32).
-template <bool VDISP>
+template <bool VDISP, int STG = RingCfg<VDISP>::STAGES>
 __device__ __forceinline__ void ring_read_pair(const WarpRing &r, uint32_t seq, int pi, Particle &a, Particle &b)
 {
-    using C = RingCfg<VDISP>;
+    using C = RingCfg<VDISP, STG>;
     const unsigned char *src = r.buf + (seq % C::STAGES) * C::STAGE_BYTES;
     const double2 x = reinterpret_cast<const double2 *>(src + 0 * C::STREAM_BYTES)[pi];
     const double2 y = reinterpret_cast<const double2 *>(src + 1 * C::STREAM_BYTES)[pi];
@@ -769,10 +775,10 @@ __device__ __forceinline__ void ring_read_pair(const WarpRing &r, uint32_t seq, 
 
 // The bulk copy of a partial tile leaves the tail of the slot untouched: fill it with the never-selected
 // sentinel the gather pads odd objects with, so that the compute loop needs no per-lane bounds checks.
-template <bool VDISP>
+template <bool VDISP, int STG = RingCfg<VDISP>::STAGES>
 __device__ __forceinline__ void ring_fill_tail(const WarpRing &r, uint32_t seq, int lane, int pairs_in_tile)
 {
-    using C = RingCfg<VDISP>;
+    using C = RingCfg<VDISP, STG>;
     unsigned char *dst = r.buf + (seq % C::STAGES) * C::STAGE_BYTES;
     for (int pi = pairs_in_tile + lane; pi < TILE_PAIRS; pi += 32) {
 #pragma unroll
@@ -787,7 +793,7 @@ __device__ __forceinline__ void ring_fill_tail(const WarpRing &r, uint32_t seq, 
 // `npairs` pairs that the still-active shells need; npr[s] = pairs in the prefix of shell s.
 // resident: every tile this warp will ever need for the task fits in its ring -> loaded by the first pass,
 // re-read from shared memory by all later ones.
-template <int S, bool SHELL, bool REDUCED, bool VDISP, bool LANES = false>
+template <int S, bool SHELL, bool REDUCED, bool VDISP, bool LANES = false, int STG = RingCfg<VDISP>::STAGES>
 __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npairs, int tile0, int tstride, int lane,
                                          WarpRing &ring, bool resident, int npairs_task, const double *frames,
                                          const int (&npr)[S], const int *nin, unsigned amask, double (&acc)[S][7],
@@ -806,7 +812,7 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
 #pragma unroll
         for (int k = 0; k < 7; k++) acc[s][k] = 0.0;
     }
-    constexpr int RING_STAGES = RingCfg<VDISP>::STAGES;
+    constexpr int RING_STAGES = STG;
     // a resident task keeps all of its tiles in the ring (slot j <-> tile tile0 + j * tstride) and just skips the
     // ones no shell needs; a streamed pass starts at the first tile some active shell still has to test
     const int tskip = resident ? 0 : tlow;
@@ -823,10 +829,10 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
     }
     if (!reuse && LANES) {
         for (int j = 0; j < min(issue_n, RING_STAGES); j++)
-            ring_issue_lanes<VDISP>(ring, seq0 + j, soa, base, tile0 + j * tstride, npairs_load, lane);
+            ring_issue_lanes<VDISP, STG>(ring, seq0 + j, soa, base, tile0 + j * tstride, npairs_load, lane);
     } else if (!reuse && lane == 0)
         for (int j = 0; j < min(issue_n, RING_STAGES); j++)
-            ring_issue<VDISP>(ring, seq0 + j, soa, base, tile0 + j * tstride, npairs_load);
+            ring_issue<VDISP, STG>(ring, seq0 + j, soa, base, tile0 + j * tstride, npairs_load);
     for (int j = 0; j < nmine; j++) {
         const int t = tile0 + j * tstride;
         const uint32_t seq = seq0 + j;
@@ -835,7 +841,7 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
             // only the last tile of the loaded range can be partial (particles past the active prefix but
             // inside the loaded range are real particles that fail every membership test)
             const int loaded = min(TILE_PAIRS, npairs_load - t * TILE_PAIRS);
-            if (loaded < TILE_PAIRS) ring_fill_tail<VDISP>(ring, seq, lane, loaded);
+            if (loaded < TILE_PAIRS) ring_fill_tail<VDISP, STG>(ring, seq, lane, loaded);
         }
         unsigned smask = 0;
 #pragma unroll
@@ -849,7 +855,7 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
         if (smask == 0) {
             // (resident tasks only)
         } else if (CPG_F32_TEST && !REDUCED) {
-            const unsigned char *tile = ring_tile<VDISP>(ring, seq);
+            const unsigned char *tile = ring_tile<VDISP, STG>(ring, seq);
 #pragma unroll 1
             for (int h = 0; h < 2; h++) pair_f32<S, SHELL, VDISP>(tile, lane + 32 * h, frames, smask, acc, cnt);
         } else if (VDISP) {
@@ -857,7 +863,7 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 Particle p[2];
-                ring_read_pair<VDISP>(ring, seq, lane + 32 * h, p[0], p[1]);
+                ring_read_pair<VDISP, STG>(ring, seq, lane + 32 * h, p[0], p[1]);
                 passk_particles<S, SHELL, REDUCED, VDISP, 2>(p, frames, smask, acc, cnt);
             }
         } else if (CPG_FP64_PAIRS) {
@@ -865,13 +871,13 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
 #pragma unroll 1
             for (int h = 0; h < 2; h++) {
                 Particle p[2];
-                ring_read_pair<VDISP>(ring, seq, lane + 32 * h, p[0], p[1]);
+                ring_read_pair<VDISP, STG>(ring, seq, lane + 32 * h, p[0], p[1]);
                 passk_particles<S, SHELL, REDUCED, VDISP, 2>(p, frames, smask, acc, cnt);
             }
         } else {
             Particle p[4];
-            ring_read_pair<VDISP>(ring, seq, lane, p[0], p[1]);
-            ring_read_pair<VDISP>(ring, seq, lane + 32, p[2], p[3]);
+            ring_read_pair<VDISP, STG>(ring, seq, lane, p[0], p[1]);
+            ring_read_pair<VDISP, STG>(ring, seq, lane + 32, p[2], p[3]);
             if (CPG_SHELL_PAIRS && !SHELL && !REDUCED && S % 2 == 0)
                 passk_shell_pairs<(S % 2 == 0 ? S : 2), 4>(p, frames, smask, reinterpret_cast<double (&)[(S % 2 == 0 ? S : 2)][7]>(acc), reinterpret_cast<int (&)[(S % 2 == 0 ? S : 2)]>(cnt));
             else
@@ -880,9 +886,9 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
         if (!resident && j + RING_STAGES < nmine) {
             __syncwarp();   // every lane has taken its data out of this slot
             if (LANES)
-                ring_issue_lanes<VDISP>(ring, seq + RING_STAGES, soa, base, t + RING_STAGES * tstride, npairs_load, lane);
+                ring_issue_lanes<VDISP, STG>(ring, seq + RING_STAGES, soa, base, t + RING_STAGES * tstride, npairs_load, lane);
             else if (lane == 0)
-                ring_issue<VDISP>(ring, seq + RING_STAGES, soa, base, t + RING_STAGES * tstride, npairs_load);
+                ring_issue<VDISP, STG>(ring, seq + RING_STAGES, soa, base, t + RING_STAGES * tstride, npairs_load);
         }
     }
     if (!reuse) {
@@ -891,7 +897,7 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
             for (int j = nmine; j < issue_n; j++) {
                 mbar_wait(ring.bar_s + ((seq0 + j) % RING_STAGES) * 8u, ((seq0 + j) / RING_STAGES) & 1u);
                 const int loaded = min(TILE_PAIRS, npairs_load - (tile0 + j * tstride) * TILE_PAIRS);
-                if (loaded < TILE_PAIRS) ring_fill_tail<VDISP>(ring, seq0 + j, lane, loaded);
+                if (loaded < TILE_PAIRS) ring_fill_tail<VDISP, STG>(ring, seq0 + j, lane, loaded);
             }
             ring.res_seq = seq0;
             ring.res_loaded = true;
@@ -899,6 +905,83 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
         } else {
             ring.seq = seq0 + nmine;
         }
+    }
+}
+
+// run_pass for kernel 1d: a warp-kernel pass (tile0 = 0, stride 1, per-lane cp.async loads) over a RUNTIME set of stages
+// [sbase, sbase + nst) of the warp's RING_MAX_STAGES-stage ring, nst a power of two.  The two task slots of a warp share
+// the ring: a task of <= 2 tiles stays resident in its slot's half, a streamed pass takes the whole ring when the other
+// slot holds nothing resident and its own half otherwise.  Which phase of a stage's mbarrier comes next is tracked in
+// `phase` (one bit per stage; every issue to a stage is waited for exactly once before the next issue to it).
+template <int S, bool SHELL, bool REDUCED, bool VDISP>
+__device__ __forceinline__ void run_pass_rt(const SoA &soa, int64_t base, int npairs, int lane, WarpRing &ring, unsigned &phase,
+                                            int sbase, int nst, bool resident, bool &res_loaded, int npairs_task,
+                                            const double *frames, const int (&npr)[S], const int *nin, unsigned amask,
+                                            double (&acc)[S][7], int (&cnt)[S])
+{
+    constexpr int STG = RING_MAX_STAGES;
+    static_assert(!VDISP, "position streams only");
+    int tin[S], tlow = 0x7fffffff;
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        tin[s] = nin[s] / TILE_PAIRS;
+        if (amask & (1u << s)) tlow = min(tlow, tin[s]);
+    }
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        cnt[s] = 0;
+#pragma unroll
+        for (int k = 0; k < 7; k++) acc[s][k] = 0.0;
+    }
+    const int tile0 = resident ? 0 : tlow;
+    const int ntiles = (npairs + TILE_PAIRS - 1) / TILE_PAIRS;
+    const int nmine = tile0 < ntiles ? ntiles - tile0 : 0;
+    const bool reuse = resident && res_loaded;
+    const int npairs_load = resident ? npairs_task : npairs;
+    const int issue_n = (resident && !reuse) ? (npairs_task + TILE_PAIRS - 1) / TILE_PAIRS : nmine;   // (resident: <= nst tiles)
+    const int smask_st = nst - 1;
+    if (!reuse)
+        for (int j = 0; j < min(issue_n, nst); j++)
+            ring_issue_lanes<VDISP, STG>(ring, (uint32_t)(sbase + j), soa, base, tile0 + j, npairs_load, lane);
+    for (int j = 0; j < nmine; j++) {
+        const int t = tile0 + j;
+        const uint32_t stage = (uint32_t)(sbase + (j & smask_st));
+        if (!reuse) {
+            mbar_wait(ring.bar_s + stage * 8u, (phase >> stage) & 1u);
+            phase ^= 1u << stage;
+            const int loaded = min(TILE_PAIRS, npairs_load - t * TILE_PAIRS);
+            if (loaded < TILE_PAIRS) ring_fill_tail<VDISP, STG>(ring, stage, lane, loaded);
+        }
+        unsigned smask = 0;
+#pragma unroll
+        for (int s = 0; s < S; s++)
+            if (t * TILE_PAIRS < npr[s] && t >= tin[s]) smask |= 1u << s;
+        smask &= amask;
+        asm volatile("" : "+r"(smask));
+#ifndef CPG_NO_TILE_STATS
+        if (smask != 0) { ring.st_tiles += 1; ring.st_tshells += __popc(smask); }
+#endif
+        if (smask != 0) {
+            Particle p[4];
+            ring_read_pair<VDISP, STG>(ring, stage, lane, p[0], p[1]);
+            ring_read_pair<VDISP, STG>(ring, stage, lane + 32, p[2], p[3]);
+            passk_particles<S, SHELL, REDUCED, VDISP, 4>(p, frames, smask, acc, cnt);
+        }
+        if (!resident && j + nst < nmine) {
+            __syncwarp();   // every lane has taken its data out of this stage
+            ring_issue_lanes<VDISP, STG>(ring, stage, soa, base, t + nst, npairs_load, lane);
+        }
+    }
+    if (!reuse && resident) {
+        // the barriers of resident tiles beyond the first pass's active range have not been waited on yet
+        for (int j = nmine; j < issue_n; j++) {
+            const uint32_t stage = (uint32_t)(sbase + j);
+            mbar_wait(ring.bar_s + stage * 8u, (phase >> stage) & 1u);
+            phase ^= 1u << stage;
+            const int loaded = min(TILE_PAIRS, npairs_load - j * TILE_PAIRS);
+            if (loaded < TILE_PAIRS) ring_fill_tail<VDISP, STG>(ring, stage, lane, loaded);
+        }
+        res_loaded = true;
     }
 }
 
@@ -1368,6 +1451,476 @@ __global__ void __launch_bounds__(WB_WARPS * 32, CPG_WARP_MINB) morph_wbatch_ker
             amask = s_amask[warp];
             if (amask == 0) have = false;
         }
+    }
+    ring_flush_stats(ring, P.stats, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 1c: the warp kernel with an ASYNCHRONOUS step.  In kernel 1 the per-iteration step (reduction, eigen-solve,
+// convergence test, next frame: 3.7 us, 28 % of a warp's time, a serial chain that keeps 4 of 32 lanes busy) sits in the
+// dependency chain of every warp; kernel 1b shares it between the warps of a CTA but makes them wait for one another at a
+// block barrier (slower).  Here the two halves of the Katz iteration are decoupled:
+//   * WA_PASS "pass" warps per CTA only stream particles.  Each owns WA_SLOTS task slots (frames, shell state, a
+//     WA_STAGES-tile ring per slot in shared memory).  After the pass of a slot the warp leaves the 8 S reduced sums in
+//     shared memory, marks the slot POSTED and goes on with its other slot -- it never executes the step and never waits
+//     for another pass warp;
+//   * ONE "step" warp per CTA polls the slot states, takes up to 32 / S posted slots at a time -- one LANE per shell, so
+//     a step costs the same chain for 32 shells as kernel 1 spends on 4 -- runs katz_step for them, publishes frames,
+//     inner-prefix lengths and active masks and marks each slot READY (next pass) or EMPTY (task finished: the pass warp
+//     pulls the next task from the queue into it).
+// Per-shell arithmetic is that of kernel 1 (same run_pass, same reduction tree, same katz_step, same operands): results
+// are identical bit for bit.  Slot states are plain shared-memory words, ordered with __threadfence_block().
+// ------------------------------------------------------------------------------------------------
+#ifndef CPG_WA_PASS
+#define CPG_WA_PASS 5      // pass warps per CTA
+#endif
+#ifndef CPG_WA_SLOTS
+#define CPG_WA_SLOTS 2     // task slots per pass warp
+#endif
+#ifndef CPG_WA_STAGES
+#define CPG_WA_STAGES 2    // tiles (4 KB) in a slot's ring: tasks of <= 128 * WA_STAGES prefix particles stay resident
+#endif
+#ifndef CPG_WA_MINB
+#define CPG_WA_MINB 2      // resident CTAs per SM the register allocator leaves room for
+#endif
+constexpr int WA_PASS = CPG_WA_PASS, WA_SLOTS = CPG_WA_SLOTS, WA_STAGES = CPG_WA_STAGES;
+constexpr int WA_NSLOT = WA_PASS * WA_SLOTS;
+constexpr int WA_THREADS = (WA_PASS + 1) * 32;
+static_assert(WA_NSLOT <= 32, "one lane of the step warp watches one slot");
+enum { WA_EMPTY = 0, WA_READY = 1, WA_POSTED = 2 };
+
+struct SlotDesc {          // what a pass needs to know about its slot's task (shared memory; written by the pass warp)
+    long long base, row0;
+    int npairs_task, resident, res_loaded, pad;
+    unsigned seq, res_seq;
+};
+
+template <int S, bool SHELL, bool REDUCED, bool VDISP>
+__global__ void __launch_bounds__(WA_THREADS, CPG_WA_MINB) morph_wasync_kernel(const MorphParams P)
+{
+    using LM = LaneMap<S>;
+    using RC = RingCfg<VDISP, WA_STAGES>;
+    constexpr int NV = 8 * S;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char s_ring_a[];   // WA_NSLOT rings
+    __shared__ __align__(16) double s_frames[WA_NSLOT][S * F_SLOTS];
+    __shared__ __align__(8) uint64_t s_bar[WA_NSLOT][RING_MAX_STAGES];
+    __shared__ double s_red[WA_NSLOT][NV];
+    __shared__ ShellSlot s_slot[WA_NSLOT][S];
+    __shared__ SlotDesc s_desc[WA_NSLOT];
+    __shared__ int s_np[WA_NSLOT][S], s_nin[WA_NSLOT][S];
+    __shared__ unsigned s_amask[WA_NSLOT];
+    __shared__ int s_state[WA_NSLOT];
+    __shared__ int s_done;
+    __shared__ float s_rr[MAX_SORT_R];
+    __shared__ uint16_t s_neff[WA_NSLOT][MAX_SORT_R];   // prefix lengths (pairs) of the slot's object
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    volatile int *state = s_state;
+    const bool use_table = !SHELL && !REDUCED && P.n_eff != nullptr && P.ptab != nullptr;
+    const bool use_inner = use_table || (SHELL && P.n_eff != nullptr);
+    if (use_inner)
+        for (int j = threadIdx.x; j < P.R; j += blockDim.x) s_rr[j] = __double2float_ru(P.rr[j]);
+    if (threadIdx.x < WA_NSLOT) s_state[threadIdx.x] = WA_EMPTY;
+    if (threadIdx.x == 0) s_done = 0;
+    __syncthreads();
+    const double *ptab = use_table ? P.ptab : nullptr;
+
+    if (warp < WA_PASS) {
+        // ---------------------------------------------------------------- pass warp
+        const LM L(lane);
+        WarpRing ring;
+        for (int j = 0; j < WA_SLOTS; j++) {
+            const int sl = warp * WA_SLOTS + j;
+            ring_init(ring, s_ring_a + sl * RC::WARP_BYTES, s_bar[sl], lane, WARP_RING_LANES ? 32u : 1u);
+            if (lane == 0) { s_desc[sl].seq = 0; s_desc[sl].res_seq = 0; s_desc[sl].res_loaded = 0; }
+        }
+        __syncwarp();
+        bool queue_done = false;
+        int cur = 0;
+#ifdef CPG_TASK_TRACE
+        long long tr_t0 = clock64(), tr_pass = 0, tr_idle = 0, tr_npass = 0, tr_nres = 0, tr_mark = tr_t0;
+#endif
+        for (;;) {
+            int run = -1, nempty = 0;
+            for (int jj = 0; jj < WA_SLOTS && run < 0; jj++) {
+                const int j = (cur + jj) % WA_SLOTS, sl = warp * WA_SLOTS + j;
+                const int stt = __shfl_sync(FULL, state[sl], 0);
+                if (stt == WA_READY) {
+                    run = sl;
+                } else if (stt == WA_EMPTY) {
+                    nempty++;
+                    // next live task of the queue into this slot (dead ones -- empty object, r200 == 0 -- are skipped)
+                    while (!queue_done && run < 0) {
+                        int t = 0;
+                        if (lane == 0) t = atomicAdd(P.task_counter, 1);
+                        t = __shfl_sync(FULL, t, 0);
+                        if (t >= P.n_tasks) { queue_done = true; break; }
+                        const Task tk = P.tasks[t];
+                        const int halo = tk.halo;
+                        if (P.skip[halo] || (P.local && P.r200[halo] == 0.0)) continue;
+                        const int N = P.soa.size[halo];
+                        const int64_t base = P.soa.poff[halo];
+                        KatzState st;
+                        st.q = 1.0; st.s = 1.0; st.iteration = 1;
+                        st.active = L.ls < tk.nshell;
+                        const int k = tk.shell0 + (st.active ? L.ls : 0);
+                        shell_geometry(P, halo, k, st.d, st.delta);
+                        const size_t out_idx = (size_t)halo * P.R + k;
+                        if (use_inner) {   // the object's prefix lengths up to the task's last shell
+                            for (int j2 = lane; j2 < tk.shell0 + tk.nshell; j2 += 32)
+                                s_neff[sl][j2] = (uint16_t)(P.n_eff[(size_t)halo * P.R + j2] >> 1);
+                            __syncwarp();
+                        }
+                        InnerPrefix ip;
+                        ip.rr = nullptr; ip.neff = nullptr;
+                        ip.rr_up = use_inner ? s_rr : nullptr;
+                        ip.npairs16 = s_neff[sl];
+                        init_frames<SHELL>(s_frames[sl], s_np[sl], s_nin[sl], L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
+                        if (L.writer) {
+                            ShellSlot &ss = s_slot[sl][L.ls];
+                            ss.q = 1.0; ss.s = 1.0; ss.d = st.d; ss.delta = st.delta; ss.out_idx = (unsigned long long)out_idx;
+                            ss.iteration = 1; ss.active = st.active ? 1 : 0; ss.k = k;
+                        }
+                        __syncwarp();
+                        const unsigned am = LM::active_mask(st.active && L.writer);
+                        int npr0[S];
+#pragma unroll
+                        for (int s = 0; s < S; s++) npr0[s] = s_np[sl][s];
+                        const int npt = active_npairs<S>(npr0, am);
+                        if (lane == 0) {
+                            s_amask[sl] = am;
+                            SlotDesc &d = s_desc[sl];
+                            d.base = base; d.row0 = (base >> 7) + halo; d.npairs_task = npt;
+                            d.resident = ((npt + TILE_PAIRS - 1) / TILE_PAIRS <= WA_STAGES) ? 1 : 0;
+                            d.res_loaded = 0;
+                            s_state[sl] = WA_READY;
+                        }
+                        __syncwarp();
+                        run = sl;
+                    }
+                }
+            }
+            if (run < 0) {
+                if (queue_done && nempty == WA_SLOTS) break;
+                __nanosleep(100);
+                continue;
+            }
+#ifdef CPG_TASK_TRACE
+            { const long long now = clock64(); tr_idle += now - tr_mark; tr_mark = now; }
+#endif
+            __threadfence_block();   // the step warp's frames, prefix lengths and mask of this slot are visible
+            {
+                const int sl = run;
+                const unsigned amask = s_amask[sl];
+                int npr[S];
+#pragma unroll
+                for (int s = 0; s < S; s++) npr[s] = s_np[sl][s];
+                const SlotDesc d = s_desc[sl];
+                ring.buf = s_ring_a + sl * RC::WARP_BYTES; ring.bar = s_bar[sl];
+                ring.buf_s = smem_u32(ring.buf); ring.bar_s = smem_u32(ring.bar);
+                ring.seq = d.seq; ring.res_seq = d.res_seq; ring.res_loaded = d.res_loaded != 0;
+                const double tadd = table_term(ptab, d.row0, s_nin[sl][(lane & (NV - 1)) >> 3], lane & 7);
+                double acc[S][7];
+                int cnt[S];
+                run_pass<S, SHELL, REDUCED, VDISP, WARP_RING_LANES, WA_STAGES>(P.soa, d.base, active_npairs<S>(npr, amask), 0, 1, lane, ring,
+                                                                               d.resident != 0, d.npairs_task, s_frames[sl], npr, s_nin[sl],
+                                                                               amask, acc, cnt);
+                double val[NV];
+                pack_values<S>(acc, cnt, val);
+                const double mine = warp_sum_transpose<NV>(val, lane) + tadd;
+                if (lane < NV) s_red[sl][lane] = mine;
+                if (lane == 0) { s_desc[sl].seq = ring.seq; s_desc[sl].res_seq = ring.res_seq; s_desc[sl].res_loaded = ring.res_loaded ? 1 : 0; }
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) state[sl] = WA_POSTED;
+                cur = (sl - warp * WA_SLOTS + 1) % WA_SLOTS;
+#ifdef CPG_TASK_TRACE
+                { const long long now = clock64(); tr_pass += now - tr_mark; tr_mark = now; tr_npass++; tr_nres += d.res_loaded ? 1 : 0; }
+#endif
+            }
+            if (ring.st_tiles > (1u << 20)) ring_flush_stats(ring, P.stats, lane);
+        }
+        ring_flush_stats(ring, P.stats, lane);
+#ifdef CPG_TASK_TRACE
+        if (lane == 0 && P.stats) {
+            atomicAdd(P.stats + 2, (unsigned long long)(clock64() - tr_t0));
+            atomicAdd(P.stats + 3, (unsigned long long)tr_pass);
+            atomicAdd(P.stats + 4, (unsigned long long)tr_idle);   // (includes task fetch + init)
+            atomicAdd(P.stats + 10, (unsigned long long)tr_npass);
+            atomicAdd(P.stats + 11, (unsigned long long)tr_nres);
+        }
+#endif
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); atomicAdd(&s_done, 1); }
+    } else {
+        // ---------------------------------------------------------------- step warp: one lane per shell
+        volatile int *done = &s_done;
+#ifdef CPG_TASK_TRACE
+        long long tr_t0 = clock64(), tr_busy = 0, tr_batches = 0, tr_slots = 0;
+#endif
+        for (;;) {
+            const int stt = lane < WA_NSLOT ? state[lane] : WA_EMPTY;
+            const unsigned posted = __ballot_sync(FULL, stt == WA_POSTED);
+            if (posted == 0) {
+                if (*done >= WA_PASS) break;
+                __nanosleep(40);
+                continue;
+            }
+            __threadfence_block();   // the pass warps' sums are visible
+#ifdef CPG_TASK_TRACE
+            const long long tr_b0 = clock64();
+#endif
+            const int which = lane / S, sh = lane % S;
+            const unsigned pos = __fns(posted, 0, which + 1);   // the (which + 1)-th posted slot
+            const bool valid = pos != 0xffffffffu;
+            const int sl = valid ? (int)pos : 0;                 // (keeps every lane's addresses in range)
+            KatzState st;
+            st.q = 1.0; st.s = 1.0; st.d = 1.0; st.delta = 1.0; st.iteration = 1; st.active = false;
+            double tot[7] = {0, 0, 0, 0, 0, 0, 0}, vprev[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+            int pts = 0, k = 0;
+            size_t out_idx = 0;
+            if (valid) {
+                const ShellSlot &ss = s_slot[sl][sh];
+                st.q = ss.q; st.s = ss.s; st.d = ss.d; st.delta = ss.delta; st.iteration = ss.iteration; st.active = ss.active != 0;
+                k = ss.k; out_idx = (size_t)ss.out_idx;
+#pragma unroll
+                for (int c = 0; c < 7; c++) tot[c] = s_red[sl][8 * sh + c];
+                pts = (int)s_red[sl][8 * sh + 7];
+#pragma unroll
+                for (int r = 0; r < 9; r++) vprev[r] = s_frames[sl][sh * F_SLOTS + F_V + r];
+            }
+            InnerPrefix ip;
+            ip.rr = nullptr; ip.neff = nullptr;
+            ip.rr_up = use_inner ? s_rr : nullptr;
+            ip.npairs16 = s_neff[sl];
+            katz_step<SHELL>(st, tot, pts, P, vprev, s_frames[sl] + sh * F_SLOTS, valid, out_idx, valid, ip, k, &s_nin[sl][sh]);
+            if (valid) {
+                ShellSlot &ss = s_slot[sl][sh];
+                ss.q = st.q; ss.s = st.s; ss.iteration = st.iteration; ss.active = st.active ? 1 : 0;
+            }
+            const unsigned b = __ballot_sync(FULL, valid && st.active);
+            const unsigned am = (b >> (which * S)) & ((1u << S) - 1u);
+            __threadfence_block();   // frames, prefix lengths, shell state before the slot changes hands
+            __syncwarp();
+            if (valid && sh == 0) {
+                s_amask[sl] = am;
+                __threadfence_block();
+                state[sl] = am ? WA_READY : WA_EMPTY;
+            }
+#ifdef CPG_TASK_TRACE
+            tr_busy += clock64() - tr_b0; tr_batches++; tr_slots += min(__popc(posted), 32 / S);
+#endif
+        }
+#ifdef CPG_TASK_TRACE
+        if (lane == 0 && P.stats) {
+            atomicAdd(P.stats + 6, (unsigned long long)(clock64() - tr_t0));
+            atomicAdd(P.stats + 7, (unsigned long long)tr_busy);
+            atomicAdd(P.stats + 8, (unsigned long long)tr_batches);
+            atomicAdd(P.stats + 9, (unsigned long long)tr_slots);
+        }
+#endif
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 1d: a warp works on WD_SLOTS independent tasks at a time and runs ONE step for all of them.  Per round the
+// warp passes over the particles of each of its live slots in turn (same run_pass as kernel 1, a WD_STAGES-tile ring per
+// slot), keeps each slot's transposed sums in one register, and then executes katz_step once with one lane per shell
+// for the WD_SLOTS * S shells of all slots: the serial chain of the step (3.7 us in kernel 1, 28 % of its time) is paid
+// once per WD_SLOTS task-iterations, with no other warp to wait for (kernel 1b) and no warp set aside for stepping
+// (kernel 1c).  A slot whose shells have all finished is refilled from the queue before the next round.  Per-shell
+// arithmetic is that of kernel 1 (same pass, same reduction tree, same katz_step).
+// ------------------------------------------------------------------------------------------------
+#ifndef CPG_WD_WARPS
+#define CPG_WD_WARPS 4
+#endif
+#ifndef CPG_WD_SLOTS
+#define CPG_WD_SLOTS 2
+#endif
+#ifndef CPG_WD_STAGES
+#define CPG_WD_STAGES 2
+#endif
+#ifndef CPG_WD_MINB
+#define CPG_WD_MINB 3
+#endif
+constexpr int WD_WARPS = CPG_WD_WARPS, WD_SLOTS = CPG_WD_SLOTS, WD_STAGES = CPG_WD_STAGES;
+constexpr int WD_NSLOT = WD_WARPS * WD_SLOTS;
+
+template <int S, bool SHELL, bool REDUCED, bool VDISP>
+__global__ void __launch_bounds__(WD_WARPS * 32, CPG_WD_MINB) morph_wduo_kernel(const MorphParams P)
+{
+    using LM = LaneMap<S>;
+    using RC = RingCfg<VDISP, RING_MAX_STAGES>;   // ONE ring of RING_MAX_STAGES tiles per warp, shared by its slots (run_pass_rt)
+    static_assert(WD_SLOTS == 2 && RING_MAX_STAGES == 4, "two slots share a 4-stage ring");
+    constexpr int NV = 8 * S;
+    constexpr unsigned FULL = 0xffffffffu;
+    static_assert(WD_SLOTS * S <= 32, "one lane per shell in the step");
+    extern __shared__ __align__(128) unsigned char s_ring_d[];   // WD_WARPS rings
+    __shared__ __align__(16) double s_frames[WD_NSLOT][S * F_SLOTS];
+    __shared__ __align__(8) uint64_t s_bar[WD_WARPS][RING_MAX_STAGES];
+    __shared__ ShellSlot s_slot[WD_NSLOT][S];
+    __shared__ SlotDesc s_desc[WD_NSLOT];
+    __shared__ int s_np[WD_NSLOT][S], s_nin[WD_NSLOT][S];
+    __shared__ unsigned s_am[WD_NSLOT];   // active-shell mask of every slot (0: no task)
+    __shared__ float s_rr[MAX_SORT_R];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool use_table = !SHELL && !REDUCED && P.n_eff != nullptr && P.ptab != nullptr;
+    const bool use_inner = use_table || (SHELL && P.n_eff != nullptr);
+    if (use_inner) {
+        for (int j = threadIdx.x; j < P.R; j += blockDim.x) s_rr[j] = __double2float_ru(P.rr[j]);
+        __syncthreads();
+    }
+    const double *ptab = use_table ? P.ptab : nullptr;
+    const LM L(lane);
+    WarpRing ring;
+    ring_init(ring, s_ring_d + warp * RC::WARP_BYTES, s_bar[warp], lane, 32u);
+    unsigned phase = 0;   // next mbarrier phase of every stage of the ring
+    __syncwarp();
+    bool queue_done = false;
+    if (lane < WD_SLOTS) s_am[warp * WD_SLOTS + lane] = 0;
+    __syncwarp();
+
+    for (;;) {
+        // ---- refill the empty slots from the queue (dead tasks -- empty object, r200 == 0 -- are skipped)
+        bool any = false;
+#pragma unroll 1
+        for (int j = 0; j < WD_SLOTS; j++) {
+            const int sl = warp * WD_SLOTS + j;
+            unsigned amj = s_am[sl];
+            while (amj == 0 && !queue_done) {
+                int t = 0;
+                if (lane == 0) t = atomicAdd(P.task_counter, 1);
+                t = __shfl_sync(FULL, t, 0);
+                if (t >= P.n_tasks) { queue_done = true; break; }
+                const Task tk = P.tasks[t];
+                const int halo = tk.halo;
+                if (P.skip[halo] || (P.local && P.r200[halo] == 0.0)) continue;
+                const int N = P.soa.size[halo];
+                const int64_t base = P.soa.poff[halo];
+                KatzState st;
+                st.q = 1.0; st.s = 1.0; st.iteration = 1;
+                st.active = L.ls < tk.nshell;
+                const int k = tk.shell0 + (st.active ? L.ls : 0);
+                shell_geometry(P, halo, k, st.d, st.delta);
+                const size_t out_idx = (size_t)halo * P.R + k;
+                InnerPrefix ip;
+                ip.rr = nullptr; ip.neff = nullptr;
+                ip.rr_up = use_inner ? s_rr : nullptr;
+                ip.npairs16 = nullptr;
+                ip.neff_g = P.n_eff ? P.n_eff + (size_t)halo * P.R : nullptr;
+                init_frames<SHELL>(s_frames[sl], s_np[sl], s_nin[sl], L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
+                if (L.writer) {
+                    ShellSlot &ss = s_slot[sl][L.ls];
+                    ss.q = 1.0; ss.s = 1.0; ss.d = st.d; ss.delta = st.delta; ss.out_idx = (unsigned long long)out_idx;
+                    ss.iteration = 1; ss.active = st.active ? 1 : 0; ss.k = k;
+                }
+                __syncwarp();
+                amj = LM::active_mask(st.active && L.writer);
+                int npr0[S];
+#pragma unroll
+                for (int s = 0; s < S; s++) npr0[s] = s_np[sl][s];
+                const int npt = active_npairs<S>(npr0, amj);
+                if (lane == 0) {
+                    s_am[sl] = amj;
+                    SlotDesc &d = s_desc[sl];
+                    d.base = base; d.row0 = (base >> 7) + halo; d.npairs_task = npt;
+                    d.resident = ((npt + TILE_PAIRS - 1) / TILE_PAIRS <= RING_MAX_STAGES / WD_SLOTS) ? 1 : 0;
+                    d.res_loaded = 0;
+                }
+                __syncwarp();
+            }
+            any = any || amj != 0;
+        }
+        if (!any) break;
+
+        // ---- one pass per live slot; each leaves its 8 S sums transposed in one register
+        // (ONE copy of the pass in the instruction stream: the loop over the slots is not unrolled, the slots' sums are
+        // steered into their registers with selects)
+        double mine[WD_SLOTS];
+#pragma unroll
+        for (int j = 0; j < WD_SLOTS; j++) mine[j] = 0.0;
+#pragma unroll 1
+        for (int j = 0; j < WD_SLOTS; j++) {
+            const int sl = warp * WD_SLOTS + j;
+            const unsigned amj = s_am[sl];
+            if (amj) {
+                int npr[S];
+#pragma unroll
+                for (int s = 0; s < S; s++) npr[s] = s_np[sl][s];
+                const SlotDesc d = s_desc[sl];
+                // the other slot's resident tiles stay where they are: stream through this slot's half of the ring then
+                const int so = warp * WD_SLOTS + (j ^ 1);
+                const bool other_res = s_am[so] != 0 && s_desc[so].resident != 0;
+                const bool whole = d.resident == 0 && !other_res;
+                const int sbase = whole ? 0 : j * (RING_MAX_STAGES / WD_SLOTS), nst = whole ? RING_MAX_STAGES : RING_MAX_STAGES / WD_SLOTS;
+                bool res_loaded = d.res_loaded != 0;
+                const double tadd = table_term(ptab, d.row0, s_nin[sl][(lane & (NV - 1)) >> 3], lane & 7);
+                double acc[S][7];
+                int cnt[S];
+                run_pass_rt<S, SHELL, REDUCED, VDISP>(P.soa, d.base, active_npairs<S>(npr, amj), lane, ring, phase, sbase, nst,
+                                                      d.resident != 0, res_loaded, d.npairs_task, s_frames[sl], npr, s_nin[sl], amj, acc, cnt);
+                if (lane == 0) s_desc[sl].res_loaded = res_loaded ? 1 : 0;
+                double val[NV];
+                pack_values<S>(acc, cnt, val);
+                const double mj = warp_sum_transpose<NV>(val, lane) + tadd;
+#pragma unroll
+                for (int jj = 0; jj < WD_SLOTS; jj++) mine[jj] = (jj == j) ? mj : mine[jj];
+            }
+        }
+        __syncwarp();
+
+        // ---- one step for the shells of all slots: lane l serves shell l % S of slot l / S
+        {
+            const int jl = (lane / S) % WD_SLOTS, sh = lane % S;
+            const int sl = warp * WD_SLOTS + jl;
+            const unsigned am_l = s_am[sl];
+            double tot[7];
+            int pts;
+            {
+                double got[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) got[c] = 0.0;
+#pragma unroll
+                for (int j = 0; j < WD_SLOTS; j++) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        const double v = __shfl_sync(FULL, mine[j], (8 * sh + c) & 31);
+                        if (j == jl) got[c] = v;
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 7; c++) tot[c] = got[c];
+                pts = (int)got[7];
+            }
+            const bool valid = lane < WD_SLOTS * S && am_l != 0;
+            KatzState st;
+            st.q = 1.0; st.s = 1.0; st.d = 1.0; st.delta = 1.0; st.iteration = 1; st.active = false;
+            double vprev[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+            int k = 0;
+            size_t out_idx = 0;
+            if (valid) {
+                const ShellSlot &ss = s_slot[sl][sh];
+                st.q = ss.q; st.s = ss.s; st.d = ss.d; st.delta = ss.delta; st.iteration = ss.iteration; st.active = ss.active != 0;
+                k = ss.k; out_idx = (size_t)ss.out_idx;
+#pragma unroll
+                for (int r = 0; r < 9; r++) vprev[r] = s_frames[sl][sh * F_SLOTS + F_V + r];
+            }
+            InnerPrefix ip;
+            ip.rr = nullptr; ip.neff = nullptr;
+            ip.rr_up = use_inner ? s_rr : nullptr;
+            ip.npairs16 = nullptr;
+            ip.neff_g = P.n_eff ? P.n_eff + (out_idx - (size_t)k) : nullptr;
+            katz_step<SHELL>(st, tot, pts, P, vprev, s_frames[sl] + sh * F_SLOTS, valid, out_idx, valid, ip, k, &s_nin[sl][sh]);
+            if (valid) {
+                ShellSlot &ss = s_slot[sl][sh];
+                ss.q = st.q; ss.s = st.s; ss.iteration = st.iteration; ss.active = st.active ? 1 : 0;
+            }
+            const unsigned b = __ballot_sync(FULL, valid && st.active);
+            __syncwarp();
+            if (lane < WD_SLOTS) s_am[warp * WD_SLOTS + lane] = (b >> (lane * S)) & ((1u << S) - 1u);
+            __syncwarp();
+        }
+        if (ring.st_tiles > (1u << 20)) ring_flush_stats(ring, P.stats, lane);
     }
     ring_flush_stats(ring, P.stats, lane);
 }
