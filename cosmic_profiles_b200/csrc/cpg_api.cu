@@ -674,7 +674,8 @@ int run_gather(cpg_ctx *c, const double *h_centers, const double *h_r200, const 
             bucket_segapply_kernel<<<nseg, 256, 0, c->stream>>>(P, hb, c->seg_tot.p);
             c->timing.kernel_launches += 3;
         }
-        gather_bucketed_kernel<<<nc, 256, GATHER_BUCKETED_SMEM, c->stream>>>(P);
+        if (CPG_GATHER_STAGED) gather_bucketed_kernel<<<nc, 256, GATHER_BUCKETED_SMEM, c->stream>>>(P);
+        else gather_bucketed2_kernel<<<nc, 256, 0, c->stream>>>(P);
         c->timing.kernel_launches += 3;
         c->sorted_valid = true;
     } else if (n > 0) {
@@ -809,7 +810,7 @@ int launch_morph(cpg_ctx *c, MorphParams P, int n_warp_tasks, int n_cluster_task
     const bool duo = n_warp_tasks >= 8 * c->sm_count * 12 || c->opt_async_step == 3;
     if (n_warp_tasks > 0 && G == 1 && !VDISP && (c->opt_async_step == 2 || c->opt_async_step == 3) && duo) {
         auto kern = morph_wduo_kernel<S, SHELL, REDUCED, false>;
-        const int smem = WD_WARPS * RingCfg<false, RING_MAX_STAGES>::WARP_BYTES;
+        const int smem = WD_WARPS * RingCfg<false, RING_MAX_STAGES>::WARP_BYTES + ((P.R + 7) & ~7) * (int)(sizeof(float) + WD_NSLOT * sizeof(uint16_t));
         CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int per_sm = 0;
         CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));

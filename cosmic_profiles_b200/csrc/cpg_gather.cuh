@@ -696,6 +696,180 @@ __global__ void __launch_bounds__(256) gather_bucketed_kernel(const SortParams P
     }
 }
 
+// The same gather without the staging of the particle data in shared memory (default; build option CPG_GATHER_STAGED=1
+// brings the kernel above back).  Only the permutation goes through shared memory -- sorted slot -> (entry of the chunk,
+// destination inside the object), 6 bytes per particle instead of 36 -- and every thread then loads the particle of its
+// sorted slot straight from the snapshot (a random 24-byte read inside the chunk's 24 KB window: L1 / L2 hits) and stores
+// it to the SoA streams, consecutive threads to consecutive slots of a bucket.  15 KB instead of 46 KB of shared
+// memory per CTA (8 resident CTAs per SM instead of 4), one shared-memory round trip less per particle.  Same slots, same
+// chunk statistics (same summation order) as the staged kernel.
+#ifndef CPG_GATHER_MLP
+#define CPG_GATHER_MLP 0
+#endif
+#ifndef CPG_GATHER_MINB
+#define CPG_GATHER_MINB 8   // 32 registers: 64 resident warps per SM (measured: gather 3.18 -> 2.99 ms on configs[1])
+#endif
+#ifndef CPG_GATHER_BALLOT
+#define CPG_GATHER_BALLOT 0
+#endif
+__global__ void __launch_bounds__(256, CPG_GATHER_MINB) gather_bucketed2_kernel(const SortParams P)
+{
+    __shared__ int s_dest[SORT_CHUNK];
+    __shared__ unsigned short s_src[SORT_CHUNK];
+    __shared__ int s_wh[9][SORT_MAX_B];
+    __shared__ double s_redm[24];
+    static_assert(SORT_CHUNK <= 65536, "16-bit entry numbers");
+    int *s_bstart = &s_wh[8][0];
+    const Chunk ck = P.chunks[blockIdx.x];
+    const int h = ck.halo, B = P.R + 1;
+    const int N = P.size[h];
+    const int64_t first = P.G.off[h], pbase = P.G.poff[h];
+    const int end = min(N, ck.start + SORT_CHUNK);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 9 * SORT_MAX_B; i += blockDim.x) (&s_wh[0][0])[i] = 0;
+    __syncthreads();
+    // every warp owns a contiguous eighth of the chunk, so that "earlier warp" == "earlier in the catalogue"
+    constexpr int PER_WARP = SORT_CHUNK / 8, ROUNDS = PER_WARP / 32;
+    const int w_lo = ck.start + warp * PER_WARP;
+    int bk[ROUNDS];
+    unsigned pe[ROUNDS];   // lanes of the warp with the same bucket in this round (kept for the ranking below)
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        const int i = w_lo + r * 32 + lane;
+        bk[r] = (i < end) ? (int)P.bucket[first + i] : -1;
+    }
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+#if CPG_GATHER_BALLOT
+        {   // the lanes with the same 9-bit key (bucket, or all ones for "no particle"), from one ballot per key bit
+            unsigned m = 0xffffffffu;
+#pragma unroll
+            for (int bit = 0; bit < 9; bit++) {
+                const bool on = (bk[r] >> bit) & 1;
+                const unsigned v = __ballot_sync(0xffffffffu, on);
+                m &= on ? v : ~v;
+            }
+            pe[r] = m;
+        }
+#else
+        pe[r] = __match_any_sync(0xffffffffu, bk[r]);
+#endif
+        if (bk[r] >= 0 && lane == __ffs(pe[r]) - 1) s_wh[warp][bk[r]] += __popc(pe[r]);
+        __syncwarp();
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < B) {   // per bucket: exclusive prefix over the warps, total into s_bstart
+        int run = 0;
+        for (int w = 0; w < 8; w++) {
+            const int t = s_wh[w][threadIdx.x];
+            s_wh[w][threadIdx.x] = run;
+            run += t;
+        }
+        s_bstart[threadIdx.x] = run;
+    }
+    __syncthreads();
+    if (warp == 0) {   // exclusive scan of the bucket totals: where each bucket starts inside the chunk
+        int carry = 0;
+        for (int k0 = 0; k0 < B; k0 += 32) {
+            const int k = k0 + lane;
+            const int t = k < B ? s_bstart[k] : 0;
+            int incl = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (k < B) s_bstart[k] = carry + incl - t;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        const int b = bk[r];
+        const unsigned peers = pe[r];
+        int rin = 0;
+        if (b >= 0) rin = s_wh[warp][b] + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+        if (b >= 0 && lane == __ffs(peers) - 1) s_wh[warp][b] += __popc(peers);
+        __syncwarp();
+        if (b >= 0) {
+            const int i = w_lo + r * 32 + lane;
+            const int lp = s_bstart[b] + rin;
+            const int gd = P.tile_hist[(size_t)blockIdx.x * B + b] + rin;
+            s_src[lp] = (unsigned short)(i - ck.start);
+            s_dest[lp] = gd;
+            if (P.dest) P.dest[first + i] = gd;
+        }
+    }
+    __syncthreads();
+    const int n = end - ck.start;
+    double msum = 0.0, mlo = 1e300, mhi = -1e300;
+#if CPG_GATHER_MLP
+    {   // all loads of the thread's SORT_CHUNK / 256 particles first, then the stores (the compiler may not move loads across
+        // the stores itself: the streams could alias the snapshot)
+        constexpr int NJ = SORT_CHUNK / 256;
+        double dxs[NJ], dys[NJ], dzs[NJ], ms[NJ];
+        int64_t os[NJ];
+#pragma unroll
+        for (int r = 0; r < NJ; r++) {
+            const int j = threadIdx.x + 256 * r;
+            if (j < n) {
+                const int i = ck.start + (int)s_src[j];
+                int64_t g;
+                load_relative(P.G, h, first, first + i, dxs[r], dys[r], dzs[r], g);
+                ms[r] = P.G.masses[g];
+                os[r] = pbase + s_dest[j];
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < NJ; r++) {
+            const int j = threadIdx.x + 256 * r;
+            if (j < n) {
+                P.G.dx[os[r]] = dxs[r]; P.G.dy[os[r]] = dys[r]; P.G.dz[os[r]] = dzs[r]; P.G.m[os[r]] = ms[r];
+                msum += ms[r];
+                mlo = fmin(mlo, ms[r]); mhi = fmax(mhi, ms[r]);
+            }
+        }
+    }
+#else
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const int i = ck.start + (int)s_src[j];
+        double dx, dy, dz;
+        int64_t g;
+        load_relative(P.G, h, first, first + i, dx, dy, dz, g);
+        const double mj = P.G.masses[g];
+        const int64_t o = pbase + s_dest[j];
+        P.G.dx[o] = dx; P.G.dy[o] = dy; P.G.dz[o] = dz; P.G.m[o] = mj;
+        msum += mj;
+        mlo = fmin(mlo, mj); mhi = fmax(mhi, mj);
+    }
+#endif
+    if (P.part_mass) {   // fixed reduction order: deterministic chunk totals
+        for (int o = 16; o > 0; o >>= 1) {
+            msum += __shfl_xor_sync(0xffffffffu, msum, o);
+            mlo = fmin(mlo, __shfl_xor_sync(0xffffffffu, mlo, o));
+            mhi = fmax(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
+        }
+        if (lane == 0) { s_redm[warp] = msum; s_redm[8 + warp] = mlo; s_redm[16 + warp] = mhi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0, lo = 1e300, hi = -1e300;
+            for (int w = 0; w < 8; w++) { t += s_redm[w]; lo = fmin(lo, s_redm[8 + w]); hi = fmax(hi, s_redm[16 + w]); }
+            P.part_mass[blockIdx.x] = t;
+            P.part_spread[blockIdx.x] = 1;
+            P.part_mminmax[2 * blockIdx.x] = lo; P.part_mminmax[2 * blockIdx.x + 1] = hi;
+        }
+    }
+    if (threadIdx.x == 0 && end == N && (N & 1)) {   // pad element of an odd-sized object
+        P.G.dx[pbase + N] = 1e150; P.G.dy[pbase + N] = 1e150; P.G.dz[pbase + N] = 1e150; P.G.m[pbase + N] = 0.0;
+    }
+}
+
+#ifndef CPG_GATHER_STAGED
+#define CPG_GATHER_STAGED 0
+#endif
+
 constexpr size_t GATHER_BUCKETED_SMEM = (size_t)SORT_CHUNK * (4 * sizeof(double) + sizeof(int)) + 9 * SORT_MAX_B * sizeof(int);
 
 // ------------------------------------------------------------------------------------------------

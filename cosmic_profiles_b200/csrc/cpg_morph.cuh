@@ -1746,6 +1746,11 @@ __global__ void __launch_bounds__(WA_THREADS, CPG_WA_MINB) morph_wasync_kernel(c
 constexpr int WD_WARPS = CPG_WD_WARPS, WD_SLOTS = CPG_WD_SLOTS, WD_STAGES = CPG_WD_STAGES;
 constexpr int WD_NSLOT = WD_WARPS * WD_SLOTS;
 
+struct DuoDesc {           // what a pass of kernel 1d needs to know about its slot's task
+    long long base, row0;
+    int npairs_task, resident, res_loaded, pad;
+};
+
 template <int S, bool SHELL, bool REDUCED, bool VDISP>
 __global__ void __launch_bounds__(WD_WARPS * 32, CPG_WD_MINB) morph_wduo_kernel(const MorphParams P)
 {
@@ -1759,13 +1764,17 @@ __global__ void __launch_bounds__(WD_WARPS * 32, CPG_WD_MINB) morph_wduo_kernel(
     __shared__ __align__(16) double s_frames[WD_NSLOT][S * F_SLOTS];
     __shared__ __align__(8) uint64_t s_bar[WD_WARPS][RING_MAX_STAGES];
     __shared__ ShellSlot s_slot[WD_NSLOT][S];
-    __shared__ SlotDesc s_desc[WD_NSLOT];
+    __shared__ DuoDesc s_desc[WD_NSLOT];
     __shared__ int s_np[WD_NSLOT][S], s_nin[WD_NSLOT][S];
     __shared__ unsigned s_am[WD_NSLOT];   // active-shell mask of every slot (0: no task)
-    __shared__ float s_rr[MAX_SORT_R];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool use_table = !SHELL && !REDUCED && P.n_eff != nullptr && P.ptab != nullptr;
     const bool use_inner = use_table || (SHELL && P.n_eff != nullptr);
+    // behind the rings (dynamic, sized by R so that three CTAs fit an SM for the usual R <= 100): the shell radii rounded
+    // up to fp32 and the prefix lengths (pairs) of every slot's object, R rounded up to 8 entries each
+    const int rpad = (P.R + 7) & ~7;
+    float *s_rr = reinterpret_cast<float *>(s_ring_d + WD_WARPS * RC::WARP_BYTES);
+    uint16_t *s_neff = reinterpret_cast<uint16_t *>(s_rr + rpad);
     if (use_inner) {
         for (int j = threadIdx.x; j < P.R; j += blockDim.x) s_rr[j] = __double2float_ru(P.rr[j]);
         __syncthreads();
@@ -1779,6 +1788,12 @@ __global__ void __launch_bounds__(WD_WARPS * 32, CPG_WD_MINB) morph_wduo_kernel(
     bool queue_done = false;
     if (lane < WD_SLOTS) s_am[warp * WD_SLOTS + lane] = 0;
     __syncwarp();
+#ifdef CPG_TASK_TRACE
+    long long tr_t0 = clock64(), tr_mark = tr_t0, tr_fill = 0, tr_pass = 0, tr_step = 0, tr_rounds = 0, tr_npass = 0, tr_nshell = 0;
+#define CPG_TR(acc) { const long long now_ = clock64(); acc += now_ - tr_mark; tr_mark = now_; }
+#else
+#define CPG_TR(acc)
+#endif
 
     for (;;) {
         // ---- refill the empty slots from the queue (dead tasks -- empty object, r200 == 0 -- are skipped)
@@ -1803,11 +1818,15 @@ __global__ void __launch_bounds__(WD_WARPS * 32, CPG_WD_MINB) morph_wduo_kernel(
                 const int k = tk.shell0 + (st.active ? L.ls : 0);
                 shell_geometry(P, halo, k, st.d, st.delta);
                 const size_t out_idx = (size_t)halo * P.R + k;
+                if (use_inner) {   // the object's prefix lengths up to the task's last shell
+                    for (int j2 = lane; j2 < tk.shell0 + tk.nshell; j2 += 32)
+                        s_neff[sl * rpad + j2] = (uint16_t)(P.n_eff[(size_t)halo * P.R + j2] >> 1);   // objects < 131072 particles
+                    __syncwarp();
+                }
                 InnerPrefix ip;
                 ip.rr = nullptr; ip.neff = nullptr;
                 ip.rr_up = use_inner ? s_rr : nullptr;
-                ip.npairs16 = nullptr;
-                ip.neff_g = P.n_eff ? P.n_eff + (size_t)halo * P.R : nullptr;
+                ip.npairs16 = s_neff + sl * rpad;
                 init_frames<SHELL>(s_frames[sl], s_np[sl], s_nin[sl], L, st, (P.n_eff && st.active) ? P.n_eff[out_idx] : N, ip, k);
                 if (L.writer) {
                     ShellSlot &ss = s_slot[sl][L.ls];
@@ -1822,7 +1841,7 @@ __global__ void __launch_bounds__(WD_WARPS * 32, CPG_WD_MINB) morph_wduo_kernel(
                 const int npt = active_npairs<S>(npr0, amj);
                 if (lane == 0) {
                     s_am[sl] = amj;
-                    SlotDesc &d = s_desc[sl];
+                    DuoDesc &d = s_desc[sl];
                     d.base = base; d.row0 = (base >> 7) + halo; d.npairs_task = npt;
                     d.resident = ((npt + TILE_PAIRS - 1) / TILE_PAIRS <= RING_MAX_STAGES / WD_SLOTS) ? 1 : 0;
                     d.res_loaded = 0;
@@ -1832,6 +1851,7 @@ __global__ void __launch_bounds__(WD_WARPS * 32, CPG_WD_MINB) morph_wduo_kernel(
             any = any || amj != 0;
         }
         if (!any) break;
+        CPG_TR(tr_fill)
 
         // ---- one pass per live slot; each leaves its 8 S sums transposed in one register
         // (ONE copy of the pass in the instruction stream: the loop over the slots is not unrolled, the slots' sums are
@@ -1847,7 +1867,7 @@ __global__ void __launch_bounds__(WD_WARPS * 32, CPG_WD_MINB) morph_wduo_kernel(
                 int npr[S];
 #pragma unroll
                 for (int s = 0; s < S; s++) npr[s] = s_np[sl][s];
-                const SlotDesc d = s_desc[sl];
+                const DuoDesc d = s_desc[sl];
                 // the other slot's resident tiles stay where they are: stream through this slot's half of the ring then
                 const int so = warp * WD_SLOTS + (j ^ 1);
                 const bool other_res = s_am[so] != 0 && s_desc[so].resident != 0;
@@ -1868,6 +1888,11 @@ __global__ void __launch_bounds__(WD_WARPS * 32, CPG_WD_MINB) morph_wduo_kernel(
             }
         }
         __syncwarp();
+        CPG_TR(tr_pass)
+#ifdef CPG_TASK_TRACE
+        tr_rounds++;
+        for (int j = 0; j < WD_SLOTS; j++) { const unsigned m_ = s_am[warp * WD_SLOTS + j]; tr_npass += m_ ? 1 : 0; tr_nshell += __popc(m_); }
+#endif
 
         // ---- one step for the shells of all slots: lane l serves shell l % S of slot l / S
         {
@@ -1908,8 +1933,7 @@ __global__ void __launch_bounds__(WD_WARPS * 32, CPG_WD_MINB) morph_wduo_kernel(
             InnerPrefix ip;
             ip.rr = nullptr; ip.neff = nullptr;
             ip.rr_up = use_inner ? s_rr : nullptr;
-            ip.npairs16 = nullptr;
-            ip.neff_g = P.n_eff ? P.n_eff + (out_idx - (size_t)k) : nullptr;
+            ip.npairs16 = s_neff + sl * rpad;
             katz_step<SHELL>(st, tot, pts, P, vprev, s_frames[sl] + sh * F_SLOTS, valid, out_idx, valid, ip, k, &s_nin[sl][sh]);
             if (valid) {
                 ShellSlot &ss = s_slot[sl][sh];
@@ -1920,9 +1944,22 @@ __global__ void __launch_bounds__(WD_WARPS * 32, CPG_WD_MINB) morph_wduo_kernel(
             if (lane < WD_SLOTS) s_am[warp * WD_SLOTS + lane] = (b >> (lane * S)) & ((1u << S) - 1u);
             __syncwarp();
         }
+        CPG_TR(tr_step)
         if (ring.st_tiles > (1u << 20)) ring_flush_stats(ring, P.stats, lane);
     }
     ring_flush_stats(ring, P.stats, lane);
+#ifdef CPG_TASK_TRACE
+    if (lane == 0 && P.stats) {
+        atomicAdd(P.stats + 2, (unsigned long long)(clock64() - tr_t0));
+        atomicAdd(P.stats + 3, (unsigned long long)tr_pass);
+        atomicAdd(P.stats + 4, (unsigned long long)tr_fill);
+        atomicAdd(P.stats + 5, (unsigned long long)tr_step);
+        atomicAdd(P.stats + 8, (unsigned long long)tr_rounds);
+        atomicAdd(P.stats + 10, (unsigned long long)tr_npass);
+        atomicAdd(P.stats + 12, (unsigned long long)tr_nshell);
+    }
+#endif
+#undef CPG_TR
 }
 
 // ------------------------------------------------------------------------------------------------

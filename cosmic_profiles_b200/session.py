@@ -11,7 +11,7 @@ devices = None          # list of CUDA device ordinals to shard objects over; No
 gpu_centers = True      # centres on the device (cpg_centers); False: the reference's numpy arithmetic on the host
 options = {}            # forwarded to cpg_set_option on every context (e.g. {"shells_per_pass": 4})
 DEFAULT_OPTIONS = {"shells_per_pass": 0, "large_halo_min": 0, "cluster_size": 0, "radial_order": 1, "shell_groups": 0, "grid_halo_min": 0,
-                   "prefix_table": 1, "upload_threads": 8, "direct_results": 1, "snapshot_cache": 1, "detect_ranges": 1, "batched_step": 0}
+                   "prefix_table": 1, "upload_threads": 8, "direct_results": 1, "snapshot_cache": 1, "detect_ranges": 1, "batched_step": 0, "async_step": 2}
 
 
 allow_duplicate_devices = False   # tests on a single-GPU box: several slots of a cpg_multi handle on one device

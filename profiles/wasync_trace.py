@@ -36,3 +36,7 @@ print("pass warps: total %.3g cycles, in passes %.1f %%, waiting / fetching %.1f
       % (w[2], 100.0 * w[3] / max(w[2], 1), 100.0 * w[4] / max(w[2], 1), w[10], w[3] / max(w[10], 1), w[11]))
 print("step warps: total %.3g cycles, busy %.1f %%; %d batches (%.0f cycles each), %.2f slots per batch"
       % (w[6], 100.0 * w[7] / max(w[6], 1), w[8], w[7] / max(w[8], 1), w[9] / max(w[8], 1)))
+if w[5]:
+    print("kernel 1d: total %.3g warp-cycles: passes %.1f %%, steps %.1f %%, refill %.1f %%; %d rounds, %.2f passes and %.2f shells per round; "
+          "%.0f cycles per pass, %.0f per step, %.0f refill per round"
+          % (w[2], 100.0 * w[3] / w[2], 100.0 * w[5] / w[2], 100.0 * w[4] / w[2], w[8], w[10] / w[8], w[12] / w[8], w[3] / w[10], w[5] / w[8], w[4] / w[8]))

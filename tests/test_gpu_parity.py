@@ -129,10 +129,19 @@ SCHED = [dict(shells_per_pass=1, large_halo_min=1 << 40, cluster_size=0),     # 
          dict(shells_per_pass=4, shell_groups=2, large_halo_min=8000, cluster_size=2, radial_order=0),
          dict(shells_per_pass=4, large_halo_min=1 << 40, cluster_size=0, grid_halo_min=2000),   # grid-per-iteration path
          dict(shells_per_pass=2, large_halo_min=1 << 40, cluster_size=0, grid_halo_min=6000, radial_order=0),
-         dict(shells_per_pass=4, large_halo_min=4000, cluster_size=2, prefix_table=0)]   # radial order, no prefix table
+         dict(shells_per_pass=4, large_halo_min=4000, cluster_size=2, prefix_table=0),   # radial order, no prefix table
+         # warp kernel 1d (two task slots per warp share one step; forced: the default takes it for long queues only)
+         dict(shells_per_pass=4, large_halo_min=1 << 40, cluster_size=0, async_step=3),
+         dict(shells_per_pass=2, large_halo_min=1 << 40, cluster_size=0, async_step=3, radial_order=0),
+         dict(shells_per_pass=1, large_halo_min=1 << 40, cluster_size=0, async_step=3),
+         dict(shells_per_pass=4, large_halo_min=5000, cluster_size=2, async_step=3, prefix_table=0),
+         # warp kernel 1c (pass warps + asynchronous step warp), kernel 1 (a warp per task, its own step)
+         dict(shells_per_pass=4, large_halo_min=1 << 40, cluster_size=0, async_step=1),
+         dict(shells_per_pass=2, large_halo_min=1 << 40, cluster_size=0, async_step=1, radial_order=0),
+         dict(shells_per_pass=4, large_halo_min=1 << 40, cluster_size=0, async_step=0)]
 
 
-@pytest.mark.parametrize("sched", SCHED, ids=lambda s: "S%d_L%d_C%d_R%d_G%d_grid%d" % (s["shells_per_pass"], min(s["large_halo_min"], 99999), s["cluster_size"], s.get("radial_order", 1), s.get("shell_groups", 0), s.get("grid_halo_min", 0)) + ("_notable" if s.get("prefix_table", 1) == 0 else ""))
+@pytest.mark.parametrize("sched", SCHED, ids=lambda s: "S%d_L%d_C%d_R%d_G%d_grid%d" % (s["shells_per_pass"], min(s["large_halo_min"], 99999), s["cluster_size"], s.get("radial_order", 1), s.get("shell_groups", 0), s.get("grid_halo_min", 0)) + ("_notable" if s.get("prefix_table", 1) == 0 else "") + ("_async%d" % s["async_step"] if "async_step" in s else ""))
 def test_oracle_shapes_all_schedules(gpu, big, sched):
     S, D, sess = gpu
     cat, rr, cen, _ = big
