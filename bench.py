@@ -694,7 +694,7 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None
         traffic_src = None
-        for fn in ("r2_traffic.json", "r1d_traffic.json"):   # DRAM bytes of the local-shape kernels under ncu, same workload
+        for fn in ("r3_traffic.json", "r2_traffic.json", "r1d_traffic.json"):   # DRAM bytes of the local-shape kernels under ncu, same workload
             try:
                 tr = json.load(open(os.path.join(ROOT, "profiles", fn)))
                 if int(tr.get("workload_halos", -1)) == a.halos and world == 1:
@@ -705,9 +705,10 @@ def main():
                 pass
         pipe_occ = None
         try:   # ncu: sm__inst_executed_pipe_fp64 of the two local-shape kernels / the microbenchmark's ceiling in the same units
-            po = json.load(open(os.path.join(ROOT, "profiles", "r2_fp64_pipe.json")))
+            pf = "r3_fp64_pipe.json" if os.path.exists(os.path.join(ROOT, "profiles", "r3_fp64_pipe.json")) else "r2_fp64_pipe.json"
+            po = json.load(open(os.path.join(ROOT, "profiles", pf)))
             pipe_occ = {"warp_kernel": po["warp_kernel_pct"] / po["dfma_ceiling_pct"],
-                        "cluster_kernel": po["cluster_kernel_pct"] / po["dfma_ceiling_pct"], "source": "profiles/r2_fp64_pipe.json"}
+                        "cluster_kernel": po["cluster_kernel_pct"] / po["dfma_ceiling_pct"], "source": "profiles/" + pf}
         except Exception:
             pass
         kern_mean = kern_sum / world
@@ -733,7 +734,7 @@ def main():
                 "roofline": {"bound": "fp64", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
                              "frac": achieved_tflops / peak_tflops if peak_tflops else None, "traffic": traffic,
                              "traffic_source": traffic_src,
-                             "kernel": "morph_warp_kernel/morph_cluster_kernel (local shapes)",
+                             "kernel": "morph_wduo_kernel/morph_cluster_kernel (local shapes)",
                              "peak_source": "measured in this run: cpg_measure_fp64_peak (independent DFMA chains on every SM, "
                                             "CUDA events), x2 flop per multiply-add (of measured)",
                              "fp64_fma_per_launch_set": fma_all / world,

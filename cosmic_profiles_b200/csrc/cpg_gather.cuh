@@ -460,8 +460,10 @@ __global__ void __launch_bounds__(256) bucket_hist_kernel(const SortParams P)
 // the prefix lengths n_eff.  A warp per object, lanes over buckets.
 __global__ void __launch_bounds__(256) bucket_scan_kernel(const SortParams P, int n_obj)
 {
-    // A CTA per object: warp w owns buckets w, w + 8, ...; its lanes run over the object's chunks 32 at a time (an
-    // object of 10^6 particles has ~10^3 chunks: one warp walking them bucket group by bucket group was a 0.35 ms tail).
+    // A CTA per object.  The (chunk, bucket) histogram of the object is row-major in the chunk: the warps split the
+    // object's chunks into 8 contiguous segments and walk them row by row with the LANES OVER THE BUCKETS (coalesced rows,
+    // independent loads; lanes over chunks read one word per 284-byte row and made an object of 10^3 chunks a 0.27 ms tail).
+    __shared__ int s_part[8][SORT_MAX_B];
     __shared__ int s_tot[SORT_MAX_B], s_start[SORT_MAX_B];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = blockIdx.x;
@@ -469,11 +471,27 @@ __global__ void __launch_bounds__(256) bucket_scan_kernel(const SortParams P, in
     const int R = P.R, B = R + 1;
     const int c0 = P.chunk_first[h], c1 = P.chunk_first[h + 1];
     if (c1 - c0 > BIG_OBJECT_CHUNKS) return;   // the three segment kernels below
-    for (int b = warp; b < B; b += 8) {
+    const int per = (c1 - c0 + 7) / 8;
+    const int s0 = min(c1, c0 + warp * per), s1 = min(c1, s0 + per);   // this warp's chunks
+    constexpr int NB = SORT_MAX_B / 32;                               // buckets per lane: b = lane + 32 j
+    int sum[NB];
+#pragma unroll
+    for (int j = 0; j < NB; j++) sum[j] = 0;
+#pragma unroll 4
+    for (int c = s0; c < s1; c++) {
+        const int32_t *row = P.tile_hist + (size_t)c * B;
+#pragma unroll
+        for (int j = 0; j < NB; j++)
+            if (lane + 32 * j < B) sum[j] += row[lane + 32 * j];
+    }
+#pragma unroll
+    for (int j = 0; j < NB; j++)
+        if (lane + 32 * j < B) s_part[warp][lane + 32 * j] = sum[j];
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
         int tot = 0;
-        for (int c = c0 + lane; c < c1; c += 32) tot += P.tile_hist[(size_t)c * B + b];
-        tot = __reduce_add_sync(0xffffffffu, tot);
-        if (lane == 0) s_tot[b] = tot;
+        for (int w = 0; w < 8; w++) tot += s_part[w][b];
+        s_tot[b] = tot;
     }
     __syncthreads();
     if (warp == 0) {   // exclusive scan over the buckets: where each bucket starts inside the object
@@ -493,19 +511,29 @@ __global__ void __launch_bounds__(256) bucket_scan_kernel(const SortParams P, in
         }
     }
     __syncthreads();
-    for (int b = warp; b < B; b += 8) {   // per chunk: offset of its share of bucket b (chunk order = catalogue order)
-        int run = s_start[b];
-        for (int cb = c0; cb < c1; cb += 32) {
-            const int c = cb + lane;
-            const int t = c < c1 ? P.tile_hist[(size_t)c * B + b] : 0;
-            int incl = t;
+    // per chunk: offset of its share of bucket b (chunk order = catalogue order): bucket start + earlier segments + the
+    // running count inside this warp's segment
+    int run[NB];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
+    for (int j = 0; j < NB; j++) {
+        run[j] = 0;
+        const int b = lane + 32 * j;
+        if (b < B) {
+            run[j] = s_start[b];
+            for (int w = 0; w < warp; w++) run[j] += s_part[w][b];
+        }
+    }
+#pragma unroll 4
+    for (int c = s0; c < s1; c++) {
+        int32_t *row = P.tile_hist + (size_t)c * B;
+#pragma unroll
+        for (int j = 0; j < NB; j++) {
+            const int b = lane + 32 * j;
+            if (b < B) {
+                const int t = row[b];
+                row[b] = run[j];
+                run[j] += t;
             }
-            if (c < c1) P.tile_hist[(size_t)c * B + b] = run + incl - t;
-            run += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
 }
@@ -710,7 +738,7 @@ __global__ void __launch_bounds__(256) gather_bucketed_kernel(const SortParams P
 #define CPG_GATHER_MINB 8   // 32 registers: 64 resident warps per SM (measured: gather 3.18 -> 2.99 ms on configs[1])
 #endif
 #ifndef CPG_GATHER_BALLOT
-#define CPG_GATHER_BALLOT 0
+#define CPG_GATHER_BALLOT 1   // peers from one ballot per key bit instead of MATCH.ANY (measured: gather 2.99 -> 2.91 ms)
 #endif
 __global__ void __launch_bounds__(256, CPG_GATHER_MINB) gather_bucketed2_kernel(const SortParams P)
 {

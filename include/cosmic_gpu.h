@@ -300,6 +300,15 @@ CPG_API int cpg_multi_get_info(cpg_multi *m, int32_t slot, int32_t *device, int3
  *   "shells_per_pass"  1,2,4 or 0=auto   how many shells of one object share one read of its particles
  *   "shell_groups"     1 (default, also 0) or 2 groups of 4 shells per warp task: the groups are passed over one after
  *                      the other and share one reduction / eigen-solve step per Katz iteration (slower on configs[1])
+ *   "async_step"       which warp kernel serves the objects below "large_halo_min" (position shapes; same results):
+ *                      2 (default): kernel 1d when the call has >= 8 x 12 x SMs tasks -- every warp works on TWO tasks at a
+ *                      time and runs one eigen-solve / convergence step for the shells of both (one lane per shell), so the
+ *                      serial chain of the step is paid once per two task-iterations (configs[1]: local-shape kernels
+ *                      17.5 -> 17.0 ms) -- and kernel 1 (a warp per task, its own step) for shorter queues and for the
+ *                      velocity-dispersion variant; 3: kernel 1d whatever the queue length; 1: kernel 1c, five "pass" warps
+ *                      per CTA that only stream particles and hand their sums to one "step" warp through shared memory
+ *                      (measured 17.45 - 18.1 ms: the step leaves the pass warps' chain, but a twelfth of the warps no longer
+ *                      streams and the pass warps wait 19 % of the time for the step warp); 0: kernel 1 always
  *   "batched_step"     1: the warps of a CTA of the warp kernel meet once per Katz iteration and ONE of them runs the
  *                      eigen-solve / convergence step for all their shells (16 useful lanes per fp64 instruction instead
  *                      of 4).  Same results; measured slower (22.2 against 19.2 ms on configs[1]: the wait for one another

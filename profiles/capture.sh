@@ -12,6 +12,6 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 fi
 if [ "$what" != launches ]; then
 # a step launches cluster<4>, warp<4> (local shapes) then cluster<1>, warp<1> (global shape); -s 12 = 4th step
-ncu --set full --clock-control none --import-source on -k 'regex:morph_(warp|cluster)_kernel' -s 12 -c 2 -f -o gpurun_out/${tag}_morph $B > gpurun_out/${tag}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k 'regex:morph_(warp|wduo|wasync|cluster)_kernel' -s 12 -c 2 -f -o gpurun_out/${tag}_morph $B > gpurun_out/${tag}_ncu_full.log 2>&1
 fi
 ls -la gpurun_out
