@@ -1718,7 +1718,13 @@ CPG_API int cpg_fit_profiles(cpg_ctx *c, const double *radii, const double *lmed
     // NFW: half as many objects in flight outweighs the shorter evaluation.  The template parameter is kept.)
     const int W = 1;
     const int grid = (n_obj + FIT_WARPS / W - 1) / (FIT_WARPS / W);
-#define CPG_FIT_LAUNCH(NP, WW) fit_profiles_kernel<NP, WW><<<grid, FIT_WARPS * 32, 0, c->stream>>>(Q)
+    const int fit_smem = 3 * (FIT_WARPS / W) * ((R + 1) & ~1) * (int)sizeof(double);   // 12 KB at 128 bins, 96 KB at 1024
+#define CPG_FIT_LAUNCH(NP, WW)                                                                                              \
+    do {                                                                                                                    \
+        if (fit_smem > 48 * 1024)                                                                                           \
+            CPG_CUDA(cudaFuncSetAttribute(fit_profiles_kernel<NP, WW>, cudaFuncAttributeMaxDynamicSharedMemorySize, fit_smem)); \
+        fit_profiles_kernel<NP, WW><<<grid, FIT_WARPS * 32, fit_smem, c->stream>>>(Q);                                      \
+    } while (0)
     if (W == 1) {
         if (npar == 2) CPG_FIT_LAUNCH(2, 1); else if (npar == 3) CPG_FIT_LAUNCH(3, 1); else CPG_FIT_LAUNCH(5, 1);
     } else {

@@ -5,7 +5,7 @@
 // bounds=...) over the objects in a process pool; the minimiser is scipy's (1.18.1, scipy/optimize/_optimize.py):
 // _minimize_powell with _linesearch_powell / _line_for_search / _minimize_scalar_bounded.  Here one WARP (two for
 // more than 32 bins) fits one object: the Powell / fmin control flow is uniform over its lanes (every lane carries the
-// same scalars), the n <= 128 terms of the objective are spread over the lanes and summed in NumPy's pairwise order, so that every function value is the
+// same scalars), the n <= 1024 terms of the objective are spread over the lanes and summed in NumPy's pairwise order (blocks of 128, halved recursively), so that every function value is the
 // reference's up to the last-bit differences between CUDA's and NumPy's log / pow / exp / tan.
 //
 // Arithmetic is written with explicit round-to-nearest intrinsics: no FMA contraction (Python floats and NumPy
@@ -15,7 +15,8 @@
 
 namespace cpg {
 
-constexpr int FIT_MAX_BINS = 128;   // NumPy's pairwise sum is a single block up to 128 elements
+constexpr int FIT_MAX_BINS = 1024;   // bins per profile (shared memory: 3 arrays of R doubles per object)
+constexpr int FIT_PW_BLOCK = 128;    // NumPy's pairwise sum is a single block up to 128 elements (PW_BLOCKSIZE)
 constexpr int FIT_WARPS = 4;        // warps per CTA (4 objects, or 2 objects of two warps each)
 enum { FIT_NFW = 0, FIT_HERNQUIST = 1, FIT_EINASTO = 2, FIT_ABG = 3 };
 
@@ -88,6 +89,40 @@ struct Problem {
     bool aborted;           // scipy's _MaxFuncCallError
     double lb[N], ub[N];
 
+    // NumPy's pairwise sum (numpy/_core/src/umath/loops_utils.h.src) of a[0..n): one block of at most 128 elements --
+    // n < 8 sequential, else 8 accumulators (lane j & 7 carries accumulator j), a fixed combine tree, a sequential tail
+    __device__ double pw_block(const double *a, int n) const
+    {
+        double res;
+        if (n < 8) {
+            res = n > 0 ? a[0] : 0.0;
+            for (int i = 1; i < n; i++) res = add(res, a[i]);
+        } else {
+            const int j = lane & 7;
+            double r = a[j];
+            int i = 8;
+            for (; i < n - (n % 8); i += 8) r = add(r, a[i + j]);
+            const double r0 = __shfl_sync(0xffffffffu, r, 0), r1 = __shfl_sync(0xffffffffu, r, 1);
+            const double r2 = __shfl_sync(0xffffffffu, r, 2), r3 = __shfl_sync(0xffffffffu, r, 3);
+            const double r4 = __shfl_sync(0xffffffffu, r, 4), r5 = __shfl_sync(0xffffffffu, r, 5);
+            const double r6 = __shfl_sync(0xffffffffu, r, 6), r7 = __shfl_sync(0xffffffffu, r, 7);
+            res = add(add(add(r0, r1), add(r2, r3)), add(add(r4, r5), add(r6, r7)));
+            for (; i < n; i++) res = add(res, a[i]);
+        }
+        return res;
+    }
+
+    // ... and longer arrays: split at n2 = n / 2 rounded down to a multiple of 8, the two halves summed recursively
+    // (depth 3 at FIT_MAX_BINS; uniform over the lanes)
+    __device__ double pw_sum(const double *a, int n) const
+    {
+        if (n <= FIT_PW_BLOCK) return pw_block(a, n);
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        const double lo = pw_sum(a, n2);
+        return add(lo, pw_sum(a + n2, n - n2));
+    }
+
     // toMinimize (dens_profs_tools.py:227-230) behind scipy's call counter; np.sum in NumPy's pairwise order
     __device__ double eval(const double (&x)[N])
     {
@@ -103,22 +138,7 @@ struct Problem {
             terms[i] = dvd(mul(t, t), dn);
         }
         obj_sync();
-        double res;
-        if (n < 8) {
-            res = n > 0 ? terms[0] : 0.0;
-            for (int i = 1; i < n; i++) res = add(res, terms[i]);
-        } else {
-            const int j = lane & 7;
-            double r = terms[j];
-            int i = 8;
-            for (; i < n - (n % 8); i += 8) r = add(r, terms[i + j]);
-            const double r0 = __shfl_sync(0xffffffffu, r, 0), r1 = __shfl_sync(0xffffffffu, r, 1);
-            const double r2 = __shfl_sync(0xffffffffu, r, 2), r3 = __shfl_sync(0xffffffffu, r, 3);
-            const double r4 = __shfl_sync(0xffffffffu, r, 4), r5 = __shfl_sync(0xffffffffu, r, 5);
-            const double r6 = __shfl_sync(0xffffffffu, r, 6), r7 = __shfl_sync(0xffffffffu, r, 7);
-            res = add(add(add(r0, r1), add(r2, r3)), add(add(r4, r5), add(r6, r7)));
-            for (; i < n; i++) res = add(res, terms[i]);
-        }
+        const double res = n <= FIT_PW_BLOCK ? pw_block(terms, n) : pw_sum(terms, n);
         obj_sync();   // nobody overwrites the terms before every warp has summed them
         return res;
     }
@@ -361,9 +381,8 @@ template <int N, int W>
 __global__ void __launch_bounds__(FIT_WARPS * 32) fit_profiles_kernel(const FitParams Q)
 {
     constexpr int OBJS = FIT_WARPS / W;   // objects per CTA
-    __shared__ double s_terms[OBJS][FIT_MAX_BINS];
-    __shared__ double s_radii[OBJS][FIT_MAX_BINS];
-    __shared__ double s_lmed[OBJS][FIT_MAX_BINS];
+    extern __shared__ __align__(16) double s_fit[];   // terms, radii, ln(median) of every object: 3 x OBJS rows of R (even) doubles
+    const int rpad = (Q.R + 1) & ~1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int slot = warp / W, sub = warp % W;
     const int obj = blockIdx.x * OBJS + slot;
@@ -372,11 +391,11 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) fit_profiles_kernel(const FitP
     P.n = Q.n_valid[obj];
     P.lane = lane; P.tid = sub * 32 + lane; P.nthreads = 32 * W; P.bar_id = 1 + slot;
     for (int i = P.tid; i < P.n; i += P.nthreads) {
-        s_radii[slot][i] = Q.radii[(size_t)obj * Q.R + i];
-        s_lmed[slot][i] = Q.lmed[(size_t)obj * Q.R + i];
+        s_fit[(OBJS + slot) * rpad + i] = Q.radii[(size_t)obj * Q.R + i];
+        s_fit[(2 * OBJS + slot) * rpad + i] = Q.lmed[(size_t)obj * Q.R + i];
     }
     P.obj_sync();
-    P.radii = s_radii[slot]; P.lmed = s_lmed[slot]; P.terms = s_terms[slot];
+    P.radii = s_fit + (OBJS + slot) * rpad; P.lmed = s_fit + (2 * OBJS + slot) * rpad; P.terms = s_fit + slot * rpad;
     P.profile = Q.profile; P.ncalls = 0; P.maxfun = N * 1000; P.aborted = false;
     double x[N];
 #pragma unroll

@@ -15,7 +15,7 @@ from ._lib import CosmicGpuError
 
 PROFILE_ID = {"nfw": 0, "hernquist": 1, "einasto": 2, "alpha_beta_gamma": 3}
 NPARS = {"nfw": 2, "hernquist": 2, "einasto": 3, "alpha_beta_gamma": 5}
-MAX_BINS = 128
+MAX_BINS = 1024
 last_info = {}
 
 

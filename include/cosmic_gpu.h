@@ -223,7 +223,7 @@ CPG_API int cpg_get_particles(cpg_ctx *ctx, double *xyz, double *vxyz, double *m
  * (rho_s, alpha, beta, gamma, r_s).  Inputs as the reference prepares them in NumPy (:254-258, :277):
  * radii (n_obj,R) = ROverR200 * r200 and lmed (n_obj,R) = log(median / average(median)), NaN bins removed and the
  * n_valid[p] kept values stored first; avg (n_obj) = average(median); x0 (n_obj,npar) initial guesses; lb / ub
- * (npar) bounds, ub = +inf where free (every lb finite).  R <= 128.
+ * (npar) bounds, ub = +inf where free (every lb finite).  R <= 1024 (NumPy's pairwise summation order restated: blocks of 128, halved recursively).
  * Outputs: best (n_obj,npar) with best[:,0] multiplied by avg (:320); fun (n_obj) final psi^2, nfev, nit (n_obj)
  * function evaluations / Powell iterations as scipy counts them (any may be NULL except best).
  */

@@ -24,16 +24,19 @@ NPARS = {"nfw": 2, "hernquist": 2, "einasto": 3, "alpha_beta_gamma": 5}
 
 
 def pairwise_sum(a):
-    """numpy's float64 add.reduce over a contiguous 1-D array of n <= 128 elements (pairwise_sum in
-    numpy/_core/src/umath/loops_utils.h.src): n < 8 sequential; else 8 accumulators, a fixed combine tree and a
-    sequential remainder."""
+    """numpy's float64 add.reduce over a contiguous 1-D array (pairwise_sum in numpy/_core/src/umath/loops_utils.h.src):
+    n < 8 sequential; n <= 128 (PW_BLOCKSIZE) 8 accumulators, a fixed combine tree and a sequential remainder; longer
+    arrays are split at n2 = n / 2 rounded down to a multiple of 8 and the two halves summed recursively."""
     n = len(a)
+    if n > 128:
+        n2 = n // 2
+        n2 -= n2 % 8
+        return pairwise_sum(a[:n2]) + pairwise_sum(a[n2:])
     if n < 8:
         res = 0.0 if n == 0 else a[0]     # reduce starts from the first element ... (-0.0 + x identities aside)
         for i in range(1, n):
             res += a[i]
         return res
-    assert n <= 128
     r = [a[j] for j in range(8)]
     i = 8
     while i < n - (n % 8):

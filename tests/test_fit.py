@@ -46,7 +46,7 @@ def test_oracle_reproduces_reference_fits(case):
 
 def test_pairwise_sum_is_numpys():
     rng = np.random.default_rng(0)
-    for n in list(range(0, 20)) + [31, 32, 33, 40, 64, 100, 127, 128]:
+    for n in list(range(0, 20)) + [31, 32, 33, 40, 64, 100, 127, 128, 129, 130, 136, 137, 200, 255, 256, 257, 300, 513, 1000, 1024]:
         a = rng.normal(size=n) * 10.0 ** rng.integers(-8, 8, size=n)
         assert F.pairwise_sum([float(v) for v in a]) == float(np.sum(a)), n
 
@@ -115,7 +115,7 @@ def test_gpu_fits_golden(case):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nbins", [5, 8, 33, 70])
+@pytest.mark.parametrize("nbins", [5, 8, 33, 70, 150, 300])
 def test_gpu_fits_vs_restatement_bin_counts(nbins):
     """Bin counts on both sides of NumPy's pairwise-sum regimes (n < 8 sequential; 8 accumulators; a remainder) and
     of the 32-lane round boundary, against the CPU restatement (which is pinned to the reference)."""
