@@ -807,15 +807,24 @@ int launch_morph(cpg_ctx *c, MorphParams P, int n_warp_tasks, int n_cluster_task
         c->timing.hot_kernel_launches++;
     }
     // kernel 1d keeps two tasks per warp: only worth it when the queue is long enough to keep every slot of the GPU busy
-    const bool duo = n_warp_tasks >= 8 * c->sm_count * 12 || c->opt_async_step == 3;
-    if (n_warp_tasks > 0 && G == 1 && !VDISP && (c->opt_async_step == 2 || c->opt_async_step == 3) && duo) {
+    bool duo = n_warp_tasks > 0 && G == 1 && !VDISP &&
+               ((c->opt_async_step == 2 && n_warp_tasks >= 8 * c->sm_count * 12) || c->opt_async_step == 3);
+    int duo_per_sm = 0;
+    const int duo_smem = WD_WARPS * RingCfg<false, RING_MAX_STAGES>::WARP_BYTES + ((P.R + 7) & ~7) * (int)(sizeof(float) + WD_NSLOT * sizeof(uint16_t));
+    if (duo) {
         auto kern = morph_wduo_kernel<S, SHELL, REDUCED, false>;
-        const int smem = WD_WARPS * RingCfg<false, RING_MAX_STAGES>::WARP_BYTES + ((P.R + 7) & ~7) * (int)(sizeof(float) + WD_NSLOT * sizeof(uint16_t));
-        CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int per_sm = 0;
+        CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, duo_smem));
         CPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, WD_WARPS * 32, smem));
-        if (getenv("CPG_DEBUG")) fprintf(stderr, "[cpg] morph_wduo_kernel: %d CTAs per SM (smem %d dynamic)\n", per_sm, smem);
+        CPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&duo_per_sm, kern, WD_WARPS * 32, duo_smem));
+        if (getenv("CPG_DEBUG")) fprintf(stderr, "[cpg] morph_wduo_kernel: %d CTAs per SM (smem %d dynamic)\n", duo_per_sm, duo_smem);
+        // the radii / prefix-length tables grow with R: above R ~ 100 only two CTAs (8 warps) fit an SM, and kernel 1 with its 12
+        // warps is the faster one (measured: 19.7 against 17.5 ms on configs[1])
+        if (duo_per_sm < CPG_WD_MINB && c->opt_async_step == 2) duo = false;
+    }
+    if (duo) {
+        auto kern = morph_wduo_kernel<S, SHELL, REDUCED, false>;
+        const int smem = duo_smem;
+        int per_sm = duo_per_sm;
         if (per_sm < 1) per_sm = 1;
         if (c->opt_warp_ctas_per_sm > 0) per_sm = std::min(per_sm, c->opt_warp_ctas_per_sm);
         const int grid = std::min((n_warp_tasks + WD_NSLOT - 1) / WD_NSLOT, c->sm_count * per_sm);

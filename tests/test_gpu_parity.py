@@ -281,11 +281,16 @@ def test_unusual_radii_and_limits(gpu, big):
         (np.logspace(-1.2, 0, 300), 1e-2, 100, 10),                   # R > 255
         (np.logspace(-1.5, 0, 9), 1e-3, 4, 10),                       # IT_WALL hit by most shells
         (np.logspace(-1.5, 0, 9), 1e-2, 100, 2500),                   # IT_MIN rejects the inner shells
+        (np.logspace(-1.2, 0, 200), 1e-2, 100, 10, dict(async_step=3)),  # kernel 1d with its largest radius / prefix tables
+        (np.array([0.7]), 1e-2, 100, 10, dict(async_step=3)),         # ... and one shell per task slot
     ]
     sub = slice(3, 12)   # a few mid-size objects keep the R=300 case cheap for the CPU oracle
     off = cat["offsets"]
     idx = I[off[3]:off[12]]
-    for rr, tol, wall, itmin in cases:
+    for case in cases:
+        rr, tol, wall, itmin = case[:4]
+        sess.options.clear()
+        sess.options.update(case[4] if len(case) > 4 else {})
         for shell in (False, True):
             ref, (nit, npt, _, _) = O.morph(X, None, M, R2[sub], idx, Z[sub], 0.0, rr, tol, wall, itmin, "com", False,
                                             shell, True, centers=cen[sub])
@@ -295,6 +300,7 @@ def test_unusual_radii_and_limits(gpu, big):
             P.assert_ints(S.last_info["n_iter"], nit, tag + " n_iter")
             P.assert_ints(S.last_info["n_pts"], npt, tag + " n_pts")
             P.assert_shape_tuple(got, ref, tag)
+    sess.options.clear()
 
 
 def test_device_centres_large_objects(gpu):
