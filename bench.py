@@ -756,7 +756,8 @@ def main():
                                      "two kernels under ncu / what a pure DFMA stream reads on the same counter (92 %): about half; the "
                                      "per-iteration eigen-solves and the compares share that half with the streaming loop.  The kernels are "
                                      "bound by the dependency chain of each warp (12 resident warps per SM at 168 registers, stall reason "
-                                     "'wait' 63 %), not by the pipe: profiles/README.md.  hbm.physical = DRAM bytes under ncu / kernel time; "
+                                     "'wait' 51 %, instruction fetch 10 %; every warp of the default kernel 1d works on two tasks and pays "
+                                     "the eigen-solve step once for both), not by the pipe: profiles/README.md.  hbm.physical = DRAM bytes under ncu / kernel time; "
                                      "hbm.algorithmic = 32 B x particle-iterations (the contract's SURVEY 8(d) figure), > peak because the "
                                      "radial ordering and the prefix tensor table let an iteration skip most of an object's particles."},
                 "cpu_baseline": cpu, "clocks": clk, "breakdown_ms_per_step_rank0": {k_: round(v_, 3) for k_, v_ in brk.items()},
