@@ -523,16 +523,22 @@ __global__ void __launch_bounds__(256) bucket_scan_kernel(const SortParams P, in
             for (int w = 0; w < warp; w++) run[j] += s_part[w][b];
         }
     }
-#pragma unroll 4
-    for (int c = s0; c < s1; c++) {
-        int32_t *row = P.tile_hist + (size_t)c * B;
+    // (8 rows are loaded before the first of them is overwritten: the compiler may not move a load above a store to the
+    // same array, and one row per L2 round trip made the largest object a 0.18 ms tail)
 #pragma unroll
-        for (int j = 0; j < NB; j++) {
-            const int b = lane + 32 * j;
-            if (b < B) {
-                const int t = row[b];
-                row[b] = run[j];
-                run[j] += t;
+    for (int j = 0; j < NB; j++) {
+        if (32 * j >= B) break;   // warp-uniform
+        const int b = lane + 32 * j;
+        const bool on = b < B;
+        int r = run[j];
+        for (int c = s0; c < s1; c += 8) {
+            int t[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) t[u] = (on && c + u < s1) ? P.tile_hist[(size_t)(c + u) * B + b] : 0;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                if (on && c + u < s1) P.tile_hist[(size_t)(c + u) * B + b] = r;
+                r += t[u];
             }
         }
     }
@@ -961,11 +967,16 @@ __global__ void __launch_bounds__(256) tile_tensor_scan_kernel(const SoA soa, in
     const int per = (nt + 7) / 8;
     const int t_lo = min(nt, warp * per), t_hi = min(nt, t_lo + per);
     double carry[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    double nxt[6];   // the next 32 rows are loaded before this round's stores (no load may move above a store to the same array)
+#pragma unroll
+    for (int c = 0; c < 6; c++) nxt[c] = t_lo + lane < t_hi ? rows[(size_t)(t_lo + lane) * 6 + c] : 0.0;
     for (int t0 = t_lo; t0 < t_hi; t0 += 32) {
         const int t = t0 + lane;
         double v[6];
 #pragma unroll
-        for (int c = 0; c < 6; c++) v[c] = t < t_hi ? rows[(size_t)t * 6 + c] : 0.0;
+        for (int c = 0; c < 6; c++) v[c] = nxt[c];
+#pragma unroll
+        for (int c = 0; c < 6; c++) nxt[c] = t + 32 < t_hi ? rows[(size_t)(t + 32) * 6 + c] : 0.0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
 #pragma unroll
