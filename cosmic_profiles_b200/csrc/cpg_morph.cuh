@@ -913,6 +913,36 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
 // the ring: a task of <= 2 tiles stays resident in its slot's half, a streamed pass takes the whole ring when the other
 // slot holds nothing resident and its own half otherwise.  Which phase of a stage's mbarrier comes next is tracked in
 // `phase` (one bit per stage; every issue to a stage is waited for exactly once before the next issue to it).
+// The per-lane copies of ring_issue_lanes as a cp.async GROUP of the issuing thread (no mbarrier): lane l copies -- and later
+// consumes -- pairs l and l + 32 of every stream, so a thread only ever reads shared memory that it filled itself and
+// cp.async.wait_group is all the synchronisation a streamed tile needs.
+#ifndef CPG_RT_GROUPS
+#define CPG_RT_GROUPS 1
+#endif
+template <bool VDISP, int STG>
+__device__ __forceinline__ void ring_issue_group(const WarpRing &r, uint32_t stage, const SoA &soa, int64_t base, int t, int npairs, int lane)
+{
+    using C = RingCfg<VDISP, STG>;
+    const int n = min(TILE_PAIRS, npairs - t * TILE_PAIRS);
+    const uint32_t dst = r.buf_s + stage * C::STAGE_BYTES;
+    const int64_t o = base + (int64_t)t * (2 * TILE_PAIRS);
+    const double *src[7] = {soa.dx, soa.dy, soa.dz, soa.m, soa.vx, soa.vy, soa.vz};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int pi = lane + 32 * h;
+        if (pi < n) {
+#pragma unroll
+            for (int st = 0; st < C::NSTREAM; st++)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + st * C::STREAM_BYTES + pi * 16u),
+                             "l"(src[st] + o + 2 * pi)
+                             : "memory");
+        }
+    }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int S, bool SHELL, bool REDUCED, bool VDISP>
 __device__ __forceinline__ void run_pass_rt(const SoA &soa, int64_t base, int npairs, int lane, WarpRing &ring, unsigned &phase,
                                             int sbase, int nst, bool resident, bool &res_loaded, int npairs_task,
@@ -940,17 +970,34 @@ __device__ __forceinline__ void run_pass_rt(const SoA &soa, int64_t base, int np
     const int npairs_load = resident ? npairs_task : npairs;
     const int issue_n = (resident && !reuse) ? (npairs_task + TILE_PAIRS - 1) / TILE_PAIRS : nmine;   // (resident: <= nst tiles)
     const int smask_st = nst - 1;
-    if (!reuse)
-        for (int j = 0; j < min(issue_n, nst); j++)
-            ring_issue_lanes<VDISP, STG>(ring, (uint32_t)(sbase + j), soa, base, tile0 + j, npairs_load, lane);
+    if (!reuse) {
+        if (CPG_RT_GROUPS) {
+            // exactly nst groups in flight at any time (empty ones where there is nothing to copy): tile j is complete when
+            // at most nst - 1 younger groups are pending
+            for (int j = 0; j < nst; j++) {
+                if (j < issue_n) ring_issue_group<VDISP, STG>(ring, (uint32_t)(sbase + j), soa, base, tile0 + j, npairs_load, lane);
+                cp_async_commit();
+            }
+        } else {
+            for (int j = 0; j < min(issue_n, nst); j++)
+                ring_issue_lanes<VDISP, STG>(ring, (uint32_t)(sbase + j), soa, base, tile0 + j, npairs_load, lane);
+        }
+    }
     for (int j = 0; j < nmine; j++) {
         const int t = tile0 + j;
         const uint32_t stage = (uint32_t)(sbase + (j & smask_st));
         if (!reuse) {
-            mbar_wait(ring.bar_s + stage * 8u, (phase >> stage) & 1u);
-            phase ^= 1u << stage;
+            if (CPG_RT_GROUPS) {
+                if (nst == 4) cp_async_wait<3>(); else cp_async_wait<1>();
+            } else {
+                mbar_wait(ring.bar_s + stage * 8u, (phase >> stage) & 1u);
+                phase ^= 1u << stage;
+            }
             const int loaded = min(TILE_PAIRS, npairs_load - t * TILE_PAIRS);
-            if (loaded < TILE_PAIRS) ring_fill_tail<VDISP, STG>(ring, stage, lane, loaded);
+            if (loaded < TILE_PAIRS) {
+                if (CPG_RT_GROUPS) __syncwarp();   // the fill touches other lanes' pairs: they are done with the stage's previous tile
+                ring_fill_tail<VDISP, STG>(ring, stage, lane, loaded);
+            }
         }
         unsigned smask = 0;
 #pragma unroll
@@ -967,17 +1014,29 @@ __device__ __forceinline__ void run_pass_rt(const SoA &soa, int64_t base, int np
             ring_read_pair<VDISP, STG>(ring, stage, lane + 32, p[2], p[3]);
             passk_particles<S, SHELL, REDUCED, VDISP, 4>(p, frames, smask, acc, cnt);
         }
-        if (!resident && j + nst < nmine) {
+        if (CPG_RT_GROUPS) {
+            if (!reuse) {
+                // (a lane overwrites only the pairs it has just read itself: no warp barrier)
+                if (!resident && j + nst < nmine) ring_issue_group<VDISP, STG>(ring, stage, soa, base, t + nst, npairs_load, lane);
+                cp_async_commit();
+            }
+        } else if (!resident && j + nst < nmine) {
             __syncwarp();   // every lane has taken its data out of this stage
             ring_issue_lanes<VDISP, STG>(ring, stage, soa, base, t + nst, npairs_load, lane);
         }
     }
+    if (CPG_RT_GROUPS && !reuse) {
+        cp_async_wait<0>();   // nothing in flight between passes (resident tiles beyond the active range included)
+        __syncwarp();
+    }
     if (!reuse && resident) {
-        // the barriers of resident tiles beyond the first pass's active range have not been waited on yet
+        // the resident tiles beyond the first pass's active range have not been waited on / completed yet
         for (int j = nmine; j < issue_n; j++) {
             const uint32_t stage = (uint32_t)(sbase + j);
-            mbar_wait(ring.bar_s + stage * 8u, (phase >> stage) & 1u);
-            phase ^= 1u << stage;
+            if (!CPG_RT_GROUPS) {
+                mbar_wait(ring.bar_s + stage * 8u, (phase >> stage) & 1u);
+                phase ^= 1u << stage;
+            }
             const int loaded = min(TILE_PAIRS, npairs_load - j * TILE_PAIRS);
             if (loaded < TILE_PAIRS) ring_fill_tail<VDISP, STG>(ring, stage, lane, loaded);
         }
