@@ -789,6 +789,36 @@ __device__ __forceinline__ void ring_fill_tail(const WarpRing &r, uint32_t seq, 
     __syncwarp();
 }
 
+// The per-lane copies of ring_issue_lanes as a cp.async GROUP of the issuing thread (no mbarrier): lane l copies -- and later
+// consumes -- pairs l and l + 32 of every stream, so a thread only ever reads shared memory that it filled itself and
+// cp.async.wait_group is all the synchronisation a streamed tile needs.
+#ifndef CPG_RT_GROUPS
+#define CPG_RT_GROUPS 1
+#endif
+template <bool VDISP, int STG>
+__device__ __forceinline__ void ring_issue_group(const WarpRing &r, uint32_t stage, const SoA &soa, int64_t base, int t, int npairs, int lane)
+{
+    using C = RingCfg<VDISP, STG>;
+    const int n = min(TILE_PAIRS, npairs - t * TILE_PAIRS);
+    const uint32_t dst = r.buf_s + stage * C::STAGE_BYTES;
+    const int64_t o = base + (int64_t)t * (2 * TILE_PAIRS);
+    const double *src[7] = {soa.dx, soa.dy, soa.dz, soa.m, soa.vx, soa.vy, soa.vz};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int pi = lane + 32 * h;
+        if (pi < n) {
+#pragma unroll
+            for (int st = 0; st < C::NSTREAM; st++)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + st * C::STREAM_BYTES + pi * 16u),
+                             "l"(src[st] + o + 2 * pi)
+                             : "memory");
+        }
+    }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // One full pass over the object's radial prefix.  This warp consumes tiles tile0, tile0+tstride, ... of the
 // `npairs` pairs that the still-active shells need; npr[s] = pairs in the prefix of shell s.
 // resident: every tile this warp will ever need for the task fits in its ring -> loaded by the first pass,
@@ -827,7 +857,13 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
         const int nt_task = (npairs_task + TILE_PAIRS - 1) / TILE_PAIRS;
         issue_n = tile0 < nt_task ? (nt_task - tile0 + tstride - 1) / tstride : 0;
     }
-    if (!reuse && LANES) {
+    constexpr bool GROUPS = LANES && CPG_RT_GROUPS;   // per-lane cp.async groups instead of mbarriers (see ring_issue_group)
+    if (!reuse && GROUPS) {
+        for (int j = 0; j < RING_STAGES; j++) {   // exactly RING_STAGES groups in flight at any time (empty ones included)
+            if (j < issue_n) ring_issue_group<VDISP, STG>(ring, (seq0 + j) % RING_STAGES, soa, base, tile0 + j * tstride, npairs_load, lane);
+            cp_async_commit();
+        }
+    } else if (!reuse && LANES) {
         for (int j = 0; j < min(issue_n, RING_STAGES); j++)
             ring_issue_lanes<VDISP, STG>(ring, seq0 + j, soa, base, tile0 + j * tstride, npairs_load, lane);
     } else if (!reuse && lane == 0)
@@ -837,11 +873,15 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
         const int t = tile0 + j * tstride;
         const uint32_t seq = seq0 + j;
         if (!reuse) {
-            mbar_wait(ring.bar_s + (seq % RING_STAGES) * 8u, (seq / RING_STAGES) & 1u);
+            if (GROUPS) cp_async_wait<RING_STAGES - 1>();
+            else mbar_wait(ring.bar_s + (seq % RING_STAGES) * 8u, (seq / RING_STAGES) & 1u);
             // only the last tile of the loaded range can be partial (particles past the active prefix but
             // inside the loaded range are real particles that fail every membership test)
             const int loaded = min(TILE_PAIRS, npairs_load - t * TILE_PAIRS);
-            if (loaded < TILE_PAIRS) ring_fill_tail<VDISP, STG>(ring, seq, lane, loaded);
+            if (loaded < TILE_PAIRS) {
+                if (GROUPS) __syncwarp();   // the fill touches other lanes' pairs: they are done with the slot's previous tile
+                ring_fill_tail<VDISP, STG>(ring, seq, lane, loaded);
+            }
         }
         unsigned smask = 0;
 #pragma unroll
@@ -883,7 +923,13 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
             else
                 passk_particles<S, SHELL, REDUCED, VDISP, 4>(p, frames, smask, acc, cnt);
         }
-        if (!resident && j + RING_STAGES < nmine) {
+        if (GROUPS) {
+            if (!reuse) {   // (a lane overwrites only the pairs it has just read itself: no warp barrier)
+                if (!resident && j + RING_STAGES < nmine)
+                    ring_issue_group<VDISP, STG>(ring, seq % RING_STAGES, soa, base, t + RING_STAGES * tstride, npairs_load, lane);
+                cp_async_commit();
+            }
+        } else if (!resident && j + RING_STAGES < nmine) {
             __syncwarp();   // every lane has taken its data out of this slot
             if (LANES)
                 ring_issue_lanes<VDISP, STG>(ring, seq + RING_STAGES, soa, base, t + RING_STAGES * tstride, npairs_load, lane);
@@ -892,10 +938,14 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
         }
     }
     if (!reuse) {
+        if (GROUPS) {
+            cp_async_wait<0>();   // nothing in flight between passes (resident tiles beyond the active range included)
+            __syncwarp();
+        }
         if (resident) {
             // the barriers of resident tiles beyond the first pass's active range have not been waited on yet
             for (int j = nmine; j < issue_n; j++) {
-                mbar_wait(ring.bar_s + ((seq0 + j) % RING_STAGES) * 8u, ((seq0 + j) / RING_STAGES) & 1u);
+                if (!GROUPS) mbar_wait(ring.bar_s + ((seq0 + j) % RING_STAGES) * 8u, ((seq0 + j) / RING_STAGES) & 1u);
                 const int loaded = min(TILE_PAIRS, npairs_load - (tile0 + j * tstride) * TILE_PAIRS);
                 if (loaded < TILE_PAIRS) ring_fill_tail<VDISP, STG>(ring, seq0 + j, lane, loaded);
             }
@@ -913,36 +963,6 @@ __device__ __forceinline__ void run_pass(const SoA &soa, int64_t base, int npair
 // the ring: a task of <= 2 tiles stays resident in its slot's half, a streamed pass takes the whole ring when the other
 // slot holds nothing resident and its own half otherwise.  Which phase of a stage's mbarrier comes next is tracked in
 // `phase` (one bit per stage; every issue to a stage is waited for exactly once before the next issue to it).
-// The per-lane copies of ring_issue_lanes as a cp.async GROUP of the issuing thread (no mbarrier): lane l copies -- and later
-// consumes -- pairs l and l + 32 of every stream, so a thread only ever reads shared memory that it filled itself and
-// cp.async.wait_group is all the synchronisation a streamed tile needs.
-#ifndef CPG_RT_GROUPS
-#define CPG_RT_GROUPS 1
-#endif
-template <bool VDISP, int STG>
-__device__ __forceinline__ void ring_issue_group(const WarpRing &r, uint32_t stage, const SoA &soa, int64_t base, int t, int npairs, int lane)
-{
-    using C = RingCfg<VDISP, STG>;
-    const int n = min(TILE_PAIRS, npairs - t * TILE_PAIRS);
-    const uint32_t dst = r.buf_s + stage * C::STAGE_BYTES;
-    const int64_t o = base + (int64_t)t * (2 * TILE_PAIRS);
-    const double *src[7] = {soa.dx, soa.dy, soa.dz, soa.m, soa.vx, soa.vy, soa.vz};
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int pi = lane + 32 * h;
-        if (pi < n) {
-#pragma unroll
-            for (int st = 0; st < C::NSTREAM; st++)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + st * C::STREAM_BYTES + pi * 16u),
-                             "l"(src[st] + o + 2 * pi)
-                             : "memory");
-        }
-    }
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 template <int S, bool SHELL, bool REDUCED, bool VDISP>
 __device__ __forceinline__ void run_pass_rt(const SoA &soa, int64_t base, int npairs, int lane, WarpRing &ring, unsigned &phase,
                                             int sbase, int nst, bool resident, bool &res_loaded, int npairs_task,
