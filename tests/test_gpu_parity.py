@@ -316,6 +316,27 @@ def test_unusual_radii_and_limits(gpu, big):
     sess.options.clear()
 
 
+def test_centres_cache_keeps_the_gather_resident(gpu, big):
+    """The reference's class recomputes the centres in every driver from the same arrays; the device returns the cached
+    ones, so getShapeCatGlobal right after getShapeCatLocal neither recomputes centres nor gathers again -- and a new
+    snapshot invalidates the cache."""
+    S, D, sess = gpu
+    cat, rr, _, _ = big
+    X, M, R2, I, Z = _args(cat)
+    a = S.calcMorphLocal(X, M, R2, I, Z, 0.0, rr, 1e-2, 100, 10, "com", False, False)
+    t_local = S.last_info["timing"][0]
+    b = S.calcMorphGlobal(X, M, R2, I, Z, 0.0, 1e-2, 100, 10, "com", 6.0, False)
+    t_global = S.last_info["timing"][0]
+    assert t_local["gather_ms"] > 0.0
+    assert t_global["gather_ms"] < 0.02, t_global            # resident SoA reused (an event pair around nothing)
+    assert np.array_equal(a[6], b[6])                        # same centres
+    X2 = X + 0.25                                            # another snapshot: new centres, new gather
+    c = S.calcMorphGlobal(X2, M, R2, I, Z, 0.0, 1e-2, 100, 10, "com", 6.0, False)
+    assert S.last_info["timing"][0]["gather_ms"] > 0.0
+    np.testing.assert_allclose(c[6], b[6] + 0.25, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(c[1], b[1], rtol=1e-9)        # q of a translated catalogue
+
+
 def test_device_centres_large_objects(gpu):
     """Objects above the cluster threshold of cpg_centers (8 CTAs per object, slice-local compaction, partial sums
     exchanged through distributed shared memory): same 'mode' / 'com' centres as the numpy restatement, with and
